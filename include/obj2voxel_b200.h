@@ -1,0 +1,119 @@
+/* Additive C-ABI of libobj2voxel_b200.so: bulk / device-resident entry points around the same kernels that serve
+ * obj2voxel_voxelize().  Plain pointers and sizes only (no torch / C++ types).
+ *
+ * What each entry point stands in for in the reference:
+ *   o2v_b200_voxelize_device   the hot path itself — obj2voxel::Voxelizer::voxelize() per (triangle, chunk)
+ *                              (src/voxelization.cpp:480-526) together with the driver steps that feed it
+ *                              (findMeshBounds / computeMeshTransform / applyMeshTransform / chunk sort / voxelizeChunk,
+ *                              src/obj2voxel.cpp:180-314,370-402) — with inputs and outputs in HBM
+ *   o2v_b200_voxelize_host     the same with host buffers (H2D + kernels + D2H), i.e. obj2voxel_voxelize() without the
+ *                              one-indirect-call-per-triangle ITriangleStream (src/obj2voxel.cpp:585-588)
+ *   obj2voxel_b200_set_input_triangles   bulk replacement for obj2voxel_set_input_callback (include/obj2voxel.h:177)
+ *   slab_z0 / slab_z1          the unit of multi-GPU partitioning: a Z-slab of 64^3-chunk rows
+ *                              (src/obj2voxel.cpp:245-252 computeChunkBounds gives the reference's clip boxes)
+ */
+#ifndef OBJ2VOXEL_B200_HEADER
+#define OBJ2VOXEL_B200_HEADER
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "obj2voxel.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct o2v_b200_engine o2v_b200_engine;
+
+/* obj2voxel::TriangleType, reference src/triangle.hpp:21-30 */
+#define O2V_B200_TRI_MATERIALLESS 1
+#define O2V_B200_TRI_UNTEXTURED 2
+#define O2V_B200_TRI_TEXTURED 3
+
+typedef struct o2v_b200_params {
+    uint32_t resolution;        /* output resolution R */
+    uint32_t supersampling;     /* 1 or 2 (sample resolution S = R * supersampling) */
+    uint32_t strategy;          /* OBJ2VOXEL_MAX_STRATEGY / OBJ2VOXEL_BLEND_STRATEGY */
+    uint32_t bounds_known;      /* 0: compute mesh bounds on the device */
+    float bounds[6];            /* min xyz, max xyz */
+    int32_t unit_transform[9];  /* row-major */
+    uint32_t slab_z0, slab_z1;  /* owned sample-space z range [z0, z1), multiples of 8; 0,0 = the whole grid */
+    int32_t variant;            /* kernel variant, -1 = default */
+    int32_t prefilter;          /* 1 = conservative SAT prefilter on (default); 0 = off (validation only) */
+} o2v_b200_params;
+
+typedef struct o2v_b200_mesh {
+    const float *verts;          /* 9 floats per triangle, model space */
+    const float *uvs;            /* 6 floats per triangle or NULL */
+    const uint8_t *types;        /* O2V_B200_TRI_* per triangle or NULL (textured if uvs and textures, else materialless) */
+    const float *colors;         /* 3 floats per triangle or NULL (O2V_B200_TRI_UNTEXTURED) */
+    const uint32_t *texture_ids; /* per-triangle index into the texture array or NULL (0) */
+    uint64_t count;
+} o2v_b200_mesh;
+
+typedef struct o2v_b200_texture {
+    const uint8_t *pixels; /* row-major, `channels` bytes per pixel */
+    uint32_t width, height;
+    uint32_t channels; /* 3 or 4 */
+    uint32_t wrap;     /* OBJ2VOXEL_UV_CLAMP / OBJ2VOXEL_UV_WRAP */
+} o2v_b200_texture;
+
+typedef struct o2v_b200_stats {
+    uint64_t voxels;            /* emitted voxels */
+    uint64_t leaves;            /* sub-triangles after the reference's subdivision */
+    uint64_t pairs;             /* (leaf, tile) pairs */
+    uint64_t active_tiles;
+    uint64_t candidate_voxels;  /* sum of leaf AABB volumes */
+    uint64_t clip_calls;        /* exact six-plane clips executed */
+    uint64_t contributions;     /* (triangle, voxel) merges = N_contrib */
+    uint64_t dropped_triangles; /* zero-area / non-finite */
+    uint64_t depth_overflow;
+    uint64_t out_capacity;
+    float ms_total, ms_setup, ms_voxelize; /* device time, CUDA events on the run stream */
+    float transform[12];
+    int32_t kernel_launches;
+    int32_t voxelize_launches;
+} o2v_b200_stats;
+
+/* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */
+o2v_b200_engine *o2v_b200_engine_create(int device);
+void o2v_b200_engine_destroy(o2v_b200_engine *engine);
+const char *o2v_b200_last_error(void);
+int o2v_b200_sm_count(const o2v_b200_engine *engine);
+void o2v_b200_default_params(o2v_b200_params *params);
+
+/* All pointers inside mesh and textures[].pixels are DEVICE pointers; textures itself is a host array.
+ * cuda_stream is a cudaStream_t (NULL = default stream).  Returns 0 or a negative error code. */
+int o2v_b200_voxelize_device(o2v_b200_engine *engine, const o2v_b200_params *params, const o2v_b200_mesh *mesh,
+                             const o2v_b200_texture *textures, uint32_t texture_count, void *cuda_stream,
+                             o2v_b200_stats *out_stats);
+
+/* Result of the last run: `count` records of {int32 x, y, z; uint32 argb} in device memory owned by the engine. */
+const void *o2v_b200_result_device(const o2v_b200_engine *engine);
+uint64_t o2v_b200_result_count(const o2v_b200_engine *engine);
+int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda_stream);
+
+/* Host-buffer convenience: uploads the mesh (and textures), runs, downloads up to out_capacity records into out_voxels
+ * (4 u32 each).  *out_count receives the number of voxels produced (may exceed out_capacity: then nothing past the
+ * capacity is written and -5 is returned). */
+int o2v_b200_voxelize_host(o2v_b200_engine *engine, const o2v_b200_params *params, const o2v_b200_mesh *mesh,
+                           const o2v_b200_texture *textures, uint32_t texture_count, uint32_t *out_voxels,
+                           uint64_t out_capacity, uint64_t *out_count, o2v_b200_stats *out_stats);
+
+/* ---- additive setters on the reference-compatible instance ------------------------------------------------------- */
+
+/* Bulk input: count triangles as 9 floats each (+ 6 uv floats each and a texture when textured).  The arrays are not
+ * copied and must stay valid until obj2voxel_voxelize() returns. */
+void obj2voxel_b200_set_input_triangles(obj2voxel_instance *instance, const float *vertices, const float *uvs,
+                                        size_t count, obj2voxel_texture *texture);
+/* Restrict the job to a Z-slab of the sample grid (multiples of 8). */
+void obj2voxel_b200_set_slab(obj2voxel_instance *instance, uint32_t z0, uint32_t z1);
+/* Statistics of the last obj2voxel_voxelize() on this instance. */
+void obj2voxel_b200_get_stats(obj2voxel_instance *instance, o2v_b200_stats *out_stats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* OBJ2VOXEL_B200_HEADER */

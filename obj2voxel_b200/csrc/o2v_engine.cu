@@ -1,0 +1,344 @@
+// o2v::Engine — buffer management and kernel sequencing for one GPU (see o2v_engine.h).
+#include "o2v_engine.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace o2v {
+
+#define O2V_CUDA(expr)                                                                                  \
+    do {                                                                                                \
+        const cudaError_t err__ = (expr);                                                               \
+        if (err__ != cudaSuccess) {                                                                     \
+            return fail(kErrCuda, std::string(#expr) + ": " + cudaGetErrorString(err__));               \
+        }                                                                                               \
+    } while (0)
+
+DeviceBuffer::~DeviceBuffer()
+{
+    if (ptr_ != nullptr) {
+        cudaFree(ptr_);
+    }
+}
+
+bool DeviceBuffer::ensure(size_t bytes)
+{
+    if (bytes <= size_) {
+        return true;
+    }
+    // grow with head-room so repeated runs of slightly different sizes do not reallocate every time
+    const size_t wanted = bytes + bytes / 8 + 256;
+    void *fresh = nullptr;
+    if (cudaMalloc(&fresh, wanted) != cudaSuccess) {
+        cudaGetLastError();
+        if (cudaMalloc(&fresh, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        size_ = bytes;
+    }
+    else {
+        size_ = wanted;
+    }
+    if (ptr_ != nullptr) {
+        cudaFree(ptr_);
+    }
+    ptr_ = fresh;
+    return true;
+}
+
+Engine *Engine::create(int device, std::string *error)
+{
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        if (error != nullptr) {
+            *error = std::string("no CUDA device available (") + cudaGetErrorString(err) +
+                     "); obj2voxel_b200 has no CPU fallback";
+        }
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        if (error != nullptr) {
+            *error = "invalid CUDA device index";
+        }
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess) {
+        if (error != nullptr) {
+            *error = cudaGetErrorString(err);
+        }
+        return nullptr;
+    }
+    Engine *e = new Engine();
+    e->device_ = device;
+    e->smCount_ = prop.multiProcessorCount;
+    e->totalMemory_ = prop.totalGlobalMem;
+    bool ok = cudaMallocHost(&e->hostCounters_, sizeof(RunCounters)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&e->hostCountersInit_, sizeof(RunCounters)) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->evStart_) == cudaSuccess && cudaEventCreate(&e->evSetup_) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->evVoxStart_) == cudaSuccess && cudaEventCreate(&e->evVoxEnd_) == cudaSuccess;
+    ok = ok && e->counters_.ensure(sizeof(RunCounters));
+    if (!ok) {
+        if (error != nullptr) {
+            *error = std::string("engine setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        }
+        delete e;
+        return nullptr;
+    }
+    memset(e->hostCountersInit_, 0, sizeof(RunCounters));
+    for (int i = 0; i < 3; ++i) {
+        e->hostCountersInit_->boundsMinBits[i] = 0xffffffffu;
+        e->hostCountersInit_->boundsMaxBits[i] = 0u;
+    }
+    return e;
+}
+
+Engine::~Engine()
+{
+    cudaSetDevice(device_);
+    if (hostCounters_ != nullptr) {
+        cudaFreeHost(hostCounters_);
+    }
+    if (hostCountersInit_ != nullptr) {
+        cudaFreeHost(hostCountersInit_);
+    }
+    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_}) {
+        if (ev != nullptr) {
+            cudaEventDestroy(ev);
+        }
+    }
+}
+
+int Engine::fail(int code, const std::string &message)
+{
+    error_ = message;
+    cudaGetLastError();
+    return code;
+}
+
+int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t textureCount,
+                     const EngineParams &params, cudaStream_t stream, RunStats *stats)
+{
+    error_.clear();
+    voxelCount_ = 0;
+    RunStats local;
+    RunStats &st = stats != nullptr ? *stats : local;
+    st = RunStats();
+
+    if (params.resolution == 0 || params.supersampling == 0 || params.supersampling > 2 || params.strategy > 1) {
+        return fail(kErrBadParams, "resolution must be > 0, supersampling 1 or 2, strategy 0 or 1");
+    }
+    const unsigned long long sampleRes64 = (unsigned long long) params.resolution * params.supersampling;
+    if (sampleRes64 > 8192ull) {
+        return fail(kErrTooLarge, "sample resolution above 8192 is not supported");
+    }
+    if (mesh.count >= (1ull << 32)) {
+        return fail(kErrTooLarge, "more than 2^32-1 triangles");
+    }
+    const uint32_t S = (uint32_t) sampleRes64;
+    O2V_CUDA(cudaSetDevice(device_));
+
+    RunCounters *dCounters = counters_.as<RunCounters>();
+    O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+    O2V_CUDA(cudaEventRecord(evStart_, stream));
+    memset(&st.counters, 0, sizeof st.counters);
+    if (mesh.count == 0) {
+        return kErrOk;  // src/obj2voxel.cpp:590-594: empty model, empty output
+    }
+
+    // ---- bounds + transform (src/obj2voxel.cpp:475-482) ----
+    float meshMin[3], meshMax[3];
+    if (params.boundsKnown) {
+        memcpy(meshMin, params.bounds, sizeof meshMin);
+        memcpy(meshMax, params.bounds + 3, sizeof meshMax);
+    }
+    else {
+        launchBounds(mesh, dCounters, stream);
+        launchFinishBounds(dCounters, stream);
+        st.kernelLaunches += 2;
+        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        memcpy(meshMin, hostCounters_->boundsMin, sizeof meshMin);
+        memcpy(meshMax, hostCounters_->boundsMax, sizeof meshMax);
+    }
+
+    GridView grid;
+    computeMeshTransform(meshMin, meshMax, S, params.unitTransform, grid.xf);
+    memcpy(st.transform, grid.xf, sizeof st.transform);
+    grid.sampleRes = S;
+    grid.tilesPerAxis = (S + kTileEdge - 1) / kTileEdge;
+    const uint32_t gridZ = grid.tilesPerAxis * kTileEdge;
+    uint32_t z0 = params.slabZ0, z1 = params.slabZ1;
+    if (z0 == 0 && z1 == 0) {
+        z1 = gridZ;
+    }
+    z1 = std::min(z1, gridZ);
+    if (z0 % kTileEdge != 0 || z1 % kTileEdge != 0 || z0 > z1) {
+        return fail(kErrBadParams, "slab bounds must be multiples of 8 with z0 <= z1");
+    }
+    grid.slabZ0 = z0;
+    grid.slabZ1 = z1;
+    grid.slabTileZ0 = z0 / kTileEdge;
+    grid.slabTileZCount = (z1 - z0) / kTileEdge;
+    grid.supersampling = params.supersampling;
+    grid.strategy = params.strategy;
+    if (grid.slabTileZCount == 0) {
+        return kErrOk;
+    }
+
+    const unsigned long long tileTotal64 =
+        (unsigned long long) grid.tilesPerAxis * grid.tilesPerAxis * grid.slabTileZCount;
+    if (tileTotal64 >= (1ull << 31)) {
+        return fail(kErrTooLarge, "tile grid too large");
+    }
+    const uint32_t tileTotal = (uint32_t) tileTotal64;
+    const size_t n = (size_t) mesh.count;
+
+    const size_t scratchElems = std::max(scanScratchElems(n), scanScratchElems(tileTotal));
+    if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !tileCount_.ensure((size_t) tileTotal * 4) ||
+        !tileStart_.ensure((size_t) tileTotal * 4) || !tileFill_.ensure((size_t) tileTotal * 4) ||
+        !activeTiles_.ensure((size_t) tileTotal * 4) || !scratch_.ensure(scratchElems * 4)) {
+        return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
+    }
+    O2V_CUDA(cudaMemsetAsync(tileCount_.as<void>(), 0, (size_t) tileTotal * 4, stream));
+    O2V_CUDA(cudaMemsetAsync(tileFill_.as<void>(), 0, (size_t) tileTotal * 4, stream));
+
+    launchCountLeaves(mesh, grid, leafCount_.as<uint32_t>(), tileCount_.as<uint32_t>(), dCounters, stream);
+    launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
+                        &dCounters->leaves, stream);
+    launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
+                        &dCounters->pairs, stream);
+    launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileTotal, activeTiles_.as<uint32_t>(), dCounters, stream);
+    st.kernelLaunches += 8;
+    O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
+
+    const unsigned long long leafTotal = hostCounters_->leaves;
+    const unsigned long long pairTotal = hostCounters_->pairs;
+    const unsigned long long activeTotal = hostCounters_->activeTiles;
+    if (leafTotal >= (1ull << 32) || pairTotal >= (1ull << 32)) {
+        return fail(kErrTooLarge, "more than 2^32-1 leaves or (leaf, tile) pairs in this slab");
+    }
+
+    // Output capacity: every voxel needs at least one candidate, and a tile emits at most 512 (64 when downscaled).
+    const unsigned long long perTile = params.supersampling == 2 ? kTileVoxels / 8 : kTileVoxels;
+    unsigned long long capacity = std::min(hostCounters_->candidateVoxels, activeTotal * perTile);
+    capacity = std::max<unsigned long long>(capacity, 1);
+
+    const bool hasUv = mesh.uvs != nullptr;
+    if (!leaves_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafRecord)) ||
+        (hasUv && !leafUvs_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafUv))) ||
+        !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4)) {
+        return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
+    }
+    size_t freeBytes = 0, totalBytes = 0;
+    O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+    if (capacity * sizeof(VoxelRecord) > out_.size()) {
+        const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
+        capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
+    }
+    if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+        return fail(kErrOutOfMemory, "device allocation failed (voxel output)");
+    }
+    if (textureCount != 0) {
+        if (!textures_.ensure(textureCount * sizeof(TextureView))) {
+            return fail(kErrOutOfMemory, "device allocation failed (texture table)");
+        }
+        O2V_CUDA(cudaMemcpyAsync(textures_.as<void>(), textures, textureCount * sizeof(TextureView),
+                                 cudaMemcpyHostToDevice, stream));
+    }
+
+    launchEmitLeaves(mesh, grid, leafOffset_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileFill_.as<uint32_t>(),
+                     leaves_.as<LeafRecord>(), hasUv ? leafUvs_.as<LeafUv>() : nullptr, tileList_.as<uint32_t>(),
+                     dCounters, stream);
+    TileWork work;
+    work.activeTiles = activeTiles_.as<uint32_t>();
+    work.tileStart = tileStart_.as<uint32_t>();
+    work.tileCount = tileCount_.as<uint32_t>();
+    work.tileList = tileList_.as<uint32_t>();
+    work.activeCount = (uint32_t) activeTotal;
+    launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
+    st.kernelLaunches += 3;
+    O2V_CUDA(cudaEventRecord(evSetup_, stream));
+
+    VoxelizeArgs args;
+    args.grid = grid;
+    args.work = work;
+    args.leaves = leaves_.as<LeafRecord>();
+    args.leafUvs = hasUv ? leafUvs_.as<LeafUv>() : nullptr;
+    args.mesh = mesh;
+    args.textures = textureCount != 0 ? textures_.as<TextureView>() : nullptr;
+    args.textureCount = textureCount;
+    args.out = out_.as<VoxelRecord>();
+    args.outCapacity = capacity;
+    args.counters = dCounters;
+    args.variant = params.variant < 0 ? 0 : params.variant;
+    args.prefilter = params.prefilter;
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
+        launchVoxelizeTiles(args, smCount_, stream);
+        O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
+        ++st.voxelizeLaunches;
+        ++st.kernelLaunches;
+        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        O2V_CUDA(cudaGetLastError());
+        if (hostCounters_->outputOverflow == 0) {
+            break;
+        }
+        if (attempt == 1) {
+            return fail(kErrOutOfMemory, "voxel output does not fit device memory");
+        }
+        // the exact count is now known: grow once and redo the tile pass (setup results are still valid)
+        capacity = hostCounters_->voxels;
+        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+            return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
+        }
+        args.out = out_.as<VoxelRecord>();
+        args.outCapacity = capacity;
+        RunCounters reset = *hostCounters_;
+        reset.voxels = 0;
+        reset.contributions = 0;
+        reset.clipCalls = 0;
+        reset.outputOverflow = 0;
+        reset.tileCursor = 0;
+        *hostCountersInit_ = reset;
+        O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        memset(hostCountersInit_, 0, sizeof(RunCounters));
+        for (int i = 0; i < 3; ++i) {
+            hostCountersInit_->boundsMinBits[i] = 0xffffffffu;
+        }
+    }
+
+    st.counters = *hostCounters_;
+    st.outCapacity = capacity;
+    voxelCount_ = hostCounters_->voxels;
+    cudaEventElapsedTime(&st.msTotal, evStart_, evVoxEnd_);
+    cudaEventElapsedTime(&st.msSetup, evStart_, evSetup_);
+    cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
+    return kErrOk;
+}
+
+int Engine::download(void *hostDst, cudaStream_t stream)
+{
+    if (voxelCount_ == 0) {
+        return kErrOk;
+    }
+    O2V_CUDA(cudaSetDevice(device_));
+    O2V_CUDA(cudaMemcpyAsync(hostDst, out_.as<void>(), (size_t) voxelCount_ * sizeof(VoxelRecord),
+                             cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    return kErrOk;
+}
+
+}  // namespace o2v

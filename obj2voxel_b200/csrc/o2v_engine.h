@@ -1,0 +1,114 @@
+// Host-side driver of the B200 voxelizer: owns the device buffers of one GPU and runs the kernel pipeline of
+// o2v_kernels.cuh on a caller-provided stream.  Mirrors what src/obj2voxel.cpp:467-520 (voxelize_specialized) does on the
+// host for the reference: bounds -> transform -> (chunk sort | tile binning) -> voxelize -> sink.
+#ifndef O2V_ENGINE_H
+#define O2V_ENGINE_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "o2v_kernels.cuh"
+
+namespace o2v {
+
+/// src/obj2voxel.cpp:370-402 (computeMeshTransform), exact binary32, host side (o2v_host_math.cpp, -ffp-contract=off).
+void computeMeshTransform(const float meshMin[3], const float meshMax[3], uint32_t sampleResolution, const int unit[9],
+                          float out[12]);
+
+struct EngineParams {
+    uint32_t resolution = 0;
+    uint32_t supersampling = 1;
+    uint8_t strategy = kMax;
+    bool boundsKnown = false;
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+    int unitTransform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    uint32_t slabZ0 = 0, slabZ1 = 0;  // owned sample-space z range, multiples of 8; 0,0 = whole grid
+    int variant = -1;                 // -1 = default kernel variant
+    int prefilter = 1;
+};
+
+struct RunStats {
+    RunCounters counters;
+    float transform[12];
+    float msTotal = 0;     // device time of the whole pipeline (CUDA events on the run stream)
+    float msSetup = 0;     // bounds + count + scans + emit + sort
+    float msVoxelize = 0;  // the hot kernel
+    int voxelizeLaunches = 0;
+    int kernelLaunches = 0;
+    unsigned long long outCapacity = 0;
+};
+
+class DeviceBuffer {
+public:
+    DeviceBuffer() = default;
+    ~DeviceBuffer();
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    /// Grow-only; returns false (and leaves the old allocation) when cudaMalloc fails.
+    bool ensure(size_t bytes);
+    template <typename T>
+    T *as() const
+    {
+        return static_cast<T *>(ptr_);
+    }
+    size_t size() const { return size_; }
+
+private:
+    void *ptr_ = nullptr;
+    size_t size_ = 0;
+};
+
+class Engine {
+public:
+    /// Fails (returns nullptr, message in *error) when no CUDA device is usable: there is no CPU fallback.
+    static Engine *create(int device, std::string *error);
+    ~Engine();
+
+    int device() const { return device_; }
+    int smCount() const { return smCount_; }
+
+    /// Voxelizes a device-resident mesh.  textures: HOST array of TextureView whose pixel pointers are DEVICE pointers.
+    /// Result stays on the device (deviceVoxels / voxelCount) until the next call.  Returns 0 or a negative error.
+    int voxelize(const MeshView &mesh, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
+                 cudaStream_t stream, RunStats *stats);
+
+    const VoxelRecord *deviceVoxels() const { return out_.as<VoxelRecord>(); }
+    unsigned long long voxelCount() const { return voxelCount_; }
+    const std::string &lastError() const { return error_; }
+
+    /// Copies the result of the last run to host memory (count * 16 bytes) on `stream` and synchronises it.
+    int download(void *hostDst, cudaStream_t stream);
+
+private:
+    Engine() = default;
+    int fail(int code, const std::string &message);
+
+    int device_ = 0;
+    int smCount_ = 0;
+    size_t totalMemory_ = 0;
+    std::string error_;
+    unsigned long long voxelCount_ = 0;
+
+    RunCounters *hostCounters_ = nullptr;  // pinned
+    RunCounters *hostCountersInit_ = nullptr;  // pinned template
+    cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
+
+    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, activeTiles_, scratch_;
+    DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
+};
+
+// error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)
+enum EngineError {
+    kErrOk = 0,
+    kErrCuda = -1,
+    kErrBadParams = -2,
+    kErrOutOfMemory = -3,
+    kErrTooLarge = -4,
+};
+
+}  // namespace o2v
+
+#endif  // O2V_ENGINE_H

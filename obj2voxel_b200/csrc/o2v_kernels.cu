@@ -1,0 +1,929 @@
+// Hand-written sm_100a kernels of the B200 voxelizer (see o2v_kernels.cuh / DESIGN.md §3).
+//
+// Work decomposition (B200-first, not the reference's 64^3 chunks + worker threads):
+//   * triangles -> leaves of the reference's subdivision (exact arithmetic, deterministic order = (triangle, DFS order))
+//   * leaves are binned into 8^3-voxel tiles; every tile owns an ascending list of leaf indices
+//   * one thread block voxelizes one tile: thread = voxel, the tile's leaves stream through shared memory in list order,
+//     so the per-voxel fold order (ascending triangle index, DFS order inside a triangle) of the reference
+//     (src/obj2voxel.cpp:226-243,270-272; src/voxelization.cpp:56-63,513-526) is reproduced without atomics on voxel
+//     data, without a hash table and without a sort of contributions: accumulators live in registers and only the final
+//     16-byte Voxel32 records are written to HBM (coalesced, block-compacted).
+//   * candidate voxels are culled by a conservative triangle/box SAT (FMA allowed, margin kPrefilterMargin); survivors run
+//     the bit-exact six-plane clip of o2v_exact.cuh.
+#include "o2v_kernels.cuh"
+
+#include <stdio.h>
+
+namespace o2v {
+
+namespace {
+
+constexpr int kSetupThreads = 128;
+constexpr float kPrefilterMargin = 0.0625f;  // voxels; must exceed every rounding / planarity slack of the exact clip
+
+__device__ __forceinline__ unsigned int orderedBits(float f)
+{
+    const unsigned int b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__device__ __forceinline__ float fromOrderedBits(unsigned int u)
+{
+    const unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mesh bounds: src/obj2voxel.cpp:180-200 (min/max are exact, any reduction order gives the reference's result)
+
+__global__ void boundsKernel(const float *__restrict__ verts, unsigned long long vertexCount, RunCounters *counters)
+{
+    float mn[3] = {INFINITY, INFINITY, INFINITY};
+    float mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < vertexCount;
+         i += stride) {
+        for (int a = 0; a < 3; ++a) {
+            const float c = verts[i * 3 + a];
+            mn[a] = fminf(mn[a], c);
+            mx[a] = fmaxf(mx[a], c);
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&counters->boundsMinBits[a], orderedBits(mn[a]));
+            atomicMax(&counters->boundsMaxBits[a], orderedBits(mx[a]));
+        }
+    }
+}
+
+__global__ void finishBoundsKernel(RunCounters *counters)
+{
+    if (threadIdx.x < 3) {
+        counters->boundsMin[threadIdx.x] = fromOrderedBits(counters->boundsMinBits[threadIdx.x]);
+        counters->boundsMax[threadIdx.x] = fromOrderedBits(counters->boundsMaxBits[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// triangle setup shared by the count and emit passes
+
+template <bool UV>
+__device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridView &grid, unsigned long long i,
+                                             Tri<UV> &t, float &area)
+{
+    const float *src = mesh.verts + i * 9;
+    float in[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        in[k] = __ldg(src + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        affineApply(grid.xf, in + k * 3, t.v + k * 3);  // applyMeshTransform, src/obj2voxel.cpp:202-209
+    }
+    if (UV) {
+        const float *uv = mesh.uvs + i * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            t.t[k] = __ldg(uv + k);
+        }
+    }
+    area = triArea(t.v);
+    // weight 0 never reaches the voxel map (voxelization.cpp:466); non-finite input is a contract violation
+    return area > 0.0f && area < INFINITY;
+}
+
+/// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
+template <bool UV, typename Visit>
+__device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit)
+{
+    uint32_t rlo[3], rhi[3];
+    triVoxelBounds(root.v, rlo, rhi);
+    if (rhi[2] <= grid.slabZ0 || rlo[2] >= grid.slabZ1) {
+        return true;  // midpoints stay inside the parent's AABB, so no leaf can reach the slab
+    }
+    return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
+        uint32_t lo[3], hi[3];
+        triVoxelBounds(leaf.v, lo, hi);
+        hi[0] = min(hi[0], grid.sampleRes);
+        hi[1] = min(hi[1], grid.sampleRes);
+        lo[2] = max(lo[2], grid.slabZ0);
+        hi[2] = min(hi[2], min(grid.slabZ1, grid.sampleRes));
+        if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
+            return;
+        }
+        visit(leaf, lo, hi);
+    });
+}
+
+__device__ __forceinline__ uint32_t localTileId(const GridView &grid, uint32_t tx, uint32_t ty, uint32_t tz)
+{
+    return ((tz - grid.slabTileZ0) * grid.tilesPerAxis + ty) * grid.tilesPerAxis + tx;
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(kSetupThreads)
+countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount, uint32_t *__restrict__ tileCount,
+                  RunCounters *counters)
+{
+    unsigned long long candidates = 0, dropped = 0, overflow = 0;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
+        Tri<UV> root;
+        float area;
+        uint32_t leaves = 0;
+        if (loadTriangle<UV>(mesh, grid, i, root, area)) {
+            const bool ok = traverseLeaves<UV>(root, grid, [&](const Tri<UV> &, const uint32_t *lo, const uint32_t *hi) {
+                ++leaves;
+                candidates += (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+                for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
+                    for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
+                        for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
+                            atomicAdd(&tileCount[localTileId(grid, tx, ty, tz)], 1u);
+                        }
+                    }
+                }
+            });
+            overflow += ok ? 0 : 1;
+        }
+        else {
+            ++dropped;
+        }
+        leafCount[i] = leaves;
+    }
+    if (candidates != 0) {
+        atomicAdd(&counters->candidateVoxels, candidates);
+    }
+    if (dropped != 0) {
+        atomicAdd(&counters->droppedTriangles, dropped);
+    }
+    if (overflow != 0) {
+        atomicAdd(&counters->depthOverflow, overflow);
+    }
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(kSetupThreads)
+emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leafOffset,
+                 const uint32_t *__restrict__ tileStart, uint32_t *__restrict__ tileFill,
+                 LeafRecord *__restrict__ leaves, LeafUv *__restrict__ leafUvs, uint32_t *__restrict__ tileList)
+{
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
+        Tri<UV> root;
+        float area;
+        if (!loadTriangle<UV>(mesh, grid, i, root, area)) {
+            continue;
+        }
+        uint32_t index = leafOffset[i];
+        traverseLeaves<UV>(root, grid, [&](const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi) {
+            LeafRecord rec;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                rec.v[k] = leaf.v[k];
+            }
+            rec.tri = static_cast<uint32_t>(i);
+            rec.area = area;
+            rec.pad = 0;
+            leaves[index] = rec;
+            if (UV) {
+                LeafUv uv;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    uv.t[k] = leaf.t[k];
+                }
+                uv.pad[0] = uv.pad[1] = 0.0f;
+                leafUvs[index] = uv;
+            }
+            for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
+                for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
+                    for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
+                        const uint32_t tile = localTileId(grid, tx, ty, tz);
+                        const uint32_t slot = atomicAdd(&tileFill[tile], 1u);
+                        tileList[tileStart[tile] + slot] = index;
+                    }
+                }
+            }
+            ++index;
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// exclusive scan (u32 in, u32 out, u64 total): reduce -> single-block scan of block sums -> apply
+
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanBlock = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long blockReduceU64(unsigned long long v, unsigned long long *smem)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        smem[warp] = v;
+    }
+    __syncthreads();
+    unsigned long long total = 0;
+    if (warp == 0) {
+        total = lane < (blockDim.x >> 5) ? smem[lane] : 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            total += __shfl_xor_sync(0xffffffffu, total, o);
+        }
+    }
+    return total;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scanReduceKernel(const uint32_t *__restrict__ in, size_t n, unsigned long long *__restrict__ blockSums)
+{
+    __shared__ unsigned long long smem[32];
+    const size_t base = (size_t) blockIdx.x * kScanBlock;
+    unsigned long long sum = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const size_t i = base + (size_t) k * kScanThreads + threadIdx.x;
+        sum += i < n ? in[i] : 0u;
+    }
+    const unsigned long long total = blockReduceU64(sum, smem);
+    if (threadIdx.x == 0) {
+        blockSums[blockIdx.x] = total;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+scanTopKernel(unsigned long long *__restrict__ blockSums, size_t blocks, unsigned long long *__restrict__ total)
+{
+    __shared__ unsigned long long warpSums[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) {
+        carry = 0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (size_t base = 0; base < blocks; base += 1024) {
+        const size_t i = base + threadIdx.x;
+        const unsigned long long v = i < blocks ? blockSums[i] : 0;
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+            inc += lane >= o ? up : 0;
+        }
+        if (lane == 31) {
+            warpSums[warp] = inc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warpSums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, w, o);
+                w += lane >= o ? up : 0;
+            }
+            warpSums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long before = carry + (warp > 0 ? warpSums[warp - 1] : 0) + (inc - v);
+        if (i < blocks) {
+            blockSums[i] = before;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            carry += warpSums[31];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *total = carry;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scanApplyKernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t n,
+                const unsigned long long *__restrict__ blockSums)
+{
+    __shared__ uint32_t warpSums[kScanThreads / 32];
+    const size_t base = (size_t) blockIdx.x * kScanBlock + (size_t) threadIdx.x * kScanItems;
+    uint32_t items[kScanItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        items[k] = base + k < n ? in[base + k] : 0u;
+        sum += items[k];
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+        inc += lane >= o ? up : 0;
+    }
+    if (lane == 31) {
+        warpSums[warp] = inc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < kScanThreads / 32 ? warpSums[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, w, o);
+            w += lane >= o ? up : 0;
+        }
+        if (lane < kScanThreads / 32) {
+            warpSums[lane] = w;
+        }
+    }
+    __syncthreads();
+    uint32_t running = static_cast<uint32_t>(blockSums[blockIdx.x]) + (warp > 0 ? warpSums[warp - 1] : 0) + (inc - sum);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) {
+            out[base + k] = running;
+        }
+        running += items[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// active tile compaction (order irrelevant: tiles are independent)
+
+__global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount, uint32_t tileTotal,
+                                         uint32_t *__restrict__ activeTiles, RunCounters *counters)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < tileTotal && tileCount[i] != 0;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, active);
+    if (ballot == 0) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&counters->activeTiles, (unsigned long long) __popc(ballot));
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (active) {
+        activeTiles[base + __popc(ballot & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-tile list sort (ascending leaf index == ascending (triangle, DFS order)); the atomic fill order is arbitrary
+
+__global__ void __launch_bounds__(256)
+sortSmallListsKernel(TileWork work, uint32_t *__restrict__ tileList)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < work.activeCount; w += warpsPerGrid) {
+        const uint32_t tile = work.activeTiles[w];
+        const uint32_t n = work.tileCount[tile];
+        if (n < 2 || n > 32) {
+            continue;
+        }
+        uint32_t *list = tileList + work.tileStart[tile];
+        const uint32_t mine = lane < n ? list[lane] : 0xffffffffu;
+        uint32_t rank = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint32_t other = __shfl_sync(0xffffffffu, mine, k);
+            rank += other < mine ? 1u : 0u;
+        }
+        __syncwarp();
+        if (lane < n) {
+            list[rank] = mine;
+        }
+    }
+}
+
+constexpr uint32_t kSortSmemCap = 4096;
+
+__global__ void __launch_bounds__(512)
+sortLargeListsKernel(TileWork work, uint32_t *__restrict__ tileList)
+{
+    __shared__ uint32_t keys[kSortSmemCap];
+    for (uint32_t w = blockIdx.x; w < work.activeCount; w += gridDim.x) {
+        const uint32_t tile = work.activeTiles[w];
+        const uint32_t n = work.tileCount[tile];
+        if (n <= 32) {
+            continue;
+        }
+        uint32_t *list = tileList + work.tileStart[tile];
+        uint32_t *a = n <= kSortSmemCap ? keys : list;  // long lists are sorted in place (L2 resident)
+        if (n <= kSortSmemCap) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                keys[i] = list[i];
+            }
+        }
+        __syncthreads();
+        uint32_t padded = 1;
+        while (padded < n) {
+            padded <<= 1;
+        }
+        // ascending-only bitonic network: virtual +inf padding beyond n never moves
+        for (uint32_t k = 2; k <= padded; k <<= 1) {
+            for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+                const uint32_t l = i ^ (k - 1);
+                if (l > i && l < n) {
+                    const uint32_t x = a[i], y = a[l];
+                    if (x > y) {
+                        a[i] = y;
+                        a[l] = x;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+                    const uint32_t l = i ^ j;
+                    if (l > i && l < n) {
+                        const uint32_t x = a[i], y = a[l];
+                        if (x > y) {
+                            a[i] = y;
+                            a[l] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (n <= kSortSmemCap) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                list[i] = keys[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// the hot kernel: one block = one 8^3 tile, thread = voxel
+
+struct LeafStage {
+    float v[9];
+    float t[6];
+    float area;
+    uint32_t tri;
+    uint32_t box;      // tile-local AABB: 4 bits each lo.x lo.y lo.z hi.x hi.y hi.z (hi exclusive, <= 8)
+    float plane[4];    // n . p + d for the tile-local voxel min corner p
+    float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
+    float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
+};
+
+/// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
+/// functions on a box inflated by kPrefilterMargin).  Not exact arithmetic: FMA contraction is welcome here.
+__device__ __forceinline__ void buildPrefilter(LeafStage &s, const float origin[3])
+{
+    float p[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        p[k] = s.v[k] - origin[k % 3];
+    }
+    const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
+    const float e1[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    s.plane[0] = n[0];
+    s.plane[1] = n[1];
+    s.plane[2] = n[2];
+    s.plane[3] = n[0] * (0.5f - p[0]) + n[1] * (0.5f - p[1]) + n[2] * (0.5f - p[2]);
+    s.planeLimit = (0.5f + kPrefilterMargin) * (fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]));
+    const float grow = 1.0f + kPrefilterMargin;
+#pragma unroll
+    for (int proj = 0; proj < 3; ++proj) {
+        const int a = proj, b = (proj + 1) % 3, c = (proj + 2) % 3;  // xy (n.z), yz (n.x), zx (n.y)
+        const float sign = n[c] >= 0.0f ? 1.0f : -1.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int j = (i + 1) % 3;
+            const float ea = p[j * 3 + a] - p[i * 3 + a];
+            const float eb = p[j * 3 + b] - p[i * 3 + b];
+            const float A = -eb * sign, B = ea * sign;
+            float C = -(A * p[i * 3 + a] + B * p[i * 3 + b]);
+            C += A > 0.0f ? A * grow : -A * kPrefilterMargin;
+            C += B > 0.0f ? B * grow : -B * kPrefilterMargin;
+            s.edge[(proj * 3 + i) * 3 + 0] = A;
+            s.edge[(proj * 3 + i) * 3 + 1] = B;
+            s.edge[(proj * 3 + i) * 3 + 2] = C;
+        }
+    }
+}
+
+/// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
+__device__ __forceinline__ bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
+{
+    const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
+    if (fabsf(dist) > s.planeLimit) {
+        return false;
+    }
+    const float q[3] = {lx, ly, lz};
+#pragma unroll
+    for (int proj = 0; proj < 3; ++proj) {
+        const float qa = q[proj], qb = q[(proj + 1) % 3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float *e = s.edge + (proj * 3 + i) * 3;
+            if (e[0] * qa + e[1] * qb + e[2] < 0.0f) {
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+struct VoxelAccumulator {
+    // per-triangle uv buffer entry (voxelization.cpp:426-472) and the voxel itself (voxelization.cpp:513-526)
+    WeightedUv partial;
+    WeightedColor voxel;
+    uint32_t partialTri;
+    bool hasPartial;
+    bool hasVoxel;
+    uint32_t contributions;
+};
+
+__device__ __forceinline__ void flushPartial(VoxelAccumulator &acc, const VoxelizeArgs &args)
+{
+    if (!acc.hasPartial) {
+        return;
+    }
+    acc.hasPartial = false;
+    const uint32_t tri = acc.partialTri;
+    const MeshView &mesh = args.mesh;
+    uint8_t type;
+    if (mesh.types != nullptr) {
+        type = mesh.types[tri];
+    }
+    else {
+        type = (mesh.uvs != nullptr && args.textureCount != 0) ? kTextured : kMaterialless;
+    }
+    float rgb[3] = {1.0f, 1.0f, 1.0f};  // MATERIALLESS: triangle.hpp:186
+    if (type == kUntextured && mesh.colors != nullptr) {
+        rgb[0] = mesh.colors[(size_t) tri * 3];
+        rgb[1] = mesh.colors[(size_t) tri * 3 + 1];
+        rgb[2] = mesh.colors[(size_t) tri * 3 + 2];
+    }
+    else if (type == kTextured && args.textureCount != 0) {
+        uint32_t id = mesh.textureIds != nullptr ? mesh.textureIds[tri] : 0u;
+        id = id < args.textureCount ? id : 0u;
+        textureLookup(args.textures[id], acc.partial.u, acc.partial.v, rgb);
+    }
+    ++acc.contributions;
+    if (!acc.hasVoxel) {
+        acc.hasVoxel = true;
+        acc.voxel.w = acc.partial.w;
+        acc.voxel.r = rgb[0];
+        acc.voxel.g = rgb[1];
+        acc.voxel.b = rgb[2];
+    }
+    else {
+        combineColorInto(acc.voxel, acc.partial.w, rgb[0], rgb[1], rgb[2], args.grid.strategy == kBlend);
+    }
+}
+
+__device__ __forceinline__ void addContribution(VoxelAccumulator &acc, uint32_t tri, float w, float u, float v)
+{
+    if (acc.hasPartial) {
+        blendUvInto(acc.partial, w, u, v);  // same triangle, later leaf: insertWeighted<BLEND>
+    }
+    else {
+        acc.hasPartial = true;
+        acc.partialTri = tri;
+        acc.partial.w = w;
+        acc.partial.u = u;
+        acc.partial.v = v;
+    }
+}
+
+constexpr int kTileThreads = 512;
+
+struct TileShared {
+    LeafStage stage[kLeafBatch];
+    uint32_t tileSlot;
+    uint32_t warpCounts[kTileThreads / 32];
+    unsigned long long outBase;
+    // supersampling fold (8^3 children -> 4^3 parents)
+    float dsW[kTileVoxels], dsR[kTileVoxels], dsG[kTileVoxels], dsB[kTileVoxels];
+    uint8_t dsHas[kTileVoxels];
+};
+
+template <bool UV>
+__device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args, uint32_t leafIndex,
+                                          const uint32_t tileOrigin[3])
+{
+    const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
+    s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+    s.v[8] = c.x;
+    s.tri = __float_as_uint(c.y);
+    s.area = c.z;
+    if (UV) {
+        const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
+        const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
+        s.t[0] = u0.x; s.t[1] = u0.y; s.t[2] = u0.z; s.t[3] = u0.w;
+        s.t[4] = u1.x; s.t[5] = u1.y;
+    }
+    uint32_t lo[3], hi[3];
+    triVoxelBounds(s.v, lo, hi);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t l = lo[i] > tileOrigin[i] ? min(lo[i] - tileOrigin[i], kTileEdge) : 0u;
+        const uint32_t h = hi[i] > tileOrigin[i] ? min(hi[i] - tileOrigin[i], kTileEdge) : 0u;
+        packed |= l << (4 * i);
+        packed |= h << (12 + 4 * i);
+    }
+    s.box = packed;
+    const float origin[3] = {(float) tileOrigin[0], (float) tileOrigin[1], (float) tileOrigin[2]};
+    buildPrefilter(s, origin);
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(kTileThreads, 1)
+voxelizeTilesKernel(const VoxelizeArgs args)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    TileShared &sh = *reinterpret_cast<TileShared *>(smemRaw);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lx = tid & 7u, ly = (tid >> 3) & 7u, lz = tid >> 6;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    unsigned long long clipCalls = 0, contributions = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            sh.tileSlot = atomicAdd(&args.counters->tileCursor, 1u);
+        }
+        __syncthreads();
+        const uint32_t slot = sh.tileSlot;
+        if (slot >= args.work.activeCount) {
+            break;
+        }
+        const uint32_t tile = args.work.activeTiles[slot];
+        const uint32_t listStart = args.work.tileStart[tile];
+        const uint32_t listCount = args.work.tileCount[tile];
+        const uint32_t T = args.grid.tilesPerAxis;
+        const uint32_t tileOrigin[3] = {(tile % T) * kTileEdge, ((tile / T) % T) * kTileEdge,
+                                        (tile / (T * T) + args.grid.slabTileZ0) * kTileEdge};
+        const uint32_t px = tileOrigin[0] + lx, py = tileOrigin[1] + ly, pz = tileOrigin[2] + lz;
+
+        VoxelAccumulator acc;
+        acc.hasPartial = false;
+        acc.hasVoxel = false;
+        acc.partialTri = 0;
+        acc.contributions = 0;
+        acc.partial.w = acc.partial.u = acc.partial.v = 0.0f;
+        acc.voxel.w = acc.voxel.r = acc.voxel.g = acc.voxel.b = 0.0f;
+
+        for (uint32_t base = 0; base < listCount; base += kLeafBatch) {
+            const uint32_t count = min(kLeafBatch, listCount - base);
+            __syncthreads();
+            if (tid < count) {
+                stageLeaf<UV>(sh.stage[tid], args, args.work.tileList[listStart + base + tid], tileOrigin);
+            }
+            __syncthreads();
+
+            for (uint32_t j = 0; j < count; ++j) {
+                const LeafStage &s = sh.stage[j];
+                if (acc.hasPartial && acc.partialTri != s.tri) {
+                    flushPartial(acc, args);  // the list is ordered by triangle: this triangle's uv buffer is complete
+                }
+                const uint32_t box = s.box;
+                const bool inside = lx >= (box & 15u) && ly >= ((box >> 4) & 15u) && lz >= ((box >> 8) & 15u) &&
+                                    lx < ((box >> 12) & 15u) && ly < ((box >> 16) & 15u) && lz < ((box >> 20) & 15u);
+                if (!inside) {
+                    continue;
+                }
+                if (args.prefilter && !prefilterPass(s, (float) lx, (float) ly, (float) lz)) {
+                    continue;
+                }
+                Tri<UV> leaf;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    leaf.v[k] = s.v[k];
+                }
+                if (UV) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        leaf.t[k] = s.t[k];
+                    }
+                }
+                const ClipResult r = clipLeafInVoxel<UV>(leaf, px, py, pz, s.area);
+                ++clipCalls;
+                if (r.pieces != 0) {
+                    addContribution(acc, s.tri, r.weight, r.u, r.v);
+                }
+            }
+        }
+        flushPartial(acc, args);
+        contributions += acc.contributions;
+
+        // ---- output: optional 2x downscale (intended semantics), quantise, block-compact, store ----
+        bool emit = acc.hasVoxel;
+        int32_t ox = (int32_t) px, oy = (int32_t) py, oz = (int32_t) pz;
+        WeightedColor result = acc.voxel;
+        if (args.grid.supersampling == 2) {
+            sh.dsW[tid] = acc.voxel.w;
+            sh.dsR[tid] = acc.voxel.r;
+            sh.dsG[tid] = acc.voxel.g;
+            sh.dsB[tid] = acc.voxel.b;
+            sh.dsHas[tid] = acc.hasVoxel ? 1 : 0;
+            __syncthreads();
+            emit = false;
+            if (tid < 64) {
+                const uint32_t qx = tid & 3u, qy = (tid >> 2) & 3u, qz = tid >> 4;
+                // children in ascending Morton order (x is the most significant bit of the triple, ileave.hpp:243-246)
+                for (uint32_t child = 0; child < 8; ++child) {
+                    const uint32_t cx = 2 * qx + ((child >> 2) & 1u), cy = 2 * qy + ((child >> 1) & 1u),
+                                   cz = 2 * qz + (child & 1u);
+                    const uint32_t ci = cx + 8 * cy + 64 * cz;
+                    if (!sh.dsHas[ci]) {
+                        continue;
+                    }
+                    if (!emit) {
+                        emit = true;
+                        result.w = sh.dsW[ci];
+                        result.r = sh.dsR[ci];
+                        result.g = sh.dsG[ci];
+                        result.b = sh.dsB[ci];
+                    }
+                    else {
+                        combineColorInto(result, sh.dsW[ci], sh.dsR[ci], sh.dsG[ci], sh.dsB[ci],
+                                         args.grid.strategy == kBlend);
+                    }
+                }
+                ox = (int32_t) (tileOrigin[0] / 2 + qx);
+                oy = (int32_t) (tileOrigin[1] / 2 + qy);
+                oz = (int32_t) (tileOrigin[2] / 2 + qz);
+            }
+        }
+
+        const unsigned int ballot = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) {
+            sh.warpCounts[warp] = __popc(ballot);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t total = 0;
+            for (int w = 0; w < kTileThreads / 32; ++w) {
+                const uint32_t c = sh.warpCounts[w];
+                sh.warpCounts[w] = total;
+                total += c;
+            }
+            sh.outBase = total != 0 ? atomicAdd(&args.counters->voxels, (unsigned long long) total) : 0ull;
+        }
+        __syncthreads();
+        if (emit) {
+            const unsigned long long index = sh.outBase + sh.warpCounts[warp] + __popc(ballot & ((1u << lane) - 1u));
+            if (index < args.outCapacity) {
+                VoxelRecord rec;
+                rec.x = ox;
+                rec.y = oy;
+                rec.z = oz;
+                rec.argb = quantizeArgb(result.r, result.g, result.b);
+                *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+            }
+            else {
+                atomicAdd(&args.counters->outputOverflow, 1ull);
+            }
+        }
+    }
+
+    // per-block statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        clipCalls += __shfl_xor_sync(0xffffffffu, clipCalls, o);
+        contributions += __shfl_xor_sync(0xffffffffu, contributions, o);
+    }
+    if (lane == 0) {
+        if (clipCalls != 0) {
+            atomicAdd(&args.counters->clipCalls, clipCalls);
+        }
+        if (contributions != 0) {
+            atomicAdd(&args.counters->contributions, contributions);
+        }
+    }
+}
+
+inline int gridFor(unsigned long long n, int threads, int cap)
+{
+    unsigned long long blocks = (n + threads - 1) / threads;
+    if (blocks < 1) {
+        blocks = 1;
+    }
+    if (blocks > (unsigned long long) cap) {
+        blocks = cap;
+    }
+    return (int) blocks;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// launch wrappers
+
+void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stream)
+{
+    const unsigned long long vertices = mesh.count * 3;
+    boundsKernel<<<gridFor(vertices, 256, 148 * 8), 256, 0, stream>>>(mesh.verts, vertices, counters);
+}
+
+void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
+{
+    finishBoundsKernel<<<1, 32, 0, stream>>>(counters);
+}
+
+void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
+                       RunCounters *counters, cudaStream_t stream)
+{
+    const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
+    if (mesh.uvs != nullptr) {
+        countLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, counters);
+    }
+    else {
+        countLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, counters);
+    }
+}
+
+size_t scanScratchElems(size_t n)
+{
+    const size_t blocks = (n + kScanBlock - 1) / kScanBlock;
+    return (blocks + 1) * 2;  // u64 block sums stored in a u32 scratch array
+}
+
+void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, unsigned long long *total,
+                         cudaStream_t stream)
+{
+    const size_t blocks = (n + kScanBlock - 1) / kScanBlock;
+    auto *blockSums = reinterpret_cast<unsigned long long *>(scratch);
+    if (blocks == 0) {
+        cudaMemsetAsync(total, 0, sizeof(unsigned long long), stream);
+        return;
+    }
+    scanReduceKernel<<<(unsigned) blocks, kScanThreads, 0, stream>>>(in, n, blockSums);
+    scanTopKernel<<<1, 1024, 0, stream>>>(blockSums, blocks, total);
+    scanApplyKernel<<<(unsigned) blocks, kScanThreads, 0, stream>>>(in, out, n, blockSums);
+}
+
+void launchCompactActiveTiles(const uint32_t *tileCount, uint32_t tileTotal, uint32_t *activeTiles,
+                              RunCounters *counters, cudaStream_t stream)
+{
+    if (tileTotal == 0) {
+        return;
+    }
+    compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileTotal, activeTiles, counters);
+}
+
+void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
+                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList,
+                      RunCounters *, cudaStream_t stream)
+{
+    const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
+    if (mesh.uvs != nullptr) {
+        emitLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves,
+                                                                      leafUvs, tileList);
+    }
+    else {
+        emitLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill,
+                                                                       leaves, leafUvs, tileList);
+    }
+}
+
+void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream)
+{
+    if (work.activeCount == 0) {
+        return;
+    }
+    const int warpsPerBlock = 8;
+    const int smallBlocks = gridFor(work.activeCount, warpsPerBlock, 148 * 16);
+    sortSmallListsKernel<<<smallBlocks, warpsPerBlock * 32, 0, stream>>>(work, tileList);
+    const int largeBlocks = gridFor(work.activeCount, 1, 148 * 4);
+    sortLargeListsKernel<<<largeBlocks, 512, 0, stream>>>(work, tileList);
+}
+
+void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
+{
+    if (args.work.activeCount == 0) {
+        return;
+    }
+    const size_t smem = sizeof(TileShared);
+    unsigned blocks = (unsigned) smCount;
+    if (blocks > args.work.activeCount) {
+        blocks = args.work.activeCount;
+    }
+    if (args.mesh.uvs != nullptr) {
+        cudaFuncSetAttribute(voxelizeTilesKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        voxelizeTilesKernel<true><<<blocks, kTileThreads, smem, stream>>>(args);
+    }
+    else {
+        cudaFuncSetAttribute(voxelizeTilesKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        voxelizeTilesKernel<false><<<blocks, kTileThreads, smem, stream>>>(args);
+    }
+}
+
+}  // namespace o2v

@@ -1,0 +1,129 @@
+// Device-side data layout and kernel launch wrappers of the B200 voxelizer.  See DESIGN.md §3 for the pipeline:
+//
+//   bounds -> [host: mesh transform] -> countLeaves -> scan -> emitLeaves(+tile lists) -> sortTileLists
+//          -> voxelizeTiles (the hot kernel) -> compact Voxel32 records
+//
+// Everything here is plain CUDA (no torch types); the C-ABI in o2v_capi.cpp sits on top of o2v::Engine (o2v_engine.h).
+#ifndef O2V_KERNELS_CUH
+#define O2V_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "o2v_exact.cuh"
+
+namespace o2v {
+
+constexpr uint32_t kTileEdge = 8;  // voxels per tile edge (sample space); 8^3 = 512 voxels = one thread block
+constexpr uint32_t kTileVoxels = kTileEdge * kTileEdge * kTileEdge;
+constexpr uint32_t kLeafBatch = 32;  // leaves staged in shared memory per round
+
+/// Input mesh, model space.  All pointers are device pointers.
+struct MeshView {
+    const float *verts;        // 9 floats per triangle
+    const float *uvs;          // 6 floats per triangle or null
+    const uint8_t *types;      // TriangleType per triangle or null (= textured if uvs && textures else materialless)
+    const float *colors;       // 3 floats per triangle or null (kUntextured)
+    const uint32_t *textureIds;  // per-triangle index into textures or null (= 0)
+    uint64_t count;
+};
+
+/// Sample-space grid and this rank's Z-slab of it.
+struct GridView {
+    float xf[12];           // mesh -> voxel affine (3x3 row-major, translation)
+    uint32_t sampleRes;     // S = resolution * supersampling
+    uint32_t tilesPerAxis;  // ceil(S / 8)
+    uint32_t slabZ0, slabZ1;        // owned voxel z range [z0, z1), multiples of 8
+    uint32_t slabTileZ0, slabTileZCount;
+    uint32_t supersampling;  // 1 or 2
+    uint32_t strategy;       // ColorStrategy
+};
+
+/// One leaf of the subdivision (voxel space).  48 bytes, 16-byte aligned: three float4 loads.
+struct __align__(16) LeafRecord {
+    float v[9];
+    uint32_t tri;  // input triangle index (fold order key together with the leaf's position in the leaf array)
+    float area;    // area of the WHOLE input triangle
+    uint32_t pad;
+};
+
+struct __align__(16) LeafUv {
+    float t[6];
+    float pad[2];
+};
+
+struct __align__(16) VoxelRecord {  // voxelio Voxel32, types.hpp:59-70: {i32 x, y, z; u32 argb}
+    int32_t x, y, z;
+    uint32_t argb;
+};
+
+/// Counters produced on the device and read back once per run.
+struct RunCounters {
+    unsigned long long leaves;          // total leaf records
+    unsigned long long pairs;           // total (leaf, tile) pairs
+    unsigned long long candidateVoxels; // sum of leaf AABB volumes inside the slab (upper bound on contributions)
+    unsigned long long activeTiles;
+    unsigned long long voxels;          // emitted voxels
+    unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
+    unsigned long long clipCalls;       // exact clips executed (prefilter survivors)
+    unsigned long long depthOverflow;   // triangles that hit kMaxSubdivisionDepth
+    unsigned long long droppedTriangles;  // zero-area / non-finite input triangles
+    unsigned long long outputOverflow;  // voxels that did not fit the output buffer
+    float boundsMin[3];
+    float boundsMax[3];
+    unsigned int boundsMinBits[3];
+    unsigned int boundsMaxBits[3];
+    unsigned int tileCursor;
+    unsigned int pad;
+};
+
+struct TileWork {
+    const uint32_t *activeTiles;  // slab-local tile ids with a non-empty list
+    const uint32_t *tileStart;    // exclusive scan of tileCount (slab-local tile id -> list offset)
+    const uint32_t *tileCount;
+    const uint32_t *tileList;     // leaf indices, ascending within a tile after sortTileLists
+    uint32_t activeCount;
+};
+
+// ---- launch wrappers (o2v_kernels.cu) ----
+
+void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stream);
+void launchFinishBounds(RunCounters *counters, cudaStream_t stream);
+
+void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
+                       RunCounters *counters, cudaStream_t stream);
+
+/// Exclusive scan of n u32 values; total (u64) is written to *total.  scratch must hold scanScratchElems(n) u32.
+size_t scanScratchElems(size_t n);
+void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, unsigned long long *total,
+                         cudaStream_t stream);
+
+void launchCompactActiveTiles(const uint32_t *tileCount, uint32_t tileTotal, uint32_t *activeTiles,
+                              RunCounters *counters, cudaStream_t stream);
+
+void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
+                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList,
+                      RunCounters *counters, cudaStream_t stream);
+
+void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream);
+
+struct VoxelizeArgs {
+    GridView grid;
+    TileWork work;
+    const LeafRecord *leaves;
+    const LeafUv *leafUvs;  // null when the mesh has no uvs
+    MeshView mesh;
+    const TextureView *textures;
+    uint32_t textureCount;
+    VoxelRecord *out;
+    unsigned long long outCapacity;
+    RunCounters *counters;
+    int variant;  // 0 = per-voxel inline clip, 1 = warp-compacted clip queue
+    int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
+};
+
+void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+
+}  // namespace o2v
+
+#endif  // O2V_KERNELS_CUH
