@@ -173,8 +173,9 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     computeMeshTransform(meshMin, meshMax, S, params.unitTransform, grid.xf);
     memcpy(st.transform, grid.xf, sizeof st.transform);
     grid.sampleRes = S;
-    grid.tilesPerAxis = (S + kTileEdge - 1) / kTileEdge;
-    const uint32_t gridZ = grid.tilesPerAxis * kTileEdge;
+    grid.gridExtent = (S + 63u) / 64u * 64u;
+    grid.tilesPerAxis = grid.gridExtent / kTileEdge;
+    const uint32_t gridZ = grid.gridExtent;
     uint32_t z0 = params.slabZ0, z1 = params.slabZ1;
     if (z0 == 0 && z1 == 0) {
         z1 = gridZ;

@@ -96,8 +96,15 @@ __device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridVie
         }
     }
     area = triArea(t.v);
+    // A negative voxel-space coordinate wraps the reference's float -> u32 cast to a huge chunkMin (triangle.hpp:91-95,
+    // obj2voxel.cpp:211-219; formally UB), so the triangle lands in no chunk: dropped as a whole.
+    bool negative = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        negative |= floorf(min3(t.v[a], t.v[3 + a], t.v[6 + a])) < 0.0f;
+    }
     // weight 0 never reaches the voxel map (voxelization.cpp:466); non-finite input is a contract violation
-    return area > 0.0f && area < INFINITY;
+    return area > 0.0f && area < INFINITY && !negative;
 }
 
 /// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
@@ -112,10 +119,11 @@ __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridVi
     return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
         uint32_t lo[3], hi[3];
         triVoxelBounds(leaf.v, lo, hi);
-        hi[0] = min(hi[0], grid.sampleRes);
-        hi[1] = min(hi[1], grid.sampleRes);
+        // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
+        hi[0] = min(hi[0], grid.gridExtent);
+        hi[1] = min(hi[1], grid.gridExtent);
         lo[2] = max(lo[2], grid.slabZ0);
-        hi[2] = min(hi[2], min(grid.slabZ1, grid.sampleRes));
+        hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
         if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
             return;
         }

@@ -989,6 +989,14 @@ int o2v_oracle_voxelize(const o2v_oracle_params *params, size_t n, const float *
         }
         p->area = tri_area(&p->tri);
         tri_voxel_bounds(&p->tri, p->vmin, p->vmax);
+        /* A negative voxel-space coordinate makes the reference's float -> u32 cast wrap to a huge chunkMin
+         * (triangle.hpp:91-95, obj2voxel.cpp:211-219; formally UB): the triangle lands in no chunk and is
+         * dropped as a whole.  Reproduced here as the observed x86-64 behaviour. */
+        for (int i = 0; i < 3; ++i) {
+            if (floorf(min3f(p->tri.v[0][i], p->tri.v[1][i], p->tri.v[2][i])) < 0) {
+                p->vmin[i] = p->vmax[i] = 0; /* overlaps no chunk */
+            }
+        }
     }
 
     /* chunk grid: obj2voxel.cpp:245-252,580-581 (full coverage; the reference's lost chunks for non-power-of-two grids,

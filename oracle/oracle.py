@@ -105,9 +105,12 @@ def voxelize(verts, resolution, uvs=None, types=None, colors=None, texture=None,
     if err != 0:
         raise RuntimeError("oracle error %d" % err)
     n = r.count
-    xyz = np.ctypeslib.as_array(r.xyz, shape=(max(n, 1), 3))[:n].copy()
-    argb = np.ctypeslib.as_array(r.argb, shape=(max(n, 1),))[:n].copy()
-    wrgb = np.ctypeslib.as_array(r.wrgb, shape=(max(n, 1), 4))[:n].copy()
+    if n == 0:
+        xyz, argb, wrgb = np.zeros((0, 3), np.uint32), np.zeros((0,), np.uint32), np.zeros((0, 4), np.float32)
+    else:
+        xyz = np.ctypeslib.as_array(r.xyz, shape=(n, 3)).copy()
+        argb = np.ctypeslib.as_array(r.argb, shape=(n,)).copy()
+        wrgb = np.ctypeslib.as_array(r.wrgb, shape=(n, 4)).copy()
     result = dict(transform=np.array(list(r.transform), dtype=np.float32), contributions=int(r.contributions),
                   subtriangles=int(r.subtriangles))
     L.o2v_oracle_free_result(C.byref(r))

@@ -1,0 +1,168 @@
+"""CPU: the C-ABI shared library loads, exports every symbol include/*.h declares, and its host-side logic (argument
+checks, error codes, textures, worker bookkeeping, sinks) behaves like the reference's — all without a compute call."""
+import os
+import re
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+import obj2voxel_b200 as o2v
+from obj2voxel_b200 import _lib
+
+
+def declared_symbols(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:obj2voxel|o2v_b200)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = o2v.load()
+    ref = declared_symbols("obj2voxel.h")
+    add = declared_symbols("obj2voxel_b200.h")
+    assert len(ref) == 35  # the reference's include/obj2voxel.h declares 35 functions
+    assert sorted(ref) == sorted(_lib.REFERENCE_SYMBOLS)
+    assert sorted(add) == sorted(_lib.ADDITIVE_SYMBOLS)
+    for name in ref + add:
+        assert hasattr(lib, name), name
+
+
+def test_error_codes_follow_reference_order():  # reference test/main.cpp:68-118, src/obj2voxel.cpp:604-618
+    o2v.load().obj2voxel_set_log_level(_lib.LOG_SILENT)
+    inst = o2v.Instance()
+    inst.set_output_callback()
+    inst.set_resolution(1)
+    assert inst.voxelize() == o2v.ERR_NO_INPUT
+    inst.free()
+
+    inst = o2v.Instance()
+    inst.set_input_callback(np.zeros((1, 9), np.float32))
+    inst.set_resolution(1)
+    assert inst.voxelize() == o2v.ERR_NO_OUTPUT
+    inst.free()
+
+    inst = o2v.Instance()
+    inst.set_input_callback(np.zeros((1, 9), np.float32))
+    inst.set_output_callback()
+    assert inst.voxelize() == o2v.ERR_NO_RESOLUTION
+    inst.free()
+    o2v.load().obj2voxel_set_log_level(_lib.LOG_INFO)
+
+
+def test_getters_and_log_level():
+    lib = o2v.load()
+    inst = o2v.Instance()
+    inst.set_resolution(128)
+    assert inst.get_resolution() == 128
+    assert inst.get_chunk_size() == 64  # src/constants.hpp:10
+    lib.obj2voxel_set_log_level(_lib.LOG_WARNING)
+    assert lib.obj2voxel_get_log_level() == _lib.LOG_WARNING
+    lib.obj2voxel_set_log_level(_lib.LOG_INFO)
+    inst.free()
+
+
+def test_log_callback_receives_messages_and_null_resets():
+    lib = o2v.load()
+    seen = []
+
+    def on_log(_data, msg, level):
+        seen.append((msg.decode(), level))
+        return True
+
+    cb = _lib.LOG_CALLBACK(on_log)
+    lib.obj2voxel_set_log_callback(cb, None)
+    inst = o2v.Instance()
+    inst.set_resolution(4)
+    assert inst.voxelize() == o2v.ERR_NO_INPUT
+    inst.free()
+    lib.obj2voxel_set_log_callback(None, None)  # NULL = reset, must not crash
+    assert ("No input was specified", _lib.LOG_ERROR) in seen
+
+
+def test_texture_round_trip():
+    pixels = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    t = o2v.Texture(pixels, wrap=o2v.UV_CLAMP)
+    assert t.meta() == (7, 5, 3)
+    assert np.array_equal(t.pixels(), pixels)
+    assert not t.load_from_memory(b"not a png", "png")
+    t.free()
+
+
+def test_png_decode_through_the_texture_api():
+    import struct
+    import zlib
+
+    w, h = 6, 4
+    rgba = np.random.default_rng(1).integers(0, 256, (h, w, 4), dtype=np.uint8)
+    raw = b"".join(b"\x00" + rgba[y].tobytes() for y in range(h))
+
+    def chunk(kind, body):
+        return struct.pack(">I", len(body)) + kind + body + struct.pack(">I", zlib.crc32(kind + body))
+
+    png = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) +
+           chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+    t = o2v.Texture()
+    assert t.load_from_memory(png, "png")
+    assert t.meta() == (w, h, 4)
+    assert np.array_equal(t.pixels(), rgba)
+    t.free()
+
+
+def test_workers_block_until_stopped():  # include/obj2voxel.h worker contract, src/obj2voxel.cpp:957-1003
+    lib = o2v.load()
+    inst = o2v.Instance()
+    threads = [threading.Thread(target=lib.obj2voxel_run_worker, args=(inst.handle,)) for _ in range(3)]
+    for t in threads:
+        t.start()
+    deadline = time.time() + 5
+    while lib.obj2voxel_get_worker_count(inst.handle) != 3 and time.time() < deadline:
+        time.sleep(0.01)
+    assert lib.obj2voxel_get_worker_count(inst.handle) == 3
+    assert all(t.is_alive() for t in threads)
+    lib.obj2voxel_stop_workers(inst.handle)
+    for t in threads:
+        t.join(timeout=5)
+    assert not any(t.is_alive() for t in threads)
+    assert lib.obj2voxel_get_worker_count(inst.handle) == 0
+    lib.obj2voxel_run_worker(inst.handle)  # returns immediately after stop (src/obj2voxel.cpp:963-966)
+    inst.free()
+
+
+def test_no_cpu_fallback_without_a_device():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(o2v.DeviceError):
+        o2v.Engine(0)
+    lib = o2v.load()
+    lib.obj2voxel_set_log_level(_lib.LOG_SILENT)
+    inst = o2v.Instance()
+    inst.set_input_callback(np.array([[0, 0, 0, 0, 0, 1, 1, 0, 0]], np.float32))
+    inst.set_output_callback()
+    inst.set_resolution(16)
+    assert inst.voxelize() == o2v.ERR_DEVICE  # loud failure, not a silent CPU path
+    assert inst.collected().shape == (0, 4)
+    inst.free()
+    lib.obj2voxel_set_log_level(_lib.LOG_INFO)
+
+
+def test_product_never_references_the_oracle():
+    """The oracle is test infrastructure: no product source may include, link or import it."""
+    pkg = os.path.join(ROOT, "obj2voxel_b200")
+    for dirpath, _dirs, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if f == "test_hostmath.py":
+                    continue
+                assert "liboracle" not in text and "o2v_oracle" not in text and "from oracle" not in text and \
+                    "import oracle" not in text, os.path.join(dirpath, f)
