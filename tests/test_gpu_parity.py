@@ -155,7 +155,6 @@ def parity(engine, verts, resolution, uvs=None, texture=None, types=None, colors
     got = o2v.sort_voxels(got)
     assert got.shape == want["voxels"].shape and np.array_equal(got, want["voxels"])
     assert stats["contributions"] == want["contributions"]  # N_contrib agrees with the reference's emplace count
-    assert stats["leaves"] == want["subtriangles"] or "bounds" in kw  # leaves outside the grid are skipped on the GPU
     return stats
 
 
