@@ -301,6 +301,7 @@ def run_ours(args, cfg, workload):
     clocks = sampler.stop() if rank == 0 else None
 
     counts = [stats["voxels"], stats["contributions"], stats["clip_calls"], stats["leaves"], launches]
+    tile_split = (stats["light_tiles"], stats["heavy_tiles"])
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,7 +375,8 @@ def run_ours(args, cfg, workload):
                        "l2": "inputs (%d MB of triangles) exceed the 126 MB L2; no explicit flush" %
                              (n_tri * tri_bytes // 1000000)},
             "mvoxel_per_s": voxels / (ms_per_step * 1e-3) / 1e6, "voxels": voxels, "contributions": contributions,
-            "clip_calls": clip_calls, "leaves": leaves,
+            "clip_calls": clip_calls, "leaves": leaves, "light_tiles_rank0": tile_split[0],
+            "heavy_tiles_rank0": tile_split[1],
             "ms_setup_rank0": float(np.mean(setup_ms)), "ms_voxelize_rank0": k_ms,
             "hbm_write_gbs": 16 * stats["voxels"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
             "roofline": {"bound": "hbm", "kernel": "voxelizeTilesKernel", "achieved": achieved, "peak": peak,

@@ -74,6 +74,8 @@ typedef struct o2v_b200_stats {
     float transform[12];
     int32_t kernel_launches;
     int32_t voxelize_launches;
+    uint64_t light_tiles;       /* tiles voxelized warp-per-tile */
+    uint64_t heavy_tiles;       /* tiles voxelized block-per-tile */
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */

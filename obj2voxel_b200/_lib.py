@@ -45,7 +45,8 @@ class Stats(C.Structure):
                 ("candidate_voxels", C.c_uint64), ("clip_calls", C.c_uint64), ("contributions", C.c_uint64),
                 ("dropped_triangles", C.c_uint64), ("depth_overflow", C.c_uint64), ("out_capacity", C.c_uint64),
                 ("ms_total", C.c_float), ("ms_setup", C.c_float), ("ms_voxelize", C.c_float),
-                ("transform", C.c_float * 12), ("kernel_launches", C.c_int32), ("voxelize_launches", C.c_int32)]
+                ("transform", C.c_float * 12), ("kernel_launches", C.c_int32), ("voxelize_launches", C.c_int32),
+                ("light_tiles", C.c_uint64), ("heavy_tiles", C.c_uint64)]
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "transform"}

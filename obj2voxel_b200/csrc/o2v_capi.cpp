@@ -160,6 +160,8 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     memcpy(out->transform, in.transform, sizeof out->transform);
     out->kernel_launches = in.kernelLaunches;
     out->voxelize_launches = in.voxelizeLaunches;
+    out->light_tiles = in.counters.lightTiles;
+    out->heavy_tiles = in.counters.heavyTiles;
 }
 
 EngineParams paramsFromC(const o2v_b200_params &p)

@@ -205,18 +205,22 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     const size_t scratchElems = std::max(scanScratchElems(n), scanScratchElems(tileTotal));
     if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !tileCount_.ensure((size_t) tileTotal * 4) ||
         !tileStart_.ensure((size_t) tileTotal * 4) || !tileFill_.ensure((size_t) tileTotal * 4) ||
-        !activeTiles_.ensure((size_t) tileTotal * 4) || !scratch_.ensure(scratchElems * 4)) {
+        !activeTiles_.ensure((size_t) tileTotal * 4) || !tileCand_.ensure((size_t) tileTotal * 4) ||
+        !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
     }
     O2V_CUDA(cudaMemsetAsync(tileCount_.as<void>(), 0, (size_t) tileTotal * 4, stream));
     O2V_CUDA(cudaMemsetAsync(tileFill_.as<void>(), 0, (size_t) tileTotal * 4, stream));
+    O2V_CUDA(cudaMemsetAsync(tileCand_.as<void>(), 0, (size_t) tileTotal * 4, stream));
 
-    launchCountLeaves(mesh, grid, leafCount_.as<uint32_t>(), tileCount_.as<uint32_t>(), dCounters, stream);
+    launchCountLeaves(mesh, grid, leafCount_.as<uint32_t>(), tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(),
+                      dCounters, stream);
     launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                         &dCounters->leaves, stream);
     launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
                         &dCounters->pairs, stream);
-    launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileTotal, activeTiles_.as<uint32_t>(), dCounters, stream);
+    launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
+                             activeTiles_.as<uint32_t>(), lightTiles_.as<LightTile>(), dCounters, stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -265,7 +269,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     work.tileStart = tileStart_.as<uint32_t>();
     work.tileCount = tileCount_.as<uint32_t>();
     work.tileList = tileList_.as<uint32_t>();
-    work.activeCount = (uint32_t) activeTotal;
+    work.activeCount = (uint32_t) hostCounters_->heavyTiles;
     launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
     st.kernelLaunches += 3;
     O2V_CUDA(cudaEventRecord(evSetup_, stream));
@@ -281,15 +285,19 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     args.out = out_.as<VoxelRecord>();
     args.outCapacity = capacity;
     args.counters = dCounters;
+    args.lightTiles = lightTiles_.as<LightTile>();
+    args.lightCount = (uint32_t) hostCounters_->lightTiles;
     args.variant = params.variant < 0 ? 0 : params.variant;
     args.prefilter = params.prefilter;
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
+        launchVoxelizeLightTiles(args, smCount_, stream);
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        ++st.voxelizeLaunches;
-        ++st.kernelLaunches;
+        const int launched = (args.lightCount != 0 ? 1 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        st.voxelizeLaunches += launched;
+        st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());

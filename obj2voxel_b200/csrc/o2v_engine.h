@@ -96,7 +96,8 @@ private:
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
 
-    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, activeTiles_, scratch_;
+    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_,
+        scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
 };
 

@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t localTileId(const GridView &grid, uint32_t t
 template <bool UV>
 __global__ void __launch_bounds__(kSetupThreads)
 countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount, uint32_t *__restrict__ tileCount,
-                  RunCounters *counters)
+                  uint32_t *__restrict__ tileCandidates, RunCounters *counters)
 {
     unsigned long long candidates = 0, dropped = 0, overflow = 0;
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
@@ -153,9 +153,14 @@ countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount
                 ++leaves;
                 candidates += (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
                 for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
+                    const uint32_t dz = min(hi[2], (tz + 1) * kTileEdge) - max(lo[2], tz * kTileEdge);
                     for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
+                        const uint32_t dy = min(hi[1], (ty + 1) * kTileEdge) - max(lo[1], ty * kTileEdge);
                         for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
-                            atomicAdd(&tileCount[localTileId(grid, tx, ty, tz)], 1u);
+                            const uint32_t dx = min(hi[0], (tx + 1) * kTileEdge) - max(lo[0], tx * kTileEdge);
+                            const uint32_t tile = localTileId(grid, tx, ty, tz);
+                            atomicAdd(&tileCount[tile], 1u);
+                            atomicAdd(&tileCandidates[tile], dx * dy * dz);
                         }
                     }
                 }
@@ -362,23 +367,49 @@ scanApplyKernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, siz
 // ---------------------------------------------------------------------------------------------------------------------
 // active tile compaction (order irrelevant: tiles are independent)
 
-__global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount, uint32_t tileTotal,
-                                         uint32_t *__restrict__ activeTiles, RunCounters *counters)
+__global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
+                                         const uint32_t *__restrict__ tileCandidates,
+                                         const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
+                                         uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
+                                         RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < tileTotal && tileCount[i] != 0;
-    const unsigned int ballot = __ballot_sync(0xffffffffu, active);
-    if (ballot == 0) {
-        return;
-    }
+    const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
+    const uint32_t candidates = count != 0 ? tileCandidates[i] : 0u;
+    const bool light = count != 0 && count <= kLightMaxLeaves && candidates <= kLightMaxCandidates;
+    const bool heavy = count != 0 && !light;
     const int lane = threadIdx.x & 31;
-    unsigned long long base = 0;
-    if (lane == 0) {
-        base = atomicAdd(&counters->activeTiles, (unsigned long long) __popc(ballot));
+    const unsigned int below = (1u << lane) - 1u;
+
+    const unsigned int lightBallot = __ballot_sync(0xffffffffu, light);
+    if (lightBallot != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&counters->lightTiles, (unsigned long long) __popc(lightBallot));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (light) {
+            LightTile d;
+            d.tile = i;
+            d.listStart = tileStart[i];
+            d.leafCount = count;
+            d.candidates = candidates;
+            lightTiles[base + __popc(lightBallot & below)] = d;
+        }
     }
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (active) {
-        activeTiles[base + __popc(ballot & ((1u << lane) - 1u))] = i;
+    const unsigned int heavyBallot = __ballot_sync(0xffffffffu, heavy);
+    if (heavyBallot != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&counters->heavyTiles, (unsigned long long) __popc(heavyBallot));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (heavy) {
+            heavyTiles[base + __popc(heavyBallot & below)] = i;
+        }
+    }
+    if (lane == 0 && (lightBallot | heavyBallot) != 0) {
+        atomicAdd(&counters->activeTiles, (unsigned long long) (__popc(lightBallot) + __popc(heavyBallot)));
     }
 }
 
@@ -482,6 +513,7 @@ struct LeafStage {
     float plane[4];    // n . p + d for the tile-local voxel min corner p
     float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
     float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
+    uint32_t pad;      // 51 words: odd stride, so lanes reading the same field of different leaves hit distinct banks
 };
 
 /// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
@@ -818,6 +850,328 @@ voxelizeTilesKernel(const VoxelizeArgs args)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// light tiles: one warp = one tile.  Lanes enumerate the candidate voxels of every leaf (leaf-major), the SAT survivors are
+// ballot-compacted into a dense queue, the exact clip runs on full warps, and the surviving contributions are sorted by
+// (voxel, list position) inside the warp so that one lane per voxel can replay the reference's fold order
+// (ascending triangle index, DFS order within a triangle) — still without atomics on voxel data.
+
+constexpr int kLightWarpsPerBlock = 4;
+
+struct LightWarpShared {
+    LeafStage stage[kLightMaxLeaves];
+    uint32_t candPrefix[kLightMaxLeaves + 1];  // exclusive prefix of per-leaf candidate counts
+    uint16_t queue[kLightMaxCandidates];       // (list slot << 9) | local voxel (x | y << 3 | z << 6)
+    uint32_t sortKey[kLightMaxCandidates];     // (voxel key << 13) | (list slot << 8) | contribution slot
+    float cW[kLightMaxCandidates];
+    float cU[kLightMaxCandidates];
+    float cV[kLightMaxCandidates];
+};
+
+/// Voxel key: parent (2x2x2 block) index in the high 6 bits, child Morton code (x most significant, ileave.hpp:243-246) in
+/// the low 3 — ascending keys visit the children of one parent in ascending Morton order, which is the downscale order.
+__device__ __forceinline__ uint32_t voxelKey(uint32_t x, uint32_t y, uint32_t z)
+{
+    const uint32_t parent = (x >> 1) | ((y >> 1) << 2) | ((z >> 1) << 4);
+    const uint32_t child = ((x & 1u) << 2) | ((y & 1u) << 1) | (z & 1u);
+    return (parent << 3) | child;
+}
+
+__device__ __forceinline__ void resetAccumulator(VoxelAccumulator &acc)
+{
+    acc.hasPartial = false;
+    acc.hasVoxel = false;
+    acc.partialTri = 0;
+    acc.contributions = 0;
+    acc.partial.w = acc.partial.u = acc.partial.v = 0.0f;
+    acc.voxel.w = acc.voxel.r = acc.voxel.g = acc.voxel.b = 0.0f;
+}
+
+template <bool UV>
+__global__ void __launch_bounds__(kLightWarpsPerBlock * 32)
+voxelizeLightTilesKernel(const VoxelizeArgs args)
+{
+    __shared__ LightWarpShared shAll[kLightWarpsPerBlock];
+    LightWarpShared &sh = shAll[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t full = 0xffffffffu;
+    const uint32_t warpsTotal = gridDim.x * kLightWarpsPerBlock;
+    const bool blend = args.grid.strategy == kBlend;
+    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t groupShift = downscale ? 16u : 13u;  // group = parent voxel when downscaling, else the voxel
+    const uint32_t T = args.grid.tilesPerAxis;
+    unsigned long long clipCalls = 0, contributions = 0;
+
+    for (uint32_t t = blockIdx.x * kLightWarpsPerBlock + (threadIdx.x >> 5); t < args.lightCount; t += warpsTotal) {
+        const LightTile d = args.lightTiles[t];
+        const uint32_t tileOrigin[3] = {(d.tile % T) * kTileEdge, ((d.tile / T) % T) * kTileEdge,
+                                        (d.tile / (T * T) + args.grid.slabTileZ0) * kTileEdge};
+
+        // ---- 1. the tile's leaf list in ascending order (the atomic fill order is arbitrary): rank sort by shuffles ----
+        const uint32_t mine = lane < d.leafCount ? args.work.tileList[d.listStart + lane] : 0xffffffffu;
+        uint32_t rank = 0;
+        for (uint32_t k = 0; k < d.leafCount; ++k) {
+            const uint32_t other = __shfl_sync(full, mine, k);
+            rank += other < mine ? 1u : 0u;
+        }
+        __syncwarp();
+        if (lane < d.leafCount) {
+            sh.sortKey[rank] = mine;
+        }
+        __syncwarp();
+        const uint32_t leafIndex = lane < d.leafCount ? sh.sortKey[lane] : 0u;
+        __syncwarp();
+
+        // ---- 2. lane j stages leaf j (geometry, tile-local AABB, SAT coefficients) ----
+        uint32_t candidates = 0;
+        if (lane < d.leafCount) {
+            stageLeaf<UV>(sh.stage[lane], args, leafIndex, tileOrigin);
+            const uint32_t box = sh.stage[lane].box;
+            candidates = (((box >> 12) & 15u) - (box & 15u)) * (((box >> 16) & 15u) - ((box >> 4) & 15u)) *
+                         (((box >> 20) & 15u) - ((box >> 8) & 15u));
+        }
+        uint32_t inclusive = candidates;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(full, inclusive, o);
+            inclusive += lane >= (uint32_t) o ? up : 0u;
+        }
+        sh.candPrefix[lane + 1] = inclusive;
+        if (lane == 0) {
+            sh.candPrefix[0] = 0;
+        }
+        const uint32_t total = min(__shfl_sync(full, inclusive, 31), kLightMaxCandidates);
+        __syncwarp();
+
+        // ---- 3. candidate voxels (leaf-major) -> conservative SAT -> dense queue ----
+        uint32_t queued = 0;
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t c = base + lane;
+            bool pass = false;
+            uint32_t entry = 0;
+            if (c < total) {
+                uint32_t lo = 0, hi = d.leafCount;  // candPrefix[lo] <= c < candPrefix[hi]
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (sh.candPrefix[mid] <= c) {
+                        lo = mid;
+                    }
+                    else {
+                        hi = mid;
+                    }
+                }
+                const uint32_t q = c - sh.candPrefix[lo];
+                const uint32_t box = sh.stage[lo].box;
+                const uint32_t x0 = box & 15u, y0 = (box >> 4) & 15u, z0 = (box >> 8) & 15u;
+                const uint32_t dx = ((box >> 12) & 15u) - x0, dy = ((box >> 16) & 15u) - y0;
+                const uint32_t x = x0 + q % dx, y = y0 + (q / dx) % dy, z = z0 + q / (dx * dy);
+                pass = !args.prefilter || prefilterPass(sh.stage[lo], (float) x, (float) y, (float) z);
+                entry = (lo << 9) | x | (y << 3) | (z << 6);
+            }
+            const uint32_t ballot = __ballot_sync(full, pass);
+            if (pass) {
+                sh.queue[queued + __popc(ballot & below)] = (uint16_t) entry;
+            }
+            queued += __popc(ballot);
+        }
+        __syncwarp();
+
+        // ---- 4. exact six-plane clip on dense warps -> contributions ----
+        uint32_t kept = 0;
+        for (uint32_t base = 0; base < queued; base += 32) {
+            const uint32_t e = base + lane;
+            bool keep = false;
+            ClipResult r;
+            r.pieces = 0;
+            r.weight = r.u = r.v = 0.0f;
+            uint32_t slotJ = 0, vkey = 0;
+            if (e < queued) {
+                const uint32_t entry = sh.queue[e];
+                slotJ = entry >> 9;
+                const uint32_t x = entry & 7u, y = (entry >> 3) & 7u, z = (entry >> 6) & 7u;
+                vkey = voxelKey(x, y, z);
+                const LeafStage &s = sh.stage[slotJ];
+                Tri<UV> leaf;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    leaf.v[k] = s.v[k];
+                }
+                if (UV) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        leaf.t[k] = s.t[k];
+                    }
+                }
+                r = clipLeafInVoxel<UV>(leaf, tileOrigin[0] + x, tileOrigin[1] + y, tileOrigin[2] + z, s.area);
+                ++clipCalls;
+                keep = r.pieces != 0;
+            }
+            const uint32_t ballot = __ballot_sync(full, keep);
+            if (keep) {
+                const uint32_t pos = kept + __popc(ballot & below);
+                sh.sortKey[pos] = (vkey << 13) | (slotJ << 8) | pos;
+                sh.cW[pos] = r.weight;
+                if (UV) {
+                    sh.cU[pos] = r.u;
+                    sh.cV[pos] = r.v;
+                }
+            }
+            kept += __popc(ballot);
+        }
+        __syncwarp();
+        if (kept == 0) {
+            continue;
+        }
+
+        // ---- 5. sort the contributions by (voxel key, list slot) ----
+        if (kept <= 32) {
+            uint32_t key = lane < kept ? sh.sortKey[lane] : 0xffffffffu;
+            for (uint32_t k = 2; k <= 32; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint32_t other = __shfl_xor_sync(full, key, j);
+                    const bool ascending = (lane & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    key = (lower == ascending) ? min(key, other) : max(key, other);
+                }
+            }
+            sh.sortKey[lane] = key;
+        }
+        else {
+            const uint32_t padded = kept <= 64 ? 64u : 128u;
+            for (uint32_t i = kept + lane; i < padded; i += 32) {
+                sh.sortKey[i] = 0xffffffffu;
+            }
+            __syncwarp();
+            for (uint32_t k = 2; k <= padded; k <<= 1) {
+                for (uint32_t i = lane; i < padded; i += 32) {
+                    const uint32_t l = i ^ (k - 1);
+                    if (l > i) {
+                        const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
+                        if (a > b) {
+                            sh.sortKey[i] = b;
+                            sh.sortKey[l] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < padded; i += 32) {
+                        const uint32_t l = i ^ j;
+                        if (l > i) {
+                            const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
+                            if (a > b) {
+                                sh.sortKey[i] = b;
+                                sh.sortKey[l] = a;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- 6. one lane per output voxel replays the fold in order; block-free compaction through one atomic per tile ----
+        uint32_t runs = 0;
+        for (uint32_t base = 0; base < kept; base += 32) {
+            const uint32_t p = base + lane;
+            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
+            runs += __popc(__ballot_sync(full, start));
+        }
+        unsigned long long outBase = 0;
+        if (lane == 0) {
+            outBase = atomicAdd(&args.counters->voxels, (unsigned long long) runs);
+        }
+        outBase = __shfl_sync(full, outBase, 0);
+        uint32_t emitted = 0;
+        for (uint32_t base = 0; base < kept; base += 32) {
+            const uint32_t p = base + lane;
+            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
+            const uint32_t ballot = __ballot_sync(full, start);
+            if (start) {
+                const uint32_t group = sh.sortKey[p] >> groupShift;
+                uint32_t currentVoxel = (sh.sortKey[p] >> 13) & 511u;
+                VoxelAccumulator child;
+                resetAccumulator(child);
+                WeightedColor parent;
+                parent.w = parent.r = parent.g = parent.b = 0.0f;
+                bool hasParent = false;
+                for (uint32_t q = p; q < kept; ++q) {
+                    const uint32_t key = sh.sortKey[q];
+                    if ((key >> groupShift) != group) {
+                        break;
+                    }
+                    const uint32_t vk = (key >> 13) & 511u, slotJ = (key >> 8) & 31u, slot = key & 255u;
+                    if (vk != currentVoxel) {  // next child of the same parent (downscale only)
+                        flushPartial(child, args);
+                        contributions += child.contributions;
+                        if (!hasParent) {
+                            hasParent = true;
+                            parent = child.voxel;
+                        }
+                        else {
+                            combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        }
+                        resetAccumulator(child);
+                        currentVoxel = vk;
+                    }
+                    const uint32_t tri = sh.stage[slotJ].tri;
+                    if (child.hasPartial && child.partialTri != tri) {
+                        flushPartial(child, args);
+                    }
+                    addContribution(child, tri, sh.cW[slot], UV ? sh.cU[slot] : 0.0f, UV ? sh.cV[slot] : 0.0f);
+                }
+                flushPartial(child, args);
+                contributions += child.contributions;
+                WeightedColor result = child.voxel;
+                const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
+                int32_t ox, oy, oz;
+                if (downscale) {
+                    if (hasParent) {
+                        combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        result = parent;
+                    }
+                    ox = (int32_t) (tileOrigin[0] / 2 + (pk & 3u));
+                    oy = (int32_t) (tileOrigin[1] / 2 + ((pk >> 2) & 3u));
+                    oz = (int32_t) (tileOrigin[2] / 2 + ((pk >> 4) & 3u));
+                }
+                else {
+                    ox = (int32_t) (tileOrigin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
+                    oy = (int32_t) (tileOrigin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
+                    oz = (int32_t) (tileOrigin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
+                }
+                const unsigned long long index = outBase + emitted + __popc(ballot & below);
+                if (index < args.outCapacity) {
+                    VoxelRecord rec;
+                    rec.x = ox;
+                    rec.y = oy;
+                    rec.z = oz;
+                    rec.argb = quantizeArgb(result.r, result.g, result.b);
+                    *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                }
+                else {
+                    atomicAdd(&args.counters->outputOverflow, 1ull);
+                }
+            }
+            emitted += __popc(ballot);
+        }
+        __syncwarp();
+    }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        clipCalls += __shfl_xor_sync(full, clipCalls, o);
+        contributions += __shfl_xor_sync(full, contributions, o);
+    }
+    if (lane == 0) {
+        if (clipCalls != 0) {
+            atomicAdd(&args.counters->clipCalls, clipCalls);
+        }
+        if (contributions != 0) {
+            atomicAdd(&args.counters->contributions, contributions);
+        }
+    }
+}
+
 inline int gridFor(unsigned long long n, int threads, int cap)
 {
     unsigned long long blocks = (n + threads - 1) / threads;
@@ -847,14 +1201,16 @@ void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
 }
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       RunCounters *counters, cudaStream_t stream)
+                       uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
     if (mesh.uvs != nullptr) {
-        countLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, counters);
+        countLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
+                                                                       counters);
     }
     else {
-        countLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, counters);
+        countLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
+                                                                        counters);
     }
 }
 
@@ -878,13 +1234,15 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
     scanApplyKernel<<<(unsigned) blocks, kScanThreads, 0, stream>>>(in, out, n, blockSums);
 }
 
-void launchCompactActiveTiles(const uint32_t *tileCount, uint32_t tileTotal, uint32_t *activeTiles,
-                              RunCounters *counters, cudaStream_t stream)
+void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
+                              uint32_t tileTotal, uint32_t *heavyTiles, LightTile *lightTiles, RunCounters *counters,
+                              cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
-    compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileTotal, activeTiles, counters);
+    compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
+                                                                          tileTotal, heavyTiles, lightTiles, counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
@@ -931,6 +1289,31 @@ void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t str
     else {
         cudaFuncSetAttribute(voxelizeTilesKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         voxelizeTilesKernel<false><<<blocks, kTileThreads, smem, stream>>>(args);
+    }
+}
+
+void launchVoxelizeLightTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
+{
+    if (args.lightCount == 0) {
+        return;
+    }
+    const int threads = kLightWarpsPerBlock * 32;
+    int perSm = 0;
+    if (args.mesh.uvs != nullptr) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, voxelizeLightTilesKernel<true>, threads, 0);
+    }
+    else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, voxelizeLightTilesKernel<false>, threads, 0);
+    }
+    perSm = perSm < 1 ? 1 : perSm;
+    unsigned long long blocks = (unsigned long long) smCount * perSm;  // persistent: a multiple of the SM count
+    const unsigned long long needed = (args.lightCount + kLightWarpsPerBlock - 1) / kLightWarpsPerBlock;
+    blocks = blocks < needed ? blocks : needed;
+    if (args.mesh.uvs != nullptr) {
+        voxelizeLightTilesKernel<true><<<(unsigned) blocks, threads, 0, stream>>>(args);
+    }
+    else {
+        voxelizeLightTilesKernel<false><<<(unsigned) blocks, threads, 0, stream>>>(args);
     }
 }
 

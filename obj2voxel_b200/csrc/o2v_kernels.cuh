@@ -17,6 +17,8 @@ namespace o2v {
 constexpr uint32_t kTileEdge = 8;  // voxels per tile edge (sample space); 8^3 = 512 voxels = one thread block
 constexpr uint32_t kTileVoxels = kTileEdge * kTileEdge * kTileEdge;
 constexpr uint32_t kLeafBatch = 32;  // leaves staged in shared memory per round
+constexpr uint32_t kLightMaxLeaves = 32;       // a light tile's whole list fits one warp (one leaf per lane)
+constexpr uint32_t kLightMaxCandidates = 128;  // ... and its candidate voxels fit the per-warp queues
 
 /// Input mesh, model space.  All pointers are device pointers.
 struct MeshView {
@@ -63,7 +65,9 @@ struct RunCounters {
     unsigned long long leaves;          // total leaf records
     unsigned long long pairs;           // total (leaf, tile) pairs
     unsigned long long candidateVoxels; // sum of leaf AABB volumes inside the slab (upper bound on contributions)
-    unsigned long long activeTiles;
+    unsigned long long activeTiles;     // light + heavy
+    unsigned long long lightTiles;      // tiles voxelized warp-per-tile (<= kLightMaxLeaves leaves, <= kLightMaxCandidates candidates)
+    unsigned long long heavyTiles;      // tiles voxelized block-per-tile
     unsigned long long voxels;          // emitted voxels
     unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
     unsigned long long clipCalls;       // exact clips executed (prefilter survivors)
@@ -78,8 +82,16 @@ struct RunCounters {
     unsigned int pad;
 };
 
+/// Descriptor of a light tile: everything the warp needs in one 16-byte load.
+struct __align__(16) LightTile {
+    uint32_t tile;        // slab-local tile id
+    uint32_t listStart;   // offset into tileList
+    uint32_t leafCount;   // <= kLightMaxLeaves
+    uint32_t candidates;  // sum of leaf AABB volumes clipped to the tile, <= kLightMaxCandidates
+};
+
 struct TileWork {
-    const uint32_t *activeTiles;  // slab-local tile ids with a non-empty list
+    const uint32_t *activeTiles;  // slab-local ids of the HEAVY tiles (block-per-tile kernel)
     const uint32_t *tileStart;    // exclusive scan of tileCount (slab-local tile id -> list offset)
     const uint32_t *tileCount;
     const uint32_t *tileList;     // leaf indices, ascending within a tile after sortTileLists
@@ -92,15 +104,17 @@ void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stre
 void launchFinishBounds(RunCounters *counters, cudaStream_t stream);
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       RunCounters *counters, cudaStream_t stream);
+                       uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream);
 
 /// Exclusive scan of n u32 values; total (u64) is written to *total.  scratch must hold scanScratchElems(n) u32.
 size_t scanScratchElems(size_t n);
 void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *scratch, unsigned long long *total,
                          cudaStream_t stream);
 
-void launchCompactActiveTiles(const uint32_t *tileCount, uint32_t tileTotal, uint32_t *activeTiles,
-                              RunCounters *counters, cudaStream_t stream);
+/// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
+void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
+                              uint32_t tileTotal, uint32_t *heavyTiles, LightTile *lightTiles, RunCounters *counters,
+                              cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList,
@@ -119,11 +133,16 @@ struct VoxelizeArgs {
     VoxelRecord *out;
     unsigned long long outCapacity;
     RunCounters *counters;
-    int variant;  // 0 = per-voxel inline clip, 1 = warp-compacted clip queue
+    const LightTile *lightTiles;
+    uint32_t lightCount;
+    int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
 };
 
+/// Heavy tiles: one 512-thread block per tile, thread = voxel.
 void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+/// Light tiles: one warp per tile, lanes = candidate voxels, dense clip queue, in-warp sort + ordered fold.
+void launchVoxelizeLightTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 
 }  // namespace o2v
 

@@ -9,8 +9,8 @@ from oracle import oracle
 def diff(name, got, want, stats):
     got = o2v.sort_voxels(got)
     ok = got.shape == want.shape and np.array_equal(got, want)
-    print("%-34s %s gpu=%d oracle=%d leaves=%d pairs=%d tiles=%d clips=%d contrib=%d ms=%.3f (setup %.3f vox %.3f)" % (
-        name, "OK " if ok else "BAD", len(got), len(want), stats["leaves"], stats["pairs"], stats["active_tiles"],
+    print("%-34s %s gpu=%d oracle=%d leaves=%d pairs=%d tiles=%d(light %d) clips=%d contrib=%d ms=%.3f (setup %.3f vox %.3f)" % (
+        name, "OK " if ok else "BAD", len(got), len(want), stats["leaves"], stats["pairs"], stats["active_tiles"], stats["light_tiles"],
         stats["clip_calls"], stats["contributions"], stats["ms_total"], stats["ms_setup"], stats["ms_voxelize"]), flush=True)
     if not ok:
         gs = set(map(tuple, got[:, :3].tolist())); ws = set(map(tuple, want[:, :3].tolist()))
