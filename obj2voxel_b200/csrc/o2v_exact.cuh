@@ -15,8 +15,10 @@
 
 #if defined(__CUDACC__)
 #define O2V_HD __host__ __device__ __forceinline__
+#define O2V_UNROLL _Pragma("unroll")
 #else
 #define O2V_HD inline
+#define O2V_UNROLL
 #endif
 
 namespace o2v {
@@ -263,21 +265,27 @@ O2V_HD void setVertex(Tri<UV> &dst, int k, const float *p, const float *t)
     }
 }
 
-/// One half-space clip.  keepHi = the DISCARD_LO passes (plane = pos[axis]), otherwise DISCARD_HI (plane = pos[axis]+1).
-/// Writes the kept pieces in the reference's push order into o0 (and o1) and returns how many were kept (0, 1 or 2).
-template <bool UV>
-O2V_HD int splitKeep(const Tri<UV> &t, int axis, float plane, bool keepHi, Tri<UV> &o0, Tri<UV> &o1)
+/// Result of clipping one leaf against one voxel: src/voxelization.cpp:383-424.
+struct ClipResult {
+    int pieces;    // number of surviving pieces (0 => no contribution)
+    float weight;  // pieces-fold repeated sum of the whole-triangle area (SURVEY fact 4)
+    float u, v;    // sequential weighted mean of the piece UV centres (only when UV)
+};
+
+/// What one half-space does to a triangle (the switch of src/voxelization.cpp:192-234 without the geometry).
+enum ClipAction : int { kClipKeep = 0, kClipDrop = 1, kClipSplitRegular = 2, kClipSplitOnePlanar = 3 };
+
+/// Classifies triangle `v` against plane `planePos` on `axis`.  For the split actions `pivot` is the isolated vertex
+/// (regular case, splitTriangle_regularCase :289-293) or the planar vertex (one-planar case, :245-246) and `pivotIsLo`
+/// tells on which side the piece that starts at the pivot's successor... see splitAt().
+O2V_HD ClipAction classifyAgainstPlane(const float *v, int axis, float planePos, bool keepHi, int &pivot, bool &sideLo)
 {
-    // SplittingValues, voxelization.cpp:110-153
-    const float c0 = axisOf(t.v, axis), c1 = axisOf(t.v + 3, axis), c2 = axisOf(t.v + 6, axis);
-    const bool p0 = isZero(xsub(c0, plane)), p1 = isZero(xsub(c1, plane)), p2 = isZero(xsub(c2, plane));
-    const bool l0 = c0 < plane, l1 = c1 < plane, l2 = c2 < plane;
+    const float c0 = axisOf(v, axis), c1 = axisOf(v + 3, axis), c2 = axisOf(v + 6, axis);
+    const bool p0 = isZero(xsub(c0, planePos)), p1 = isZero(xsub(c1, planePos)), p2 = isZero(xsub(c2, planePos));
+    const bool l0 = c0 < planePos, l1 = c1 < planePos, l2 = c2 < planePos;
     const int loSum = int(l0) + int(l1) + int(l2);
     const int planarSum = int(p0) + int(p1) + int(p2);
-
-    // unsplit cases of the switch, voxelization.cpp:192-217: decide lo/hi for the whole triangle
-    bool whole = true;
-    bool wholeIsLo = false;
+    bool wholeIsLo;
     if (loSum == 0) {
         wholeIsLo = false;
     }
@@ -291,101 +299,58 @@ O2V_HD int splitKeep(const Tri<UV> &t, int axis, float plane, bool keepHi, Tri<U
         wholeIsLo = !p0 ? l0 : (!p1 ? l1 : l2);  // loVertices[firstNonplanar()]
     }
     else if (planarSum == 1) {
-        // splitTriangle_onePlanarCase, voxelization.cpp:240-277
         const int p = p0 ? 0 : (p1 ? 1 : 2);
-        const int a = (p + 1) % 3, b = (p + 2) % 3;
-        const bool la = a == 0 ? l0 : (a == 1 ? l1 : l2);
-        const bool lb = b == 0 ? l0 : (b == 1 ? l1 : l2);
-        if (la == lb) {
-            wholeIsLo = la;  // nonPlanarLoSum == 2 -> lo, == 0 -> hi
+        const bool la = p == 0 ? l1 : (p == 1 ? l2 : l0);  // vertex (p + 1) % 3
+        const bool lb = p == 0 ? l2 : (p == 1 ? l0 : l1);  // vertex (p + 2) % 3
+        if (la != lb) {
+            pivot = p;
+            sideLo = la;
+            return kClipSplitOnePlanar;
         }
-        else {
-            whole = false;
-            const float *va = t.v + a * 3, *vb = t.v + b * 3, *vp = t.v + p * 3;
-            const float *ta = t.t + (UV ? a * 2 : 0), *tb = t.t + (UV ? b * 2 : 0), *tp = t.t + (UV ? p * 2 : 0);
-            const float s = intersectAxisPlane(va, vb, axis, plane);
-            float geo[3], tex[2] = {0.0f, 0.0f};
-            for (int i = 0; i < 3; ++i) {
-                geo[i] = mix1(va[i], vb[i], s);
-            }
-            if (UV) {
-                for (int i = 0; i < 2; ++i) {
-                    tex[i] = mix1(ta[i], tb[i], s);
-                }
-            }
-            // first = (planar, a, X) is lo iff a is lo; second = (planar, X, b) is on the other side
-            const bool keepFirst = la != keepHi;
-            if (keepFirst) {
-                setVertex<UV>(o0, 0, vp, tp);
-                setVertex<UV>(o0, 1, va, ta);
-                setVertex<UV>(o0, 2, geo, tex);
-            }
-            else {
-                setVertex<UV>(o0, 0, vp, tp);
-                setVertex<UV>(o0, 1, geo, tex);
-                setVertex<UV>(o0, 2, vb, tb);
-            }
-            return 1;
-        }
+        wholeIsLo = la;
     }
     else {
-        // splitTriangle_regularCase, voxelization.cpp:279-331
-        whole = false;
         const bool isoLo = loSum == 1;
-        const int iso = isoLo ? (l0 ? 0 : (l1 ? 1 : 2)) : (!l0 ? 0 : (!l1 ? 1 : 2));
-        const int a = (iso + 1) % 3, b = (iso + 2) % 3;
-        const float *vi = t.v + iso * 3, *va = t.v + a * 3, *vb = t.v + b * 3;
-        const float *ti = t.t + (UV ? iso * 2 : 0), *ta = t.t + (UV ? a * 2 : 0), *tb = t.t + (UV ? b * 2 : 0);
-        const float s0 = intersectAxisPlane(vi, va, axis, plane);
-        const float s1 = intersectAxisPlane(vi, vb, axis, plane);
-        float g0[3], g1[3], x0[2] = {0.0f, 0.0f}, x1[2] = {0.0f, 0.0f};
-        for (int i = 0; i < 3; ++i) {
-            g0[i] = mix1(vi[i], va[i], s0);
-            g1[i] = mix1(vi[i], vb[i], s1);
-        }
-        if (UV) {
-            for (int i = 0; i < 2; ++i) {
-                x0[i] = mix1(ti[i], ta[i], s0);
-                x1[i] = mix1(ti[i], tb[i], s1);
-            }
-        }
-        if (isoLo != keepHi) {
-            // the isolated corner is on the kept side
-            setVertex<UV>(o0, 0, vi, ti);
-            setVertex<UV>(o0, 1, g0, x0);
-            setVertex<UV>(o0, 2, g1, x1);
-            return 1;
-        }
-        // the quad is on the kept side: (X0, a, b) then (X0, X1, b)
-        setVertex<UV>(o0, 0, g0, x0);
-        setVertex<UV>(o0, 1, va, ta);
-        setVertex<UV>(o0, 2, vb, tb);
-        setVertex<UV>(o1, 0, g0, x0);
-        setVertex<UV>(o1, 1, g1, x1);
-        setVertex<UV>(o1, 2, vb, tb);
-        return 2;
+        pivot = isoLo ? (l0 ? 0 : (l1 ? 1 : 2)) : (!l0 ? 0 : (!l1 ? 1 : 2));
+        sideLo = isoLo;
+        return kClipSplitRegular;
     }
-
-    if (whole) {
-        if (wholeIsLo != keepHi) {
-            o0 = t;
-            return 1;
-        }
-        return 0;
-    }
-    return 0;
+    return wholeIsLo != keepHi ? kClipKeep : kClipDrop;
 }
 
-/// Result of clipping one leaf against one voxel: src/voxelization.cpp:383-424.
-struct ClipResult {
-    int pieces;    // number of surviving pieces (0 => no contribution)
-    float weight;  // pieces-fold repeated sum of the whole-triangle area (SURVEY fact 4)
-    float u, v;    // sequential weighted mean of the piece UV centres (only when UV)
-};
+/// Rotates the triangle so that vertex `pivot` comes first (keeps the cyclic order, i.e. (pivot+1)%3 and (pivot+2)%3
+/// become vertices 1 and 2 exactly like otherIndices / nonPlanarIndices in the reference).
+template <bool UV>
+O2V_HD void rotateToPivot(Tri<UV> &t, int pivot)
+{
+    if (pivot == 0) {
+        return;
+    }
+    Tri<UV> r;
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        r.v[i] = pivot == 1 ? t.v[3 + i] : t.v[6 + i];
+        r.v[3 + i] = pivot == 1 ? t.v[6 + i] : t.v[i];
+        r.v[6 + i] = pivot == 1 ? t.v[i] : t.v[3 + i];
+    }
+    if (UV) {
+O2V_UNROLL
+        for (int i = 0; i < 2; ++i) {
+            r.t[i] = pivot == 1 ? t.t[2 + i] : t.t[4 + i];
+            r.t[2 + i] = pivot == 1 ? t.t[4 + i] : t.t[i];
+            r.t[4 + i] = pivot == 1 ? t.t[i] : t.t[2 + i];
+        }
+    }
+    t = r;
+}
 
 /// Six sequential half-space clips of `leaf` against voxel (px,py,pz), visiting surviving pieces in the reference's list
 /// order (a depth-first walk over the clip tree yields the same left-to-right leaf order as its breadth-first ping-pong
 /// buffers), then the weighted fold of voxelization.cpp:414-420 / util.hpp:160-165.
+///
+/// SIMT shape: every lane runs the same two-phase loop — a cheap classify/advance loop (no geometry) until its current
+/// piece needs a real split, then ONE shared split step — so the lanes of a warp execute the expensive split code together
+/// instead of serialising on the reference's 16-way case switch.
 template <bool UV>
 O2V_HD ClipResult clipLeafInVoxel(const Tri<UV> &leaf, uint32_t px, uint32_t py, uint32_t pz, float wholeArea)
 {
@@ -402,43 +367,114 @@ O2V_HD ClipResult clipLeafInVoxel(const Tri<UV> &leaf, uint32_t px, uint32_t py,
     Tri<UV> cur = leaf;
     int plane = 0;
     for (;;) {
-        bool alive = true;
-        while (plane < 6) {
-            const int axis = plane < 3 ? plane : plane - 3;
-            const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
-            const float planePos = static_cast<float>(base + (plane < 3 ? 0u : 1u));
-            Tri<UV> a, b;
-            const int kept = splitKeep<UV>(cur, axis, planePos, plane < 3, a, b);
-            if (kept == 0) {
-                alive = false;
-                break;
+        // ---- phase A: advance through planes that keep or drop the piece whole; pop finished / dead pieces ----
+        ClipAction action = kClipKeep;
+        int pivot = 0;
+        bool sideLo = false;
+        bool finished = false;
+        for (;;) {
+            if (plane == 6) {
+                // a surviving piece: result = mix(result, {area, textureCenter}) (util.hpp:160-165, triangle.hpp:127-131)
+                const float weightSum = xadd(r.weight, wholeArea);
+                if (UV) {
+                    const float cu = xdiv(xadd(xadd(cur.t[0], cur.t[2]), cur.t[4]), 3.0f);
+                    const float cv = xdiv(xadd(xadd(cur.t[1], cur.t[3]), cur.t[5]), 3.0f);
+                    r.u = xdiv(xadd(xmul(r.weight, r.u), xmul(wholeArea, cu)), weightSum);
+                    r.v = xdiv(xadd(xmul(r.weight, r.v), xmul(wholeArea, cv)), weightSum);
+                }
+                r.weight = weightSum;
+                ++r.pieces;
+                action = kClipDrop;  // done with this piece: take the next pending one
             }
-            if (kept == 2) {
-                pending[sp] = b;
-                pendingPlane[sp] = static_cast<uint8_t>(plane + 1);
-                ++sp;
+            else {
+                const int axis = plane < 3 ? plane : plane - 3;
+                const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
+                const float planePos = static_cast<float>(base + (plane < 3 ? 0u : 1u));
+                action = classifyAgainstPlane(cur.v, axis, planePos, plane < 3, pivot, sideLo);
             }
-            cur = a;
-            ++plane;
+            if (action == kClipKeep) {
+                ++plane;
+                continue;
+            }
+            if (action == kClipDrop) {
+                if (sp == 0) {
+                    finished = true;
+                    break;
+                }
+                --sp;
+                cur = pending[sp];
+                plane = pendingPlane[sp];
+                continue;
+            }
+            break;  // a split is needed
         }
-        if (alive) {
-            // result = mix(result, {area, textureCenter}): util.hpp:160-165, triangle.hpp:127-131
-            const float weightSum = xadd(r.weight, wholeArea);
-            if (UV) {
-                const float cu = xdiv(xadd(xadd(cur.t[0], cur.t[2]), cur.t[4]), 3.0f);
-                const float cv = xdiv(xadd(xadd(cur.t[1], cur.t[3]), cur.t[5]), 3.0f);
-                r.u = xdiv(xadd(xmul(r.weight, r.u), xmul(wholeArea, cu)), weightSum);
-                r.v = xdiv(xadd(xmul(r.weight, r.v), xmul(wholeArea, cv)), weightSum);
-            }
-            r.weight = weightSum;
-            ++r.pieces;
-        }
-        if (sp == 0) {
+        if (finished) {
             break;
         }
-        --sp;
-        cur = pending[sp];
-        plane = pendingPlane[sp];
+
+        // ---- phase B: one split (the expensive geometry), shared by all lanes that reached it ----
+        const int axis = plane < 3 ? plane : plane - 3;
+        const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
+        const float planePos = static_cast<float>(base + (plane < 3 ? 0u : 1u));
+        const bool keepHi = plane < 3;
+        rotateToPivot<UV>(cur, pivot);
+        if (action == kClipSplitRegular) {
+            // splitTriangle_regularCase, voxelization.cpp:279-331: pivot = isolated vertex, X0/X1 on its two edges
+            const float s0 = intersectAxisPlane(cur.v, cur.v + 3, axis, planePos);
+            const float s1 = intersectAxisPlane(cur.v, cur.v + 6, axis, planePos);
+            float g0[3], g1[3], x0[2] = {0.0f, 0.0f}, x1[2] = {0.0f, 0.0f};
+O2V_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                g0[i] = mix1(cur.v[i], cur.v[3 + i], s0);
+                g1[i] = mix1(cur.v[i], cur.v[6 + i], s1);
+            }
+            if (UV) {
+O2V_UNROLL
+                for (int i = 0; i < 2; ++i) {
+                    x0[i] = mix1(cur.t[i], cur.t[2 + i], s0);
+                    x1[i] = mix1(cur.t[i], cur.t[4 + i], s1);
+                }
+            }
+            if (sideLo != keepHi) {
+                // the isolated corner (iso, X0, X1) is kept
+                setVertex<UV>(cur, 1, g0, x0);
+                setVertex<UV>(cur, 2, g1, x1);
+            }
+            else {
+                // the quad is kept: (X0, a, b) first, (X0, X1, b) pending for the next plane
+                Tri<UV> second;
+                setVertex<UV>(second, 0, g0, x0);
+                setVertex<UV>(second, 1, g1, x1);
+                setVertex<UV>(second, 2, cur.v + 6, cur.t + (UV ? 4 : 0));
+                pending[sp] = second;
+                pendingPlane[sp] = static_cast<uint8_t>(plane + 1);
+                ++sp;
+                setVertex<UV>(cur, 0, g0, x0);
+            }
+        }
+        else {
+            // splitTriangle_onePlanarCase, voxelization.cpp:240-277: pivot = planar vertex, X on the opposite edge a -> b;
+            // (p, a, X) lies on a's side, (p, X, b) on the other
+            const float s = intersectAxisPlane(cur.v + 3, cur.v + 6, axis, planePos);
+            float geo[3], tex[2] = {0.0f, 0.0f};
+O2V_UNROLL
+            for (int i = 0; i < 3; ++i) {
+                geo[i] = mix1(cur.v[3 + i], cur.v[6 + i], s);
+            }
+            if (UV) {
+O2V_UNROLL
+                for (int i = 0; i < 2; ++i) {
+                    tex[i] = mix1(cur.t[2 + i], cur.t[4 + i], s);
+                }
+            }
+            if (sideLo != keepHi) {
+                setVertex<UV>(cur, 2, geo, tex);  // keep (p, a, X)
+            }
+            else {
+                setVertex<UV>(cur, 1, geo, tex);  // keep (p, X, b)
+            }
+        }
+        ++plane;
     }
     return r;
 }

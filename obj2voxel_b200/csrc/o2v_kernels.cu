@@ -13,6 +13,7 @@
 #include "o2v_kernels.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace o2v {
 
@@ -1306,6 +1307,12 @@ void launchVoxelizeLightTiles(const VoxelizeArgs &args, int smCount, cudaStream_
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, voxelizeLightTilesKernel<false>, threads, 0);
     }
     perSm = perSm < 1 ? 1 : perSm;
+    if (const char *env = getenv("O2V_B200_LIGHT_BLOCKS_PER_SM")) {  // tuning knob: fewer resident blocks leave more L1
+        const int wanted = atoi(env);
+        if (wanted >= 1 && wanted < perSm) {
+            perSm = wanted;
+        }
+    }
     unsigned long long blocks = (unsigned long long) smCount * perSm;  // persistent: a multiple of the SM count
     const unsigned long long needed = (args.lightCount + kLightWarpsPerBlock - 1) / kLightWarpsPerBlock;
     blocks = blocks < needed ? blocks : needed;

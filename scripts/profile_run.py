@@ -1,0 +1,28 @@
+"""Runs one workload device-resident a few times (for ncu / timing experiments).  Usage: profile_run.py [workload] [steps]"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import obj2voxel_b200 as o2v
+from obj2voxel_b200 import meshes
+import bench
+
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+cfg = bench.workload_spec(name)
+dev = torch.device("cuda", 0)
+eng = o2v.Engine(0)
+if cfg["kind"] == "sphere":
+    verts = torch.from_numpy(meshes.lumpy_sphere()).to(dev); uvs = None
+elif cfg["kind"] == "single":
+    verts = torch.from_numpy(meshes.single_triangle()).to(dev); uvs = None
+else:
+    verts = meshes.random_triangles_torch(cfg["n"], cfg["extent"], seed=1, device=dev)
+    uvs = meshes.random_uvs_torch(cfg["n"], seed=2, device=dev) if cfg.get("textured") else None
+textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(dev), o2v.UV_WRAP)] if uvs is not None else []
+params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
+                         bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")))
+for i in range(steps):
+    st = eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
+    torch.cuda.synchronize()
+    print(json.dumps({k: st[k] for k in ("voxels", "leaves", "pairs", "light_tiles", "heavy_tiles", "clip_calls",
+                                         "contributions", "candidate_voxels", "ms_total", "ms_setup", "ms_voxelize")}), flush=True)
