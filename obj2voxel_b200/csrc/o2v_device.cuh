@@ -1,0 +1,202 @@
+// Device-side helpers shared by the tile kernels (o2v_kernels.cu: block-per-tile; o2v_sparse.cu: staged sparse path).
+#ifndef O2V_DEVICE_CUH
+#define O2V_DEVICE_CUH
+
+#include "o2v_kernels.cuh"
+
+namespace o2v {
+namespace {
+
+constexpr float kPrefilterMargin = 0.0625f;  // voxels; must exceed every rounding / planarity slack of the exact clip
+
+struct LeafStage {
+    float v[9];
+    float t[6];
+    float area;
+    uint32_t tri;
+    uint32_t box;      // tile-local AABB: 4 bits each lo.x lo.y lo.z hi.x hi.y hi.z (hi exclusive, <= 8)
+    float plane[4];    // n . p + d for the tile-local voxel min corner p
+    float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
+    float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
+    uint32_t pad;      // 51 words: odd stride, so lanes reading the same field of different leaves hit distinct banks
+};
+
+/// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
+/// functions on a box inflated by kPrefilterMargin).  Not exact arithmetic: FMA contraction is welcome here.
+__device__ __forceinline__ void buildPrefilter(LeafStage &s, const float origin[3])
+{
+    float p[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        p[k] = s.v[k] - origin[k % 3];
+    }
+    const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
+    const float e1[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    s.plane[0] = n[0];
+    s.plane[1] = n[1];
+    s.plane[2] = n[2];
+    s.plane[3] = n[0] * (0.5f - p[0]) + n[1] * (0.5f - p[1]) + n[2] * (0.5f - p[2]);
+    s.planeLimit = (0.5f + kPrefilterMargin) * (fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]));
+    const float grow = 1.0f + kPrefilterMargin;
+#pragma unroll
+    for (int proj = 0; proj < 3; ++proj) {
+        const int a = proj, b = (proj + 1) % 3, c = (proj + 2) % 3;  // xy (n.z), yz (n.x), zx (n.y)
+        const float sign = n[c] >= 0.0f ? 1.0f : -1.0f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int j = (i + 1) % 3;
+            const float ea = p[j * 3 + a] - p[i * 3 + a];
+            const float eb = p[j * 3 + b] - p[i * 3 + b];
+            const float A = -eb * sign, B = ea * sign;
+            float C = -(A * p[i * 3 + a] + B * p[i * 3 + b]);
+            C += A > 0.0f ? A * grow : -A * kPrefilterMargin;
+            C += B > 0.0f ? B * grow : -B * kPrefilterMargin;
+            s.edge[(proj * 3 + i) * 3 + 0] = A;
+            s.edge[(proj * 3 + i) * 3 + 1] = B;
+            s.edge[(proj * 3 + i) * 3 + 2] = C;
+        }
+    }
+}
+
+/// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
+__device__ __forceinline__ bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
+{
+    const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
+    if (fabsf(dist) > s.planeLimit) {
+        return false;
+    }
+    const float q[3] = {lx, ly, lz};
+#pragma unroll
+    for (int proj = 0; proj < 3; ++proj) {
+        const float qa = q[proj], qb = q[(proj + 1) % 3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float *e = s.edge + (proj * 3 + i) * 3;
+            if (e[0] * qa + e[1] * qb + e[2] < 0.0f) {
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+struct VoxelAccumulator {
+    // per-triangle uv buffer entry (voxelization.cpp:426-472) and the voxel itself (voxelization.cpp:513-526)
+    WeightedUv partial;
+    WeightedColor voxel;
+    uint32_t partialTri;
+    bool hasPartial;
+    bool hasVoxel;
+    uint32_t contributions;
+};
+
+__device__ __forceinline__ void flushPartial(VoxelAccumulator &acc, const VoxelizeArgs &args)
+{
+    if (!acc.hasPartial) {
+        return;
+    }
+    acc.hasPartial = false;
+    const uint32_t tri = acc.partialTri;
+    const MeshView &mesh = args.mesh;
+    uint8_t type;
+    if (mesh.types != nullptr) {
+        type = mesh.types[tri];
+    }
+    else {
+        type = (mesh.uvs != nullptr && args.textureCount != 0) ? kTextured : kMaterialless;
+    }
+    float rgb[3] = {1.0f, 1.0f, 1.0f};  // MATERIALLESS: triangle.hpp:186
+    if (type == kUntextured && mesh.colors != nullptr) {
+        rgb[0] = mesh.colors[(size_t) tri * 3];
+        rgb[1] = mesh.colors[(size_t) tri * 3 + 1];
+        rgb[2] = mesh.colors[(size_t) tri * 3 + 2];
+    }
+    else if (type == kTextured && args.textureCount != 0) {
+        uint32_t id = mesh.textureIds != nullptr ? mesh.textureIds[tri] : 0u;
+        id = id < args.textureCount ? id : 0u;
+        textureLookup(args.textures[id], acc.partial.u, acc.partial.v, rgb);
+    }
+    ++acc.contributions;
+    if (!acc.hasVoxel) {
+        acc.hasVoxel = true;
+        acc.voxel.w = acc.partial.w;
+        acc.voxel.r = rgb[0];
+        acc.voxel.g = rgb[1];
+        acc.voxel.b = rgb[2];
+    }
+    else {
+        combineColorInto(acc.voxel, acc.partial.w, rgb[0], rgb[1], rgb[2], args.grid.strategy == kBlend);
+    }
+}
+
+__device__ __forceinline__ void addContribution(VoxelAccumulator &acc, uint32_t tri, float w, float u, float v)
+{
+    if (acc.hasPartial) {
+        blendUvInto(acc.partial, w, u, v);  // same triangle, later leaf: insertWeighted<BLEND>
+    }
+    else {
+        acc.hasPartial = true;
+        acc.partialTri = tri;
+        acc.partial.w = w;
+        acc.partial.u = u;
+        acc.partial.v = v;
+    }
+}
+
+template <bool UV>
+__device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args, uint32_t leafIndex,
+                                          const uint32_t tileOrigin[3])
+{
+    const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
+    s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+    s.v[8] = c.x;
+    s.tri = __float_as_uint(c.y);
+    s.area = c.z;
+    if (UV) {
+        const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
+        const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
+        s.t[0] = u0.x; s.t[1] = u0.y; s.t[2] = u0.z; s.t[3] = u0.w;
+        s.t[4] = u1.x; s.t[5] = u1.y;
+    }
+    uint32_t lo[3], hi[3];
+    triVoxelBounds(s.v, lo, hi);
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t l = lo[i] > tileOrigin[i] ? min(lo[i] - tileOrigin[i], kTileEdge) : 0u;
+        const uint32_t h = hi[i] > tileOrigin[i] ? min(hi[i] - tileOrigin[i], kTileEdge) : 0u;
+        packed |= l << (4 * i);
+        packed |= h << (12 + 4 * i);
+    }
+    s.box = packed;
+    const float origin[3] = {(float) tileOrigin[0], (float) tileOrigin[1], (float) tileOrigin[2]};
+    buildPrefilter(s, origin);
+}
+
+/// Voxel key: parent (2x2x2 block) index in the high 6 bits, child Morton code (x most significant, ileave.hpp:243-246) in
+/// the low 3 — ascending keys visit the children of one parent in ascending Morton order, which is the downscale order.
+__device__ __forceinline__ uint32_t voxelKey(uint32_t x, uint32_t y, uint32_t z)
+{
+    const uint32_t parent = (x >> 1) | ((y >> 1) << 2) | ((z >> 1) << 4);
+    const uint32_t child = ((x & 1u) << 2) | ((y & 1u) << 1) | (z & 1u);
+    return (parent << 3) | child;
+}
+
+__device__ __forceinline__ void resetAccumulator(VoxelAccumulator &acc)
+{
+    acc.hasPartial = false;
+    acc.hasVoxel = false;
+    acc.partialTri = 0;
+    acc.contributions = 0;
+    acc.partial.w = acc.partial.u = acc.partial.v = 0.0f;
+    acc.voxel.w = acc.voxel.r = acc.voxel.g = acc.voxel.b = 0.0f;
+}
+
+
+}  // namespace
+}  // namespace o2v
+
+#endif  // O2V_DEVICE_CUH

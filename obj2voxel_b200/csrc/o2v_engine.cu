@@ -205,7 +205,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     const size_t scratchElems = std::max(scanScratchElems(n), scanScratchElems(tileTotal));
     if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !tileCount_.ensure((size_t) tileTotal * 4) ||
         !tileStart_.ensure((size_t) tileTotal * 4) || !tileFill_.ensure((size_t) tileTotal * 4) ||
-        !activeTiles_.ensure((size_t) tileTotal * 4) || !tileCand_.ensure((size_t) tileTotal * 4) ||
+        !activeTiles_.ensure((size_t) tileTotal * 4) || !allTiles_.ensure((size_t) tileTotal * 4) ||
+        !tileCand_.ensure((size_t) tileTotal * 4) ||
         !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
     }
@@ -220,7 +221,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
                         &dCounters->pairs, stream);
     launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
-                             activeTiles_.as<uint32_t>(), lightTiles_.as<LightTile>(), dCounters, stream);
+                             allTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(), lightTiles_.as<LightTile>(), dCounters,
+                             stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -241,7 +243,10 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     const bool hasUv = mesh.uvs != nullptr;
     if (!leaves_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafRecord)) ||
         (hasUv && !leafUvs_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafUv))) ||
-        !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4)) {
+        !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
+        !pairTile_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
+        !pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
+        !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
     }
     size_t freeBytes = 0, totalBytes = 0;
@@ -263,8 +268,10 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
 
     launchEmitLeaves(mesh, grid, leafOffset_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileFill_.as<uint32_t>(),
                      leaves_.as<LeafRecord>(), hasUv ? leafUvs_.as<LeafUv>() : nullptr, tileList_.as<uint32_t>(),
-                     dCounters, stream);
+                     pairTile_.as<uint32_t>(), dCounters, stream);
     TileWork work;
+    work.allTiles = allTiles_.as<uint32_t>();
+    work.allCount = (uint32_t) activeTotal;
     work.activeTiles = activeTiles_.as<uint32_t>();
     work.tileStart = tileStart_.as<uint32_t>();
     work.tileCount = tileCount_.as<uint32_t>();
@@ -272,7 +279,6 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     work.activeCount = (uint32_t) hostCounters_->heavyTiles;
     launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
     st.kernelLaunches += 3;
-    O2V_CUDA(cudaEventRecord(evSetup_, stream));
 
     VoxelizeArgs args;
     args.grid = grid;
@@ -290,12 +296,52 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     args.variant = params.variant < 0 ? 0 : params.variant;
     args.prefilter = params.prefilter;
 
+    // ---- staged sparse path, stages 1-2: SAT survivors of every (leaf, light tile) pair, compacted in list order ----
+    SparseView &sparse = args.sparse;
+    sparse.pairTile = pairTile_.as<uint32_t>();
+    sparse.tileCandidates = tileCand_.as<uint32_t>();
+    sparse.pairCount = (uint32_t) pairTotal;
+    sparse.pairSurvivors = pairSurvivors_.as<uint32_t>();
+    sparse.pairOffset = pairOffset_.as<uint32_t>();
+    sparse.entries = nullptr;
+    sparse.weights = nullptr;
+    sparse.uvs = nullptr;
+    unsigned long long survivorTotal = 0;
+    if (args.lightCount != 0) {
+        O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
+        launchSparseSurvivors(args, false, stream);
+        launchExclusiveScan(pairSurvivors_.as<uint32_t>(), pairOffset_.as<uint32_t>(), (size_t) pairTotal + 1,
+                            scratch_.as<uint32_t>(), &dCounters->survivors, stream);
+        st.kernelLaunches += 4;
+        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        O2V_CUDA(cudaGetLastError());
+        survivorTotal = hostCounters_->survivors;
+        if (survivorTotal >= (1ull << 32)) {
+            return fail(kErrTooLarge, "more than 2^32-1 candidate voxels on the sparse path of this slab");
+        }
+        if (!entries_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(uint2)) ||
+            !weights_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(float)) ||
+            (hasUv && !contribUvs_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(float2)))) {
+            return fail(kErrOutOfMemory, "device allocation failed (sparse path buffers)");
+        }
+        sparse.entries = entries_.as<uint2>();
+        sparse.weights = weights_.as<float>();
+        sparse.uvs = hasUv ? contribUvs_.as<float2>() : nullptr;
+        launchSparseSurvivors(args, true, stream);
+        ++st.kernelLaunches;
+    }
+    O2V_CUDA(cudaEventRecord(evSetup_, stream));
+
     for (int attempt = 0; attempt < 2; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
-        launchVoxelizeLightTiles(args, smCount_, stream);
+        if (args.lightCount != 0 && survivorTotal != 0) {
+            launchSparseClip(args, smCount_, stream);
+            launchSparseFold(args, smCount_, stream);
+        }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (args.lightCount != 0 ? 1 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (args.lightCount != 0 && survivorTotal != 0 ? 2 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
@@ -329,6 +375,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
     }
 
+    hostCounters_->clipCalls += survivorTotal;  // every sparse-path survivor is one exact clip
     st.counters = *hostCounters_;
     st.outCapacity = capacity;
     voxelCount_ = hostCounters_->voxels;

@@ -11,6 +11,7 @@
 //   * candidate voxels are culled by a conservative triangle/box SAT (FMA allowed, margin kPrefilterMargin); survivors run
 //     the bit-exact six-plane clip of o2v_exact.cuh.
 #include "o2v_kernels.cuh"
+#include "o2v_device.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -20,7 +21,6 @@ namespace o2v {
 namespace {
 
 constexpr int kSetupThreads = 128;
-constexpr float kPrefilterMargin = 0.0625f;  // voxels; must exceed every rounding / planarity slack of the exact clip
 
 __device__ __forceinline__ unsigned int orderedBits(float f)
 {
@@ -188,7 +188,8 @@ template <bool UV>
 __global__ void __launch_bounds__(kSetupThreads)
 emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leafOffset,
                  const uint32_t *__restrict__ tileStart, uint32_t *__restrict__ tileFill,
-                 LeafRecord *__restrict__ leaves, LeafUv *__restrict__ leafUvs, uint32_t *__restrict__ tileList)
+                 LeafRecord *__restrict__ leaves, LeafUv *__restrict__ leafUvs, uint32_t *__restrict__ tileList,
+                 uint32_t *__restrict__ pairTile)
 {
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
@@ -224,6 +225,7 @@ emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leaf
                         const uint32_t tile = localTileId(grid, tx, ty, tz);
                         const uint32_t slot = atomicAdd(&tileFill[tile], 1u);
                         tileList[tileStart[tile] + slot] = index;
+                        pairTile[tileStart[tile] + slot] = tile;
                     }
                 }
             }
@@ -371,13 +373,13 @@ scanApplyKernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, siz
 __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
                                          const uint32_t *__restrict__ tileCandidates,
                                          const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
-                                         uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
-                                         RunCounters *counters)
+                                         uint32_t *__restrict__ allTiles, uint32_t *__restrict__ heavyTiles,
+                                         LightTile *__restrict__ lightTiles, RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
     const uint32_t candidates = count != 0 ? tileCandidates[i] : 0u;
-    const bool light = count != 0 && count <= kLightMaxLeaves && candidates <= kLightMaxCandidates;
+    const bool light = count != 0 && candidates <= kLightMaxCandidates;
     const bool heavy = count != 0 && !light;
     const int lane = threadIdx.x & 31;
     const unsigned int below = (1u << lane) - 1u;
@@ -409,8 +411,16 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
             heavyTiles[base + __popc(heavyBallot & below)] = i;
         }
     }
-    if (lane == 0 && (lightBallot | heavyBallot) != 0) {
-        atomicAdd(&counters->activeTiles, (unsigned long long) (__popc(lightBallot) + __popc(heavyBallot)));
+    const unsigned int anyBallot = lightBallot | heavyBallot;
+    if (anyBallot != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&counters->activeTiles, (unsigned long long) __popc(anyBallot));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (count != 0) {
+            allTiles[base + __popc(anyBallot & below)] = i;
+        }
     }
 }
 
@@ -422,8 +432,8 @@ sortSmallListsKernel(TileWork work, uint32_t *__restrict__ tileList)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < work.activeCount; w += warpsPerGrid) {
-        const uint32_t tile = work.activeTiles[w];
+    for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < work.allCount; w += warpsPerGrid) {
+        const uint32_t tile = work.allTiles[w];
         const uint32_t n = work.tileCount[tile];
         if (n < 2 || n > 32) {
             continue;
@@ -448,8 +458,8 @@ __global__ void __launch_bounds__(512)
 sortLargeListsKernel(TileWork work, uint32_t *__restrict__ tileList)
 {
     __shared__ uint32_t keys[kSortSmemCap];
-    for (uint32_t w = blockIdx.x; w < work.activeCount; w += gridDim.x) {
-        const uint32_t tile = work.activeTiles[w];
+    for (uint32_t w = blockIdx.x; w < work.allCount; w += gridDim.x) {
+        const uint32_t tile = work.allTiles[w];
         const uint32_t n = work.tileCount[tile];
         if (n <= 32) {
             continue;
@@ -505,141 +515,6 @@ sortLargeListsKernel(TileWork work, uint32_t *__restrict__ tileList)
 // ---------------------------------------------------------------------------------------------------------------------
 // the hot kernel: one block = one 8^3 tile, thread = voxel
 
-struct LeafStage {
-    float v[9];
-    float t[6];
-    float area;
-    uint32_t tri;
-    uint32_t box;      // tile-local AABB: 4 bits each lo.x lo.y lo.z hi.x hi.y hi.z (hi exclusive, <= 8)
-    float plane[4];    // n . p + d for the tile-local voxel min corner p
-    float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
-    float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
-    uint32_t pad;      // 51 words: odd stride, so lanes reading the same field of different leaves hit distinct banks
-};
-
-/// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
-/// functions on a box inflated by kPrefilterMargin).  Not exact arithmetic: FMA contraction is welcome here.
-__device__ __forceinline__ void buildPrefilter(LeafStage &s, const float origin[3])
-{
-    float p[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        p[k] = s.v[k] - origin[k % 3];
-    }
-    const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
-    const float e1[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
-    const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-    s.plane[0] = n[0];
-    s.plane[1] = n[1];
-    s.plane[2] = n[2];
-    s.plane[3] = n[0] * (0.5f - p[0]) + n[1] * (0.5f - p[1]) + n[2] * (0.5f - p[2]);
-    s.planeLimit = (0.5f + kPrefilterMargin) * (fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]));
-    const float grow = 1.0f + kPrefilterMargin;
-#pragma unroll
-    for (int proj = 0; proj < 3; ++proj) {
-        const int a = proj, b = (proj + 1) % 3, c = (proj + 2) % 3;  // xy (n.z), yz (n.x), zx (n.y)
-        const float sign = n[c] >= 0.0f ? 1.0f : -1.0f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int j = (i + 1) % 3;
-            const float ea = p[j * 3 + a] - p[i * 3 + a];
-            const float eb = p[j * 3 + b] - p[i * 3 + b];
-            const float A = -eb * sign, B = ea * sign;
-            float C = -(A * p[i * 3 + a] + B * p[i * 3 + b]);
-            C += A > 0.0f ? A * grow : -A * kPrefilterMargin;
-            C += B > 0.0f ? B * grow : -B * kPrefilterMargin;
-            s.edge[(proj * 3 + i) * 3 + 0] = A;
-            s.edge[(proj * 3 + i) * 3 + 1] = B;
-            s.edge[(proj * 3 + i) * 3 + 2] = C;
-        }
-    }
-}
-
-/// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
-__device__ __forceinline__ bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
-{
-    const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
-    if (fabsf(dist) > s.planeLimit) {
-        return false;
-    }
-    const float q[3] = {lx, ly, lz};
-#pragma unroll
-    for (int proj = 0; proj < 3; ++proj) {
-        const float qa = q[proj], qb = q[(proj + 1) % 3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float *e = s.edge + (proj * 3 + i) * 3;
-            if (e[0] * qa + e[1] * qb + e[2] < 0.0f) {
-                return false;
-            }
-        }
-    }
-    return true;
-}
-
-struct VoxelAccumulator {
-    // per-triangle uv buffer entry (voxelization.cpp:426-472) and the voxel itself (voxelization.cpp:513-526)
-    WeightedUv partial;
-    WeightedColor voxel;
-    uint32_t partialTri;
-    bool hasPartial;
-    bool hasVoxel;
-    uint32_t contributions;
-};
-
-__device__ __forceinline__ void flushPartial(VoxelAccumulator &acc, const VoxelizeArgs &args)
-{
-    if (!acc.hasPartial) {
-        return;
-    }
-    acc.hasPartial = false;
-    const uint32_t tri = acc.partialTri;
-    const MeshView &mesh = args.mesh;
-    uint8_t type;
-    if (mesh.types != nullptr) {
-        type = mesh.types[tri];
-    }
-    else {
-        type = (mesh.uvs != nullptr && args.textureCount != 0) ? kTextured : kMaterialless;
-    }
-    float rgb[3] = {1.0f, 1.0f, 1.0f};  // MATERIALLESS: triangle.hpp:186
-    if (type == kUntextured && mesh.colors != nullptr) {
-        rgb[0] = mesh.colors[(size_t) tri * 3];
-        rgb[1] = mesh.colors[(size_t) tri * 3 + 1];
-        rgb[2] = mesh.colors[(size_t) tri * 3 + 2];
-    }
-    else if (type == kTextured && args.textureCount != 0) {
-        uint32_t id = mesh.textureIds != nullptr ? mesh.textureIds[tri] : 0u;
-        id = id < args.textureCount ? id : 0u;
-        textureLookup(args.textures[id], acc.partial.u, acc.partial.v, rgb);
-    }
-    ++acc.contributions;
-    if (!acc.hasVoxel) {
-        acc.hasVoxel = true;
-        acc.voxel.w = acc.partial.w;
-        acc.voxel.r = rgb[0];
-        acc.voxel.g = rgb[1];
-        acc.voxel.b = rgb[2];
-    }
-    else {
-        combineColorInto(acc.voxel, acc.partial.w, rgb[0], rgb[1], rgb[2], args.grid.strategy == kBlend);
-    }
-}
-
-__device__ __forceinline__ void addContribution(VoxelAccumulator &acc, uint32_t tri, float w, float u, float v)
-{
-    if (acc.hasPartial) {
-        blendUvInto(acc.partial, w, u, v);  // same triangle, later leaf: insertWeighted<BLEND>
-    }
-    else {
-        acc.hasPartial = true;
-        acc.partialTri = tri;
-        acc.partial.w = w;
-        acc.partial.u = u;
-        acc.partial.v = v;
-    }
-}
-
 constexpr int kTileThreads = 512;
 
 struct TileShared {
@@ -651,38 +526,6 @@ struct TileShared {
     float dsW[kTileVoxels], dsR[kTileVoxels], dsG[kTileVoxels], dsB[kTileVoxels];
     uint8_t dsHas[kTileVoxels];
 };
-
-template <bool UV>
-__device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args, uint32_t leafIndex,
-                                          const uint32_t tileOrigin[3])
-{
-    const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
-    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
-    s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
-    s.v[8] = c.x;
-    s.tri = __float_as_uint(c.y);
-    s.area = c.z;
-    if (UV) {
-        const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
-        const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
-        s.t[0] = u0.x; s.t[1] = u0.y; s.t[2] = u0.z; s.t[3] = u0.w;
-        s.t[4] = u1.x; s.t[5] = u1.y;
-    }
-    uint32_t lo[3], hi[3];
-    triVoxelBounds(s.v, lo, hi);
-    uint32_t packed = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const uint32_t l = lo[i] > tileOrigin[i] ? min(lo[i] - tileOrigin[i], kTileEdge) : 0u;
-        const uint32_t h = hi[i] > tileOrigin[i] ? min(hi[i] - tileOrigin[i], kTileEdge) : 0u;
-        packed |= l << (4 * i);
-        packed |= h << (12 + 4 * i);
-    }
-    s.box = packed;
-    const float origin[3] = {(float) tileOrigin[0], (float) tileOrigin[1], (float) tileOrigin[2]};
-    buildPrefilter(s, origin);
-}
 
 template <bool UV>
 __global__ void __launch_bounds__(kTileThreads, 1)
@@ -851,328 +694,6 @@ voxelizeTilesKernel(const VoxelizeArgs args)
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// light tiles: one warp = one tile.  Lanes enumerate the candidate voxels of every leaf (leaf-major), the SAT survivors are
-// ballot-compacted into a dense queue, the exact clip runs on full warps, and the surviving contributions are sorted by
-// (voxel, list position) inside the warp so that one lane per voxel can replay the reference's fold order
-// (ascending triangle index, DFS order within a triangle) — still without atomics on voxel data.
-
-constexpr int kLightWarpsPerBlock = 4;
-
-struct LightWarpShared {
-    LeafStage stage[kLightMaxLeaves];
-    uint32_t candPrefix[kLightMaxLeaves + 1];  // exclusive prefix of per-leaf candidate counts
-    uint16_t queue[kLightMaxCandidates];       // (list slot << 9) | local voxel (x | y << 3 | z << 6)
-    uint32_t sortKey[kLightMaxCandidates];     // (voxel key << 13) | (list slot << 8) | contribution slot
-    float cW[kLightMaxCandidates];
-    float cU[kLightMaxCandidates];
-    float cV[kLightMaxCandidates];
-};
-
-/// Voxel key: parent (2x2x2 block) index in the high 6 bits, child Morton code (x most significant, ileave.hpp:243-246) in
-/// the low 3 — ascending keys visit the children of one parent in ascending Morton order, which is the downscale order.
-__device__ __forceinline__ uint32_t voxelKey(uint32_t x, uint32_t y, uint32_t z)
-{
-    const uint32_t parent = (x >> 1) | ((y >> 1) << 2) | ((z >> 1) << 4);
-    const uint32_t child = ((x & 1u) << 2) | ((y & 1u) << 1) | (z & 1u);
-    return (parent << 3) | child;
-}
-
-__device__ __forceinline__ void resetAccumulator(VoxelAccumulator &acc)
-{
-    acc.hasPartial = false;
-    acc.hasVoxel = false;
-    acc.partialTri = 0;
-    acc.contributions = 0;
-    acc.partial.w = acc.partial.u = acc.partial.v = 0.0f;
-    acc.voxel.w = acc.voxel.r = acc.voxel.g = acc.voxel.b = 0.0f;
-}
-
-template <bool UV>
-__global__ void __launch_bounds__(kLightWarpsPerBlock * 32)
-voxelizeLightTilesKernel(const VoxelizeArgs args)
-{
-    __shared__ LightWarpShared shAll[kLightWarpsPerBlock];
-    LightWarpShared &sh = shAll[threadIdx.x >> 5];
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t below = (1u << lane) - 1u;
-    const uint32_t full = 0xffffffffu;
-    const uint32_t warpsTotal = gridDim.x * kLightWarpsPerBlock;
-    const bool blend = args.grid.strategy == kBlend;
-    const bool downscale = args.grid.supersampling == 2;
-    const uint32_t groupShift = downscale ? 16u : 13u;  // group = parent voxel when downscaling, else the voxel
-    const uint32_t T = args.grid.tilesPerAxis;
-    unsigned long long clipCalls = 0, contributions = 0;
-
-    for (uint32_t t = blockIdx.x * kLightWarpsPerBlock + (threadIdx.x >> 5); t < args.lightCount; t += warpsTotal) {
-        const LightTile d = args.lightTiles[t];
-        const uint32_t tileOrigin[3] = {(d.tile % T) * kTileEdge, ((d.tile / T) % T) * kTileEdge,
-                                        (d.tile / (T * T) + args.grid.slabTileZ0) * kTileEdge};
-
-        // ---- 1. the tile's leaf list in ascending order (the atomic fill order is arbitrary): rank sort by shuffles ----
-        const uint32_t mine = lane < d.leafCount ? args.work.tileList[d.listStart + lane] : 0xffffffffu;
-        uint32_t rank = 0;
-        for (uint32_t k = 0; k < d.leafCount; ++k) {
-            const uint32_t other = __shfl_sync(full, mine, k);
-            rank += other < mine ? 1u : 0u;
-        }
-        __syncwarp();
-        if (lane < d.leafCount) {
-            sh.sortKey[rank] = mine;
-        }
-        __syncwarp();
-        const uint32_t leafIndex = lane < d.leafCount ? sh.sortKey[lane] : 0u;
-        __syncwarp();
-
-        // ---- 2. lane j stages leaf j (geometry, tile-local AABB, SAT coefficients) ----
-        uint32_t candidates = 0;
-        if (lane < d.leafCount) {
-            stageLeaf<UV>(sh.stage[lane], args, leafIndex, tileOrigin);
-            const uint32_t box = sh.stage[lane].box;
-            candidates = (((box >> 12) & 15u) - (box & 15u)) * (((box >> 16) & 15u) - ((box >> 4) & 15u)) *
-                         (((box >> 20) & 15u) - ((box >> 8) & 15u));
-        }
-        uint32_t inclusive = candidates;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t up = __shfl_up_sync(full, inclusive, o);
-            inclusive += lane >= (uint32_t) o ? up : 0u;
-        }
-        sh.candPrefix[lane + 1] = inclusive;
-        if (lane == 0) {
-            sh.candPrefix[0] = 0;
-        }
-        const uint32_t total = min(__shfl_sync(full, inclusive, 31), kLightMaxCandidates);
-        __syncwarp();
-
-        // ---- 3. candidate voxels (leaf-major) -> conservative SAT -> dense queue ----
-        uint32_t queued = 0;
-        for (uint32_t base = 0; base < total; base += 32) {
-            const uint32_t c = base + lane;
-            bool pass = false;
-            uint32_t entry = 0;
-            if (c < total) {
-                uint32_t lo = 0, hi = d.leafCount;  // candPrefix[lo] <= c < candPrefix[hi]
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (sh.candPrefix[mid] <= c) {
-                        lo = mid;
-                    }
-                    else {
-                        hi = mid;
-                    }
-                }
-                const uint32_t q = c - sh.candPrefix[lo];
-                const uint32_t box = sh.stage[lo].box;
-                const uint32_t x0 = box & 15u, y0 = (box >> 4) & 15u, z0 = (box >> 8) & 15u;
-                const uint32_t dx = ((box >> 12) & 15u) - x0, dy = ((box >> 16) & 15u) - y0;
-                const uint32_t x = x0 + q % dx, y = y0 + (q / dx) % dy, z = z0 + q / (dx * dy);
-                pass = !args.prefilter || prefilterPass(sh.stage[lo], (float) x, (float) y, (float) z);
-                entry = (lo << 9) | x | (y << 3) | (z << 6);
-            }
-            const uint32_t ballot = __ballot_sync(full, pass);
-            if (pass) {
-                sh.queue[queued + __popc(ballot & below)] = (uint16_t) entry;
-            }
-            queued += __popc(ballot);
-        }
-        __syncwarp();
-
-        // ---- 4. exact six-plane clip on dense warps -> contributions ----
-        uint32_t kept = 0;
-        for (uint32_t base = 0; base < queued; base += 32) {
-            const uint32_t e = base + lane;
-            bool keep = false;
-            ClipResult r;
-            r.pieces = 0;
-            r.weight = r.u = r.v = 0.0f;
-            uint32_t slotJ = 0, vkey = 0;
-            if (e < queued) {
-                const uint32_t entry = sh.queue[e];
-                slotJ = entry >> 9;
-                const uint32_t x = entry & 7u, y = (entry >> 3) & 7u, z = (entry >> 6) & 7u;
-                vkey = voxelKey(x, y, z);
-                const LeafStage &s = sh.stage[slotJ];
-                Tri<UV> leaf;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    leaf.v[k] = s.v[k];
-                }
-                if (UV) {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        leaf.t[k] = s.t[k];
-                    }
-                }
-                r = clipLeafInVoxel<UV>(leaf, tileOrigin[0] + x, tileOrigin[1] + y, tileOrigin[2] + z, s.area);
-                ++clipCalls;
-                keep = r.pieces != 0;
-            }
-            const uint32_t ballot = __ballot_sync(full, keep);
-            if (keep) {
-                const uint32_t pos = kept + __popc(ballot & below);
-                sh.sortKey[pos] = (vkey << 13) | (slotJ << 8) | pos;
-                sh.cW[pos] = r.weight;
-                if (UV) {
-                    sh.cU[pos] = r.u;
-                    sh.cV[pos] = r.v;
-                }
-            }
-            kept += __popc(ballot);
-        }
-        __syncwarp();
-        if (kept == 0) {
-            continue;
-        }
-
-        // ---- 5. sort the contributions by (voxel key, list slot) ----
-        if (kept <= 32) {
-            uint32_t key = lane < kept ? sh.sortKey[lane] : 0xffffffffu;
-            for (uint32_t k = 2; k <= 32; k <<= 1) {
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    const uint32_t other = __shfl_xor_sync(full, key, j);
-                    const bool ascending = (lane & k) == 0;
-                    const bool lower = (lane & j) == 0;
-                    key = (lower == ascending) ? min(key, other) : max(key, other);
-                }
-            }
-            sh.sortKey[lane] = key;
-        }
-        else {
-            const uint32_t padded = kept <= 64 ? 64u : 128u;
-            for (uint32_t i = kept + lane; i < padded; i += 32) {
-                sh.sortKey[i] = 0xffffffffu;
-            }
-            __syncwarp();
-            for (uint32_t k = 2; k <= padded; k <<= 1) {
-                for (uint32_t i = lane; i < padded; i += 32) {
-                    const uint32_t l = i ^ (k - 1);
-                    if (l > i) {
-                        const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
-                        if (a > b) {
-                            sh.sortKey[i] = b;
-                            sh.sortKey[l] = a;
-                        }
-                    }
-                }
-                __syncwarp();
-                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
-                    for (uint32_t i = lane; i < padded; i += 32) {
-                        const uint32_t l = i ^ j;
-                        if (l > i) {
-                            const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
-                            if (a > b) {
-                                sh.sortKey[i] = b;
-                                sh.sortKey[l] = a;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- 6. one lane per output voxel replays the fold in order; block-free compaction through one atomic per tile ----
-        uint32_t runs = 0;
-        for (uint32_t base = 0; base < kept; base += 32) {
-            const uint32_t p = base + lane;
-            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
-            runs += __popc(__ballot_sync(full, start));
-        }
-        unsigned long long outBase = 0;
-        if (lane == 0) {
-            outBase = atomicAdd(&args.counters->voxels, (unsigned long long) runs);
-        }
-        outBase = __shfl_sync(full, outBase, 0);
-        uint32_t emitted = 0;
-        for (uint32_t base = 0; base < kept; base += 32) {
-            const uint32_t p = base + lane;
-            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
-            const uint32_t ballot = __ballot_sync(full, start);
-            if (start) {
-                const uint32_t group = sh.sortKey[p] >> groupShift;
-                uint32_t currentVoxel = (sh.sortKey[p] >> 13) & 511u;
-                VoxelAccumulator child;
-                resetAccumulator(child);
-                WeightedColor parent;
-                parent.w = parent.r = parent.g = parent.b = 0.0f;
-                bool hasParent = false;
-                for (uint32_t q = p; q < kept; ++q) {
-                    const uint32_t key = sh.sortKey[q];
-                    if ((key >> groupShift) != group) {
-                        break;
-                    }
-                    const uint32_t vk = (key >> 13) & 511u, slotJ = (key >> 8) & 31u, slot = key & 255u;
-                    if (vk != currentVoxel) {  // next child of the same parent (downscale only)
-                        flushPartial(child, args);
-                        contributions += child.contributions;
-                        if (!hasParent) {
-                            hasParent = true;
-                            parent = child.voxel;
-                        }
-                        else {
-                            combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
-                        }
-                        resetAccumulator(child);
-                        currentVoxel = vk;
-                    }
-                    const uint32_t tri = sh.stage[slotJ].tri;
-                    if (child.hasPartial && child.partialTri != tri) {
-                        flushPartial(child, args);
-                    }
-                    addContribution(child, tri, sh.cW[slot], UV ? sh.cU[slot] : 0.0f, UV ? sh.cV[slot] : 0.0f);
-                }
-                flushPartial(child, args);
-                contributions += child.contributions;
-                WeightedColor result = child.voxel;
-                const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
-                int32_t ox, oy, oz;
-                if (downscale) {
-                    if (hasParent) {
-                        combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
-                        result = parent;
-                    }
-                    ox = (int32_t) (tileOrigin[0] / 2 + (pk & 3u));
-                    oy = (int32_t) (tileOrigin[1] / 2 + ((pk >> 2) & 3u));
-                    oz = (int32_t) (tileOrigin[2] / 2 + ((pk >> 4) & 3u));
-                }
-                else {
-                    ox = (int32_t) (tileOrigin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
-                    oy = (int32_t) (tileOrigin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
-                    oz = (int32_t) (tileOrigin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
-                }
-                const unsigned long long index = outBase + emitted + __popc(ballot & below);
-                if (index < args.outCapacity) {
-                    VoxelRecord rec;
-                    rec.x = ox;
-                    rec.y = oy;
-                    rec.z = oz;
-                    rec.argb = quantizeArgb(result.r, result.g, result.b);
-                    *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
-                }
-                else {
-                    atomicAdd(&args.counters->outputOverflow, 1ull);
-                }
-            }
-            emitted += __popc(ballot);
-        }
-        __syncwarp();
-    }
-
-    for (int o = 16; o > 0; o >>= 1) {
-        clipCalls += __shfl_xor_sync(full, clipCalls, o);
-        contributions += __shfl_xor_sync(full, contributions, o);
-    }
-    if (lane == 0) {
-        if (clipCalls != 0) {
-            atomicAdd(&args.counters->clipCalls, clipCalls);
-        }
-        if (contributions != 0) {
-            atomicAdd(&args.counters->contributions, contributions);
-        }
-    }
-}
-
 inline int gridFor(unsigned long long n, int threads, int cap)
 {
     unsigned long long blocks = (n + threads - 1) / threads;
@@ -1236,40 +757,41 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 }
 
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
-                              uint32_t tileTotal, uint32_t *heavyTiles, LightTile *lightTiles, RunCounters *counters,
-                              cudaStream_t stream)
+                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *heavyTiles, LightTile *lightTiles,
+                              RunCounters *counters, cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
     compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
-                                                                          tileTotal, heavyTiles, lightTiles, counters);
+                                                                          tileTotal, allTiles, heavyTiles, lightTiles,
+                                                                          counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
-                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList,
+                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
                       RunCounters *, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
     if (mesh.uvs != nullptr) {
         emitLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves,
-                                                                      leafUvs, tileList);
+                                                                      leafUvs, tileList, pairTile);
     }
     else {
         emitLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill,
-                                                                       leaves, leafUvs, tileList);
+                                                                       leaves, leafUvs, tileList, pairTile);
     }
 }
 
 void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream)
 {
-    if (work.activeCount == 0) {
+    if (work.allCount == 0) {
         return;
     }
     const int warpsPerBlock = 8;
-    const int smallBlocks = gridFor(work.activeCount, warpsPerBlock, 148 * 16);
+    const int smallBlocks = gridFor(work.allCount, warpsPerBlock, 148 * 16);
     sortSmallListsKernel<<<smallBlocks, warpsPerBlock * 32, 0, stream>>>(work, tileList);
-    const int largeBlocks = gridFor(work.activeCount, 1, 148 * 4);
+    const int largeBlocks = gridFor(work.allCount, 1, 148 * 4);
     sortLargeListsKernel<<<largeBlocks, 512, 0, stream>>>(work, tileList);
 }
 
@@ -1290,37 +812,6 @@ void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t str
     else {
         cudaFuncSetAttribute(voxelizeTilesKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
         voxelizeTilesKernel<false><<<blocks, kTileThreads, smem, stream>>>(args);
-    }
-}
-
-void launchVoxelizeLightTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
-{
-    if (args.lightCount == 0) {
-        return;
-    }
-    const int threads = kLightWarpsPerBlock * 32;
-    int perSm = 0;
-    if (args.mesh.uvs != nullptr) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, voxelizeLightTilesKernel<true>, threads, 0);
-    }
-    else {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, voxelizeLightTilesKernel<false>, threads, 0);
-    }
-    perSm = perSm < 1 ? 1 : perSm;
-    if (const char *env = getenv("O2V_B200_LIGHT_BLOCKS_PER_SM")) {  // tuning knob: fewer resident blocks leave more L1
-        const int wanted = atoi(env);
-        if (wanted >= 1 && wanted < perSm) {
-            perSm = wanted;
-        }
-    }
-    unsigned long long blocks = (unsigned long long) smCount * perSm;  // persistent: a multiple of the SM count
-    const unsigned long long needed = (args.lightCount + kLightWarpsPerBlock - 1) / kLightWarpsPerBlock;
-    blocks = blocks < needed ? blocks : needed;
-    if (args.mesh.uvs != nullptr) {
-        voxelizeLightTilesKernel<true><<<(unsigned) blocks, threads, 0, stream>>>(args);
-    }
-    else {
-        voxelizeLightTilesKernel<false><<<(unsigned) blocks, threads, 0, stream>>>(args);
     }
 }
 

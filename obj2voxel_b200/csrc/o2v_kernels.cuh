@@ -17,8 +17,7 @@ namespace o2v {
 constexpr uint32_t kTileEdge = 8;  // voxels per tile edge (sample space); 8^3 = 512 voxels = one thread block
 constexpr uint32_t kTileVoxels = kTileEdge * kTileEdge * kTileEdge;
 constexpr uint32_t kLeafBatch = 32;  // leaves staged in shared memory per round
-constexpr uint32_t kLightMaxLeaves = 32;       // a light tile's whole list fits one warp (one leaf per lane)
-constexpr uint32_t kLightMaxCandidates = 128;  // ... and its candidate voxels fit the per-warp queues
+constexpr uint32_t kLightMaxCandidates = 128;  // tiles up to this many candidate voxels take the staged sparse path
 
 /// Input mesh, model space.  All pointers are device pointers.
 struct MeshView {
@@ -66,8 +65,9 @@ struct RunCounters {
     unsigned long long pairs;           // total (leaf, tile) pairs
     unsigned long long candidateVoxels; // sum of leaf AABB volumes inside the slab (upper bound on contributions)
     unsigned long long activeTiles;     // light + heavy
-    unsigned long long lightTiles;      // tiles voxelized warp-per-tile (<= kLightMaxLeaves leaves, <= kLightMaxCandidates candidates)
+    unsigned long long lightTiles;      // tiles on the staged sparse path (<= kLightMaxCandidates candidate voxels)
     unsigned long long heavyTiles;      // tiles voxelized block-per-tile
+    unsigned long long survivors;       // sparse path: candidates that passed the SAT prefilter (= exact clips there)
     unsigned long long voxels;          // emitted voxels
     unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
     unsigned long long clipCalls;       // exact clips executed (prefilter survivors)
@@ -86,11 +86,13 @@ struct RunCounters {
 struct __align__(16) LightTile {
     uint32_t tile;        // slab-local tile id
     uint32_t listStart;   // offset into tileList
-    uint32_t leafCount;   // <= kLightMaxLeaves
+    uint32_t leafCount;   // <= candidates
     uint32_t candidates;  // sum of leaf AABB volumes clipped to the tile, <= kLightMaxCandidates
 };
 
 struct TileWork {
+    const uint32_t *allTiles;     // slab-local ids of every non-empty tile (list sorting)
+    uint32_t allCount;
     const uint32_t *activeTiles;  // slab-local ids of the HEAVY tiles (block-per-tile kernel)
     const uint32_t *tileStart;    // exclusive scan of tileCount (slab-local tile id -> list offset)
     const uint32_t *tileCount;
@@ -113,14 +115,26 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 
 /// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
-                              uint32_t tileTotal, uint32_t *heavyTiles, LightTile *lightTiles, RunCounters *counters,
-                              cudaStream_t stream);
+                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *heavyTiles, LightTile *lightTiles,
+                              RunCounters *counters, cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
-                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList,
+                      uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
                       RunCounters *counters, cudaStream_t stream);
 
 void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream);
+
+/// Buffers of the staged sparse path (o2v_sparse.cu).  A "pair" is one (leaf, tile) entry of tileList.
+struct SparseView {
+    const uint32_t *pairTile;        // per pair: slab-local tile id
+    const uint32_t *tileCandidates;  // per tile: candidate voxel count (classifies the tile)
+    uint32_t pairCount;
+    uint32_t *pairSurvivors;         // per pair (+1): SAT survivors, scanned into pairOffset
+    uint32_t *pairOffset;            // pairCount + 1 entries
+    uint2 *entries;                  // per survivor: {pair index, tile-local voxel}
+    float *weights;                  // per survivor: clip weight (0 = no contribution)
+    float2 *uvs;                     // per survivor (textured meshes only)
+};
 
 struct VoxelizeArgs {
     GridView grid;
@@ -135,14 +149,20 @@ struct VoxelizeArgs {
     RunCounters *counters;
     const LightTile *lightTiles;
     uint32_t lightCount;
+    SparseView sparse;
     int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
 };
 
 /// Heavy tiles: one 512-thread block per tile, thread = voxel.
 void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
-/// Light tiles: one warp per tile, lanes = candidate voxels, dense clip queue, in-warp sort + ordered fold.
-void launchVoxelizeLightTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+/// Staged sparse path for light tiles.  Every stage is dense over its own work items, with stream compaction in HBM
+/// between the stages: (1) thread per (leaf, tile) pair counts / (2) writes the candidate voxels that survive the SAT
+/// prefilter, (3) thread per survivor runs the exact clip, (4) warp per tile sorts its contributions by (voxel, list
+/// position) and replays the reference's fold order, then writes the Voxel32 records.
+void launchSparseSurvivors(const VoxelizeArgs &args, bool write, cudaStream_t stream);
+void launchSparseClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 
 }  // namespace o2v
 

@@ -1,0 +1,386 @@
+// Staged sparse path: the voxelization of "light" tiles (few candidate voxels — the regime of every BASELINE config, where
+// triangles are a few voxels across).  A tile-at-a-time kernel leaves most lanes idle there (a tile holds ~2 leaves, ~25
+// candidate voxels, ~10 clips), so the work is re-batched between stages with stream compaction in HBM; every stage is
+// dense over its own unit of work:
+//
+//   survivors (count, then write)  thread = (leaf, tile) pair   conservative SAT over the pair's candidate voxels
+//   clip                           thread = surviving voxel     bit-exact six-plane clip (o2v_exact.cuh)
+//   fold                           warp   = tile                sort contributions by (voxel, list position), replay the
+//                                                               reference's fold order, write Voxel32 records
+//
+// Per-voxel order = ascending leaf index = (triangle index, DFS order) because tile lists are sorted before stage 1 and a
+// tile's survivors are laid out contiguously in list order (pairOffset is an exclusive scan in tileList order).
+// Reference semantics reproduced: src/voxelization.cpp:383-472 (clip, uv buffer), :513-526 (merge), util.hpp:160-172.
+#include <stdlib.h>
+
+#include "o2v_device.cuh"
+
+namespace o2v {
+
+namespace {
+
+constexpr int kPairThreads = 128;
+constexpr int kClipThreads = 128;
+constexpr int kFoldWarpsPerBlock = 8;
+
+__device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
+{
+    const uint32_t T = grid.tilesPerAxis;
+    origin[0] = (tile % T) * kTileEdge;
+    origin[1] = ((tile / T) % T) * kTileEdge;
+    origin[2] = (tile / (T * T) + grid.slabTileZ0) * kTileEdge;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stages 1 + 2: thread per (leaf, tile) pair
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kPairThreads)
+sparseSurvivorsKernel(const VoxelizeArgs args)
+{
+    const SparseView &sp = args.sparse;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pair = blockIdx.x * blockDim.x + threadIdx.x; pair < sp.pairCount; pair += stride) {
+        const uint32_t tile = sp.pairTile[pair];
+        uint32_t count = 0;
+        if (sp.tileCandidates[tile] <= kLightMaxCandidates) {
+            uint32_t origin[3];
+            tileOriginOf(args.grid, tile, origin);
+            LeafStage s;
+            stageLeaf<false>(s, args, args.work.tileList[pair], origin);
+            const uint32_t box = s.box;
+            const uint32_t x0 = box & 15u, y0 = (box >> 4) & 15u, z0 = (box >> 8) & 15u;
+            const uint32_t x1 = (box >> 12) & 15u, y1 = (box >> 16) & 15u, z1 = (box >> 20) & 15u;
+            uint32_t offset = WRITE ? sp.pairOffset[pair] : 0u;
+            for (uint32_t z = z0; z < z1; ++z) {
+                for (uint32_t y = y0; y < y1; ++y) {
+                    for (uint32_t x = x0; x < x1; ++x) {
+                        if (!args.prefilter || prefilterPass(s, (float) x, (float) y, (float) z)) {
+                            if (WRITE) {
+                                sp.entries[offset] = make_uint2(pair, x | (y << 3) | (z << 6));
+                                ++offset;
+                            }
+                            ++count;
+                        }
+                    }
+                }
+            }
+        }
+        if (!WRITE) {
+            sp.pairSurvivors[pair] = count;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage 3: thread per surviving candidate voxel -> exact clip
+
+template <bool UV>
+__global__ void __launch_bounds__(kClipThreads)
+sparseClipKernel(const VoxelizeArgs args)
+{
+    const SparseView &sp = args.sparse;
+    const unsigned long long total = args.counters->survivors;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const uint2 entry = sp.entries[e];
+        const uint32_t pair = entry.x;
+        const uint32_t leafIndex = __ldg(args.work.tileList + pair);
+        uint32_t origin[3];
+        tileOriginOf(args.grid, __ldg(sp.pairTile + pair), origin);
+
+        const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        Tri<UV> leaf;
+        leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
+        leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
+        leaf.v[8] = c.x;
+        const float area = c.z;
+        if (UV) {
+            const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
+            const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
+            leaf.t[0] = u0.x; leaf.t[1] = u0.y; leaf.t[2] = u0.z; leaf.t[3] = u0.w;
+            leaf.t[4] = u1.x; leaf.t[5] = u1.y;
+        }
+        const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
+        const ClipResult r = clipLeafInVoxel<UV>(leaf, origin[0] + x, origin[1] + y, origin[2] + z, area);
+        sp.weights[e] = r.pieces != 0 ? r.weight : 0.0f;  // area > 0, so a zero weight means "no contribution"
+        if (UV) {
+            sp.uvs[e] = make_float2(r.u, r.v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// stage 4: warp per tile -> ordered fold + output
+
+struct FoldWarpShared {
+    uint32_t tri[kLightMaxCandidates];      // triangle index per list slot (a tile has at most `candidates` leaves)
+    uint32_t sortKey[kLightMaxCandidates];  // (voxel key << 14) | (list slot << 7) | contribution slot
+    float cW[kLightMaxCandidates];
+    float cU[kLightMaxCandidates];
+    float cV[kLightMaxCandidates];
+};
+
+template <bool UV>
+__global__ void __launch_bounds__(kFoldWarpsPerBlock * 32)
+sparseFoldKernel(const VoxelizeArgs args)
+{
+    __shared__ FoldWarpShared shAll[kFoldWarpsPerBlock];
+    FoldWarpShared &sh = shAll[threadIdx.x >> 5];
+    const SparseView &sp = args.sparse;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t full = 0xffffffffu;
+    const uint32_t warpsTotal = gridDim.x * kFoldWarpsPerBlock;
+    const bool blend = args.grid.strategy == kBlend;
+    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t groupShift = downscale ? 17u : 14u;  // group = parent voxel when downscaling, else the voxel
+    unsigned long long contributions = 0;
+
+    for (uint32_t t = blockIdx.x * kFoldWarpsPerBlock + (threadIdx.x >> 5); t < args.lightCount; t += warpsTotal) {
+        const LightTile d = args.lightTiles[t];
+        const uint32_t begin = sp.pairOffset[d.listStart];
+        const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;  // <= d.candidates <= 128
+        if (count == 0) {
+            continue;
+        }
+        uint32_t origin[3];
+        tileOriginOf(args.grid, d.tile, origin);
+
+        for (uint32_t slot = lane; slot < d.leafCount; slot += 32) {
+            const uint32_t leafIndex = args.work.tileList[d.listStart + slot];
+            sh.tri[slot] = args.leaves[leafIndex].tri;
+        }
+
+        // ---- gather the tile's contributions (weight != 0), compacted in list order ----
+        uint32_t kept = 0;
+        for (uint32_t base = 0; base < count; base += 32) {
+            const uint32_t e = base + lane;
+            float w = 0.0f;
+            uint2 entry = make_uint2(0u, 0u);
+            if (e < count) {
+                w = sp.weights[begin + e];
+                entry = sp.entries[begin + e];
+            }
+            const bool keep = w != 0.0f;
+            const uint32_t ballot = __ballot_sync(full, keep);
+            if (keep) {
+                const uint32_t pos = kept + __popc(ballot & below);
+                const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
+                sh.sortKey[pos] = (voxelKey(x, y, z) << 14) | ((entry.x - d.listStart) << 7) | pos;
+                sh.cW[pos] = w;
+                if (UV) {
+                    const float2 uv = sp.uvs[begin + e];
+                    sh.cU[pos] = uv.x;
+                    sh.cV[pos] = uv.y;
+                }
+            }
+            kept += __popc(ballot);
+        }
+        __syncwarp();
+        if (kept == 0) {
+            continue;
+        }
+
+        // ---- sort by (voxel key, list slot) ----
+        if (kept <= 32) {
+            uint32_t key = lane < kept ? sh.sortKey[lane] : 0xffffffffu;
+            for (uint32_t k = 2; k <= 32; k <<= 1) {
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    const uint32_t other = __shfl_xor_sync(full, key, j);
+                    const bool ascending = (lane & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    key = (lower == ascending) ? min(key, other) : max(key, other);
+                }
+            }
+            sh.sortKey[lane] = key;
+        }
+        else {
+            const uint32_t padded = kept <= 64 ? 64u : 128u;
+            for (uint32_t i = kept + lane; i < padded; i += 32) {
+                sh.sortKey[i] = 0xffffffffu;
+            }
+            __syncwarp();
+            for (uint32_t k = 2; k <= padded; k <<= 1) {  // ascending-only bitonic network
+                for (uint32_t i = lane; i < padded; i += 32) {
+                    const uint32_t l = i ^ (k - 1);
+                    if (l > i) {
+                        const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
+                        if (a > b) {
+                            sh.sortKey[i] = b;
+                            sh.sortKey[l] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+                for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < padded; i += 32) {
+                        const uint32_t l = i ^ j;
+                        if (l > i) {
+                            const uint32_t a = sh.sortKey[i], b = sh.sortKey[l];
+                            if (a > b) {
+                                sh.sortKey[i] = b;
+                                sh.sortKey[l] = a;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- one lane per output voxel replays the fold in order; one atomic per tile reserves the output range ----
+        uint32_t runs = 0;
+        for (uint32_t base = 0; base < kept; base += 32) {
+            const uint32_t p = base + lane;
+            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
+            runs += __popc(__ballot_sync(full, start));
+        }
+        unsigned long long outBase = 0;
+        if (lane == 0) {
+            outBase = atomicAdd(&args.counters->voxels, (unsigned long long) runs);
+        }
+        outBase = __shfl_sync(full, outBase, 0);
+        uint32_t emitted = 0;
+        for (uint32_t base = 0; base < kept; base += 32) {
+            const uint32_t p = base + lane;
+            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
+            const uint32_t ballot = __ballot_sync(full, start);
+            if (start) {
+                const uint32_t group = sh.sortKey[p] >> groupShift;
+                uint32_t currentVoxel = (sh.sortKey[p] >> 14) & 511u;
+                VoxelAccumulator child;
+                resetAccumulator(child);
+                WeightedColor parent;
+                parent.w = parent.r = parent.g = parent.b = 0.0f;
+                bool hasParent = false;
+                for (uint32_t q = p; q < kept; ++q) {
+                    const uint32_t key = sh.sortKey[q];
+                    if ((key >> groupShift) != group) {
+                        break;
+                    }
+                    const uint32_t vk = (key >> 14) & 511u, listSlot = (key >> 7) & 127u, slot = key & 127u;
+                    if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
+                        flushPartial(child, args);
+                        contributions += child.contributions;
+                        if (!hasParent) {
+                            hasParent = true;
+                            parent = child.voxel;
+                        }
+                        else {
+                            combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        }
+                        resetAccumulator(child);
+                        currentVoxel = vk;
+                    }
+                    const uint32_t tri = sh.tri[listSlot];
+                    if (child.hasPartial && child.partialTri != tri) {
+                        flushPartial(child, args);  // the previous triangle's uv-buffer entry is complete
+                    }
+                    addContribution(child, tri, sh.cW[slot], UV ? sh.cU[slot] : 0.0f, UV ? sh.cV[slot] : 0.0f);
+                }
+                flushPartial(child, args);
+                contributions += child.contributions;
+                WeightedColor result = child.voxel;
+                const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
+                int32_t ox, oy, oz;
+                if (downscale) {
+                    if (hasParent) {
+                        combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        result = parent;
+                    }
+                    ox = (int32_t) (origin[0] / 2 + (pk & 3u));
+                    oy = (int32_t) (origin[1] / 2 + ((pk >> 2) & 3u));
+                    oz = (int32_t) (origin[2] / 2 + ((pk >> 4) & 3u));
+                }
+                else {
+                    ox = (int32_t) (origin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
+                    oy = (int32_t) (origin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
+                    oz = (int32_t) (origin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
+                }
+                const unsigned long long index = outBase + emitted + __popc(ballot & below);
+                if (index < args.outCapacity) {
+                    VoxelRecord rec;
+                    rec.x = ox;
+                    rec.y = oy;
+                    rec.z = oz;
+                    rec.argb = quantizeArgb(result.r, result.g, result.b);
+                    *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                }
+                else {
+                    atomicAdd(&args.counters->outputOverflow, 1ull);
+                }
+            }
+            emitted += __popc(ballot);
+        }
+        __syncwarp();
+    }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        contributions += __shfl_xor_sync(full, contributions, o);
+    }
+    if (lane == 0 && contributions != 0) {
+        atomicAdd(&args.counters->contributions, contributions);
+    }
+}
+
+template <typename Kernel>
+unsigned persistentBlocks(Kernel kernel, int threads, int smCount, unsigned long long needed)
+{
+    int perSm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0);
+    perSm = perSm < 1 ? 1 : perSm;
+    unsigned long long blocks = (unsigned long long) smCount * perSm;  // a multiple of the SM count
+    blocks = blocks < needed ? blocks : needed;
+    return (unsigned) (blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+void launchSparseSurvivors(const VoxelizeArgs &args, bool write, cudaStream_t stream)
+{
+    if (args.sparse.pairCount == 0) {
+        return;
+    }
+    const unsigned blocks = (args.sparse.pairCount + kPairThreads - 1) / kPairThreads;
+    if (write) {
+        sparseSurvivorsKernel<true><<<blocks, kPairThreads, 0, stream>>>(args);
+    }
+    else {
+        sparseSurvivorsKernel<false><<<blocks, kPairThreads, 0, stream>>>(args);
+    }
+}
+
+void launchSparseClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
+{
+    // the survivor count lives on the device (RunCounters::survivors): persistent grid-stride kernel
+    if (args.mesh.uvs != nullptr) {
+        const unsigned blocks = persistentBlocks(sparseClipKernel<true>, kClipThreads, smCount, ~0ull);
+        sparseClipKernel<true><<<blocks, kClipThreads, 0, stream>>>(args);
+    }
+    else {
+        const unsigned blocks = persistentBlocks(sparseClipKernel<false>, kClipThreads, smCount, ~0ull);
+        sparseClipKernel<false><<<blocks, kClipThreads, 0, stream>>>(args);
+    }
+}
+
+void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
+{
+    if (args.lightCount == 0) {
+        return;
+    }
+    const int threads = kFoldWarpsPerBlock * 32;
+    const unsigned long long needed = (args.lightCount + kFoldWarpsPerBlock - 1) / kFoldWarpsPerBlock;
+    if (args.mesh.uvs != nullptr) {
+        sparseFoldKernel<true><<<persistentBlocks(sparseFoldKernel<true>, threads, smCount, needed), threads, 0,
+                                 stream>>>(args);
+    }
+    else {
+        sparseFoldKernel<false><<<persistentBlocks(sparseFoldKernel<false>, threads, smCount, needed), threads, 0,
+                                  stream>>>(args);
+    }
+}
+
+}  // namespace o2v
