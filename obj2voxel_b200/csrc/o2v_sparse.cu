@@ -82,31 +82,43 @@ sparseClipKernel(const VoxelizeArgs args)
     const SparseView &sp = args.sparse;
     const unsigned long long total = args.counters->survivors;
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long e = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const uint2 entry = sp.entries[e];
-        const uint32_t pair = entry.x;
-        const uint32_t leafIndex = __ldg(args.work.tileList + pair);
-        uint32_t origin[3];
-        tileOriginOf(args.grid, __ldg(sp.pairTile + pair), origin);
-
-        const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
-        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    const uint32_t lane = threadIdx.x & 31u;
+    // warp-uniform loop: the clip is warp-synchronous, so whole warps stay in the loop and idle lanes pass valid = false
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total;
+         base += stride) {
+        const unsigned long long e = base + lane;
+        const bool valid = e < total;
         Tri<UV> leaf;
-        leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
-        leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
-        leaf.v[8] = c.x;
-        const float area = c.z;
-        if (UV) {
-            const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
-            const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
-            leaf.t[0] = u0.x; leaf.t[1] = u0.y; leaf.t[2] = u0.z; leaf.t[3] = u0.w;
-            leaf.t[4] = u1.x; leaf.t[5] = u1.y;
+        float area = 0.0f;
+        uint32_t vx = 0, vy = 0, vz = 0;
+        if (valid) {
+            const uint2 entry = sp.entries[e];
+            const uint32_t pair = entry.x;
+            const uint32_t leafIndex = __ldg(args.work.tileList + pair);
+            uint32_t origin[3];
+            tileOriginOf(args.grid, __ldg(sp.pairTile + pair), origin);
+            const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+            leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
+            leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
+            leaf.v[8] = c.x;
+            area = c.z;
+            if (UV) {
+                const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
+                const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
+                leaf.t[0] = u0.x; leaf.t[1] = u0.y; leaf.t[2] = u0.z; leaf.t[3] = u0.w;
+                leaf.t[4] = u1.x; leaf.t[5] = u1.y;
+            }
+            vx = origin[0] + (entry.y & 7u);
+            vy = origin[1] + ((entry.y >> 3) & 7u);
+            vz = origin[2] + ((entry.y >> 6) & 7u);
         }
-        const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
-        const ClipResult r = clipLeafInVoxel<UV>(leaf, origin[0] + x, origin[1] + y, origin[2] + z, area);
-        sp.weights[e] = r.pieces != 0 ? r.weight : 0.0f;  // area > 0, so a zero weight means "no contribution"
-        if (UV) {
-            sp.uvs[e] = make_float2(r.u, r.v);
+        const ClipResult r = clipLeafInVoxelWarp<UV>(valid, leaf, vx, vy, vz, area);
+        if (valid) {
+            sp.weights[e] = r.pieces != 0 ? r.weight : 0.0f;  // area > 0, so a zero weight means "no contribution"
+            if (UV) {
+                sp.uvs[e] = make_float2(r.u, r.v);
+            }
         }
     }
 }

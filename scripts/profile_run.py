@@ -9,6 +9,8 @@ import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg4"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = bench.workload_spec(name)
+if len(sys.argv) > 3:
+    cfg["n"] = int(sys.argv[3])
 dev = torch.device("cuda", 0)
 eng = o2v.Engine(0)
 if cfg["kind"] == "sphere":
