@@ -206,6 +206,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !tileCount_.ensure((size_t) tileTotal * 4) ||
         !tileStart_.ensure((size_t) tileTotal * 4) || !tileFill_.ensure((size_t) tileTotal * 4) ||
         !activeTiles_.ensure((size_t) tileTotal * 4) || !allTiles_.ensure((size_t) tileTotal * 4) ||
+        !longTiles_.ensure((size_t) tileTotal * 4) ||
         !tileCand_.ensure((size_t) tileTotal * 4) ||
         !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
@@ -221,8 +222,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
                         &dCounters->pairs, stream);
     launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
-                             allTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(), lightTiles_.as<LightTile>(), dCounters,
-                             stream);
+                             allTiles_.as<uint32_t>(), longTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(),
+                             lightTiles_.as<LightTile>(), dCounters, stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -272,6 +273,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     TileWork work;
     work.allTiles = allTiles_.as<uint32_t>();
     work.allCount = (uint32_t) activeTotal;
+    work.longTiles = longTiles_.as<uint32_t>();
+    work.longCount = (uint32_t) hostCounters_->longTiles;
     work.activeTiles = activeTiles_.as<uint32_t>();
     work.tileStart = tileStart_.as<uint32_t>();
     work.tileCount = tileCount_.as<uint32_t>();

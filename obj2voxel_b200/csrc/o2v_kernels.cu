@@ -373,8 +373,9 @@ scanApplyKernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, siz
 __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
                                          const uint32_t *__restrict__ tileCandidates,
                                          const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
-                                         uint32_t *__restrict__ allTiles, uint32_t *__restrict__ heavyTiles,
-                                         LightTile *__restrict__ lightTiles, RunCounters *counters)
+                                         uint32_t *__restrict__ allTiles, uint32_t *__restrict__ longTiles,
+                                         uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
+                                         RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
@@ -409,6 +410,17 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
         base = __shfl_sync(0xffffffffu, base, 0);
         if (heavy) {
             heavyTiles[base + __popc(heavyBallot & below)] = i;
+        }
+    }
+    const unsigned int longBallot = __ballot_sync(0xffffffffu, count > 32u);
+    if (longBallot != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&counters->longTiles, (unsigned long long) __popc(longBallot));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (count > 32u) {
+            longTiles[base + __popc(longBallot & below)] = i;
         }
     }
     const unsigned int anyBallot = lightBallot | heavyBallot;
@@ -458,8 +470,8 @@ __global__ void __launch_bounds__(512)
 sortLargeListsKernel(TileWork work, uint32_t *__restrict__ tileList)
 {
     __shared__ uint32_t keys[kSortSmemCap];
-    for (uint32_t w = blockIdx.x; w < work.allCount; w += gridDim.x) {
-        const uint32_t tile = work.allTiles[w];
+    for (uint32_t w = blockIdx.x; w < work.longCount; w += gridDim.x) {
+        const uint32_t tile = work.longTiles[w];
         const uint32_t n = work.tileCount[tile];
         if (n <= 32) {
             continue;
@@ -757,15 +769,15 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 }
 
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
-                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *heavyTiles, LightTile *lightTiles,
-                              RunCounters *counters, cudaStream_t stream)
+                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
+                              LightTile *lightTiles, RunCounters *counters, cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
     compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
-                                                                          tileTotal, allTiles, heavyTiles, lightTiles,
-                                                                          counters);
+                                                                          tileTotal, allTiles, longTiles, heavyTiles,
+                                                                          lightTiles, counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
@@ -791,8 +803,10 @@ void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t 
     const int warpsPerBlock = 8;
     const int smallBlocks = gridFor(work.allCount, warpsPerBlock, 148 * 16);
     sortSmallListsKernel<<<smallBlocks, warpsPerBlock * 32, 0, stream>>>(work, tileList);
-    const int largeBlocks = gridFor(work.allCount, 1, 148 * 4);
-    sortLargeListsKernel<<<largeBlocks, 512, 0, stream>>>(work, tileList);
+    if (work.longCount != 0) {
+        const int largeBlocks = gridFor(work.longCount, 1, 148 * 4);
+        sortLargeListsKernel<<<largeBlocks, 512, 0, stream>>>(work, tileList);
+    }
 }
 
 void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t stream)

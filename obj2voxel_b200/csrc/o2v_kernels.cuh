@@ -17,7 +17,7 @@ namespace o2v {
 constexpr uint32_t kTileEdge = 8;  // voxels per tile edge (sample space); 8^3 = 512 voxels = one thread block
 constexpr uint32_t kTileVoxels = kTileEdge * kTileEdge * kTileEdge;
 constexpr uint32_t kLeafBatch = 32;  // leaves staged in shared memory per round
-constexpr uint32_t kLightMaxCandidates = 128;  // tiles up to this many candidate voxels take the staged sparse path
+constexpr uint32_t kLightMaxCandidates = 512;  // tiles up to this many candidate voxels take the staged sparse path
 
 /// Input mesh, model space.  All pointers are device pointers.
 struct MeshView {
@@ -67,6 +67,7 @@ struct RunCounters {
     unsigned long long activeTiles;     // light + heavy
     unsigned long long lightTiles;      // tiles on the staged sparse path (<= kLightMaxCandidates candidate voxels)
     unsigned long long heavyTiles;      // tiles voxelized block-per-tile
+    unsigned long long longTiles;       // tiles with more than 32 leaves (block-level list sort)
     unsigned long long survivors;       // sparse path: candidates that passed the SAT prefilter (= exact clips there)
     unsigned long long voxels;          // emitted voxels
     unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
@@ -93,6 +94,8 @@ struct __align__(16) LightTile {
 struct TileWork {
     const uint32_t *allTiles;     // slab-local ids of every non-empty tile (list sorting)
     uint32_t allCount;
+    const uint32_t *longTiles;    // the subset whose list is longer than one warp (> 32 leaves)
+    uint32_t longCount;
     const uint32_t *activeTiles;  // slab-local ids of the HEAVY tiles (block-per-tile kernel)
     const uint32_t *tileStart;    // exclusive scan of tileCount (slab-local tile id -> list offset)
     const uint32_t *tileCount;
@@ -115,8 +118,8 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 
 /// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
-                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *heavyTiles, LightTile *lightTiles,
-                              RunCounters *counters, cudaStream_t stream);
+                              uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
+                              LightTile *lightTiles, RunCounters *counters, cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,

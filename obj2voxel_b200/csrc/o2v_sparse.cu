@@ -21,7 +21,7 @@ namespace {
 
 constexpr int kPairThreads = 128;
 constexpr int kClipThreads = 128;
-constexpr int kFoldWarpsPerBlock = 8;
+constexpr int kFoldWarpsPerBlock = 4;
 
 __device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
 {
@@ -126,20 +126,31 @@ sparseClipKernel(const VoxelizeArgs args)
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 4: warp per tile -> ordered fold + output
 
-struct FoldWarpShared {
-    uint32_t tri[kLightMaxCandidates];      // triangle index per list slot (a tile has at most `candidates` leaves)
-    uint32_t sortKey[kLightMaxCandidates];  // (voxel key << 14) | (list slot << 7) | contribution slot
-    float cW[kLightMaxCandidates];
-    float cU[kLightMaxCandidates];
-    float cV[kLightMaxCandidates];
+/// Per-warp scratch, carved out of dynamic shared memory: tri | sortKey | cW [| cU | cV], kLightMaxCandidates entries each.
+/// Sort key = (voxel key << 18) | (list slot << 9) | contribution slot — 9 bits each.
+template <bool UV>
+struct FoldWarpLayout {
+    static constexpr uint32_t kArrays = UV ? 5u : 3u;
+    static constexpr size_t kBytesPerWarp = (size_t) kArrays * kLightMaxCandidates * 4u;
 };
 
 template <bool UV>
 __global__ void __launch_bounds__(kFoldWarpsPerBlock * 32)
 sparseFoldKernel(const VoxelizeArgs args)
 {
-    __shared__ FoldWarpShared shAll[kFoldWarpsPerBlock];
-    FoldWarpShared &sh = shAll[threadIdx.x >> 5];
+    extern __shared__ __align__(16) unsigned char foldSmem[];
+    struct {
+        uint32_t *tri, *sortKey;
+        float *cW, *cU, *cV;
+    } sh;
+    {
+        uint32_t *warpBase = reinterpret_cast<uint32_t *>(foldSmem + (threadIdx.x >> 5) * FoldWarpLayout<UV>::kBytesPerWarp);
+        sh.tri = warpBase;
+        sh.sortKey = warpBase + kLightMaxCandidates;
+        sh.cW = reinterpret_cast<float *>(warpBase + 2 * kLightMaxCandidates);
+        sh.cU = UV ? sh.cW + kLightMaxCandidates : sh.cW;
+        sh.cV = UV ? sh.cW + 2 * kLightMaxCandidates : sh.cW;
+    }
     const SparseView &sp = args.sparse;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t below = (1u << lane) - 1u;
@@ -147,13 +158,13 @@ sparseFoldKernel(const VoxelizeArgs args)
     const uint32_t warpsTotal = gridDim.x * kFoldWarpsPerBlock;
     const bool blend = args.grid.strategy == kBlend;
     const bool downscale = args.grid.supersampling == 2;
-    const uint32_t groupShift = downscale ? 17u : 14u;  // group = parent voxel when downscaling, else the voxel
+    const uint32_t groupShift = downscale ? 21u : 18u;  // group = parent voxel when downscaling, else the voxel
     unsigned long long contributions = 0;
 
     for (uint32_t t = blockIdx.x * kFoldWarpsPerBlock + (threadIdx.x >> 5); t < args.lightCount; t += warpsTotal) {
         const LightTile d = args.lightTiles[t];
         const uint32_t begin = sp.pairOffset[d.listStart];
-        const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;  // <= d.candidates <= 128
+        const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;  // <= d.candidates <= 512
         if (count == 0) {
             continue;
         }
@@ -180,7 +191,7 @@ sparseFoldKernel(const VoxelizeArgs args)
             if (keep) {
                 const uint32_t pos = kept + __popc(ballot & below);
                 const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
-                sh.sortKey[pos] = (voxelKey(x, y, z) << 14) | ((entry.x - d.listStart) << 7) | pos;
+                sh.sortKey[pos] = (voxelKey(x, y, z) << 18) | ((entry.x - d.listStart) << 9) | pos;
                 sh.cW[pos] = w;
                 if (UV) {
                     const float2 uv = sp.uvs[begin + e];
@@ -209,7 +220,10 @@ sparseFoldKernel(const VoxelizeArgs args)
             sh.sortKey[lane] = key;
         }
         else {
-            const uint32_t padded = kept <= 64 ? 64u : 128u;
+            uint32_t padded = 64u;
+            while (padded < kept) {
+                padded <<= 1;
+            }
             for (uint32_t i = kept + lane; i < padded; i += 32) {
                 sh.sortKey[i] = 0xffffffffu;
             }
@@ -262,7 +276,7 @@ sparseFoldKernel(const VoxelizeArgs args)
             const uint32_t ballot = __ballot_sync(full, start);
             if (start) {
                 const uint32_t group = sh.sortKey[p] >> groupShift;
-                uint32_t currentVoxel = (sh.sortKey[p] >> 14) & 511u;
+                uint32_t currentVoxel = (sh.sortKey[p] >> 18) & 511u;
                 VoxelAccumulator child;
                 resetAccumulator(child);
                 WeightedColor parent;
@@ -273,7 +287,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                     if ((key >> groupShift) != group) {
                         break;
                     }
-                    const uint32_t vk = (key >> 14) & 511u, listSlot = (key >> 7) & 127u, slot = key & 127u;
+                    const uint32_t vk = (key >> 18) & 511u, listSlot = (key >> 9) & 511u, slot = key & 511u;
                     if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
                         flushPartial(child, args);
                         contributions += child.contributions;
@@ -339,10 +353,10 @@ sparseFoldKernel(const VoxelizeArgs args)
 }
 
 template <typename Kernel>
-unsigned persistentBlocks(Kernel kernel, int threads, int smCount, unsigned long long needed)
+unsigned persistentBlocks(Kernel kernel, int threads, int smCount, unsigned long long needed, size_t dynamicSmem = 0)
 {
     int perSm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, dynamicSmem);
     perSm = perSm < 1 ? 1 : perSm;
     unsigned long long blocks = (unsigned long long) smCount * perSm;  // a multiple of the SM count
     blocks = blocks < needed ? blocks : needed;
@@ -386,12 +400,16 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
     const int threads = kFoldWarpsPerBlock * 32;
     const unsigned long long needed = (args.lightCount + kFoldWarpsPerBlock - 1) / kFoldWarpsPerBlock;
     if (args.mesh.uvs != nullptr) {
-        sparseFoldKernel<true><<<persistentBlocks(sparseFoldKernel<true>, threads, smCount, needed), threads, 0,
+        const size_t smem = FoldWarpLayout<true>::kBytesPerWarp * kFoldWarpsPerBlock;
+        cudaFuncSetAttribute(sparseFoldKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        sparseFoldKernel<true><<<persistentBlocks(sparseFoldKernel<true>, threads, smCount, needed, smem), threads, smem,
                                  stream>>>(args);
     }
     else {
-        sparseFoldKernel<false><<<persistentBlocks(sparseFoldKernel<false>, threads, smCount, needed), threads, 0,
-                                  stream>>>(args);
+        const size_t smem = FoldWarpLayout<false>::kBytesPerWarp * kFoldWarpsPerBlock;
+        cudaFuncSetAttribute(sparseFoldKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        sparseFoldKernel<false><<<persistentBlocks(sparseFoldKernel<false>, threads, smCount, needed, smem), threads,
+                                  smem, stream>>>(args);
     }
 }
 
