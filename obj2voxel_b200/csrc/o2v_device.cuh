@@ -177,37 +177,63 @@ __device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args
 }
 
 /// Warp-synchronous form of clipLeafInVoxel (o2v_exact.cuh) — identical arithmetic and piece order, but all 32 lanes of the
-/// warp must call it together (lanes without work pass valid = false).  The per-thread version leaves reconvergence to
-/// the compiler, which serialises the lanes of a warp through the data-dependent loops (measured: 1.9 active lanes per
-/// instruction); here every lane steps through the same two phases under explicit warp votes: a cheap classify/advance
-/// step repeated until no lane can advance, then one shared split step.
+/// warp drive it together.  The per-thread version leaves reconvergence to the compiler, which serialises the lanes of a
+/// warp through the data-dependent loops (measured: 1.9 active lanes per instruction); here every lane steps through the
+/// same two phases under explicit warp votes: a cheap classify/advance step repeated until no lane can advance, then one
+/// shared split step.  The state is a struct so that a persistent kernel can refill finished lanes between rounds.
 template <bool UV>
-__device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<UV> &leaf, uint32_t px, uint32_t py,
-                                                          uint32_t pz, float wholeArea)
-{
-    const unsigned int full = 0xffffffffu;
+struct ClipStack {  // pieces waiting for their remaining planes; kept apart from WarpClipper so that only this array is
+    Tri<UV> piece[6];  // dynamically indexed (local memory) while the clipper's scalars stay in registers
+    uint8_t plane[6];
+};
+
+template <bool UV>
+struct WarpClipper {
+    Tri<UV> cur;
     ClipResult r;
-    r.pieces = 0;
-    r.weight = 0.0f;
-    r.u = 0.0f;
-    r.v = 0.0f;
+    float wholeArea;
+    uint32_t px, py, pz;
+    int sp;
+    int plane;
+    bool done;  // no piece left (or the lane never had work)
 
-    Tri<UV> pending[6];
-    uint8_t pendingPlane[6];
-    int sp = 0;
-    Tri<UV> cur = leaf;
-    int plane = 0;
-    bool done = !valid;
+    __device__ __forceinline__ void idle()
+    {
+        done = true;
+        sp = 0;
+        plane = 0;
+    }
 
-    for (;;) {
-        // ---- phase A: advance while the piece is kept or dropped whole; stop at the first real split ----
+    __device__ __forceinline__ void begin(const Tri<UV> &leaf, uint32_t x, uint32_t y, uint32_t z, float area)
+    {
+        cur = leaf;
+        px = x;
+        py = y;
+        pz = z;
+        wholeArea = area;
+        r.pieces = 0;
+        r.weight = 0.0f;
+        r.u = 0.0f;
+        r.v = 0.0f;
+        sp = 0;
+        plane = 0;
+        done = false;
+    }
+
+    /// One round for the whole warp: every lane that still has a piece advances it to its next real split (phase A) and
+    /// performs that split (phase B).  Must be called by all 32 lanes.
+    __device__ __forceinline__ void round(ClipStack<UV> &stack)
+    {
+        const unsigned int full = 0xffffffffu;
         ClipAction action = kClipKeep;
         int pivot = 0;
         bool sideLo = false;
         bool needSplit = false;
+        // ---- phase A: advance while the piece is kept or dropped whole; stop at the first real split ----
         while (__any_sync(full, !done && !needSplit)) {
             if (!done && !needSplit) {
                 if (plane == 6) {
+                    // a surviving piece: result = mix(result, {area, textureCenter}) (util.hpp:160-165, triangle.hpp:127-131)
                     const float weightSum = xadd(r.weight, wholeArea);
                     if (UV) {
                         const float cu = xdiv(xadd(xadd(cur.t[0], cur.t[2]), cur.t[4]), 3.0f);
@@ -234,17 +260,14 @@ __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<
                     }
                     else {
                         --sp;
-                        cur = pending[sp];
-                        plane = pendingPlane[sp];
+                        cur = stack.piece[sp];
+                        plane = stack.plane[sp];
                     }
                 }
                 else {
                     needSplit = true;
                 }
             }
-        }
-        if (__all_sync(full, done)) {
-            break;
         }
 
         // ---- phase B: one split for every lane that needs one ----
@@ -255,6 +278,7 @@ __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<
             const bool keepHi = plane < 3;
             rotateToPivot<UV>(cur, pivot);
             if (action == kClipSplitRegular) {
+                // splitTriangle_regularCase, voxelization.cpp:279-331: pivot = isolated vertex, X0/X1 on its two edges
                 const float s0 = intersectAxisPlane(cur.v, cur.v + 3, axis, planePos);
                 const float s1 = intersectAxisPlane(cur.v, cur.v + 6, axis, planePos);
                 float g0[3], g1[3], x0[2] = {0.0f, 0.0f}, x1[2] = {0.0f, 0.0f};
@@ -271,21 +295,22 @@ __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<
                     }
                 }
                 if (sideLo != keepHi) {
-                    setVertex<UV>(cur, 1, g0, x0);
+                    setVertex<UV>(cur, 1, g0, x0);  // the isolated corner (iso, X0, X1) is kept
                     setVertex<UV>(cur, 2, g1, x1);
                 }
                 else {
-                    Tri<UV> second;
+                    Tri<UV> second;  // the quad is kept: (X0, a, b) now, (X0, X1, b) pending for the next plane
                     setVertex<UV>(second, 0, g0, x0);
                     setVertex<UV>(second, 1, g1, x1);
                     setVertex<UV>(second, 2, cur.v + 6, cur.t + (UV ? 4 : 0));
-                    pending[sp] = second;
-                    pendingPlane[sp] = static_cast<uint8_t>(plane + 1);
+                    stack.piece[sp] = second;
+                    stack.plane[sp] = static_cast<uint8_t>(plane + 1);
                     ++sp;
                     setVertex<UV>(cur, 0, g0, x0);
                 }
             }
             else {
+                // splitTriangle_onePlanarCase, voxelization.cpp:240-277: pivot = planar vertex, X on the opposite edge
                 const float s = intersectAxisPlane(cur.v + 3, cur.v + 6, axis, planePos);
                 float geo[3], tex[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -299,17 +324,33 @@ __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<
                     }
                 }
                 if (sideLo != keepHi) {
-                    setVertex<UV>(cur, 2, geo, tex);
+                    setVertex<UV>(cur, 2, geo, tex);  // keep (p, a, X)
                 }
                 else {
-                    setVertex<UV>(cur, 1, geo, tex);
+                    setVertex<UV>(cur, 1, geo, tex);  // keep (p, X, b)
                 }
             }
             ++plane;
         }
         __syncwarp(full);
     }
-    return r;
+};
+
+/// Clips one leaf per lane to completion (all 32 lanes call it together; lanes without work pass valid = false).
+template <bool UV>
+__device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<UV> &leaf, uint32_t px, uint32_t py,
+                                                          uint32_t pz, float wholeArea)
+{
+    WarpClipper<UV> clipper;
+    ClipStack<UV> stack;
+    clipper.begin(leaf, px, py, pz, wholeArea);
+    if (!valid) {
+        clipper.idle();
+    }
+    while (!__all_sync(0xffffffffu, clipper.done)) {
+        clipper.round(stack);
+    }
+    return clipper.r;
 }
 
 /// Voxel key: parent (2x2x2 block) index in the high 6 bits, child Morton code (x most significant, ileave.hpp:243-246) in

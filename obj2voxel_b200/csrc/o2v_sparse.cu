@@ -75,50 +75,82 @@ sparseSurvivorsKernel(const VoxelizeArgs args)
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 3: thread per surviving candidate voxel -> exact clip
 
+constexpr uint32_t kRefillThreshold = 8;  // idle lanes needed before the warp pays the load latency of a refill
+
+/// Persistent lanes: each warp owns a contiguous range of survivors; a lane that finishes its clip stores the result and
+/// fetches the next entry while the other lanes keep going (dynamic refill between the rounds of the warp-synchronous
+/// clipper), so the long tail of one voxel's clip tree does not idle the other 31 lanes.
 template <bool UV>
 __global__ void __launch_bounds__(kClipThreads)
 sparseClipKernel(const VoxelizeArgs args)
 {
     const SparseView &sp = args.sparse;
+    const unsigned int full = 0xffffffffu;
     const unsigned long long total = args.counters->survivors;
-    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
     const uint32_t lane = threadIdx.x & 31u;
-    // warp-uniform loop: the clip is warp-synchronous, so whole warps stay in the loop and idle lanes pass valid = false
-    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < total;
-         base += stride) {
-        const unsigned long long e = base + lane;
-        const bool valid = e < total;
-        Tri<UV> leaf;
-        float area = 0.0f;
-        uint32_t vx = 0, vy = 0, vz = 0;
-        if (valid) {
-            const uint2 entry = sp.entries[e];
-            const uint32_t pair = entry.x;
-            const uint32_t leafIndex = __ldg(args.work.tileList + pair);
-            uint32_t origin[3];
-            tileOriginOf(args.grid, __ldg(sp.pairTile + pair), origin);
-            const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
-            const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-            leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
-            leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
-            leaf.v[8] = c.x;
-            area = c.z;
-            if (UV) {
-                const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
-                const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
-                leaf.t[0] = u0.x; leaf.t[1] = u0.y; leaf.t[2] = u0.z; leaf.t[3] = u0.w;
-                leaf.t[4] = u1.x; leaf.t[5] = u1.y;
-            }
-            vx = origin[0] + (entry.y & 7u);
-            vy = origin[1] + ((entry.y >> 3) & 7u);
-            vz = origin[2] + ((entry.y >> 6) & 7u);
+    const uint32_t below = (1u << lane) - 1u;
+    const unsigned long long warpsTotal = (unsigned long long) gridDim.x * (blockDim.x >> 5);
+    const unsigned long long warpIndex = (unsigned long long) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const unsigned long long chunk = ((total + warpsTotal - 1) / warpsTotal + 31ull) & ~31ull;
+    unsigned long long cursor = warpIndex * chunk;
+    const unsigned long long end = cursor + chunk < total ? cursor + chunk : total;
+
+    WarpClipper<UV> clipper;
+    ClipStack<UV> stack;
+    clipper.idle();
+    clipper.r.pieces = 0;
+    clipper.r.weight = clipper.r.u = clipper.r.v = 0.0f;
+    bool hasEntry = false;
+    unsigned long long current = 0;
+
+    for (;;) {
+        const unsigned int idle = __ballot_sync(full, clipper.done);
+        const bool moreWork = cursor < end;
+        if (idle == full && !moreWork) {
+            break;
         }
-        const ClipResult r = clipLeafInVoxelWarp<UV>(valid, leaf, vx, vy, vz, area);
-        if (valid) {
-            sp.weights[e] = r.pieces != 0 ? r.weight : 0.0f;  // area > 0, so a zero weight means "no contribution"
-            if (UV) {
-                sp.uvs[e] = make_float2(r.u, r.v);
+        if (moreWork && (__popc(idle) >= (int) kRefillThreshold || idle == full)) {
+            if (clipper.done) {
+                if (hasEntry) {
+                    sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;  // 0 = "no contribution"
+                    if (UV) {
+                        sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
+                    }
+                    hasEntry = false;
+                }
+                const unsigned long long e = cursor + __popc(idle & below);
+                if (e < end) {
+                    const uint2 entry = sp.entries[e];
+                    const uint32_t pair = entry.x;
+                    const uint32_t leafIndex = __ldg(args.work.tileList + pair);
+                    uint32_t origin[3];
+                    tileOriginOf(args.grid, __ldg(sp.pairTile + pair), origin);
+                    const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+                    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+                    Tri<UV> leaf;
+                    leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
+                    leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
+                    leaf.v[8] = c.x;
+                    if (UV) {
+                        const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
+                        const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);
+                        leaf.t[0] = u0.x; leaf.t[1] = u0.y; leaf.t[2] = u0.z; leaf.t[3] = u0.w;
+                        leaf.t[4] = u1.x; leaf.t[5] = u1.y;
+                    }
+                    clipper.begin(leaf, origin[0] + (entry.y & 7u), origin[1] + ((entry.y >> 3) & 7u),
+                                  origin[2] + ((entry.y >> 6) & 7u), c.z);
+                    hasEntry = true;
+                    current = e;
+                }
             }
+            cursor += __popc(idle);
+        }
+        clipper.round(stack);
+    }
+    if (hasEntry) {
+        sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;
+        if (UV) {
+            sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
         }
     }
 }
