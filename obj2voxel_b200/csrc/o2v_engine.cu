@@ -344,7 +344,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (args.lightCount != 0 && survivorTotal != 0 ? 2 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (args.lightCount != 0 && survivorTotal != 0 ? 3 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));

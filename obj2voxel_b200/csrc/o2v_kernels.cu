@@ -593,11 +593,9 @@ voxelizeTilesKernel(const VoxelizeArgs args)
                 const uint32_t box = s.box;
                 const bool inside = lx >= (box & 15u) && ly >= ((box >> 4) & 15u) && lz >= ((box >> 8) & 15u) &&
                                     lx < ((box >> 12) & 15u) && ly < ((box >> 16) & 15u) && lz < ((box >> 20) & 15u);
-                if (!inside) {
-                    continue;
-                }
-                if (args.prefilter && !prefilterPass(s, (float) lx, (float) ly, (float) lz)) {
-                    continue;
+                const bool hit = inside && (!args.prefilter || prefilterPass(s, (float) lx, (float) ly, (float) lz));
+                if (!__any_sync(0xffffffffu, hit)) {
+                    continue;  // warp-uniform: none of this warp's 32 voxels can touch the leaf
                 }
                 Tri<UV> leaf;
 #pragma unroll
@@ -610,10 +608,13 @@ voxelizeTilesKernel(const VoxelizeArgs args)
                         leaf.t[k] = s.t[k];
                     }
                 }
-                const ClipResult r = clipLeafInVoxel<UV>(leaf, px, py, pz, s.area);
-                ++clipCalls;
-                if (r.pieces != 0) {
-                    addContribution(acc, s.tri, r.weight, r.u, r.v);
+                // warp-synchronous exact clip: the lanes that hit run the classify / split phases in lockstep
+                const ClipResult r = clipLeafInVoxelWarp<UV>(hit, leaf, px, py, pz, s.area);
+                if (hit) {
+                    ++clipCalls;
+                    if (r.pieces != 0) {
+                        addContribution(acc, s.tri, r.weight, r.u, r.v);
+                    }
                 }
             }
         }

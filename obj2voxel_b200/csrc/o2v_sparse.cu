@@ -22,6 +22,8 @@ namespace {
 constexpr int kPairThreads = 128;
 constexpr int kClipThreads = 128;
 constexpr int kFoldWarpsPerBlock = 4;
+constexpr uint32_t kTinyFoldMax = 24;  // survivors per tile up to which one thread folds the whole tile
+constexpr int kTinyFoldThreads = 128;
 
 __device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
 {
@@ -197,8 +199,8 @@ sparseFoldKernel(const VoxelizeArgs args)
         const LightTile d = args.lightTiles[t];
         const uint32_t begin = sp.pairOffset[d.listStart];
         const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;  // <= d.candidates <= 512
-        if (count == 0) {
-            continue;
+        if (count <= kTinyFoldMax) {
+            continue;  // folded by sparseTinyFoldKernel (thread per tile)
         }
         uint32_t origin[3];
         tileOriginOf(args.grid, d.tile, origin);
@@ -384,6 +386,149 @@ sparseFoldKernel(const VoxelizeArgs args)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// stage 4, tiny tiles: thread per tile.  With ~10 contributions per tile a whole warp per tile leaves most lanes idle; here
+// every lane sorts and folds its own tile (insertion sort of <= kTinyFoldMax keys), and the warp reserves its output range
+// with one atomic.
+
+template <bool UV>
+__global__ void __launch_bounds__(kTinyFoldThreads)
+sparseTinyFoldKernel(const VoxelizeArgs args)
+{
+    const SparseView &sp = args.sparse;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t full = 0xffffffffu;
+    const bool blend = args.grid.strategy == kBlend;
+    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t groupShift = downscale ? 21u : 18u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long contributions = 0;
+
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < args.lightCount; base += stride) {
+        const uint32_t t = base + lane;
+        uint32_t key[kTinyFoldMax];
+        uint32_t n = 0, begin = 0, listStart = 0;
+        uint32_t origin[3] = {0, 0, 0};
+        if (t < args.lightCount) {
+            const LightTile d = args.lightTiles[t];
+            begin = sp.pairOffset[d.listStart];
+            const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;
+            if (count != 0 && count <= kTinyFoldMax) {
+                listStart = d.listStart;
+                tileOriginOf(args.grid, d.tile, origin);
+                for (uint32_t e = 0; e < count; ++e) {
+                    if (sp.weights[begin + e] != 0.0f) {
+                        const uint2 entry = sp.entries[begin + e];
+                        const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
+                        // insertion sort by (voxel key, list slot); e identifies the contribution
+                        const uint32_t k = (voxelKey(x, y, z) << 18) | ((entry.x - listStart) << 9) | e;
+                        uint32_t i = n;
+                        while (i > 0 && key[i - 1] > k) {
+                            key[i] = key[i - 1];
+                            --i;
+                        }
+                        key[i] = k;
+                        ++n;
+                    }
+                }
+            }
+        }
+        uint32_t runs = 0;
+        for (uint32_t p = 0; p < n; ++p) {
+            runs += (p == 0 || (key[p] >> groupShift) != (key[p - 1] >> groupShift)) ? 1u : 0u;
+        }
+        // warp-aggregated output reservation
+        uint32_t inclusive = runs;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(full, inclusive, o);
+            inclusive += lane >= (uint32_t) o ? up : 0u;
+        }
+        const uint32_t warpRuns = __shfl_sync(full, inclusive, 31);
+        unsigned long long outIndex = 0;
+        if (lane == 31 && warpRuns != 0) {
+            outIndex = atomicAdd(&args.counters->voxels, (unsigned long long) warpRuns);
+        }
+        outIndex = __shfl_sync(full, outIndex, 31) + (inclusive - runs);
+
+        uint32_t p = 0;
+        while (p < n) {
+            const uint32_t group = key[p] >> groupShift;
+            uint32_t currentVoxel = (key[p] >> 18) & 511u;
+            VoxelAccumulator child;
+            resetAccumulator(child);
+            WeightedColor parent;
+            parent.w = parent.r = parent.g = parent.b = 0.0f;
+            bool hasParent = false;
+            for (; p < n && (key[p] >> groupShift) == group; ++p) {
+                const uint32_t vk = (key[p] >> 18) & 511u, listSlot = (key[p] >> 9) & 511u, e = key[p] & 511u;
+                if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
+                    flushPartial(child, args);
+                    contributions += child.contributions;
+                    if (!hasParent) {
+                        hasParent = true;
+                        parent = child.voxel;
+                    }
+                    else {
+                        combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                    }
+                    resetAccumulator(child);
+                    currentVoxel = vk;
+                }
+                const uint32_t tri = args.leaves[args.work.tileList[listStart + listSlot]].tri;
+                if (child.hasPartial && child.partialTri != tri) {
+                    flushPartial(child, args);
+                }
+                float u = 0.0f, v = 0.0f;
+                if (UV) {
+                    const float2 uv = sp.uvs[begin + e];
+                    u = uv.x;
+                    v = uv.y;
+                }
+                addContribution(child, tri, sp.weights[begin + e], u, v);
+            }
+            flushPartial(child, args);
+            contributions += child.contributions;
+            WeightedColor result = child.voxel;
+            const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
+            int32_t ox, oy, oz;
+            if (downscale) {
+                if (hasParent) {
+                    combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                    result = parent;
+                }
+                ox = (int32_t) (origin[0] / 2 + (pk & 3u));
+                oy = (int32_t) (origin[1] / 2 + ((pk >> 2) & 3u));
+                oz = (int32_t) (origin[2] / 2 + ((pk >> 4) & 3u));
+            }
+            else {
+                ox = (int32_t) (origin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
+                oy = (int32_t) (origin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
+                oz = (int32_t) (origin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
+            }
+            if (outIndex < args.outCapacity) {
+                VoxelRecord rec;
+                rec.x = ox;
+                rec.y = oy;
+                rec.z = oz;
+                rec.argb = quantizeArgb(result.r, result.g, result.b);
+                *reinterpret_cast<int4 *>(args.out + outIndex) = *reinterpret_cast<const int4 *>(&rec);
+            }
+            else {
+                atomicAdd(&args.counters->outputOverflow, 1ull);
+            }
+            ++outIndex;
+        }
+        __syncwarp(full);
+    }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        contributions += __shfl_xor_sync(full, contributions, o);
+    }
+    if (lane == 0 && contributions != 0) {
+        atomicAdd(&args.counters->contributions, contributions);
+    }
+}
+
 template <typename Kernel>
 unsigned persistentBlocks(Kernel kernel, int threads, int smCount, unsigned long long needed, size_t dynamicSmem = 0)
 {
@@ -428,6 +573,18 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 {
     if (args.lightCount == 0) {
         return;
+    }
+    {
+        const unsigned long long tinyBlocks = (args.lightCount + kTinyFoldThreads - 1) / kTinyFoldThreads;
+        if (args.mesh.uvs != nullptr) {
+            sparseTinyFoldKernel<true><<<persistentBlocks(sparseTinyFoldKernel<true>, kTinyFoldThreads, smCount, tinyBlocks),
+                                         kTinyFoldThreads, 0, stream>>>(args);
+        }
+        else {
+            sparseTinyFoldKernel<false><<<persistentBlocks(sparseTinyFoldKernel<false>, kTinyFoldThreads, smCount,
+                                                           tinyBlocks),
+                                          kTinyFoldThreads, 0, stream>>>(args);
+        }
     }
     const int threads = kFoldWarpsPerBlock * 32;
     const unsigned long long needed = (args.lightCount + kFoldWarpsPerBlock - 1) / kFoldWarpsPerBlock;
