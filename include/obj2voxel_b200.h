@@ -76,6 +76,9 @@ typedef struct o2v_b200_stats {
     int32_t voxelize_launches;
     uint64_t light_tiles;       /* tiles voxelized warp-per-tile */
     uint64_t heavy_tiles;       /* tiles voxelized block-per-tile */
+    uint64_t survivors;         /* sparse path: SAT survivors = exact clips */
+    float ms_clip;              /* duration of the dominant kernel (exact clip), CUDA events */
+    float reserved;
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */

@@ -162,6 +162,8 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->voxelize_launches = in.voxelizeLaunches;
     out->light_tiles = in.counters.lightTiles;
     out->heavy_tiles = in.counters.heavyTiles;
+    out->survivors = in.counters.survivors;
+    out->ms_clip = in.msClip;
 }
 
 EngineParams paramsFromC(const o2v_b200_params &p)

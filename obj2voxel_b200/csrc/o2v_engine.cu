@@ -84,6 +84,7 @@ Engine *Engine::create(int device, std::string *error)
     ok = ok && cudaMallocHost(&e->hostCountersInit_, sizeof(RunCounters)) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evStart_) == cudaSuccess && cudaEventCreate(&e->evSetup_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evVoxStart_) == cudaSuccess && cudaEventCreate(&e->evVoxEnd_) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->evClipStart_) == cudaSuccess && cudaEventCreate(&e->evClipEnd_) == cudaSuccess;
     ok = ok && e->counters_.ensure(sizeof(RunCounters));
     if (!ok) {
         if (error != nullptr) {
@@ -109,7 +110,7 @@ Engine::~Engine()
     if (hostCountersInit_ != nullptr) {
         cudaFreeHost(hostCountersInit_);
     }
-    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_}) {
+    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_}) {
         if (ev != nullptr) {
             cudaEventDestroy(ev);
         }
@@ -250,9 +251,9 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
     }
-    size_t freeBytes = 0, totalBytes = 0;
-    O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
-    if (capacity * sizeof(VoxelRecord) > out_.size()) {
+    if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
+        size_t freeBytes = 0, totalBytes = 0;
+        O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
         const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
         capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
     }
@@ -309,23 +310,31 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     sparse.entries = nullptr;
     sparse.weights = nullptr;
     sparse.uvs = nullptr;
-    unsigned long long survivorTotal = 0;
-    if (args.lightCount != 0) {
+    // Survivors <= candidate voxels (known from the first read-back).  When that bound is affordable the queue is sized
+    // by it and the exact count stays on the device (no host round trip between the stages).
+    const unsigned long long candidateBound = hostCounters_->candidateVoxels;
+    const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 12ull <= (8ull << 30);
+    bool sparseActive = args.lightCount != 0;
+    if (sparseActive) {
         O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
         launchSparseSurvivors(args, false, stream);
         launchExclusiveScan(pairSurvivors_.as<uint32_t>(), pairOffset_.as<uint32_t>(), (size_t) pairTotal + 1,
                             scratch_.as<uint32_t>(), &dCounters->survivors, stream);
         st.kernelLaunches += 4;
-        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
-        O2V_CUDA(cudaStreamSynchronize(stream));
-        O2V_CUDA(cudaGetLastError());
-        survivorTotal = hostCounters_->survivors;
-        if (survivorTotal >= (1ull << 32)) {
-            return fail(kErrTooLarge, "more than 2^32-1 candidate voxels on the sparse path of this slab");
+        unsigned long long entryCapacity = candidateBound;
+        if (!boundAffordable) {
+            O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+            O2V_CUDA(cudaStreamSynchronize(stream));
+            O2V_CUDA(cudaGetLastError());
+            entryCapacity = hostCounters_->survivors;
+            if (entryCapacity >= (1ull << 32)) {
+                return fail(kErrTooLarge, "more than 2^32-1 candidate voxels on the sparse path of this slab");
+            }
         }
-        if (!entries_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(uint2)) ||
-            !weights_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(float)) ||
-            (hasUv && !contribUvs_.ensure((size_t) std::max<unsigned long long>(survivorTotal, 1) * sizeof(float2)))) {
+        entryCapacity = std::max<unsigned long long>(entryCapacity, 1);
+        if (!entries_.ensure((size_t) entryCapacity * sizeof(uint2)) ||
+            !weights_.ensure((size_t) entryCapacity * sizeof(float)) ||
+            (hasUv && !contribUvs_.ensure((size_t) entryCapacity * sizeof(float2)))) {
             return fail(kErrOutOfMemory, "device allocation failed (sparse path buffers)");
         }
         sparse.entries = entries_.as<uint2>();
@@ -338,13 +347,15 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
 
     for (int attempt = 0; attempt < 2; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
-        if (args.lightCount != 0 && survivorTotal != 0) {
+        if (sparseActive) {
+            O2V_CUDA(cudaEventRecord(evClipStart_, stream));
             launchSparseClip(args, smCount_, stream);
+            O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
             launchSparseFold(args, smCount_, stream);
         }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (args.lightCount != 0 && survivorTotal != 0 ? 3 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (sparseActive ? 3 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
@@ -378,13 +389,16 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
     }
 
-    hostCounters_->clipCalls += survivorTotal;  // every sparse-path survivor is one exact clip
+    hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor is one exact clip
     st.counters = *hostCounters_;
     st.outCapacity = capacity;
     voxelCount_ = hostCounters_->voxels;
     cudaEventElapsedTime(&st.msTotal, evStart_, evVoxEnd_);
     cudaEventElapsedTime(&st.msSetup, evStart_, evSetup_);
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
+    if (sparseActive) {
+        cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
+    }
     return kErrOk;
 }
 

@@ -35,7 +35,8 @@ struct RunStats {
     float transform[12];
     float msTotal = 0;     // device time of the whole pipeline (CUDA events on the run stream)
     float msSetup = 0;     // bounds + count + scans + emit + sort
-    float msVoxelize = 0;  // the hot kernel
+    float msVoxelize = 0;  // clip + fold + heavy tiles
+    float msClip = 0;      // the dominant kernel alone (sparseClipKernel)
     int voxelizeLaunches = 0;
     int kernelLaunches = 0;
     unsigned long long outCapacity = 0;
@@ -95,6 +96,7 @@ private:
     RunCounters *hostCounters_ = nullptr;  // pinned
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
+    cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr;
 
     DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_,
         scratch_;
