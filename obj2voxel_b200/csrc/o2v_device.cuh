@@ -181,6 +181,14 @@ __device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args
 /// warp through the data-dependent loops (measured: 1.9 active lanes per instruction); here every lane steps through the
 /// same two phases under explicit warp votes: a cheap classify/advance step repeated until no lane can advance, then one
 /// shared split step.  The state is a struct so that a persistent kernel can refill finished lanes between rounds.
+/// Fills the 64-entry case table (index = (planar flags << 3) | lo flags) cooperatively; the caller synchronises.
+__device__ __forceinline__ void fillClipCaseTable(uint8_t *table)
+{
+    for (uint32_t i = threadIdx.x; i < 64u; i += blockDim.x) {
+        table[i] = static_cast<uint8_t>(clipCaseOf(i >> 3, i & 7u));
+    }
+}
+
 template <bool UV>
 struct ClipStack {  // pieces waiting for their remaining planes; kept apart from WarpClipper so that only this array is
     Tri<UV> piece[6];  // dynamically indexed (local memory) while the clipper's scalars stay in registers
@@ -222,53 +230,71 @@ struct WarpClipper {
 
     /// One round for the whole warp: every lane that still has a piece advances it to its next real split (phase A) and
     /// performs that split (phase B).  Must be called by all 32 lanes.
-    __device__ __forceinline__ void round(ClipStack<UV> &stack)
+    __device__ __forceinline__ void popOrFinish(ClipStack<UV> &stack)
+    {
+        if (sp == 0) {
+            done = true;
+        }
+        else {
+            --sp;
+            cur = stack.piece[sp];
+            plane = stack.plane[sp];
+        }
+    }
+
+    /// One round for the whole warp = one node of every lane's clip tree: classify the current piece against all six
+    /// voxel planes in one straight-line block (no per-lane axis selects, no data-dependent inner loop; the 16-way case
+    /// switch is a 64-entry shared-memory table, clipCaseOf), then either count it as a survivor, drop it, or split it at
+    /// the first plane >= `plane` that cuts it.  Must be called by all 32 lanes.
+    __device__ __forceinline__ void round(ClipStack<UV> &stack, const uint8_t *caseTable)
     {
         const unsigned int full = 0xffffffffu;
-        ClipAction action = kClipKeep;
-        int pivot = 0;
-        bool sideLo = false;
         bool needSplit = false;
-        // ---- phase A: advance while the piece is kept or dropped whole; stop at the first real split ----
-        while (__any_sync(full, !done && !needSplit)) {
-            if (!done && !needSplit) {
-                if (plane == 6) {
-                    // a surviving piece: result = mix(result, {area, textureCenter}) (util.hpp:160-165, triangle.hpp:127-131)
-                    const float weightSum = xadd(r.weight, wholeArea);
-                    if (UV) {
-                        const float cu = xdiv(xadd(xadd(cur.t[0], cur.t[2]), cur.t[4]), 3.0f);
-                        const float cv = xdiv(xadd(xadd(cur.t[1], cur.t[3]), cur.t[5]), 3.0f);
-                        r.u = xdiv(xadd(xmul(r.weight, r.u), xmul(wholeArea, cu)), weightSum);
-                        r.v = xdiv(xadd(xmul(r.weight, r.v), xmul(wholeArea, cv)), weightSum);
-                    }
-                    r.weight = weightSum;
-                    ++r.pieces;
-                    action = kClipDrop;
+        uint32_t code = 0;
+        if (!done) {
+            uint32_t nonKeep = 0, dropMask = 0, codes = 0;
+#pragma unroll
+            for (int axis = 0; axis < 3; ++axis) {
+                const float c0 = cur.v[axis], c1 = cur.v[3 + axis], c2 = cur.v[6 + axis];
+                const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
+                // plane `axis` keeps the hi side (DISCARD_LO), plane `3 + axis` = base + 1 keeps the lo side
+                const uint32_t a = caseTable[planeFlags(c0, c1, c2, static_cast<float>(base))];
+                const uint32_t b = caseTable[planeFlags(c0, c1, c2, static_cast<float>(base + 1u))];
+                nonKeep |= ((a & 7u) == 0u ? 0u : 1u) << axis;          // kept whole iff unsplit and not lo
+                nonKeep |= ((b & 7u) == 4u ? 0u : 1u) << (3 + axis);    // kept whole iff unsplit and lo
+                dropMask |= ((a & 7u) == 4u ? 1u : 0u) << axis;
+                dropMask |= ((b & 7u) == 0u ? 1u : 0u) << (3 + axis);
+                codes |= (a << (5 * axis)) | (b << (5 * (3 + axis)));
+            }
+            const uint32_t cutting = nonKeep & 63u & ~((1u << plane) - 1u);  // planes still ahead of this piece
+            if (cutting == 0) {
+                // survived every remaining plane: result = mix(result, {area, textureCenter}) (util.hpp:160-165)
+                const float weightSum = xadd(r.weight, wholeArea);
+                if (UV) {
+                    const float cu = xdiv(xadd(xadd(cur.t[0], cur.t[2]), cur.t[4]), 3.0f);
+                    const float cv = xdiv(xadd(xadd(cur.t[1], cur.t[3]), cur.t[5]), 3.0f);
+                    r.u = xdiv(xadd(xmul(r.weight, r.u), xmul(wholeArea, cu)), weightSum);
+                    r.v = xdiv(xadd(xmul(r.weight, r.v), xmul(wholeArea, cv)), weightSum);
                 }
-                else {
-                    const int axis = plane < 3 ? plane : plane - 3;
-                    const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
-                    const float planePos = static_cast<float>(base + (plane < 3 ? 0u : 1u));
-                    action = classifyAgainstPlane(cur.v, axis, planePos, plane < 3, pivot, sideLo);
-                }
-                if (action == kClipKeep) {
-                    ++plane;
-                }
-                else if (action == kClipDrop) {
-                    if (sp == 0) {
-                        done = true;
-                    }
-                    else {
-                        --sp;
-                        cur = stack.piece[sp];
-                        plane = stack.plane[sp];
-                    }
+                r.weight = weightSum;
+                ++r.pieces;
+                popOrFinish(stack);
+            }
+            else {
+                const int first = __ffs(cutting) - 1;
+                if ((dropMask >> first) & 1u) {
+                    popOrFinish(stack);
                 }
                 else {
                     needSplit = true;
+                    plane = first;
+                    code = (codes >> (5 * first)) & 31u;
                 }
             }
         }
+        const ClipAction action = (code & 3u) == 1u ? kClipSplitRegular : kClipSplitOnePlanar;
+        const int pivot = static_cast<int>(code >> 3);
+        const bool sideLo = (code & 4u) != 0;
 
         // ---- phase B: one split for every lane that needs one ----
         if (needSplit) {
@@ -339,7 +365,7 @@ struct WarpClipper {
 /// Clips one leaf per lane to completion (all 32 lanes call it together; lanes without work pass valid = false).
 template <bool UV>
 __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<UV> &leaf, uint32_t px, uint32_t py,
-                                                          uint32_t pz, float wholeArea)
+                                                          uint32_t pz, float wholeArea, const uint8_t *caseTable)
 {
     WarpClipper<UV> clipper;
     ClipStack<UV> stack;
@@ -348,7 +374,7 @@ __device__ __forceinline__ ClipResult clipLeafInVoxelWarp(bool valid, const Tri<
         clipper.idle();
     }
     while (!__all_sync(0xffffffffu, clipper.done)) {
-        clipper.round(stack);
+        clipper.round(stack, caseTable);
     }
     return clipper.r;
 }

@@ -275,47 +275,74 @@ struct ClipResult {
 /// What one half-space does to a triangle (the switch of src/voxelization.cpp:192-234 without the geometry).
 enum ClipAction : int { kClipKeep = 0, kClipDrop = 1, kClipSplitRegular = 2, kClipSplitOnePlanar = 3 };
 
-/// Classifies triangle `v` against plane `planePos` on `axis`.  For the split actions `pivot` is the isolated vertex
-/// (regular case, splitTriangle_regularCase :289-293) or the planar vertex (one-planar case, :245-246) and `pivotIsLo`
-/// tells on which side the piece that starts at the pivot's successor... see splitAt().
-O2V_HD ClipAction classifyAgainstPlane(const float *v, int axis, float planePos, bool keepHi, int &pivot, bool &sideLo)
+/// The reference's 16-way case switch (src/voxelization.cpp:192-234) as a function of the three "planar" flags P and the
+/// three "lo" flags L (bit k = vertex k).  Packed result: bits 1:0 = kind (0 unsplit, 1 regular split, 2 one-planar
+/// split), bit 2 = the unsplit triangle is lo / the piece that starts at the pivot is lo, bits 4:3 = pivot vertex
+/// (isolated vertex of the regular case :289-293, planar vertex of the one-planar case :245-246).
+O2V_HD uint32_t clipCaseOf(uint32_t P, uint32_t L)
 {
-    const float c0 = axisOf(v, axis), c1 = axisOf(v + 3, axis), c2 = axisOf(v + 6, axis);
-    const bool p0 = isZero(xsub(c0, planePos)), p1 = isZero(xsub(c1, planePos)), p2 = isZero(xsub(c2, planePos));
-    const bool l0 = c0 < planePos, l1 = c1 < planePos, l2 = c2 < planePos;
+    const bool p0 = (P & 1u) != 0, p1 = (P & 2u) != 0, p2 = (P & 4u) != 0;
+    const bool l0 = (L & 1u) != 0, l1 = (L & 2u) != 0, l2 = (L & 4u) != 0;
     const int loSum = int(l0) + int(l1) + int(l2);
     const int planarSum = int(p0) + int(p1) + int(p2);
-    bool wholeIsLo;
+    uint32_t kind = 0, pivot = 0;
+    bool flag;
     if (loSum == 0) {
-        wholeIsLo = false;
+        flag = false;
     }
     else if (loSum == 3) {
-        wholeIsLo = true;
+        flag = true;
     }
     else if (planarSum == 3) {
-        wholeIsLo = false;  // IS_LO_BIASED == false
+        flag = false;  // IS_LO_BIASED == false
     }
     else if (planarSum == 2) {
-        wholeIsLo = !p0 ? l0 : (!p1 ? l1 : l2);  // loVertices[firstNonplanar()]
+        flag = !p0 ? l0 : (!p1 ? l1 : l2);  // loVertices[firstNonplanar()]
     }
     else if (planarSum == 1) {
-        const int p = p0 ? 0 : (p1 ? 1 : 2);
+        const uint32_t p = p0 ? 0u : (p1 ? 1u : 2u);
         const bool la = p == 0 ? l1 : (p == 1 ? l2 : l0);  // vertex (p + 1) % 3
         const bool lb = p == 0 ? l2 : (p == 1 ? l0 : l1);  // vertex (p + 2) % 3
+        flag = la;
         if (la != lb) {
+            kind = 2;
             pivot = p;
-            sideLo = la;
-            return kClipSplitOnePlanar;
         }
-        wholeIsLo = la;
     }
     else {
         const bool isoLo = loSum == 1;
-        pivot = isoLo ? (l0 ? 0 : (l1 ? 1 : 2)) : (!l0 ? 0 : (!l1 ? 1 : 2));
-        sideLo = isoLo;
-        return kClipSplitRegular;
+        kind = 1;
+        pivot = isoLo ? (l0 ? 0u : (l1 ? 1u : 2u)) : (!l0 ? 0u : (!l1 ? 1u : 2u));
+        flag = isoLo;
     }
-    return wholeIsLo != keepHi ? kClipKeep : kClipDrop;
+    return kind | (flag ? 4u : 0u) | (pivot << 3);
+}
+
+/// Planar / lo flags of the three vertices against one axis plane (SplittingValues, src/voxelization.cpp:110-153),
+/// packed as (P << 3) | L for clipCaseOf / the case table.
+O2V_HD uint32_t planeFlags(float c0, float c1, float c2, float planePos)
+{
+    const uint32_t P = (isZero(xsub(c0, planePos)) ? 1u : 0u) | (isZero(xsub(c1, planePos)) ? 2u : 0u) |
+                       (isZero(xsub(c2, planePos)) ? 4u : 0u);
+    const uint32_t L = (c0 < planePos ? 1u : 0u) | (c1 < planePos ? 2u : 0u) | (c2 < planePos ? 4u : 0u);
+    return (P << 3) | L;
+}
+
+/// Classifies triangle `v` against plane `planePos` on `axis`.  For the split actions `pivot` is the isolated vertex
+/// (regular case) or the planar vertex (one-planar case) and `sideLo` tells whether the piece at the pivot
+/// (regular: the isolated corner; one-planar: (p, a, X)) lies on the lo side.
+O2V_HD ClipAction classifyAgainstPlane(const float *v, int axis, float planePos, bool keepHi, int &pivot, bool &sideLo)
+{
+    const uint32_t flags = planeFlags(axisOf(v, axis), axisOf(v + 3, axis), axisOf(v + 6, axis), planePos);
+    const uint32_t code = clipCaseOf(flags >> 3, flags & 7u);
+    const uint32_t kind = code & 3u;
+    const bool flag = (code & 4u) != 0;
+    if (kind == 0) {
+        return flag != keepHi ? kClipKeep : kClipDrop;
+    }
+    pivot = int(code >> 3);
+    sideLo = flag;
+    return kind == 1 ? kClipSplitRegular : kClipSplitOnePlanar;
 }
 
 /// Rotates the triangle so that vertex `pivot` comes first (keeps the cyclic order, i.e. (pivot+1)%3 and (pivot+2)%3

@@ -537,6 +537,7 @@ struct TileShared {
     // supersampling fold (8^3 children -> 4^3 parents)
     float dsW[kTileVoxels], dsR[kTileVoxels], dsG[kTileVoxels], dsB[kTileVoxels];
     uint8_t dsHas[kTileVoxels];
+    uint8_t caseTable[64];  // clipCaseOf lookup for the warp-synchronous clip
 };
 
 template <bool UV>
@@ -550,6 +551,7 @@ voxelizeTilesKernel(const VoxelizeArgs args)
     const uint32_t lx = tid & 7u, ly = (tid >> 3) & 7u, lz = tid >> 6;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     unsigned long long clipCalls = 0, contributions = 0;
+    fillClipCaseTable(sh.caseTable);
 
     for (;;) {
         __syncthreads();
@@ -609,7 +611,7 @@ voxelizeTilesKernel(const VoxelizeArgs args)
                     }
                 }
                 // warp-synchronous exact clip: the lanes that hit run the classify / split phases in lockstep
-                const ClipResult r = clipLeafInVoxelWarp<UV>(hit, leaf, px, py, pz, s.area);
+                const ClipResult r = clipLeafInVoxelWarp<UV>(hit, leaf, px, py, pz, s.area, sh.caseTable);
                 if (hit) {
                     ++clipCalls;
                     if (r.pieces != 0) {

@@ -97,6 +97,9 @@ sparseClipKernel(const VoxelizeArgs args)
     unsigned long long cursor = warpIndex * chunk;
     const unsigned long long end = cursor + chunk < total ? cursor + chunk : total;
 
+    __shared__ uint8_t caseTable[64];
+    fillClipCaseTable(caseTable);
+    __syncthreads();
     WarpClipper<UV> clipper;
     ClipStack<UV> stack;
     clipper.idle();
@@ -147,7 +150,7 @@ sparseClipKernel(const VoxelizeArgs args)
             }
             cursor += __popc(idle);
         }
-        clipper.round(stack);
+        clipper.round(stack, caseTable);
     }
     if (hasEntry) {
         sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;
