@@ -312,8 +312,15 @@ def run_ours(args, cfg, workload):
     ms_per_step = elapsed_ms / args.steps
 
     # ---- end to end through the reference-facing C API with HOST buffers (H2D + kernels + D2H timed) ----
-    host_verts = verts.cpu().numpy()
-    host_uvs = uvs.cpu().numpy() if uvs is not None else None
+    # host inputs live in pinned memory (the contract's "host->device copy ... from pinned host memory")
+    pinned_verts = torch.empty(verts.shape, dtype=verts.dtype, pin_memory=True)
+    pinned_verts.copy_(verts)
+    host_verts = pinned_verts.numpy()
+    host_uvs = None
+    if uvs is not None:
+        pinned_uvs = torch.empty(uvs.shape, dtype=uvs.dtype, pin_memory=True)
+        pinned_uvs.copy_(uvs)
+        host_uvs = pinned_uvs.numpy()
     tex_obj = o2v.Texture(meshes.random_texture(256, 256, 3), wrap=o2v.UV_WRAP) if uvs is not None else None
     lib = o2v.load()
     lib.obj2voxel_set_log_level(o2v._lib.LOG_ERROR)

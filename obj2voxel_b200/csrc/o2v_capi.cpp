@@ -434,7 +434,15 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     RunStats stats;
     {
         std::lock_guard<std::mutex> lock{gEngineMutex};  // one job at a time per process-wide engine
-        UploadedMesh uploaded;
+        // the mesh staging buffers are kept per device across jobs (grow-only) like the engine's own buffers
+        static std::unordered_map<int, std::unique_ptr<UploadedMesh>> uploads;
+        std::unique_ptr<UploadedMesh> &slot = uploads[engine->device()];
+        if (slot == nullptr) {
+            slot.reset(new UploadedMesh());
+        }
+        UploadedMesh &uploaded = *slot;
+        uploaded.texturePixels.clear();
+        uploaded.textureViews.clear();
         if (!uploaded.upload(mesh, textures.data(), (uint32_t) textures.size(), stream, &error)) {
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, error);
             return OBJ2VOXEL_ERR_DEVICE;
@@ -447,36 +455,53 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
         }
         statsToC(stats, &inst.stats);
 
-        // ---- sink: stream the compacted Voxel32 records back in bounded batches ----
+        // ---- sink: stream the compacted Voxel32 records back through two pinned staging buffers; the D2H copy of batch
+        // k+1 overlaps the sink call of batch k ----
         const unsigned long long total = engine->voxelCount();
-        const size_t batch = 1u << 20;  // 16 MiB of records per sink call
-        std::vector<uint32_t> staging;
-        void *pinned = nullptr;
-        const size_t stagingRecords = (size_t) std::min<unsigned long long>(total, batch);
-        if (stagingRecords != 0 && cudaMallocHost(&pinned, stagingRecords * 16) != cudaSuccess) {
-            cudaGetLastError();
-            pinned = nullptr;
-            staging.resize(stagingRecords * 4);
-        }
-        uint32_t *hostBuffer = pinned != nullptr ? static_cast<uint32_t *>(pinned) : staging.data();
+        const size_t batch = 1u << 21;  // 32 MiB of records per sink call
         const auto *deviceRecords = reinterpret_cast<const unsigned char *>(engine->deviceVoxels());
-        bool sinkOk = true;
-        for (unsigned long long done = 0; done < total && sinkOk; done += batch) {
-            const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
-            if (cudaMemcpyAsync(hostBuffer, deviceRecords + done * 16, count * 16, cudaMemcpyDeviceToHost, stream) !=
-                    cudaSuccess ||
-                cudaStreamSynchronize(stream) != cudaSuccess) {
-                logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, std::string("voxel download failed: ") +
-                                                          cudaGetErrorString(cudaGetLastError()));
-                if (pinned != nullptr) {
-                    cudaFreeHost(pinned);
-                }
-                return OBJ2VOXEL_ERR_DEVICE;
+        uint32_t *staging[2] = {nullptr, nullptr};
+        std::vector<uint32_t> pageable;
+        if (total != 0) {
+            staging[0] = static_cast<uint32_t *>(engine->pinnedStaging(0, batch * 16));
+            staging[1] = static_cast<uint32_t *>(engine->pinnedStaging(1, batch * 16));
+            if (staging[0] == nullptr || staging[1] == nullptr) {  // pinned memory exhausted: plain host memory still works
+                pageable.resize(batch * 4 * 2);
+                staging[0] = pageable.data();
+                staging[1] = pageable.data() + batch * 4;
             }
-            sinkOk = inst.sink->write(hostBuffer, count);
         }
-        if (pinned != nullptr) {
-            cudaFreeHost(pinned);
+        cudaEvent_t copied[2] = {nullptr, nullptr};
+        cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming);
+        auto startCopy = [&](unsigned long long done, int slot) -> bool {
+            const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
+            return cudaMemcpyAsync(staging[slot], deviceRecords + done * 16, count * 16, cudaMemcpyDeviceToHost, stream) ==
+                       cudaSuccess &&
+                   cudaEventRecord(copied[slot], stream) == cudaSuccess;
+        };
+        bool sinkOk = true, deviceOk = true;
+        int slot = 0;
+        if (total != 0) {
+            deviceOk = startCopy(0, 0);
+        }
+        for (unsigned long long done = 0; done < total && sinkOk && deviceOk; done += batch, slot ^= 1) {
+            const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
+            if (done + batch < total) {
+                deviceOk = startCopy(done + batch, slot ^ 1);
+            }
+            deviceOk = deviceOk && cudaEventSynchronize(copied[slot]) == cudaSuccess;
+            if (deviceOk) {
+                sinkOk = inst.sink->write(staging[slot], count);
+            }
+        }
+        cudaStreamSynchronize(stream);
+        cudaEventDestroy(copied[0]);
+        cudaEventDestroy(copied[1]);
+        if (!deviceOk) {
+            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR,
+                       std::string("voxel download failed: ") + cudaGetErrorString(cudaGetLastError()));
+            return OBJ2VOXEL_ERR_DEVICE;
         }
         if (!sinkOk || !inst.sink->good()) {
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed because of IO error");

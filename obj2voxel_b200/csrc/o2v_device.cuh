@@ -181,6 +181,21 @@ __device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args
 /// warp through the data-dependent loops (measured: 1.9 active lanes per instruction); here every lane steps through the
 /// same two phases under explicit warp votes: a cheap classify/advance step repeated until no lane can advance, then one
 /// shared split step.  The state is a struct so that a persistent kernel can refill finished lanes between rounds.
+/// planeFlags (o2v_exact.cuh) from sign bits: c < p  <=>  (c - p) is negative, and |c - p| < eps  <=>  (|c - p| - eps) is
+/// negative — IEEE subtraction never flips the sign of a non-zero exact difference and yields +0 for equal operands, so the
+/// six flags are the sign bits of six correctly-rounded differences (no compare / select chain).
+__device__ __forceinline__ uint32_t planeFlagsFast(float c0, float c1, float c2, float planePos)
+{
+    const float d0 = __fsub_rn(c0, planePos), d1 = __fsub_rn(c1, planePos), d2 = __fsub_rn(c2, planePos);
+    const float e0 = __fsub_rn(fabsf(d0), kEpsilon), e1 = __fsub_rn(fabsf(d1), kEpsilon),
+                e2 = __fsub_rn(fabsf(d2), kEpsilon);
+    const uint32_t L = (__float_as_uint(d0) >> 31) | ((__float_as_uint(d1) >> 31) << 1) |
+                       ((__float_as_uint(d2) >> 31) << 2);
+    const uint32_t P = (__float_as_uint(e0) >> 31) | ((__float_as_uint(e1) >> 31) << 1) |
+                       ((__float_as_uint(e2) >> 31) << 2);
+    return (P << 3) | L;
+}
+
 /// Fills the 64-entry case table (index = (planar flags << 3) | lo flags) cooperatively; the caller synchronises.
 __device__ __forceinline__ void fillClipCaseTable(uint8_t *table)
 {
@@ -258,8 +273,8 @@ struct WarpClipper {
                 const float c0 = cur.v[axis], c1 = cur.v[3 + axis], c2 = cur.v[6 + axis];
                 const uint32_t base = axis == 0 ? px : (axis == 1 ? py : pz);
                 // plane `axis` keeps the hi side (DISCARD_LO), plane `3 + axis` = base + 1 keeps the lo side
-                const uint32_t a = caseTable[planeFlags(c0, c1, c2, static_cast<float>(base))];
-                const uint32_t b = caseTable[planeFlags(c0, c1, c2, static_cast<float>(base + 1u))];
+                const uint32_t a = caseTable[planeFlagsFast(c0, c1, c2, static_cast<float>(base))];
+                const uint32_t b = caseTable[planeFlagsFast(c0, c1, c2, static_cast<float>(base + 1u))];
                 nonKeep |= ((a & 7u) == 0u ? 0u : 1u) << axis;          // kept whole iff unsplit and not lo
                 nonKeep |= ((b & 7u) == 4u ? 0u : 1u) << (3 + axis);    // kept whole iff unsplit and lo
                 dropMask |= ((a & 7u) == 4u ? 1u : 0u) << axis;

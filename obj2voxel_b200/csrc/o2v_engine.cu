@@ -110,6 +110,11 @@ Engine::~Engine()
     if (hostCountersInit_ != nullptr) {
         cudaFreeHost(hostCountersInit_);
     }
+    for (void *p : staging_) {
+        if (p != nullptr) {
+            cudaFreeHost(p);
+        }
+    }
     for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_}) {
         if (ev != nullptr) {
             cudaEventDestroy(ev);
@@ -400,6 +405,27 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
     }
     return kErrOk;
+}
+
+void *Engine::pinnedStaging(int slot, size_t bytes)
+{
+    if (slot < 0 || slot > 1) {
+        return nullptr;
+    }
+    if (bytes > stagingBytes_[slot]) {
+        if (staging_[slot] != nullptr) {
+            cudaFreeHost(staging_[slot]);
+            staging_[slot] = nullptr;
+            stagingBytes_[slot] = 0;
+        }
+        if (cudaMallocHost(&staging_[slot], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            staging_[slot] = nullptr;
+            return nullptr;
+        }
+        stagingBytes_[slot] = bytes;
+    }
+    return staging_[slot];
 }
 
 int Engine::download(void *hostDst, cudaStream_t stream)

@@ -83,6 +83,9 @@ public:
     /// Copies the result of the last run to host memory (count * 16 bytes) on `stream` and synchronises it.
     int download(void *hostDst, cudaStream_t stream);
 
+    /// Engine-owned pinned host buffer `slot` (0 or 1) of at least `bytes` (grow-only); nullptr if pinning fails.
+    void *pinnedStaging(int slot, size_t bytes);
+
 private:
     Engine() = default;
     int fail(int code, const std::string &message);
@@ -93,6 +96,8 @@ private:
     std::string error_;
     unsigned long long voxelCount_ = 0;
 
+    void *staging_[2] = {nullptr, nullptr};  // pinned, for host sinks
+    size_t stagingBytes_[2] = {0, 0};
     RunCounters *hostCounters_ = nullptr;  // pinned
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
