@@ -436,11 +436,11 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
         std::lock_guard<std::mutex> lock{gEngineMutex};  // one job at a time per process-wide engine
         // the mesh staging buffers are kept per device across jobs (grow-only) like the engine's own buffers
         static std::unordered_map<int, std::unique_ptr<UploadedMesh>> uploads;
-        std::unique_ptr<UploadedMesh> &slot = uploads[engine->device()];
-        if (slot == nullptr) {
-            slot.reset(new UploadedMesh());
+        std::unique_ptr<UploadedMesh> &uploadSlot = uploads[engine->device()];
+        if (uploadSlot == nullptr) {
+            uploadSlot.reset(new UploadedMesh());
         }
-        UploadedMesh &uploaded = *slot;
+        UploadedMesh &uploaded = *uploadSlot;
         uploaded.texturePixels.clear();
         uploaded.textureViews.clear();
         if (!uploaded.upload(mesh, textures.data(), (uint32_t) textures.size(), stream, &error)) {
