@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -160,7 +161,7 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     memcpy(out->transform, in.transform, sizeof out->transform);
     out->kernel_launches = in.kernelLaunches;
     out->voxelize_launches = in.voxelizeLaunches;
-    out->light_tiles = in.counters.lightTiles;
+    out->light_tiles = in.counters.lightTiles + in.counters.bigLightTiles;
     out->heavy_tiles = in.counters.heavyTiles;
     out->survivors = in.counters.survivors;
     out->ms_clip = in.msClip;
@@ -432,6 +433,10 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     }
 
     RunStats stats;
+    const auto tJob = std::chrono::steady_clock::now();
+    auto msSince = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     {
         std::lock_guard<std::mutex> lock{gEngineMutex};  // one job at a time per process-wide engine
         // the mesh staging buffers are kept per device across jobs (grow-only) like the engine's own buffers
@@ -447,8 +452,13 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, error);
             return OBJ2VOXEL_ERR_DEVICE;
         }
+        cudaStreamSynchronize(stream);
+        const double msUpload = msSince(tJob);
+        const auto tRun = std::chrono::steady_clock::now();
         const int rc = engine->voxelize(uploaded.view, uploaded.textureViews.data(),
                                         (uint32_t) uploaded.textureViews.size(), params, stream, &stats);
+        const double msRun = msSince(tRun);
+        const auto tSink = std::chrono::steady_clock::now();
         if (rc != 0) {
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed on the device: " + engine->lastError());
             return OBJ2VOXEL_ERR_DEVICE;
@@ -507,6 +517,10 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed because of IO error");
             return OBJ2VOXEL_ERR_IO_ERROR_DURING_VOXEL_WRITE;
         }
+        char timing[160];
+        snprintf(timing, sizeof timing, "timing: upload %.2f ms, device run %.2f ms (kernels %.2f), download+sink %.2f ms",
+                 msUpload, msRun, stats.msTotal, msSince(tSink));
+        logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, timing);
     }
 
     logMessage(OBJ2VOXEL_LOG_LEVEL_INFO,

@@ -214,7 +214,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         !activeTiles_.ensure((size_t) tileTotal * 4) || !allTiles_.ensure((size_t) tileTotal * 4) ||
         !longTiles_.ensure((size_t) tileTotal * 4) ||
         !tileCand_.ensure((size_t) tileTotal * 4) ||
-        !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
+        !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) ||
+        !bigLightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
     }
     O2V_CUDA(cudaMemsetAsync(tileCount_.as<void>(), 0, (size_t) tileTotal * 4, stream));
@@ -229,7 +230,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
                         &dCounters->pairs, stream);
     launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
                              allTiles_.as<uint32_t>(), longTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(),
-                             lightTiles_.as<LightTile>(), dCounters, stream);
+                             lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(), dCounters, stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -302,6 +303,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     args.counters = dCounters;
     args.lightTiles = lightTiles_.as<LightTile>();
     args.lightCount = (uint32_t) hostCounters_->lightTiles;
+    args.bigLightTiles = bigLightTiles_.as<LightTile>();
+    args.bigLightCount = (uint32_t) hostCounters_->bigLightTiles;
     args.variant = params.variant < 0 ? 0 : params.variant;
     args.prefilter = params.prefilter;
 
@@ -319,7 +322,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     // by it and the exact count stays on the device (no host round trip between the stages).
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
     const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 12ull <= (8ull << 30);
-    bool sparseActive = args.lightCount != 0;
+    bool sparseActive = args.lightCount != 0 || args.bigLightCount != 0;
     if (sparseActive) {
         O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
         launchSparseSurvivors(args, false, stream);
@@ -360,7 +363,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (sparseActive ? 3 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (sparseActive ? 4 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));

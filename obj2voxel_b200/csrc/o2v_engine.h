@@ -103,7 +103,7 @@ private:
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
     cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr;
 
-    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_,
+    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, entries_, weights_, contribUvs_;

@@ -375,13 +375,15 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
                                          const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
                                          uint32_t *__restrict__ allTiles, uint32_t *__restrict__ longTiles,
                                          uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
-                                         RunCounters *counters)
+                                         LightTile *__restrict__ bigLightTiles, RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
     const uint32_t candidates = count != 0 ? tileCandidates[i] : 0u;
-    const bool light = count != 0 && candidates <= kLightMaxCandidates;
-    const bool heavy = count != 0 && !light;
+    const bool sparse = count != 0 && candidates <= kLightMaxCandidates;
+    const bool light = sparse && candidates <= kWarpFoldMax;
+    const bool bigLight = sparse && !light;
+    const bool heavy = count != 0 && !sparse;
     const int lane = threadIdx.x & 31;
     const unsigned int below = (1u << lane) - 1u;
 
@@ -399,6 +401,22 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
             d.leafCount = count;
             d.candidates = candidates;
             lightTiles[base + __popc(lightBallot & below)] = d;
+        }
+    }
+    const unsigned int bigBallot = __ballot_sync(0xffffffffu, bigLight);
+    if (bigBallot != 0) {
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(&counters->bigLightTiles, (unsigned long long) __popc(bigBallot));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (bigLight) {
+            LightTile d;
+            d.tile = i;
+            d.listStart = tileStart[i];
+            d.leafCount = count;
+            d.candidates = candidates;
+            bigLightTiles[base + __popc(bigBallot & below)] = d;
         }
     }
     const unsigned int heavyBallot = __ballot_sync(0xffffffffu, heavy);
@@ -423,7 +441,7 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
             longTiles[base + __popc(longBallot & below)] = i;
         }
     }
-    const unsigned int anyBallot = lightBallot | heavyBallot;
+    const unsigned int anyBallot = lightBallot | bigBallot | heavyBallot;
     if (anyBallot != 0) {
         unsigned long long base = 0;
         if (lane == 0) {
@@ -773,14 +791,15 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, RunCounters *counters, cudaStream_t stream)
+                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
+                              cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
     compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
                                                                           tileTotal, allTiles, longTiles, heavyTiles,
-                                                                          lightTiles, counters);
+                                                                          lightTiles, bigLightTiles, counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,

@@ -17,7 +17,8 @@ namespace o2v {
 constexpr uint32_t kTileEdge = 8;  // voxels per tile edge (sample space); 8^3 = 512 voxels = one thread block
 constexpr uint32_t kTileVoxels = kTileEdge * kTileEdge * kTileEdge;
 constexpr uint32_t kLeafBatch = 32;  // leaves staged in shared memory per round
-constexpr uint32_t kLightMaxCandidates = 512;  // tiles up to this many candidate voxels take the staged sparse path
+constexpr uint32_t kWarpFoldMax = 512;  // light tiles up to this many candidates are folded by a thread or a warp, above by a block
+constexpr uint32_t kLightMaxCandidates = 4096;  // tiles up to this many candidate voxels take the staged sparse path
 
 /// Input mesh, model space.  All pointers are device pointers.
 struct MeshView {
@@ -65,6 +66,7 @@ struct RunCounters {
     unsigned long long pairs;           // total (leaf, tile) pairs
     unsigned long long candidateVoxels; // sum of leaf AABB volumes inside the slab (upper bound on contributions)
     unsigned long long activeTiles;     // light + heavy
+    unsigned long long bigLightTiles;   // light tiles with more than kWarpFoldMax candidates (block-level fold)
     unsigned long long lightTiles;      // tiles on the staged sparse path (<= kLightMaxCandidates candidate voxels)
     unsigned long long heavyTiles;      // tiles voxelized block-per-tile
     unsigned long long longTiles;       // tiles with more than 32 leaves (block-level list sort)
@@ -119,7 +121,8 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 /// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, RunCounters *counters, cudaStream_t stream);
+                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
+                              cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
@@ -150,8 +153,10 @@ struct VoxelizeArgs {
     VoxelRecord *out;
     unsigned long long outCapacity;
     RunCounters *counters;
-    const LightTile *lightTiles;
+    const LightTile *lightTiles;     // <= kWarpFoldMax candidates
     uint32_t lightCount;
+    const LightTile *bigLightTiles;  // kWarpFoldMax < candidates <= kLightMaxCandidates
+    uint32_t bigLightCount;
     SparseView sparse;
     int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)

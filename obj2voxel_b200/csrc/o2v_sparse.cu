@@ -22,6 +22,7 @@ namespace {
 constexpr int kPairThreads = 128;
 constexpr int kClipThreads = 128;
 constexpr int kFoldWarpsPerBlock = 4;
+constexpr int kBlockFoldThreads = 128;   // above that (up to kLightMaxCandidates) one block folds the tile
 constexpr uint32_t kTinyFoldMax = 24;  // survivors per tile up to which one thread folds the whole tile
 constexpr int kTinyFoldThreads = 128;
 
@@ -163,12 +164,12 @@ sparseClipKernel(const VoxelizeArgs args)
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 4: warp per tile -> ordered fold + output
 
-/// Per-warp scratch, carved out of dynamic shared memory: tri | sortKey | cW [| cU | cV], kLightMaxCandidates entries each.
+/// Per-warp scratch, carved out of dynamic shared memory: tri | sortKey | cW [| cU | cV], kWarpFoldMax entries each.
 /// Sort key = (voxel key << 18) | (list slot << 9) | contribution slot — 9 bits each.
 template <bool UV>
 struct FoldWarpLayout {
     static constexpr uint32_t kArrays = UV ? 5u : 3u;
-    static constexpr size_t kBytesPerWarp = (size_t) kArrays * kLightMaxCandidates * 4u;
+    static constexpr size_t kBytesPerWarp = (size_t) kArrays * kWarpFoldMax * 4u;
 };
 
 template <bool UV>
@@ -183,10 +184,10 @@ sparseFoldKernel(const VoxelizeArgs args)
     {
         uint32_t *warpBase = reinterpret_cast<uint32_t *>(foldSmem + (threadIdx.x >> 5) * FoldWarpLayout<UV>::kBytesPerWarp);
         sh.tri = warpBase;
-        sh.sortKey = warpBase + kLightMaxCandidates;
-        sh.cW = reinterpret_cast<float *>(warpBase + 2 * kLightMaxCandidates);
-        sh.cU = UV ? sh.cW + kLightMaxCandidates : sh.cW;
-        sh.cV = UV ? sh.cW + 2 * kLightMaxCandidates : sh.cW;
+        sh.sortKey = warpBase + kWarpFoldMax;
+        sh.cW = reinterpret_cast<float *>(warpBase + 2 * kWarpFoldMax);
+        sh.cU = UV ? sh.cW + kWarpFoldMax : sh.cW;
+        sh.cV = UV ? sh.cW + 2 * kWarpFoldMax : sh.cW;
     }
     const SparseView &sp = args.sparse;
     const uint32_t lane = threadIdx.x & 31u;
@@ -532,6 +533,185 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// stage 4, large tiles (kWarpFoldMax < survivors <= kLightMaxCandidates): block per tile.  Same algorithm with 64-bit sort
+// keys in shared memory ((voxel key << 40) | (list slot << 20) | entry index); payloads are read back from HBM/L2 by index.
+
+template <bool UV>
+__global__ void __launch_bounds__(kBlockFoldThreads)
+sparseBlockFoldKernel(const VoxelizeArgs args)
+{
+    __shared__ unsigned long long keys[kLightMaxCandidates];
+    __shared__ uint32_t keptShared, runsShared, emittedShared;
+    __shared__ unsigned long long outBaseShared;
+    const SparseView &sp = args.sparse;
+    const bool blend = args.grid.strategy == kBlend;
+    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t groupShift = downscale ? 43u : 40u;
+    unsigned long long contributions = 0;
+
+    for (uint32_t t = blockIdx.x; t < args.bigLightCount; t += gridDim.x) {
+        const LightTile d = args.bigLightTiles[t];
+        const uint32_t begin = sp.pairOffset[d.listStart];
+        const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;  // <= d.candidates <= 4096
+        if (count == 0) {
+            continue;  // block-uniform
+        }
+        uint32_t origin[3];
+        tileOriginOf(args.grid, d.tile, origin);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            keptShared = 0;
+            runsShared = 0;
+            emittedShared = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < count; e += blockDim.x) {
+            if (sp.weights[begin + e] != 0.0f) {
+                const uint2 entry = sp.entries[begin + e];
+                const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
+                const uint32_t pos = atomicAdd(&keptShared, 1u);  // order is irrelevant before the sort
+                keys[pos] = ((unsigned long long) voxelKey(x, y, z) << 40) |
+                            ((unsigned long long) (entry.x - d.listStart) << 20) | e;
+            }
+        }
+        __syncthreads();
+        const uint32_t kept = keptShared;
+        if (kept == 0) {
+            continue;
+        }
+        uint32_t padded = 1;
+        while (padded < kept) {
+            padded <<= 1;
+        }
+        for (uint32_t i = kept + threadIdx.x; i < padded; i += blockDim.x) {
+            keys[i] = ~0ull;
+        }
+        __syncthreads();
+        for (uint32_t k = 2; k <= padded; k <<= 1) {  // ascending-only bitonic network
+            for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+                const uint32_t l = i ^ (k - 1);
+                if (l > i) {
+                    const unsigned long long a = keys[i], b = keys[l];
+                    if (a > b) {
+                        keys[i] = b;
+                        keys[l] = a;
+                    }
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+                for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x) {
+                    const uint32_t l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long a = keys[i], b = keys[l];
+                        if (a > b) {
+                            keys[i] = b;
+                            keys[l] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // reserve the output range: one atomic per tile
+        uint32_t myRuns = 0;
+        for (uint32_t p = threadIdx.x; p < kept; p += blockDim.x) {
+            myRuns += (p == 0 || (keys[p] >> groupShift) != (keys[p - 1] >> groupShift)) ? 1u : 0u;
+        }
+        if (myRuns != 0) {
+            atomicAdd(&runsShared, myRuns);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            outBaseShared = atomicAdd(&args.counters->voxels, (unsigned long long) runsShared);
+        }
+        __syncthreads();
+        for (uint32_t p = threadIdx.x; p < kept; p += blockDim.x) {
+            if (!(p == 0 || (keys[p] >> groupShift) != (keys[p - 1] >> groupShift))) {
+                continue;
+            }
+            const unsigned long long group = keys[p] >> groupShift;
+            uint32_t currentVoxel = (uint32_t) (keys[p] >> 40) & 511u;
+            VoxelAccumulator child;
+            resetAccumulator(child);
+            WeightedColor parent;
+            parent.w = parent.r = parent.g = parent.b = 0.0f;
+            bool hasParent = false;
+            for (uint32_t q = p; q < kept; ++q) {
+                const unsigned long long key = keys[q];
+                if ((key >> groupShift) != group) {
+                    break;
+                }
+                const uint32_t vk = (uint32_t) (key >> 40) & 511u, listSlot = (uint32_t) (key >> 20) & 0xfffffu,
+                               e = (uint32_t) key & 0xfffffu;
+                if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
+                    flushPartial(child, args);
+                    contributions += child.contributions;
+                    if (!hasParent) {
+                        hasParent = true;
+                        parent = child.voxel;
+                    }
+                    else {
+                        combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                    }
+                    resetAccumulator(child);
+                    currentVoxel = vk;
+                }
+                const uint32_t tri = args.leaves[args.work.tileList[d.listStart + listSlot]].tri;
+                if (child.hasPartial && child.partialTri != tri) {
+                    flushPartial(child, args);
+                }
+                float u = 0.0f, v = 0.0f;
+                if (UV) {
+                    const float2 uv = sp.uvs[begin + e];
+                    u = uv.x;
+                    v = uv.y;
+                }
+                addContribution(child, tri, sp.weights[begin + e], u, v);
+            }
+            flushPartial(child, args);
+            contributions += child.contributions;
+            WeightedColor result = child.voxel;
+            const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
+            int32_t ox, oy, oz;
+            if (downscale) {
+                if (hasParent) {
+                    combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                    result = parent;
+                }
+                ox = (int32_t) (origin[0] / 2 + (pk & 3u));
+                oy = (int32_t) (origin[1] / 2 + ((pk >> 2) & 3u));
+                oz = (int32_t) (origin[2] / 2 + ((pk >> 4) & 3u));
+            }
+            else {
+                ox = (int32_t) (origin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
+                oy = (int32_t) (origin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
+                oz = (int32_t) (origin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
+            }
+            const unsigned long long index = outBaseShared + atomicAdd(&emittedShared, 1u);
+            if (index < args.outCapacity) {
+                VoxelRecord rec;
+                rec.x = ox;
+                rec.y = oy;
+                rec.z = oz;
+                rec.argb = quantizeArgb(result.r, result.g, result.b);
+                *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+            }
+            else {
+                atomicAdd(&args.counters->outputOverflow, 1ull);
+            }
+        }
+    }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        contributions += __shfl_xor_sync(0xffffffffu, contributions, o);
+    }
+    if ((threadIdx.x & 31) == 0 && contributions != 0) {
+        atomicAdd(&args.counters->contributions, contributions);
+    }
+}
+
 template <typename Kernel>
 unsigned persistentBlocks(Kernel kernel, int threads, int smCount, unsigned long long needed, size_t dynamicSmem = 0)
 {
@@ -574,9 +754,6 @@ void launchSparseClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 
 void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
 {
-    if (args.lightCount == 0) {
-        return;
-    }
     {
         const unsigned long long tinyBlocks = (args.lightCount + kTinyFoldThreads - 1) / kTinyFoldThreads;
         if (args.mesh.uvs != nullptr) {
@@ -588,6 +765,21 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
                                                            tinyBlocks),
                                           kTinyFoldThreads, 0, stream>>>(args);
         }
+    }
+    if (args.bigLightCount != 0) {
+        if (args.mesh.uvs != nullptr) {
+            sparseBlockFoldKernel<true><<<persistentBlocks(sparseBlockFoldKernel<true>, kBlockFoldThreads, smCount,
+                                                           args.bigLightCount),
+                                          kBlockFoldThreads, 0, stream>>>(args);
+        }
+        else {
+            sparseBlockFoldKernel<false><<<persistentBlocks(sparseBlockFoldKernel<false>, kBlockFoldThreads, smCount,
+                                                            args.bigLightCount),
+                                           kBlockFoldThreads, 0, stream>>>(args);
+        }
+    }
+    if (args.lightCount == 0) {
+        return;
     }
     const int threads = kFoldWarpsPerBlock * 32;
     const unsigned long long needed = (args.lightCount + kFoldWarpsPerBlock - 1) / kFoldWarpsPerBlock;

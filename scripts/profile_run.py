@@ -21,8 +21,9 @@ else:
     verts = meshes.random_triangles_torch(cfg["n"], cfg["extent"], seed=1, device=dev)
     uvs = meshes.random_uvs_torch(cfg["n"], seed=2, device=dev) if cfg.get("textured") else None
 textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(dev), o2v.UV_WRAP)] if uvs is not None else []
+slab = tuple(int(x) for x in os.environ["O2V_SLAB"].split(",")) if "O2V_SLAB" in os.environ else None
 params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
-                         bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")))
+                         bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")), slab=slab)
 for i in range(steps):
     st = eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
     torch.cuda.synchronize()
