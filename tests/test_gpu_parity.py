@@ -111,6 +111,22 @@ def test_colored_triangles_voxelize_white_like_the_reference():
     inst.free()
 
 
+def test_reference_test_program_passes_against_this_library():
+    """The reference's own test/main.cpp + testutil.hpp, compiled unmodified and linked against libobj2voxel_b200.so
+    (oracle/Makefile target _ref/obj2voxel-test-b200; built where /root/reference exists, the binary travels)."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "obj2voxel-test-b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/obj2voxel-test-b200 not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "All tests passed" in out.stdout
+
+
 # ---- golden fixtures from the unmodified reference -----------------------------------------------------------------
 
 @pytest.mark.parametrize("name", EXACT)
