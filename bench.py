@@ -423,7 +423,8 @@ def run_ours(args, cfg, workload):
             "ms_setup_rank0": float(np.mean(setup_ms)), "ms_voxelize_rank0": k_ms, "ms_clip_kernel_rank0": c_ms,
             "hbm_write_gbs": 16 * stats["voxels"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
             "roofline": {"bound": "hbm", "kernel": "sparseClipKernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(workload),
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (profiled_traffic(workload) // world) if profiled_traffic(workload) else None,
                          "peak_source": peak_source,
                          "note": "algorithmic bytes = 16 B x voxels + %d B x triangles per launch / CUDA-event duration of "
                                  "the clip kernel; the kernel is bound by FP32/ALU issue of the exact clip (ncu: issue "

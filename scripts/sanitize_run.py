@@ -1,0 +1,22 @@
+"""Small mixed workload for compute-sanitizer (memcheck / racecheck / initcheck): touches every kernel path."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import obj2voxel_b200 as o2v
+from obj2voxel_b200 import meshes
+eng = o2v.Engine(0)
+cases = [
+    (meshes.unit_cube(), dict(resolution=64), {}),                                             # aligned, big leaves
+    (meshes.random_triangles(3000, 0.03), dict(resolution=128, strategy=1, bounds=meshes.UNIT_BOUNDS), {}),
+    (meshes.random_triangles(3000, 0.03), dict(resolution=64, supersampling=2, strategy=1, bounds=meshes.UNIT_BOUNDS), {}),
+    (meshes.random_triangles(40, 0.4, seed=5), dict(resolution=128, strategy=1), {}),           # deep subdivision
+    (meshes.lumpy_sphere(40, 41), dict(resolution=128), {}),                                    # block fold tiles
+    (meshes.random_triangles(6000, 0.02, seed=23) * np.float32(0.1), dict(resolution=32, strategy=1, bounds=[0, 0, 0, 1, 1, 1]), {}),  # heavy tiles, long lists
+    (meshes.random_triangles(2000, 0.03), dict(resolution=128, strategy=1, bounds=meshes.UNIT_BOUNDS),
+     dict(uvs=meshes.random_uvs(2000) * 3 - 1, textures=[(meshes.random_texture(32, 16, 3), 1)])),
+]
+for verts, kw, extra in cases:
+    v, st = eng.voxelize_host(verts, o2v.make_params(**kw), **extra)
+    print(len(v), st["light_tiles"], st["heavy_tiles"], flush=True)
+eng.close()
+print("sanitize run done")
