@@ -254,6 +254,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
         !pairTile_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
         !pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
+        !pairMask_.ensure((size_t) (pairTotal + 1) * 8) || !pairBox_.ensure((size_t) (pairTotal + 1) * 4) ||
         !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
     }
@@ -315,13 +316,16 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     sparse.pairCount = (uint32_t) pairTotal;
     sparse.pairSurvivors = pairSurvivors_.as<uint32_t>();
     sparse.pairOffset = pairOffset_.as<uint32_t>();
+    sparse.pairMask = pairMask_.as<unsigned long long>();
+    sparse.pairBox = pairBox_.as<uint32_t>();
     sparse.entries = nullptr;
     sparse.weights = nullptr;
+    sparse.tris = nullptr;
     sparse.uvs = nullptr;
     // Survivors <= candidate voxels (known from the first read-back).  When that bound is affordable the queue is sized
     // by it and the exact count stays on the device (no host round trip between the stages).
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
-    const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 12ull <= (8ull << 30);
+    const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 16ull <= (8ull << 30);
     bool sparseActive = args.lightCount != 0 || args.bigLightCount != 0;
     if (sparseActive) {
         O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
@@ -342,11 +346,13 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         entryCapacity = std::max<unsigned long long>(entryCapacity, 1);
         if (!entries_.ensure((size_t) entryCapacity * sizeof(uint2)) ||
             !weights_.ensure((size_t) entryCapacity * sizeof(float)) ||
+            !contribTris_.ensure((size_t) entryCapacity * sizeof(uint32_t)) ||
             (hasUv && !contribUvs_.ensure((size_t) entryCapacity * sizeof(float2)))) {
             return fail(kErrOutOfMemory, "device allocation failed (sparse path buffers)");
         }
         sparse.entries = entries_.as<uint2>();
         sparse.weights = weights_.as<float>();
+        sparse.tris = contribTris_.as<uint32_t>();
         sparse.uvs = hasUv ? contribUvs_.as<float2>() : nullptr;
         launchSparseSurvivors(args, true, stream);
         ++st.kernelLaunches;

@@ -136,9 +136,12 @@ struct SparseView {
     const uint32_t *tileCandidates;  // per tile: candidate voxel count (classifies the tile)
     uint32_t pairCount;
     uint32_t *pairSurvivors;         // per pair (+1): SAT survivors, scanned into pairOffset
+    unsigned long long *pairMask;    // per pair with <= 64 candidates: survivor bit per candidate (z, y, x order) ...
+    uint32_t *pairBox;               // ... and its tile-local AABB, so the write pass does not redo the SAT
     uint32_t *pairOffset;            // pairCount + 1 entries
     uint2 *entries;                  // per survivor: {pair index, tile-local voxel}
     float *weights;                  // per survivor: clip weight (0 = no contribution)
+    uint32_t *tris;                  // per survivor: input triangle index (fold order / colour lookup)
     float2 *uvs;                     // per survivor (textured meshes only)
 };
 

@@ -37,6 +37,9 @@ __device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile
 // ---------------------------------------------------------------------------------------------------------------------
 // stages 1 + 2: thread per (leaf, tile) pair
 
+/// Pass 1 (WRITE = false) evaluates the SAT for every candidate voxel of the pair, counts the survivors and, when the pair
+/// has at most 64 candidates (always, for triangles up to 4 voxels across), keeps them as a bit mask; pass 2 (WRITE = true)
+/// runs after the scan and only expands the mask into survivor entries (pairs with more candidates redo the SAT).
 template <bool WRITE>
 __global__ void __launch_bounds__(kPairThreads)
 sparseSurvivorsKernel(const VoxelizeArgs args)
@@ -47,25 +50,55 @@ sparseSurvivorsKernel(const VoxelizeArgs args)
         const uint32_t tile = sp.pairTile[pair];
         uint32_t count = 0;
         if (sp.tileCandidates[tile] <= kLightMaxCandidates) {
-            uint32_t origin[3];
-            tileOriginOf(args.grid, tile, origin);
+            uint32_t box;
             LeafStage s;
-            stageLeaf<false>(s, args, args.work.tileList[pair], origin);
-            const uint32_t box = s.box;
+            bool masked = false;
+            unsigned long long mask = 0;
+            if (WRITE) {
+                box = sp.pairBox[pair];
+                masked = (box >> 31) != 0;
+                if (masked) {
+                    mask = sp.pairMask[pair];
+                }
+            }
+            if (!WRITE || !masked) {
+                uint32_t origin[3];
+                tileOriginOf(args.grid, tile, origin);
+                stageLeaf<false>(s, args, args.work.tileList[pair], origin);
+                box = s.box;
+            }
             const uint32_t x0 = box & 15u, y0 = (box >> 4) & 15u, z0 = (box >> 8) & 15u;
             const uint32_t x1 = (box >> 12) & 15u, y1 = (box >> 16) & 15u, z1 = (box >> 20) & 15u;
+            const bool small = (x1 - x0) * (y1 - y0) * (z1 - z0) <= 64u;
             uint32_t offset = WRITE ? sp.pairOffset[pair] : 0u;
+            uint32_t bit = 0;
             for (uint32_t z = z0; z < z1; ++z) {
                 for (uint32_t y = y0; y < y1; ++y) {
-                    for (uint32_t x = x0; x < x1; ++x) {
-                        if (!args.prefilter || prefilterPass(s, (float) x, (float) y, (float) z)) {
+                    for (uint32_t x = x0; x < x1; ++x, ++bit) {
+                        bool pass;
+                        if (WRITE && masked) {
+                            pass = ((mask >> bit) & 1ull) != 0;
+                        }
+                        else {
+                            pass = !args.prefilter || prefilterPass(s, (float) x, (float) y, (float) z);
+                        }
+                        if (pass) {
                             if (WRITE) {
                                 sp.entries[offset] = make_uint2(pair, x | (y << 3) | (z << 6));
                                 ++offset;
                             }
+                            else if (small) {
+                                mask |= 1ull << bit;
+                            }
                             ++count;
                         }
                     }
+                }
+            }
+            if (!WRITE) {
+                sp.pairBox[pair] = (box & 0x00ffffffu) | (small ? 0x80000000u : 0u);
+                if (small) {
+                    sp.pairMask[pair] = mask;
                 }
             }
         }
@@ -108,6 +141,7 @@ sparseClipKernel(const VoxelizeArgs args)
     clipper.r.weight = clipper.r.u = clipper.r.v = 0.0f;
     bool hasEntry = false;
     unsigned long long current = 0;
+    uint32_t currentTri = 0;
 
     for (;;) {
         const unsigned int idle = __ballot_sync(full, clipper.done);
@@ -119,6 +153,7 @@ sparseClipKernel(const VoxelizeArgs args)
             if (clipper.done) {
                 if (hasEntry) {
                     sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;  // 0 = "no contribution"
+                    sp.tris[current] = currentTri;
                     if (UV) {
                         sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
                     }
@@ -147,6 +182,7 @@ sparseClipKernel(const VoxelizeArgs args)
                                   origin[2] + ((entry.y >> 6) & 7u), c.z);
                     hasEntry = true;
                     current = e;
+                    currentTri = __float_as_uint(c.y);
                 }
             }
             cursor += __popc(idle);
@@ -155,6 +191,7 @@ sparseClipKernel(const VoxelizeArgs args)
     }
     if (hasEntry) {
         sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;
+        sp.tris[current] = currentTri;
         if (UV) {
             sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
         }
@@ -209,10 +246,6 @@ sparseFoldKernel(const VoxelizeArgs args)
         uint32_t origin[3];
         tileOriginOf(args.grid, d.tile, origin);
 
-        for (uint32_t slot = lane; slot < d.leafCount; slot += 32) {
-            const uint32_t leafIndex = args.work.tileList[d.listStart + slot];
-            sh.tri[slot] = args.leaves[leafIndex].tri;
-        }
 
         // ---- gather the tile's contributions (weight != 0), compacted in list order ----
         uint32_t kept = 0;
@@ -231,6 +264,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                 const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
                 sh.sortKey[pos] = (voxelKey(x, y, z) << 18) | ((entry.x - d.listStart) << 9) | pos;
                 sh.cW[pos] = w;
+                sh.tri[pos] = sp.tris[begin + e];
                 if (UV) {
                     const float2 uv = sp.uvs[begin + e];
                     sh.cU[pos] = uv.x;
@@ -339,7 +373,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                         resetAccumulator(child);
                         currentVoxel = vk;
                     }
-                    const uint32_t tri = sh.tri[listSlot];
+                    const uint32_t tri = sh.tri[slot];
                     if (child.hasPartial && child.partialTri != tri) {
                         flushPartial(child, args);  // the previous triangle's uv-buffer entry is complete
                     }
@@ -478,7 +512,7 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
                     resetAccumulator(child);
                     currentVoxel = vk;
                 }
-                const uint32_t tri = args.leaves[args.work.tileList[listStart + listSlot]].tri;
+                const uint32_t tri = sp.tris[begin + e];
                 if (child.hasPartial && child.partialTri != tri) {
                     flushPartial(child, args);
                 }
@@ -658,7 +692,7 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
                     resetAccumulator(child);
                     currentVoxel = vk;
                 }
-                const uint32_t tri = args.leaves[args.work.tileList[d.listStart + listSlot]].tri;
+                const uint32_t tri = sp.tris[begin + e];
                 if (child.hasPartial && child.partialTri != tri) {
                     flushPartial(child, args);
                 }
