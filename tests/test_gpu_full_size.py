@@ -1,0 +1,50 @@
+"""GPU (-m gpu): BASELINE.json's full-size configurations against checksums of the reference itself
+(tests/golden/full_size_checksums.json, produced by tests/golden/make_full_size_checksums.py from oracle/_ref):
+voxel count and CRC32 of the (x, y, z)-sorted Voxel32 list must be identical — bit-exact occupancy, indices and ARGB8 at
+the sizes the benchmark is quoted on."""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+import obj2voxel_b200 as o2v
+from obj2voxel_b200 import meshes
+
+pytestmark = pytest.mark.gpu
+
+PATH = os.path.join(GOLDEN_DIR, "full_size_checksums.json")
+CHECKSUMS = json.load(open(PATH)) if os.path.exists(PATH) else {}
+
+
+@pytest.mark.parametrize("name", sorted(CHECKSUMS))
+def test_full_size_config_matches_reference_checksum(engine, name):
+    import torch
+
+    import bench
+
+    ref = CHECKSUMS[name]
+    cfg = bench.workload_spec(name)
+    dev = torch.device("cuda", 0)
+    if cfg["kind"] == "sphere":
+        verts = torch.from_numpy(meshes.lumpy_sphere()).to(dev)
+        uvs = None
+    else:
+        verts = meshes.random_triangles_torch(cfg["n"], cfg["extent"], seed=1, device=dev)
+        uvs = meshes.random_uvs_torch(cfg["n"], seed=2, device=dev) if cfg.get("textured") else None
+    assert verts.shape[0] == ref["triangles"]
+    textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(dev), o2v.UV_WRAP)] if uvs is not None else []
+    params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"],
+                             strategy=cfg["strategy"], bounds=cfg["bounds"])
+    engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
+    del verts, uvs
+    assert engine.result_count() == ref["voxels"]
+    v = engine.result_tensor().to(torch.int64)
+    key = (v[:, 0] << 42) | (v[:, 1] << 21) | v[:, 2]
+    order = torch.argsort(key)
+    sorted_voxels = engine.result_tensor()[order].cpu().numpy().view(np.uint32)
+    del v, key, order
+    torch.cuda.empty_cache()
+    assert zlib.crc32(np.ascontiguousarray(sorted_voxels).tobytes()) == ref["crc32"]
