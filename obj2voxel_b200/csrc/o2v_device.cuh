@@ -7,7 +7,9 @@
 namespace o2v {
 namespace {
 
-constexpr float kPrefilterMargin = 0.0625f;  // voxels; must exceed every rounding / planarity slack of the exact clip
+// Inflation of the voxel box in the conservative SAT, in voxels.  It must exceed every slack of the exact clip: the
+// planarity epsilon (2^-16) plus the rounding of intersection points (two roundings of a coordinate < 8192: <= 2e-3).
+constexpr float kPrefilterMargin = 0.015625f;
 
 struct LeafStage {
     float v[9];

@@ -134,6 +134,7 @@ sparseClipKernel(const VoxelizeArgs args)
     __shared__ uint8_t caseTable[64];
     fillClipCaseTable(caseTable);
     __syncthreads();
+    const int refillThreshold = args.variant > 0 ? args.variant : (int) kRefillThreshold;
     WarpClipper<UV> clipper;
     ClipStack<UV> stack;
     clipper.idle();
@@ -149,7 +150,7 @@ sparseClipKernel(const VoxelizeArgs args)
         if (idle == full && !moreWork) {
             break;
         }
-        if (moreWork && (__popc(idle) >= (int) kRefillThreshold || idle == full)) {
+        if (moreWork && (__popc(idle) >= refillThreshold || idle == full)) {
             if (clipper.done) {
                 if (hasEntry) {
                     sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;  // 0 = "no contribution"
