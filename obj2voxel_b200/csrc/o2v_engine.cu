@@ -319,8 +319,6 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     sparse.pairMask = pairMask_.as<unsigned long long>();
     sparse.pairBox = pairBox_.as<uint32_t>();
     sparse.entries = nullptr;
-    sparse.weights = nullptr;
-    sparse.tris = nullptr;
     sparse.uvs = nullptr;
     // Survivors <= candidate voxels (known from the first read-back).  When that bound is affordable the queue is sized
     // by it and the exact count stays on the device (no host round trip between the stages).
@@ -344,15 +342,11 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
             }
         }
         entryCapacity = std::max<unsigned long long>(entryCapacity, 1);
-        if (!entries_.ensure((size_t) entryCapacity * sizeof(uint2)) ||
-            !weights_.ensure((size_t) entryCapacity * sizeof(float)) ||
-            !contribTris_.ensure((size_t) entryCapacity * sizeof(uint32_t)) ||
+        if (!entries_.ensure((size_t) entryCapacity * sizeof(uint4)) ||
             (hasUv && !contribUvs_.ensure((size_t) entryCapacity * sizeof(float2)))) {
             return fail(kErrOutOfMemory, "device allocation failed (sparse path buffers)");
         }
-        sparse.entries = entries_.as<uint2>();
-        sparse.weights = weights_.as<float>();
-        sparse.tris = contribTris_.as<uint32_t>();
+        sparse.entries = entries_.as<uint4>();
         sparse.uvs = hasUv ? contribUvs_.as<float2>() : nullptr;
         launchSparseSurvivors(args, true, stream);
         ++st.kernelLaunches;

@@ -106,7 +106,7 @@ private:
     DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
-    DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, weights_, contribTris_, contribUvs_;
+    DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

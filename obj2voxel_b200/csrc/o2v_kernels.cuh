@@ -139,9 +139,8 @@ struct SparseView {
     unsigned long long *pairMask;    // per pair with <= 64 candidates: survivor bit per candidate (z, y, x order) ...
     uint32_t *pairBox;               // ... and its tile-local AABB, so the write pass does not redo the SAT
     uint32_t *pairOffset;            // pairCount + 1 entries
-    uint2 *entries;                  // per survivor: {pair index, tile-local voxel}
-    float *weights;                  // per survivor: clip weight (0 = no contribution)
-    uint32_t *tris;                  // per survivor: input triangle index (fold order / colour lookup)
+    uint4 *entries;                  // per survivor, one 16-byte record: {pair index, tile-local voxel} written by the
+                                     // survivors pass, {clip weight bits (0 = no contribution), triangle index} by the clip
     float2 *uvs;                     // per survivor (textured meshes only)
 };
 

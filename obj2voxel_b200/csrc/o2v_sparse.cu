@@ -84,7 +84,7 @@ sparseSurvivorsKernel(const VoxelizeArgs args)
                         }
                         if (pass) {
                             if (WRITE) {
-                                sp.entries[offset] = make_uint2(pair, x | (y << 3) | (z << 6));
+                                sp.entries[offset] = make_uint4(pair, x | (y << 3) | (z << 6), 0u, 0u);
                                 ++offset;
                             }
                             else if (small) {
@@ -153,8 +153,9 @@ sparseClipKernel(const VoxelizeArgs args)
         if (moreWork && (__popc(idle) >= refillThreshold || idle == full)) {
             if (clipper.done) {
                 if (hasEntry) {
-                    sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;  // 0 = "no contribution"
-                    sp.tris[current] = currentTri;
+                    // weight 0 = "no contribution" (area > 0, so a real contribution is never 0)
+                    reinterpret_cast<uint2 *>(sp.entries + current)[1] =
+                        make_uint2(__float_as_uint(clipper.r.pieces != 0 ? clipper.r.weight : 0.0f), currentTri);
                     if (UV) {
                         sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
                     }
@@ -162,7 +163,7 @@ sparseClipKernel(const VoxelizeArgs args)
                 }
                 const unsigned long long e = cursor + __popc(idle & below);
                 if (e < end) {
-                    const uint2 entry = sp.entries[e];
+                    const uint2 entry = reinterpret_cast<const uint2 *>(sp.entries + e)[0];
                     const uint32_t pair = entry.x;
                     const uint32_t leafIndex = __ldg(args.work.tileList + pair);
                     uint32_t origin[3];
@@ -191,8 +192,8 @@ sparseClipKernel(const VoxelizeArgs args)
         clipper.round(stack, caseTable);
     }
     if (hasEntry) {
-        sp.weights[current] = clipper.r.pieces != 0 ? clipper.r.weight : 0.0f;
-        sp.tris[current] = currentTri;
+        reinterpret_cast<uint2 *>(sp.entries + current)[1] =
+            make_uint2(__float_as_uint(clipper.r.pieces != 0 ? clipper.r.weight : 0.0f), currentTri);
         if (UV) {
             sp.uvs[current] = make_float2(clipper.r.u, clipper.r.v);
         }
@@ -252,12 +253,11 @@ sparseFoldKernel(const VoxelizeArgs args)
         uint32_t kept = 0;
         for (uint32_t base = 0; base < count; base += 32) {
             const uint32_t e = base + lane;
-            float w = 0.0f;
-            uint2 entry = make_uint2(0u, 0u);
+            uint4 entry = make_uint4(0u, 0u, 0u, 0u);
             if (e < count) {
-                w = sp.weights[begin + e];
                 entry = sp.entries[begin + e];
             }
+            const float w = __uint_as_float(entry.z);
             const bool keep = w != 0.0f;
             const uint32_t ballot = __ballot_sync(full, keep);
             if (keep) {
@@ -265,7 +265,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                 const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
                 sh.sortKey[pos] = (voxelKey(x, y, z) << 18) | ((entry.x - d.listStart) << 9) | pos;
                 sh.cW[pos] = w;
-                sh.tri[pos] = sp.tris[begin + e];
+                sh.tri[pos] = entry.w;
                 if (UV) {
                     const float2 uv = sp.uvs[begin + e];
                     sh.cU[pos] = uv.x;
@@ -456,8 +456,8 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
                 listStart = d.listStart;
                 tileOriginOf(args.grid, d.tile, origin);
                 for (uint32_t e = 0; e < count; ++e) {
-                    if (sp.weights[begin + e] != 0.0f) {
-                        const uint2 entry = sp.entries[begin + e];
+                    const uint4 entry = sp.entries[begin + e];
+                    if (__uint_as_float(entry.z) != 0.0f) {
                         const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
                         // insertion sort by (voxel key, list slot); e identifies the contribution
                         const uint32_t k = (voxelKey(x, y, z) << 18) | ((entry.x - listStart) << 9) | e;
@@ -513,7 +513,8 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
                     resetAccumulator(child);
                     currentVoxel = vk;
                 }
-                const uint32_t tri = sp.tris[begin + e];
+                const uint2 clipped = reinterpret_cast<const uint2 *>(sp.entries + begin + e)[1];  // {weight, triangle}
+                const uint32_t tri = clipped.y;
                 if (child.hasPartial && child.partialTri != tri) {
                     flushPartial(child, args);
                 }
@@ -523,7 +524,7 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
                     u = uv.x;
                     v = uv.y;
                 }
-                addContribution(child, tri, sp.weights[begin + e], u, v);
+                addContribution(child, tri, __uint_as_float(clipped.x), u, v);
             }
             flushPartial(child, args);
             contributions += child.contributions;
@@ -602,8 +603,8 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
         }
         __syncthreads();
         for (uint32_t e = threadIdx.x; e < count; e += blockDim.x) {
-            if (sp.weights[begin + e] != 0.0f) {
-                const uint2 entry = sp.entries[begin + e];
+            const uint4 entry = sp.entries[begin + e];
+            if (__uint_as_float(entry.z) != 0.0f) {
                 const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
                 const uint32_t pos = atomicAdd(&keptShared, 1u);  // order is irrelevant before the sort
                 keys[pos] = ((unsigned long long) voxelKey(x, y, z) << 40) |
@@ -693,7 +694,8 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
                     resetAccumulator(child);
                     currentVoxel = vk;
                 }
-                const uint32_t tri = sp.tris[begin + e];
+                const uint2 clipped = reinterpret_cast<const uint2 *>(sp.entries + begin + e)[1];  // {weight, triangle}
+                const uint32_t tri = clipped.y;
                 if (child.hasPartial && child.partialTri != tri) {
                     flushPartial(child, args);
                 }
@@ -703,7 +705,7 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
                     u = uv.x;
                     v = uv.y;
                 }
-                addContribution(child, tri, sp.weights[begin + e], u, v);
+                addContribution(child, tri, __uint_as_float(clipped.x), u, v);
             }
             flushPartial(child, args);
             contributions += child.contributions;
