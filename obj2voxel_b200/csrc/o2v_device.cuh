@@ -20,7 +20,8 @@ struct LeafStage {
     float plane[4];    // n . p + d for the tile-local voxel min corner p
     float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
     float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
-    uint32_t pad;      // 51 words: odd stride, so lanes reading the same field of different leaves hit distinct banks
+    uint32_t flags;    // LeafRecord::flags.  51 words: odd stride, so lanes reading the same field of different leaves
+                       // hit distinct banks
 };
 
 /// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
@@ -64,6 +65,9 @@ __device__ __forceinline__ void buildPrefilter(LeafStage &s, const float origin[
 /// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
 __device__ __forceinline__ bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
 {
+    if ((s.flags & kLeafNoPrefilter) != 0) {
+        return true;  // sliver: the computed normal is too noisy for the plane test (o2v_exact.cuh, leafFlagsOf)
+    }
     const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
     if (fabsf(dist) > s.planeLimit) {
         return false;
@@ -157,6 +161,7 @@ __device__ __forceinline__ void stageLeaf(LeafStage &s, const VoxelizeArgs &args
     s.v[8] = c.x;
     s.tri = __float_as_uint(c.y);
     s.area = c.z;
+    s.flags = __float_as_uint(c.w);
     if (UV) {
         const float4 *uv = reinterpret_cast<const float4 *>(args.leafUvs + leafIndex);
         const float4 u0 = __ldg(uv), u1 = __ldg(uv + 1);

@@ -100,6 +100,54 @@ O2V_HD bool triRoughlyAxisAligned(const float *v)
     return diagonality01 < kDiagonalityLimit;
 }
 
+/// The plane-distance cull of voxelizeSubTriangle (src/voxelization.cpp:435-458) with the reference's arithmetic:
+/// planeNormal = normal() / length(normal()) (util.hpp:127-139), center = Vec3(pos) + 0.5,
+/// |dot(planeNormal, center - v0)| > 2 skips the voxel.  NaN normals (zero area) never cull.
+O2V_HD bool planeDistanceCulled(const float *v, uint32_t px, uint32_t py, uint32_t pz)
+{
+    float n[3];
+    triNormal(v, n);
+    const float len = xsqrt(dot3(n[0], n[1], n[2], n[0], n[1], n[2]));
+    const float ux = xdiv(n[0], len), uy = xdiv(n[1], len), uz = xdiv(n[2], len);
+    const float rx = xsub(xadd(static_cast<float>(px), 0.5f), v[0]);
+    const float ry = xsub(xadd(static_cast<float>(py), 0.5f), v[1]);
+    const float rz = xsub(xadd(static_cast<float>(pz), 0.5f), v[2]);
+    return fabsf(dot3(ux, uy, uz, rx, ry, rz)) > 2.0f;
+}
+
+/// true when the cull above provably cannot fire for any voxel the leaf's exact clip would contribute to, so it may be
+/// skipped: a contributing voxel's centre lies within sqrt(3)/2 + 0.02 of the leaf's plane, the limit is 2, and the
+/// computed unit normal is off by at most |dn| / |n| with |dn| <= 9 * 2^-24 * |e01| * |e02| (three roundings per
+/// component of the cross product), which is multiplied by |centre - v0| <= max(|e01|, |e02|) + 2.  Needed slack: 1.1;
+/// the test below grants itself another factor 4:  |n| > 4e-6 * |e01| * |e02| * (max(|e01|, |e02|) + 2), squared
+/// (with (m + 2)^2 <= 2 m^2 + 8).  Slivers — and NaN/inf inputs, which compare false — fail it and take the exact cull.
+/// Not part of the reference arithmetic (any float evaluation will do; the constants carry the slack).
+///
+/// The same quantity decides whether the conservative SAT prefilter (o2v_device.cuh) may be trusted: its plane test
+/// |n . (c - p0)| <= (0.5 + margin) |n|_1 stays conservative as long as |dn| (D + 0.87) <= margin |n|, margin = 1/64,
+/// i.e. |n| >= 3.5e-5 |e01| |e02| (D + 1); `slack` selects the threshold (kCullSlack / kPrefilterSlack, squared).
+O2V_HD bool planeNormalIsRobust(const float *v, float slackSquared)
+{
+    const float ax = v[3] - v[0], ay = v[4] - v[1], az = v[5] - v[2];
+    const float bx = v[6] - v[0], by = v[7] - v[1], bz = v[8] - v[2];
+    const float nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+    const float n2 = nx * nx + ny * ny + nz * nz;
+    const float a2 = ax * ax + ay * ay + az * az, b2 = bx * bx + by * by + bz * bz;
+    const float m2 = a2 < b2 ? b2 : a2;
+    return n2 > slackSquared * a2 * b2 * (2.0f * m2 + 8.0f);
+}
+
+constexpr float kCullSlackSquared = 1.6e-11f;       // (4e-6)^2
+constexpr float kPrefilterSlackSquared = 1.6e-9f;   // (4e-5)^2
+constexpr uint32_t kLeafNeedsCull = 1u;    // LeafRecord::flags: the exact distance cull must be evaluated (slivers)
+constexpr uint32_t kLeafNoPrefilter = 2u;  // the SAT prefilter's plane test is not provably conservative: skip it
+
+O2V_HD uint32_t leafFlagsOf(const float *v)
+{
+    return (planeNormalIsRobust(v, kCullSlackSquared) ? 0u : kLeafNeedsCull) |
+           (planeNormalIsRobust(v, kPrefilterSlackSquared) ? 0u : kLeafNoPrefilter);
+}
+
 // util.hpp:80-98 (std::min/std::max nesting)
 O2V_HD float min3(float a, float b, float c)
 {

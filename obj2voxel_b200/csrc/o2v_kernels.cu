@@ -208,7 +208,7 @@ emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leaf
             }
             rec.tri = static_cast<uint32_t>(i);
             rec.area = area;
-            rec.pad = 0;
+            rec.flags = leafFlagsOf(leaf.v);
             leaves[index] = rec;
             if (UV) {
                 LeafUv uv;
@@ -613,7 +613,10 @@ voxelizeTilesKernel(const VoxelizeArgs args)
                 const uint32_t box = s.box;
                 const bool inside = lx >= (box & 15u) && ly >= ((box >> 4) & 15u) && lz >= ((box >> 8) & 15u) &&
                                     lx < ((box >> 12) & 15u) && ly < ((box >> 16) & 15u) && lz < ((box >> 20) & 15u);
-                const bool hit = inside && (!args.prefilter || prefilterPass(s, (float) lx, (float) ly, (float) lz));
+                bool hit = inside && (!args.prefilter || prefilterPass(s, (float) lx, (float) ly, (float) lz));
+                if (hit && (s.flags & kLeafNeedsCull) != 0) {
+                    hit = !planeDistanceCulled(s.v, px, py, pz);  // voxelization.cpp:451-458, slivers only
+                }
                 if (!__any_sync(0xffffffffu, hit)) {
                     continue;  // warp-uniform: none of this warp's 32 voxels can touch the leaf
                 }

@@ -47,7 +47,7 @@ struct __align__(16) LeafRecord {
     float v[9];
     uint32_t tri;  // input triangle index (fold order key together with the leaf's position in the leaf array)
     float area;    // area of the WHOLE input triangle
-    uint32_t pad;
+    uint32_t flags;  // kLeafNeedsCull: the leaf's computed normal is not provably robust (slivers) -> exact distance cull
 };
 
 struct __align__(16) LeafUv {

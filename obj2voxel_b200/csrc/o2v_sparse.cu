@@ -182,6 +182,10 @@ sparseClipKernel(const VoxelizeArgs args)
                     }
                     clipper.begin(leaf, origin[0] + (entry.y & 7u), origin[1] + ((entry.y >> 3) & 7u),
                                   origin[2] + ((entry.y >> 6) & 7u), c.z);
+                    if ((__float_as_uint(c.w) & kLeafNeedsCull) != 0 &&
+                        planeDistanceCulled(leaf.v, clipper.px, clipper.py, clipper.pz)) {
+                        clipper.done = true;  // voxelization.cpp:451-458 (slivers only): skipped, no contribution
+                    }
                     hasEntry = true;
                     current = e;
                     currentTri = __float_as_uint(c.y);

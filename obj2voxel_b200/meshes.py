@@ -139,6 +139,23 @@ def random_texture(width=256, height=256, channels=3, seed=3):
     return (_splitmix64_np(idx, seed) >> np.uint64(56)).astype(np.uint8).reshape(height, width, channels)
 
 
+def slivers(n, seed=21):
+    """Needle triangles (length 0.01 .. 0.6, width 1e-9 .. 1e-5 model units) in the unit cube: their computed normals
+    are dominated by rounding, which is where the reference's plane-distance cull (voxelization.cpp:451-458) decides."""
+    rng = np.random.default_rng(seed)
+    v0 = rng.uniform(0.1, 0.9, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    perp = rng.normal(size=(n, 3))
+    perp -= (perp * d).sum(1, keepdims=True) * d
+    perp /= np.linalg.norm(perp, axis=1, keepdims=True)
+    length = rng.uniform(0.01, 0.6, (n, 1))
+    width = 10.0 ** rng.uniform(-9, -5, (n, 1))
+    v1 = v0 + length * d
+    v2 = v0 + rng.uniform(0.2, 0.8, (n, 1)) * length * d + width * perp
+    return np.clip(np.concatenate([v0, v1, v2], axis=1), 0.0, 1.0).astype(np.float32)
+
+
 # BASELINE.json configs made concrete (SURVEY §8d).  `extent` is the vertex offset half-range in model units.
 CONFIGS = {
     "cfg1": dict(kind="single", resolution=16, supersampling=1, strategy=0),

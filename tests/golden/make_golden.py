@@ -48,7 +48,11 @@ def save(name, verts, resolution, uvs=None, texture=None, types=None, colors=Non
     print("%-28s %8d voxels" % (name, len(internal["xyz"])))
 
 
-def main():
+def main(only=None):
+    global save
+    if only:
+        _save = save
+        save = lambda name, *a, **k: _save(name, *a, **k) if name in only else None  # noqa: E731
     rng = np.random.default_rng(2024)
     save("cfg1_single_r16_max", meshes.single_triangle(), 16, strategy=0)
     save("cfg1_single_r16_blend", meshes.single_triangle(), 16, strategy=1)
@@ -68,6 +72,9 @@ def main():
     save("rand500_r64_untextured_blend", v, 64, types=types, colors=cols, strategy=1, bounds=meshes.UNIT_BOUNDS)
     save("big12_r128_blend_subdivided", meshes.random_triangles(12, 0.45, seed=13), 128, strategy=1)
     save("sphere24_r64_max", meshes.lumpy_sphere(24, 25), 64, strategy=0)
+    # needle triangles: the plane-distance cull decides occupancy (their normals are rounding noise)
+    save("slivers300_r256_blend", meshes.slivers(300), 256, strategy=1, bounds=meshes.UNIT_BOUNDS)
+    save("slivers300_r64_max_autobounds", meshes.slivers(300, seed=22), 64, strategy=0)
     # supersampling: the unmodified reference yields zero voxels; pinned two ways
     save("rand500_r64_presample_of_ss2", v, 64, strategy=0, bounds=meshes.UNIT_BOUNDS)  # == resolution 32, ss 2 pre-downscale
     save("rand500_r32_ss2_patched_max", v, 32, supersampling=2, strategy=0, bounds=meshes.UNIT_BOUNDS,
@@ -77,4 +84,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(set(sys.argv[1:]))  # optional: names of the fixtures to (re)generate
