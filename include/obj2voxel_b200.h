@@ -41,6 +41,9 @@ typedef struct o2v_b200_params {
     uint32_t slab_z0, slab_z1;  /* owned sample-space z range [z0, z1), multiples of 8; 0,0 = the whole grid */
     int32_t variant;            /* kernel variant, -1 = default */
     int32_t prefilter;          /* 1 = conservative SAT prefilter on (default); 0 = off (validation only) */
+    int32_t occupancy_path;     /* 1 (default) = meshes whose every triangle is MATERIALLESS (output colour is white
+                                 * whatever the weights, reference src/triangle.hpp:186) take the occupancy-only path;
+                                 * 0 = always fold weights and colours (validation / measurement) */
 } o2v_b200_params;
 
 typedef struct o2v_b200_mesh {
@@ -77,8 +80,8 @@ typedef struct o2v_b200_stats {
     uint64_t light_tiles;       /* tiles voxelized warp-per-tile */
     uint64_t heavy_tiles;       /* tiles voxelized block-per-tile */
     uint64_t survivors;         /* sparse path: SAT survivors = exact clips */
-    float ms_clip;              /* duration of the dominant kernel (exact clip), CUDA events */
-    float reserved;
+    float ms_clip;              /* duration of the exact-clip kernel, CUDA events */
+    int32_t occupancy_path;     /* 1 = this run took the occupancy-only path (survivors = voxels the SAT left undecided) */
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */

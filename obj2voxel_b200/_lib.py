@@ -27,7 +27,8 @@ LOG_CALLBACK = C.CFUNCTYPE(C.c_bool, C.c_void_p, C.c_char_p, C.c_ubyte)
 class Params(C.Structure):
     _fields_ = [("resolution", C.c_uint32), ("supersampling", C.c_uint32), ("strategy", C.c_uint32),
                 ("bounds_known", C.c_uint32), ("bounds", C.c_float * 6), ("unit_transform", C.c_int32 * 9),
-                ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("variant", C.c_int32), ("prefilter", C.c_int32)]
+                ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("variant", C.c_int32), ("prefilter", C.c_int32),
+                ("occupancy_path", C.c_int32)]
 
 
 class Mesh(C.Structure):
@@ -47,7 +48,7 @@ class Stats(C.Structure):
                 ("ms_total", C.c_float), ("ms_setup", C.c_float), ("ms_voxelize", C.c_float),
                 ("transform", C.c_float * 12), ("kernel_launches", C.c_int32), ("voxelize_launches", C.c_int32),
                 ("light_tiles", C.c_uint64), ("heavy_tiles", C.c_uint64), ("survivors", C.c_uint64),
-                ("ms_clip", C.c_float), ("reserved", C.c_float)]
+                ("ms_clip", C.c_float), ("occupancy_path", C.c_int32)]
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "transform"}

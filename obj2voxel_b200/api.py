@@ -208,7 +208,7 @@ def sort_voxels(voxels):
 
 
 def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None, unit=None, slab=None, variant=-1,
-                prefilter=1):
+                prefilter=1, occupancy_path=1):
     p = Params()
     _lib.load().o2v_b200_default_params(C.byref(p))
     p.resolution = resolution
@@ -223,6 +223,7 @@ def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None,
         p.slab_z0, p.slab_z1 = int(slab[0]), int(slab[1])
     p.variant = variant
     p.prefilter = prefilter
+    p.occupancy_path = occupancy_path
     return p
 
 

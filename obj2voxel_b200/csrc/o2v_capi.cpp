@@ -165,6 +165,7 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->heavy_tiles = in.counters.heavyTiles;
     out->survivors = in.counters.survivors;
     out->ms_clip = in.msClip;
+    out->occupancy_path = in.occupancyPath ? 1 : 0;
 }
 
 EngineParams paramsFromC(const o2v_b200_params &p)
@@ -182,6 +183,7 @@ EngineParams paramsFromC(const o2v_b200_params &p)
     e.slabZ1 = p.slab_z1;
     e.variant = p.variant;
     e.prefilter = p.prefilter;
+    e.occupancyPath = p.occupancy_path;
     return e;
 }
 
@@ -423,6 +425,9 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     }
     if (const char *env = getenv("O2V_B200_PREFILTER")) {
         params.prefilter = atoi(env);
+    }
+    if (const char *env = getenv("O2V_B200_OCCUPANCY_PATH")) {
+        params.occupancyPath = atoi(env);
     }
 
     if (inst.supersampling > 1) {
@@ -921,6 +926,7 @@ void o2v_b200_default_params(o2v_b200_params *params)
     params->unit_transform[0] = params->unit_transform[4] = params->unit_transform[8] = 1;
     params->variant = -1;
     params->prefilter = 1;
+    params->occupancy_path = 1;
 }
 
 int o2v_b200_voxelize_device(o2v_b200_engine *engine, const o2v_b200_params *params, const o2v_b200_mesh *mesh,

@@ -3,88 +3,17 @@
 #define O2V_DEVICE_CUH
 
 #include "o2v_kernels.cuh"
+#include "o2v_sat.cuh"
 
 namespace o2v {
 namespace {
 
-// Inflation of the voxel box in the conservative SAT, in voxels.  It must exceed every slack of the exact clip: the
-// planarity epsilon (2^-16) plus the rounding of intersection points (two roundings of a coordinate < 8192: <= 2e-3).
-constexpr float kPrefilterMargin = 0.015625f;
-
-struct LeafStage {
-    float v[9];
-    float t[6];
-    float area;
-    uint32_t tri;
-    uint32_t box;      // tile-local AABB: 4 bits each lo.x lo.y lo.z hi.x hi.y hi.z (hi exclusive, <= 8)
-    float plane[4];    // n . p + d for the tile-local voxel min corner p
-    float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
-    float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
-    uint32_t flags;    // LeafRecord::flags.  51 words: odd stride, so lanes reading the same field of different leaves
-                       // hit distinct banks
-};
-
-/// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
-/// functions on a box inflated by kPrefilterMargin).  Not exact arithmetic: FMA contraction is welcome here.
-__device__ __forceinline__ void buildPrefilter(LeafStage &s, const float origin[3])
+__device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
 {
-    float p[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        p[k] = s.v[k] - origin[k % 3];
-    }
-    const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
-    const float e1[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
-    const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-    s.plane[0] = n[0];
-    s.plane[1] = n[1];
-    s.plane[2] = n[2];
-    s.plane[3] = n[0] * (0.5f - p[0]) + n[1] * (0.5f - p[1]) + n[2] * (0.5f - p[2]);
-    s.planeLimit = (0.5f + kPrefilterMargin) * (fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]));
-    const float grow = 1.0f + kPrefilterMargin;
-#pragma unroll
-    for (int proj = 0; proj < 3; ++proj) {
-        const int a = proj, b = (proj + 1) % 3, c = (proj + 2) % 3;  // xy (n.z), yz (n.x), zx (n.y)
-        const float sign = n[c] >= 0.0f ? 1.0f : -1.0f;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int j = (i + 1) % 3;
-            const float ea = p[j * 3 + a] - p[i * 3 + a];
-            const float eb = p[j * 3 + b] - p[i * 3 + b];
-            const float A = -eb * sign, B = ea * sign;
-            float C = -(A * p[i * 3 + a] + B * p[i * 3 + b]);
-            C += A > 0.0f ? A * grow : -A * kPrefilterMargin;
-            C += B > 0.0f ? B * grow : -B * kPrefilterMargin;
-            s.edge[(proj * 3 + i) * 3 + 0] = A;
-            s.edge[(proj * 3 + i) * 3 + 1] = B;
-            s.edge[(proj * 3 + i) * 3 + 2] = C;
-        }
-    }
-}
-
-/// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
-__device__ __forceinline__ bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
-{
-    if ((s.flags & kLeafNoPrefilter) != 0) {
-        return true;  // sliver: the computed normal is too noisy for the plane test (o2v_exact.cuh, leafFlagsOf)
-    }
-    const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
-    if (fabsf(dist) > s.planeLimit) {
-        return false;
-    }
-    const float q[3] = {lx, ly, lz};
-#pragma unroll
-    for (int proj = 0; proj < 3; ++proj) {
-        const float qa = q[proj], qb = q[(proj + 1) % 3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const float *e = s.edge + (proj * 3 + i) * 3;
-            if (e[0] * qa + e[1] * qb + e[2] < 0.0f) {
-                return false;
-            }
-        }
-    }
-    return true;
+    const uint32_t T = grid.tilesPerAxis;
+    origin[0] = (tile % T) * kTileEdge;
+    origin[1] = ((tile / T) % T) * kTileEdge;
+    origin[2] = (tile / (T * T) + grid.slabTileZ0) * kTileEdge;
 }
 
 struct VoxelAccumulator {

@@ -129,9 +129,18 @@ int Engine::fail(int code, const std::string &message)
     return code;
 }
 
-int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t textureCount,
+int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
                      const EngineParams &params, cudaStream_t stream, RunStats *stats)
 {
+    // Every triangle MATERIALLESS (no per-triangle types, no usable texture): the output is white wherever a voxel is
+    // occupied, whatever the weights — the occupancy-only path decides just that (o2v_occupancy.cu).
+    const bool occupancy = params.occupancyPath != 0 && meshIn.types == nullptr &&
+                           !(meshIn.uvs != nullptr && textureCount != 0);
+    MeshView mesh = meshIn;
+    if (occupancy) {
+        mesh.uvs = nullptr;     // uvs without a texture never reach a colour (flushPartial)
+        mesh.colors = nullptr;  // colours without UNTEXTURED types neither
+    }
     error_.clear();
     voxelCount_ = 0;
     RunStats local;
@@ -214,6 +223,7 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         !activeTiles_.ensure((size_t) tileTotal * 4) || !allTiles_.ensure((size_t) tileTotal * 4) ||
         !longTiles_.ensure((size_t) tileTotal * 4) ||
         !tileCand_.ensure((size_t) tileTotal * 4) ||
+        (occupancy && !tileSlot_.ensure((size_t) tileTotal * 4)) ||
         !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) ||
         !bigLightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
@@ -230,7 +240,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
                         &dCounters->pairs, stream);
     launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
                              allTiles_.as<uint32_t>(), longTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(),
-                             lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(), dCounters, stream);
+                             lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(),
+                             occupancy ? tileSlot_.as<uint32_t>() : nullptr, dCounters, stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -253,9 +264,10 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         (hasUv && !leafUvs_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafUv))) ||
         !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
         !pairTile_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
-        !pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
-        !pairMask_.ensure((size_t) (pairTotal + 1) * 8) || !pairBox_.ensure((size_t) (pairTotal + 1) * 4) ||
-        !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)) {
+        (!occupancy &&
+         (!pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
+          !pairMask_.ensure((size_t) (pairTotal + 1) * 8) || !pairBox_.ensure((size_t) (pairTotal + 1) * 4) ||
+          !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)))) {
         return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
     }
     if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
@@ -288,8 +300,10 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     work.tileCount = tileCount_.as<uint32_t>();
     work.tileList = tileList_.as<uint32_t>();
     work.activeCount = (uint32_t) hostCounters_->heavyTiles;
-    launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
-    st.kernelLaunches += 3;
+    if (!occupancy) {  // the fold order only matters when weights reach the output
+        launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
+    }
+    st.kernelLaunches += occupancy ? 1 : 3;
 
     VoxelizeArgs args;
     args.grid = grid;
@@ -325,7 +339,21 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
     const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 16ull <= (8ull << 30);
     bool sparseActive = args.lightCount != 0 || args.bigLightCount != 0;
-    if (sparseActive) {
+    unsigned long long queueCapacity = 0;
+    if (sparseActive && occupancy) {
+        // Queue of SAT-undecided voxels: a fraction of the candidates in practice (~6 %); sized at a quarter of the bound
+        // and grown to the exact need (one rerun) in the rare case that is not enough.
+        queueCapacity = std::max<unsigned long long>(std::min<unsigned long long>(candidateBound, 1ull << 20),
+                                                     candidateBound / 4);
+        if (!tileBits_.ensure((size_t) activeTotal * kTileEdge * 8) || !occQueue_.ensure((size_t) queueCapacity * 8)) {
+            return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
+        }
+        args.occ.tileSlot = tileSlot_.as<uint32_t>();
+        args.occ.tileBits = tileBits_.as<unsigned long long>();
+        args.occ.queue = occQueue_.as<uint2>();
+        args.occ.queueCapacity = queueCapacity;
+    }
+    else if (sparseActive) {
         O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
         launchSparseSurvivors(args, false, stream);
         launchExclusiveScan(pairSurvivors_.as<uint32_t>(), pairOffset_.as<uint32_t>(), (size_t) pairTotal + 1,
@@ -353,9 +381,17 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
     }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));
 
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
-        if (sparseActive) {
+        if (sparseActive && occupancy) {
+            O2V_CUDA(cudaMemsetAsync(tileBits_.as<void>(), 0, (size_t) activeTotal * kTileEdge * 8, stream));
+            launchOccupancyClassify(args, stream);
+            O2V_CUDA(cudaEventRecord(evClipStart_, stream));
+            launchOccupancyClip(args, smCount_, stream);
+            O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
+            launchOccupancyExpand(args, smCount_, stream);
+        }
+        else if (sparseActive) {
             O2V_CUDA(cudaEventRecord(evClipStart_, stream));
             launchSparseClip(args, smCount_, stream);
             O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
@@ -363,26 +399,41 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (sparseActive ? 4 : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (sparseActive ? (occupancy ? 3 : 4) : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
-        if (hostCounters_->outputOverflow == 0) {
+        const bool queueOverflow = occupancy && sparseActive && hostCounters_->survivors > queueCapacity;
+        if (hostCounters_->outputOverflow == 0 && !queueOverflow) {
             break;
         }
-        if (attempt == 1) {
+        if (attempt == 2) {
             return fail(kErrOutOfMemory, "voxel output does not fit device memory");
         }
-        // the exact count is now known: grow once and redo the tile pass (setup results are still valid)
-        capacity = hostCounters_->voxels;
-        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
-            return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
+        // the exact need is now known: grow once and redo the tile pass (setup results are still valid)
+        if (queueOverflow) {
+            // what is queued depends on which bits were already visible: leave head-room, capped by the true bound
+            queueCapacity = std::min(candidateBound, hostCounters_->survivors * 2 + (1ull << 20));
+            if (!occQueue_.ensure((size_t) queueCapacity * 8)) {
+                return fail(kErrOutOfMemory, "device allocation failed (occupancy queue, exact size)");
+            }
+            args.occ.queue = occQueue_.as<uint2>();
+            args.occ.queueCapacity = queueCapacity;
         }
-        args.out = out_.as<VoxelRecord>();
-        args.outCapacity = capacity;
+        if (hostCounters_->outputOverflow != 0 && !queueOverflow) {
+            capacity = hostCounters_->voxels;
+            if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+                return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
+            }
+            args.out = out_.as<VoxelRecord>();
+            args.outCapacity = capacity;
+        }
         RunCounters reset = *hostCounters_;
+        if (occupancy) {
+            reset.survivors = 0;
+        }
         reset.voxels = 0;
         reset.contributions = 0;
         reset.clipCalls = 0;
@@ -397,7 +448,8 @@ int Engine::voxelize(const MeshView &mesh, const TextureView *textures, uint32_t
         }
     }
 
-    hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor is one exact clip
+    hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor / queued voxel is one exact clip
+    st.occupancyPath = occupancy;
     st.counters = *hostCounters_;
     st.outCapacity = capacity;
     voxelCount_ = hostCounters_->voxels;

@@ -28,6 +28,7 @@ struct EngineParams {
     uint32_t slabZ0 = 0, slabZ1 = 0;  // owned sample-space z range, multiples of 8; 0,0 = whole grid
     int variant = -1;                 // -1 = default kernel variant
     int prefilter = 1;
+    int occupancyPath = 1;            // 1 = all-MATERIALLESS meshes take the occupancy-only path; 0 = always fold weights
 };
 
 struct RunStats {
@@ -40,6 +41,7 @@ struct RunStats {
     int voxelizeLaunches = 0;
     int kernelLaunches = 0;
     unsigned long long outCapacity = 0;
+    bool occupancyPath = false;  // this run took the occupancy-only path
 };
 
 class DeviceBuffer {
@@ -73,7 +75,7 @@ public:
 
     /// Voxelizes a device-resident mesh.  textures: HOST array of TextureView whose pixel pointers are DEVICE pointers.
     /// Result stays on the device (deviceVoxels / voxelCount) until the next call.  Returns 0 or a negative error.
-    int voxelize(const MeshView &mesh, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
+    int voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
                  cudaStream_t stream, RunStats *stats);
 
     const VoxelRecord *deviceVoxels() const { return out_.as<VoxelRecord>(); }
@@ -107,6 +109,7 @@ private:
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
+    DeviceBuffer tileSlot_, tileBits_, occQueue_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

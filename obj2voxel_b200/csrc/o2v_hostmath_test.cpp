@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include "o2v_exact.cuh"
+#include "o2v_sat.cuh"
 
 using namespace o2v;
 
@@ -79,6 +80,64 @@ void o2vt_combine(float acc[4], const float incoming[4], int blend)
     acc[1] = c.r;
     acc[2] = c.g;
     acc[3] = c.b;
+}
+
+/// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through classifyVoxel (o2v_sat.cuh) and
+/// through the reference semantics (plane-distance cull + exact clip, o2v_exact.cuh) and counts disagreements.
+/// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts the reference hits
+/// (must be 0), [6] `certain` verdicts the reference does not hit (must be 0), [7] leaves skipped (AABB too large).
+void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVolume, unsigned long long out[8])
+{
+    for (int i = 0; i < 8; ++i) {
+        out[i] = 0;
+    }
+    for (size_t l = 0; l < n; ++l) {
+        const float *v = leaves + l * 9;
+        uint32_t lo[3], hi[3];
+        triVoxelBounds(v, lo, hi);
+        const unsigned long long volume =
+            (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (unsigned long long) (hi[2] - lo[2]);
+        if (!(triArea(v) > 0.0f) || volume > maxVolume) {
+            ++out[7];
+            continue;
+        }
+        Tri<false> tri;
+        memcpy(tri.v, v, sizeof tri.v);
+        const uint32_t flags = leafFlagsOf(v);
+        for (uint32_t tz = lo[2] / 8; tz <= (hi[2] - 1) / 8; ++tz) {
+            for (uint32_t ty = lo[1] / 8; ty <= (hi[1] - 1) / 8; ++ty) {
+                for (uint32_t tx = lo[0] / 8; tx <= (hi[0] - 1) / 8; ++tx) {
+                    const float origin[3] = {(float) (tx * 8), (float) (ty * 8), (float) (tz * 8)};
+                    LeafStage s;
+                    memcpy(s.v, v, sizeof s.v);
+                    s.flags = flags;
+                    buildPrefilter(s, origin);
+                    LeafCertain c;
+                    buildCertain(c, s, origin);
+                    for (uint32_t z = tz * 8 > lo[2] ? tz * 8 : lo[2]; z < hi[2] && z < tz * 8 + 8; ++z) {
+                        for (uint32_t y = ty * 8 > lo[1] ? ty * 8 : lo[1]; y < hi[1] && y < ty * 8 + 8; ++y) {
+                            for (uint32_t x = tx * 8 > lo[0] ? tx * 8 : lo[0]; x < hi[0] && x < tx * 8 + 8; ++x) {
+                                const int verdict = classifyVoxel(s, c, (float) (x - tx * 8), (float) (y - ty * 8),
+                                                                  (float) (z - tz * 8));
+                                const bool pass = prefilterPass(s, (float) (x - tx * 8), (float) (y - ty * 8),
+                                                                (float) (z - tz * 8));
+                                const bool hit = !planeDistanceCulled(v, x, y, z) &&
+                                                 clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
+                                ++out[0];
+                                ++out[1 + verdict];
+                                out[4] += hit ? 1 : 0;
+                                out[5] += ((verdict == kSatMiss || !pass) && hit) ? 1 : 0;
+                                out[6] += (verdict == kSatCertain && !hit) ? 1 : 0;
+                                if (pass != (verdict != kSatMiss)) {
+                                    out[5] += 1000000;  // the two forms of the conservative test must agree
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
 }
 
 }  // extern "C"

@@ -375,7 +375,8 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
                                          const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
                                          uint32_t *__restrict__ allTiles, uint32_t *__restrict__ longTiles,
                                          uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
-                                         LightTile *__restrict__ bigLightTiles, RunCounters *counters)
+                                         LightTile *__restrict__ bigLightTiles, uint32_t *__restrict__ tileSlot,
+                                         RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
@@ -449,7 +450,11 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (count != 0) {
-            allTiles[base + __popc(anyBallot & below)] = i;
+            const uint32_t slot = (uint32_t) base + __popc(anyBallot & below);
+            allTiles[slot] = i;
+            if (tileSlot != nullptr) {
+                tileSlot[i] = slot;
+            }
         }
     }
 }
@@ -794,15 +799,15 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
-                              cudaStream_t stream)
+                              LightTile *lightTiles, LightTile *bigLightTiles, uint32_t *tileSlot,
+                              RunCounters *counters, cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
     compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
                                                                           tileTotal, allTiles, longTiles, heavyTiles,
-                                                                          lightTiles, bigLightTiles, counters);
+                                                                          lightTiles, bigLightTiles, tileSlot, counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,

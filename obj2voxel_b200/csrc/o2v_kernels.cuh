@@ -121,7 +121,7 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 /// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
+                              LightTile *lightTiles, LightTile *bigLightTiles, uint32_t *tileSlot, RunCounters *counters,
                               cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
@@ -144,6 +144,16 @@ struct SparseView {
     float2 *uvs;                     // per survivor (textured meshes only)
 };
 
+/// Buffers of the occupancy-only path (o2v_occupancy.cu): meshes whose every triangle is MATERIALLESS voxelize white
+/// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
+/// occupancy has to be decided — an order-independent OR.
+struct OccupancyView {
+    const uint32_t *tileSlot;        // per tile: its index in TileWork::allTiles = its bitmap slot
+    unsigned long long *tileBits;    // 8 words per slot: bit (x + 8 y) of word z = voxel (x, y, z) of the tile is occupied
+    uint2 *queue;                    // {pair index, tile-local voxel} of the voxels the SAT could not decide
+    unsigned long long queueCapacity;
+};
+
 struct VoxelizeArgs {
     GridView grid;
     TileWork work;
@@ -160,6 +170,7 @@ struct VoxelizeArgs {
     const LightTile *bigLightTiles;  // kWarpFoldMax < candidates <= kLightMaxCandidates
     uint32_t bigLightCount;
     SparseView sparse;
+    OccupancyView occ;
     int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
 };
@@ -173,6 +184,14 @@ void launchVoxelizeTiles(const VoxelizeArgs &args, int smCount, cudaStream_t str
 void launchSparseSurvivors(const VoxelizeArgs &args, bool write, cudaStream_t stream);
 void launchSparseClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+
+/// Occupancy-only path for the same light tiles (see OccupancyView): (1) thread per (leaf, tile) pair classifies the
+/// pair's candidate voxels with the three-way SAT of o2v_sat.cuh — `certain` voxels are OR-ed into the tile bitmap,
+/// `uncertain` ones are queued —, (2) the exact clip decides the queued voxels, (3) thread per tile expands the bitmap
+/// (optionally 2x downscaled) into Voxel32 records.
+void launchOccupancyClassify(const VoxelizeArgs &args, cudaStream_t stream);
+void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
+void launchOccupancyExpand(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 
 }  // namespace o2v
 

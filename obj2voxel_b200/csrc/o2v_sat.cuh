@@ -1,0 +1,169 @@
+// Triangle / unit-voxel separating-axis tests around the exact clip (host + device).  None of this is reference
+// arithmetic: it only decides which (leaf, voxel) pairs need the exact clip of o2v_exact.cuh, and every decision it
+// takes alone is provable from margins that dwarf the rounding of both sides:
+//
+//   miss      the leaf provably misses the voxel inflated by kPrefilterMargin      -> the exact clip would be empty
+//   certain   the leaf provably reaches the voxel shrunk by kCertainMargin          -> the exact clip has >= 1 piece
+//   uncertain everything in between                                                 -> run the exact clip
+//
+// SAT (Akenine-Moeller / Schwarz-Seidel form): box normals (the leaf's voxel AABB), the triangle normal (plane test)
+// and the nine edge x axis cross products (three 2-D edge-function tests per projection).  All 13 axes are evaluated
+// against the inflated box for `miss` and against the shrunk box for `certain`; one evaluation serves both.
+//
+// Why `certain` implies a surviving piece in the reference (src/voxelization.cpp:383-424): let q be a point of the leaf
+// inside the voxel shrunk by s.  Invariant over the six sequential half-space clips: some piece holds a point within
+// k * e of q, e = displacement of a computed intersection point (<= 1.5 ulp of the coordinate + 9e-8 * edge length:
+// <= 1.7e-3 at S = 8192 for a grid-sized triangle, <= 3e-4 at S <= 2048).  That piece has a vertex deeper than
+// s - k * e > 2^-16 on the kept side, so the case switch (voxelization.cpp:192-234) can only keep it whole or split it,
+// and the kept sub-triangles have their vertices within e of the exact cut polygon (same convex combination => a point
+// within e).  After six planes a piece is left, so weight = pieces * area > 0.  The plane-distance cull
+// (voxelization.cpp:451-458) cannot fire either: `certain` is only granted to leaves whose normal is robust
+// (leafFlagsOf).  Budget: s = kCertainMargin - (plane test error <= margin / 2 = 1/128, by kLeafNoPrefilter) - (edge
+// function error <= 1e-3) >= 0.022 against 6 e <= 0.0102.  tests/test_sat_classifier.py fuzzes exactly this claim.
+#ifndef O2V_SAT_CUH
+#define O2V_SAT_CUH
+
+#include "o2v_exact.cuh"
+
+namespace o2v {
+
+// Inflation of the voxel box in the conservative SAT, in voxels.  It must exceed every slack of the exact clip: the
+// planarity epsilon (2^-16) plus the rounding of intersection points (two roundings of a coordinate < 8192: <= 2e-3).
+constexpr float kPrefilterMargin = 0.015625f;
+// Shrink of the voxel box for the `certain` verdict (see the budget above).
+constexpr float kCertainMargin = 0.03125f;
+
+struct LeafStage {
+    float v[9];
+    float t[6];
+    float area;
+    uint32_t tri;
+    uint32_t box;      // tile-local AABB: 4 bits each lo.x lo.y lo.z hi.x hi.y hi.z (hi exclusive, <= 8)
+    float plane[4];    // n . p + d for the tile-local voxel min corner p
+    float planeLimit;  // (0.5 + margin) * (|nx| + |ny| + |nz|)
+    float edge[27];    // 3 projections (xy, yz, zx) x 3 edges x (A, B, C): A*p.a + B*p.b + C >= 0 inside
+    uint32_t flags;    // LeafRecord::flags.  51 words: odd stride, so lanes reading the same field of different leaves
+                       // hit distinct banks
+};
+
+/// Conservative separating-axis coefficients for leaf vs. unit voxels of the tile at `origin` (Schwarz-Seidel edge
+/// functions on a box inflated by kPrefilterMargin).  Not exact arithmetic: FMA contraction is welcome here.
+O2V_HD void buildPrefilter(LeafStage &s, const float origin[3])
+{
+    float p[9];
+O2V_UNROLL
+    for (int k = 0; k < 9; ++k) {
+        p[k] = s.v[k] - origin[k % 3];
+    }
+    const float e0[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]};
+    const float e1[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+    const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    s.plane[0] = n[0];
+    s.plane[1] = n[1];
+    s.plane[2] = n[2];
+    s.plane[3] = n[0] * (0.5f - p[0]) + n[1] * (0.5f - p[1]) + n[2] * (0.5f - p[2]);
+    s.planeLimit = (0.5f + kPrefilterMargin) * (fabsf(n[0]) + fabsf(n[1]) + fabsf(n[2]));
+    const float grow = 1.0f + kPrefilterMargin;
+O2V_UNROLL
+    for (int proj = 0; proj < 3; ++proj) {
+        const int a = proj, b = (proj + 1) % 3, c = (proj + 2) % 3;  // xy (n.z), yz (n.x), zx (n.y)
+        const float sign = n[c] >= 0.0f ? 1.0f : -1.0f;
+O2V_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            const int j = (i + 1) % 3;
+            const float ea = p[j * 3 + a] - p[i * 3 + a];
+            const float eb = p[j * 3 + b] - p[i * 3 + b];
+            const float A = -eb * sign, B = ea * sign;
+            float C = -(A * p[i * 3 + a] + B * p[i * 3 + b]);
+            C += A > 0.0f ? A * grow : -A * kPrefilterMargin;
+            C += B > 0.0f ? B * grow : -B * kPrefilterMargin;
+            s.edge[(proj * 3 + i) * 3 + 0] = A;
+            s.edge[(proj * 3 + i) * 3 + 1] = B;
+            s.edge[(proj * 3 + i) * 3 + 2] = C;
+        }
+    }
+}
+
+/// false only if the triangle provably misses the (inflated) voxel.  NaNs compare false => pass.
+O2V_HD bool prefilterPass(const LeafStage &s, float lx, float ly, float lz)
+{
+    if ((s.flags & kLeafNoPrefilter) != 0) {
+        return true;  // sliver: the computed normal is too noisy for the plane test (o2v_exact.cuh, leafFlagsOf)
+    }
+    const float dist = s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
+    if (fabsf(dist) > s.planeLimit) {
+        return false;
+    }
+    const float q[3] = {lx, ly, lz};
+O2V_UNROLL
+    for (int proj = 0; proj < 3; ++proj) {
+        const float qa = q[proj], qb = q[(proj + 1) % 3];
+O2V_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            const float *e = s.edge + (proj * 3 + i) * 3;
+            if (e[0] * qa + e[1] * qb + e[2] < 0.0f) {
+                return false;
+            }
+        }
+    }
+    return true;
+}
+
+/// Extra per-leaf constants of the three-way classification (kept apart from LeafStage, whose size is tuned for the
+/// shared-memory staging of the heavy-tile kernel).
+struct LeafCertain {
+    float planeSure;       // (0.5 - kCertainMargin) * |n|_1
+    float lo[3], hi[3];    // tile-local float AABB of the leaf
+};
+
+O2V_HD void buildCertain(LeafCertain &c, const LeafStage &s, const float origin[3])
+{
+    c.planeSure = (0.5f - kCertainMargin) * (fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]));
+O2V_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        c.lo[a] = fminf(fminf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+        c.hi[a] = fmaxf(fmaxf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+    }
+}
+
+enum SatVerdict : int { kSatMiss = 0, kSatUncertain = 1, kSatCertain = 2 };
+
+/// Three-way verdict for the voxel whose tile-local min corner is (lx, ly, lz).  Leaves with kLeafNoPrefilter are never
+/// `miss` and never `certain`.  Any NaN makes the comparisons fail towards `uncertain`.
+/// S provides plane[4], planeLimit, edge[27], flags (LeafStage or a compact copy); C provides planeSure, lo[3], hi[3].
+template <typename S, typename C>
+O2V_HD int classifyVoxel(const S &s, const C &c, float lx, float ly, float lz)
+{
+    if ((s.flags & kLeafNoPrefilter) != 0) {
+        return kSatUncertain;
+    }
+    const float dist = fabsf(s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3]);
+    if (dist > s.planeLimit) {
+        return kSatMiss;
+    }
+    bool sure = dist <= c.planeSure;
+    const float q[3] = {lx, ly, lz};
+    const float shift = kPrefilterMargin + kCertainMargin;  // inflated -> shrunk critical corner: (|A| + |B|) * shift
+O2V_UNROLL
+    for (int proj = 0; proj < 3; ++proj) {
+        const float qa = q[proj], qb = q[(proj + 1) % 3];
+O2V_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            const float *e = s.edge + (proj * 3 + i) * 3;
+            const float value = e[0] * qa + e[1] * qb + e[2];
+            if (value < 0.0f) {
+                return kSatMiss;
+            }
+            sure = sure && value >= (fabsf(e[0]) + fabsf(e[1])) * shift;
+        }
+    }
+O2V_UNROLL
+    for (int a = 0; a < 3; ++a) {  // box normals against the shrunk box [q + margin, q + 1 - margin]
+        sure = sure && (q[a] + kCertainMargin <= c.hi[a]) && (q[a] + 1.0f - kCertainMargin >= c.lo[a]);
+    }
+    return sure ? kSatCertain : kSatUncertain;
+}
+
+}  // namespace o2v
+
+#endif  // O2V_SAT_CUH

@@ -26,14 +26,6 @@ constexpr int kBlockFoldThreads = 128;   // above that (up to kLightMaxCandidate
 constexpr uint32_t kTinyFoldMax = 24;  // survivors per tile up to which one thread folds the whole tile
 constexpr int kTinyFoldThreads = 128;
 
-__device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
-{
-    const uint32_t T = grid.tilesPerAxis;
-    origin[0] = (tile % T) * kTileEdge;
-    origin[1] = ((tile / T) % T) * kTileEdge;
-    origin[2] = (tile / (T * T) + grid.slabTileZ0) * kTileEdge;
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // stages 1 + 2: thread per (leaf, tile) pair
 

@@ -23,9 +23,11 @@ else:
 textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(dev), o2v.UV_WRAP)] if uvs is not None else []
 slab = tuple(int(x) for x in os.environ["O2V_SLAB"].split(",")) if "O2V_SLAB" in os.environ else None
 params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
-                         bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")), slab=slab)
+                         bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")), slab=slab,
+                         occupancy_path=int(os.environ.get("O2V_OCC", "1")), prefilter=int(os.environ.get("O2V_PREFILTER", "1")))
 for i in range(steps):
     st = eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
     torch.cuda.synchronize()
     print(json.dumps({k: st[k] for k in ("voxels", "leaves", "pairs", "light_tiles", "heavy_tiles", "clip_calls",
-                                         "contributions", "candidate_voxels", "ms_total", "ms_setup", "ms_voxelize")}), flush=True)
+                                         "contributions", "candidate_voxels", "survivors", "occupancy_path", "ms_total", "ms_setup",
+                                         "ms_voxelize", "ms_clip")}), flush=True)

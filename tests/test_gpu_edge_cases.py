@@ -11,7 +11,11 @@ pytestmark = pytest.mark.gpu
 
 
 def both(engine, verts, resolution, **kw):
+    """These meshes are all-white: the default run takes the occupancy-only path; the weighted path must agree."""
     got, stats = engine.voxelize_host(verts, o2v.make_params(resolution=resolution, **kw))
+    weighted, wstats = engine.voxelize_host(verts, o2v.make_params(resolution=resolution, occupancy_path=0, **kw))
+    assert stats["occupancy_path"] and not wstats["occupancy_path"]
+    assert np.array_equal(o2v.sort_voxels(weighted), o2v.sort_voxels(got))
     want = oracle.voxelize(verts, resolution, **kw)["voxels"]
     return o2v.sort_voxels(got), want, stats
 

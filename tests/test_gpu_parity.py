@@ -140,6 +140,15 @@ def test_golden_bit_exact(engine, name):
     assert np.array_equal(np.asarray(stats["transform"], np.float32).view(np.uint32), g["transform_bits"])
     assert got.shape == want.shape and np.array_equal(got, want)
     assert np.array_equal(got[:, :3], g["int_xyz"])
+    materialless = "uvs" not in g and "types" not in g
+    assert bool(stats["occupancy_path"]) == materialless
+    if materialless:
+        # all-white meshes take the occupancy-only path by default; the weighted path and the occupancy path without
+        # its SAT shortcuts (every candidate through the exact clip) must give the very same records
+        for kw in (dict(occupancy_path=0), dict(prefilter=0)):
+            other, other_stats = gpu_run(engine, g, **kw)
+            assert bool(other_stats["occupancy_path"]) == ("occupancy_path" not in kw)
+            assert np.array_equal(other, want)
 
 
 @pytest.mark.parametrize("name", PATCHED)
@@ -147,7 +156,10 @@ def test_golden_supersampling(engine, name):
     """Occupancy exact; colours exact for MAX and within 1 LSB for BLEND (child fold order of the patched reference is
     unordered_map order; ours is ascending Morton)."""
     g = load_golden(name)
-    got, _ = gpu_run(engine, g)
+    got, stats = gpu_run(engine, g, occupancy_path=0)
+    fast, fast_stats = gpu_run(engine, g)
+    assert not stats["occupancy_path"] and fast_stats["occupancy_path"]
+    assert np.array_equal(fast, got)  # the occupancy-only path (default for this all-white mesh) changes nothing
     want = g["api_voxels"]
     assert np.array_equal(got[:, :3], want[:, :3])
     tol = 0 if int(g["strategy"]) == 0 else 1
@@ -163,14 +175,21 @@ def test_golden_supersampling(engine, name):
 # ---- seeded parity against the oracle ------------------------------------------------------------------------------
 
 def parity(engine, verts, resolution, uvs=None, texture=None, types=None, colors=None, **kw):
-    params = o2v.make_params(resolution=resolution, **kw)
     textures = [(texture["pixels"], texture["wrap"])] if texture is not None else []
-    got, stats = engine.voxelize_host(verts, params, uvs=uvs, types=types, colors=colors, textures=textures)
     okw = {k: v for k, v in kw.items() if k in ("strategy", "supersampling", "bounds", "unit")}
     want = oracle.voxelize(verts, resolution, uvs=uvs, texture=texture, types=types, colors=colors, **okw)
+    # weighted path (the only one for coloured / textured meshes)
+    params = o2v.make_params(resolution=resolution, occupancy_path=0, **kw)
+    got, stats = engine.voxelize_host(verts, params, uvs=uvs, types=types, colors=colors, textures=textures)
     got = o2v.sort_voxels(got)
     assert got.shape == want["voxels"].shape and np.array_equal(got, want["voxels"])
     assert stats["contributions"] == want["contributions"]  # N_contrib agrees with the reference's emplace count
+    if texture is None and types is None:
+        # all-white mesh: the default is the occupancy-only path
+        fast, fast_stats = engine.voxelize_host(verts, o2v.make_params(resolution=resolution, **kw))
+        assert fast_stats["occupancy_path"] and not stats["occupancy_path"]
+        assert np.array_equal(o2v.sort_voxels(fast), want["voxels"])
+        assert fast_stats["clip_calls"] <= stats["clip_calls"]
     return stats
 
 
