@@ -54,14 +54,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profiled_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu capture."""
+def profiled_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture."""
     path = os.path.join(ROOT, "profiles", "voxelize_traffic.json")
     if os.path.exists(path):
         try:
             data = json.load(open(path))
             if data.get("workload") == workload:
-                return data.get("dram_bytes_per_launch")
+                return data.get("kernels", {}).get(kernel, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
     return None
@@ -71,7 +71,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index):
         self.index = index
@@ -81,7 +81,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -90,7 +90,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: only later samples count."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -102,7 +106,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        t0 = getattr(self, "t0", 0.0)
+        t1 = time.time()
+        for stamp, line in self.lines:
+            if stamp < t0 or stamp > t1:
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -282,24 +290,53 @@ def run_ours(args, cfg, workload):
     # ---- device-resident steps ----
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started before the warm-up (nvidia-smi takes a while to come up); samples are windowed
     for _ in range(args.warmup):
         stats = engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    kernel_ms, setup_ms, clip_ms, launches = [], [], [], 0
+    sampler.mark()
+    kernel_ms, setup_ms, clip_ms, classify_ms, launches = [], [], [], [], 0
     start.record()
     for _ in range(args.steps):
         stats = engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
         kernel_ms.append(stats["ms_voxelize"])
         clip_ms.append(stats["ms_clip"])
+        classify_ms.append(stats["ms_classify"])
         setup_ms.append(stats["ms_setup"])
         launches += stats["kernel_launches"]
     stop.record()
     sync_all()
     elapsed_ms = start.elapsed_time(stop)
     clocks = sampler.stop() if rank == 0 else None
+    occupancy_path = bool(stats["occupancy_path"])
+
+    # The same workload with the occupancy-only path switched off (weights and colours folded for every voxel): what a
+    # coloured / textured mesh of this shape costs.  Reported beside the headline, not as the headline.
+    weighted = None
+    if occupancy_path and not distributed:
+        wparams = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"],
+                                  strategy=cfg["strategy"], bounds=cfg["bounds"], occupancy_path=0)
+        for _ in range(2):
+            wstats = engine.voxelize_device(verts, wparams, uvs=uvs, textures=textures)
+        sync_all()
+        wsteps = max(1, min(args.steps, 5))
+        wstart, wstop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wstart.record()
+        for _ in range(wsteps):
+            wstats = engine.voxelize_device(verts, wparams, uvs=uvs, textures=textures)
+        wstop.record()
+        sync_all()
+        wms = wstart.elapsed_time(wstop) / wsteps
+        if wstats["voxels"] != stats["voxels"]:
+            raise RuntimeError("weighted path emitted %d voxels, occupancy path %d" % (wstats["voxels"], stats["voxels"]))
+        weighted = {"value": n_tri / (wms * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": wms,
+                    "clip_calls": wstats["clip_calls"], "contributions": wstats["contributions"],
+                    "ms_clip_kernel": wstats["ms_clip"],
+                    "note": "same workload with occupancy_path=0: every (triangle, voxel) weight folded in reference "
+                            "order (what coloured / textured meshes cost); identical output"}
+        launches += 0  # not part of the timed region above
 
     counts = [stats["voxels"], stats["contributions"], stats["clip_calls"], stats["leaves"], launches]
     tile_split = (stats["light_tiles"], stats["heavy_tiles"])
@@ -401,11 +438,16 @@ def run_ours(args, cfg, workload):
     if rank == 0:
         peak, peak_source = measured_peak()
         tri_bytes = 64 if uvs is not None else 36  # algorithmic read per triangle
-        # dominant kernel: sparseClipKernel (exact clip); one launch processes this rank's whole slab
+        # dominant kernel of the step, by its live CUDA-event duration: the SAT classification kernel on the occupancy-only
+        # path, the exact clip otherwise; one launch processes this rank's whole slab
         k_ms = float(np.mean(kernel_ms))
         c_ms = float(np.mean(clip_ms))
+        f_ms = float(np.mean(classify_ms))
+        dominant, d_ms = ("occupancyClassifyKernel", f_ms) if f_ms > c_ms else \
+            ("occupancyClipKernel" if occupancy_path else "sparseClipKernel", c_ms)
         alg_bytes = 16 * stats["voxels"] + tri_bytes * n_tri
-        achieved = alg_bytes / (c_ms * 1e-3) / 1e9 if c_ms > 0 else 0.0
+        achieved = alg_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+        traffic = profiled_traffic(workload, dominant)
         baseline = cpu_baseline(cfg) if world == 1 else None
         line = {
             "metric": "triangles_per_second", "value": n_tri / (ms_per_step * 1e-3) / 1e6, "unit": "Mtri/s",
@@ -421,20 +463,25 @@ def run_ours(args, cfg, workload):
             "clip_calls": clip_calls, "leaves": leaves, "light_tiles_rank0": tile_split[0],
             "heavy_tiles_rank0": tile_split[1],
             "ms_setup_rank0": float(np.mean(setup_ms)), "ms_voxelize_rank0": k_ms, "ms_clip_kernel_rank0": c_ms,
-            "hbm_write_gbs": 16 * stats["voxels"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0,
-            "roofline": {"bound": "hbm", "kernel": "sparseClipKernel", "achieved": achieved, "peak": peak,
+            "ms_classify_kernel_rank0": f_ms,
+            "path": "occupancy-only (every triangle MATERIALLESS: output colour is white whatever the weights)"
+                    if occupancy_path else "weighted fold",
+            "hbm_write_gbs": 16 * stats["voxels"] / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (profiled_traffic(workload) // world) if profiled_traffic(workload) else None,
+                         "traffic": (traffic // world) if traffic else None,
                          "peak_source": peak_source,
                          "note": "algorithmic bytes = 16 B x voxels + %d B x triangles per launch / CUDA-event duration of "
-                                 "the clip kernel; the kernel is bound by FP32/ALU issue of the exact clip (ncu: issue "
-                                 "active ~80 %%, DRAM < 1 %%), not by HBM — see DESIGN.md section 4" % tri_bytes},
+                                 "the dominant kernel; the kernel is bound by instruction issue / latency of the "
+                                 "triangle-box predicates, not by HBM — see DESIGN.md section 4" % tri_bytes},
             "e2e": {"value": n_tri / e2e_seconds / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_seconds * 1e3,
                     "h2d_bytes_per_step": int(n_tri * tri_bytes), "d2h_bytes_per_step": int(16 * voxels),
                     "api": e2e_api},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if weighted is not None:
+            line["weighted_path"] = weighted
         if baseline is not None:
             line["cpu_baseline"] = baseline
         print(json.dumps(line), flush=True)

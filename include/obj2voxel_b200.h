@@ -82,6 +82,8 @@ typedef struct o2v_b200_stats {
     uint64_t survivors;         /* sparse path: SAT survivors = exact clips */
     float ms_clip;              /* duration of the exact-clip kernel, CUDA events */
     int32_t occupancy_path;     /* 1 = this run took the occupancy-only path (survivors = voxels the SAT left undecided) */
+    float ms_classify;          /* occupancy-only path: duration of the SAT classification kernel, CUDA events */
+    float reserved;
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */

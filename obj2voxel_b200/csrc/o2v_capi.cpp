@@ -166,6 +166,8 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->survivors = in.counters.survivors;
     out->ms_clip = in.msClip;
     out->occupancy_path = in.occupancyPath ? 1 : 0;
+    out->ms_classify = in.msClassify;
+    out->reserved = 0.0f;
 }
 
 EngineParams paramsFromC(const o2v_b200_params &p)

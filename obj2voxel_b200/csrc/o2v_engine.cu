@@ -85,6 +85,7 @@ Engine *Engine::create(int device, std::string *error)
     ok = ok && cudaEventCreate(&e->evStart_) == cudaSuccess && cudaEventCreate(&e->evSetup_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evVoxStart_) == cudaSuccess && cudaEventCreate(&e->evVoxEnd_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evClipStart_) == cudaSuccess && cudaEventCreate(&e->evClipEnd_) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->evClassifyStart_) == cudaSuccess;
     ok = ok && e->counters_.ensure(sizeof(RunCounters));
     if (!ok) {
         if (error != nullptr) {
@@ -115,7 +116,7 @@ Engine::~Engine()
             cudaFreeHost(p);
         }
     }
-    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_}) {
+    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_, evClassifyStart_}) {
         if (ev != nullptr) {
             cudaEventDestroy(ev);
         }
@@ -385,6 +386,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
         if (sparseActive && occupancy) {
             O2V_CUDA(cudaMemsetAsync(tileBits_.as<void>(), 0, (size_t) activeTotal * kTileEdge * 8, stream));
+            O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
             launchOccupancyClassify(args, stream);
             O2V_CUDA(cudaEventRecord(evClipStart_, stream));
             launchOccupancyClip(args, smCount_, stream);
@@ -458,6 +460,9 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
     if (sparseActive) {
         cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
+        if (occupancy) {
+            cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evClipStart_);
+        }
     }
     return kErrOk;
 }

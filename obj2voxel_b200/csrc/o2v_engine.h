@@ -37,7 +37,8 @@ struct RunStats {
     float msTotal = 0;     // device time of the whole pipeline (CUDA events on the run stream)
     float msSetup = 0;     // bounds + count + scans + emit + sort
     float msVoxelize = 0;  // clip + fold + heavy tiles
-    float msClip = 0;      // the dominant kernel alone (sparseClipKernel)
+    float msClip = 0;      // the exact-clip kernel alone (sparseClipKernel / occupancyClipKernel)
+    float msClassify = 0;  // occupancy-only path: the SAT classification kernel alone
     int voxelizeLaunches = 0;
     int kernelLaunches = 0;
     unsigned long long outCapacity = 0;
@@ -103,7 +104,7 @@ private:
     RunCounters *hostCounters_ = nullptr;  // pinned
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
-    cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr;
+    cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr;
 
     DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
