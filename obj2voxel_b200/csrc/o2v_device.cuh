@@ -8,12 +8,83 @@
 namespace o2v {
 namespace {
 
+/// Adds a per-thread tally to a global counter with one atomic per warp (all 32 lanes must call it).
+__device__ __forceinline__ void warpTally(unsigned long long *counter, unsigned long long value)
+{
+    for (int o = 16; o > 0; o >>= 1) {
+        value += __shfl_xor_sync(0xffffffffu, value, o);
+    }
+    if ((threadIdx.x & 31) == 0 && value != 0) {
+        atomicAdd(counter, value);
+    }
+}
+
 __device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile, uint32_t origin[3])
 {
     const uint32_t T = grid.tilesPerAxis;
     origin[0] = (tile % T) * kTileEdge;
     origin[1] = ((tile / T) % T) * kTileEdge;
     origin[2] = (tile / (T * T) + grid.slabTileZ0) * kTileEdge;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// triangle setup shared by the count and emit passes
+
+template <bool UV>
+__device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridView &grid, unsigned long long i,
+                                             Tri<UV> &t, float &area)
+{
+    const float *src = mesh.verts + i * 9;
+    float in[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        in[k] = __ldg(src + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        affineApply(grid.xf, in + k * 3, t.v + k * 3);  // applyMeshTransform, src/obj2voxel.cpp:202-209
+    }
+    if (UV) {
+        const float *uv = mesh.uvs + i * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            t.t[k] = __ldg(uv + k);
+        }
+    }
+    area = triArea(t.v);
+    // A negative voxel-space coordinate wraps the reference's float -> u32 cast to a huge chunkMin (triangle.hpp:91-95,
+    // obj2voxel.cpp:211-219; formally UB), so the triangle lands in no chunk: dropped as a whole.
+    bool negative = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        negative |= floorf(min3(t.v[a], t.v[3 + a], t.v[6 + a])) < 0.0f;
+    }
+    // weight 0 never reaches the voxel map (voxelization.cpp:466); non-finite input is a contract violation
+    return area > 0.0f && area < INFINITY && !negative;
+}
+
+/// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
+template <bool UV, typename Visit>
+__device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit)
+{
+    uint32_t rlo[3], rhi[3];
+    triVoxelBounds(root.v, rlo, rhi);
+    if (rhi[2] <= grid.slabZ0 || rlo[2] >= grid.slabZ1) {
+        return true;  // midpoints stay inside the parent's AABB, so no leaf can reach the slab
+    }
+    return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
+        uint32_t lo[3], hi[3];
+        triVoxelBounds(leaf.v, lo, hi);
+        // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
+        hi[0] = min(hi[0], grid.gridExtent);
+        hi[1] = min(hi[1], grid.gridExtent);
+        lo[2] = max(lo[2], grid.slabZ0);
+        hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
+        if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
+            return;
+        }
+        visit(leaf, lo, hi);
+    });
 }
 
 struct VoxelAccumulator {

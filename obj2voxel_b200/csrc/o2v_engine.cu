@@ -135,8 +135,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
 {
     // Every triangle MATERIALLESS (no per-triangle types, no usable texture): the output is white wherever a voxel is
     // occupied, whatever the weights — the occupancy-only path decides just that (o2v_occupancy.cu).
-    const bool occupancy = params.occupancyPath != 0 && meshIn.types == nullptr &&
-                           !(meshIn.uvs != nullptr && textureCount != 0);
+    bool occupancy = params.occupancyPath != 0 && meshIn.types == nullptr &&
+                     !(meshIn.uvs != nullptr && textureCount != 0);
     MeshView mesh = meshIn;
     if (occupancy) {
         mesh.uvs = nullptr;     // uvs without a texture never reach a colour (flushPartial)
@@ -209,6 +209,14 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     if (grid.slabTileZCount == 0) {
         return kErrOk;
     }
+    if (occupancy) {
+        const int rc = voxelizeOccupancy(mesh, params, grid, stream, st);
+        if (rc != kOccupancyFallback) {
+            return rc;
+        }
+        // the chunk bitmaps do not fit: fold weights like for any other mesh (same result)
+        O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+    }
 
     const unsigned long long tileTotal64 =
         (unsigned long long) grid.tilesPerAxis * grid.tilesPerAxis * grid.slabTileZCount;
@@ -224,7 +232,6 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         !activeTiles_.ensure((size_t) tileTotal * 4) || !allTiles_.ensure((size_t) tileTotal * 4) ||
         !longTiles_.ensure((size_t) tileTotal * 4) ||
         !tileCand_.ensure((size_t) tileTotal * 4) ||
-        (occupancy && !tileSlot_.ensure((size_t) tileTotal * 4)) ||
         !lightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) ||
         !bigLightTiles_.ensure((size_t) tileTotal * sizeof(LightTile)) || !scratch_.ensure(scratchElems * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (binning buffers)");
@@ -241,8 +248,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
                         &dCounters->pairs, stream);
     launchCompactActiveTiles(tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal,
                              allTiles_.as<uint32_t>(), longTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(),
-                             lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(),
-                             occupancy ? tileSlot_.as<uint32_t>() : nullptr, dCounters, stream);
+                             lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(), dCounters, stream);
     st.kernelLaunches += 8;
     O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
     O2V_CUDA(cudaStreamSynchronize(stream));
@@ -265,10 +271,9 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         (hasUv && !leafUvs_.ensure((size_t) std::max<unsigned long long>(leafTotal, 1) * sizeof(LeafUv))) ||
         !tileList_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
         !pairTile_.ensure((size_t) std::max<unsigned long long>(pairTotal, 1) * 4) ||
-        (!occupancy &&
-         (!pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
-          !pairMask_.ensure((size_t) (pairTotal + 1) * 8) || !pairBox_.ensure((size_t) (pairTotal + 1) * 4) ||
-          !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)))) {
+        !pairSurvivors_.ensure((size_t) (pairTotal + 1) * 4) || !pairOffset_.ensure((size_t) (pairTotal + 1) * 4) ||
+        !pairMask_.ensure((size_t) (pairTotal + 1) * 8) || !pairBox_.ensure((size_t) (pairTotal + 1) * 4) ||
+        !scratch_.ensure(std::max(scratchElems, scanScratchElems((size_t) pairTotal + 1)) * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (leaf buffers)");
     }
     if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
@@ -301,10 +306,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     work.tileCount = tileCount_.as<uint32_t>();
     work.tileList = tileList_.as<uint32_t>();
     work.activeCount = (uint32_t) hostCounters_->heavyTiles;
-    if (!occupancy) {  // the fold order only matters when weights reach the output
-        launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
-    }
-    st.kernelLaunches += occupancy ? 1 : 3;
+    launchSortTileLists(work, tileList_.as<uint32_t>(), stream);
+    st.kernelLaunches += 3;
 
     VoxelizeArgs args;
     args.grid = grid;
@@ -340,21 +343,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
     const bool boundAffordable = candidateBound < (1ull << 32) && candidateBound * 16ull <= (8ull << 30);
     bool sparseActive = args.lightCount != 0 || args.bigLightCount != 0;
-    unsigned long long queueCapacity = 0;
-    if (sparseActive && occupancy) {
-        // Queue of SAT-undecided voxels: a fraction of the candidates in practice (~6 %); sized at a quarter of the bound
-        // and grown to the exact need (one rerun) in the rare case that is not enough.
-        queueCapacity = std::max<unsigned long long>(std::min<unsigned long long>(candidateBound, 1ull << 20),
-                                                     candidateBound / 4);
-        if (!tileBits_.ensure((size_t) activeTotal * kTileEdge * 8) || !occQueue_.ensure((size_t) queueCapacity * 8)) {
-            return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
-        }
-        args.occ.tileSlot = tileSlot_.as<uint32_t>();
-        args.occ.tileBits = tileBits_.as<unsigned long long>();
-        args.occ.queue = occQueue_.as<uint2>();
-        args.occ.queueCapacity = queueCapacity;
-    }
-    else if (sparseActive) {
+    if (sparseActive) {
         O2V_CUDA(cudaMemsetAsync(pairSurvivors_.as<uint32_t>() + pairTotal, 0, 4, stream));
         launchSparseSurvivors(args, false, stream);
         launchExclusiveScan(pairSurvivors_.as<uint32_t>(), pairOffset_.as<uint32_t>(), (size_t) pairTotal + 1,
@@ -382,18 +371,9 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));
 
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
-        if (sparseActive && occupancy) {
-            O2V_CUDA(cudaMemsetAsync(tileBits_.as<void>(), 0, (size_t) activeTotal * kTileEdge * 8, stream));
-            O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
-            launchOccupancyClassify(args, stream);
-            O2V_CUDA(cudaEventRecord(evClipStart_, stream));
-            launchOccupancyClip(args, smCount_, stream);
-            O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
-            launchOccupancyExpand(args, smCount_, stream);
-        }
-        else if (sparseActive) {
+        if (sparseActive) {
             O2V_CUDA(cudaEventRecord(evClipStart_, stream));
             launchSparseClip(args, smCount_, stream);
             O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
@@ -401,41 +381,26 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         }
         launchVoxelizeTiles(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = (sparseActive ? (occupancy ? 3 : 4) : 0) + (args.work.activeCount != 0 ? 1 : 0);
+        const int launched = (sparseActive ? 4 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
-        const bool queueOverflow = occupancy && sparseActive && hostCounters_->survivors > queueCapacity;
-        if (hostCounters_->outputOverflow == 0 && !queueOverflow) {
+        if (hostCounters_->outputOverflow == 0) {
             break;
         }
-        if (attempt == 2) {
+        if (attempt == 1) {
             return fail(kErrOutOfMemory, "voxel output does not fit device memory");
         }
-        // the exact need is now known: grow once and redo the tile pass (setup results are still valid)
-        if (queueOverflow) {
-            // what is queued depends on which bits were already visible: leave head-room, capped by the true bound
-            queueCapacity = std::min(candidateBound, hostCounters_->survivors * 2 + (1ull << 20));
-            if (!occQueue_.ensure((size_t) queueCapacity * 8)) {
-                return fail(kErrOutOfMemory, "device allocation failed (occupancy queue, exact size)");
-            }
-            args.occ.queue = occQueue_.as<uint2>();
-            args.occ.queueCapacity = queueCapacity;
+        // the exact count is now known: grow once and redo the tile pass (setup results are still valid)
+        capacity = hostCounters_->voxels;
+        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+            return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
         }
-        if (hostCounters_->outputOverflow != 0 && !queueOverflow) {
-            capacity = hostCounters_->voxels;
-            if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
-                return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
-            }
-            args.out = out_.as<VoxelRecord>();
-            args.outCapacity = capacity;
-        }
+        args.out = out_.as<VoxelRecord>();
+        args.outCapacity = capacity;
         RunCounters reset = *hostCounters_;
-        if (occupancy) {
-            reset.survivors = 0;
-        }
         reset.voxels = 0;
         reset.contributions = 0;
         reset.clipCalls = 0;
@@ -450,8 +415,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         }
     }
 
-    hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor / queued voxel is one exact clip
-    st.occupancyPath = occupancy;
+    hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor is one exact clip
     st.counters = *hostCounters_;
     st.outCapacity = capacity;
     voxelCount_ = hostCounters_->voxels;
@@ -460,10 +424,168 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
     if (sparseActive) {
         cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
-        if (occupancy) {
-            cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evClipStart_);
+    }
+    return kErrOk;
+}
+
+int Engine::voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid,
+                              cudaStream_t stream, RunStats &st)
+{
+    RunCounters *dCounters = counters_.as<RunCounters>();
+    const size_t n = (size_t) mesh.count;
+
+    OccupancyView occ{};
+    occ.chunksPerAxis = grid.gridExtent / kChunkEdge;
+    occ.chunkZ0 = grid.slabZ0 / kChunkEdge;
+    const uint32_t chunkRows = (grid.slabZ1 + kChunkEdge - 1) / kChunkEdge - occ.chunkZ0;
+    occ.chunkTotal = occ.chunksPerAxis * occ.chunksPerAxis * chunkRows;  // <= 128^3
+    if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !scratch_.ensure(scanScratchElems(n) * 4) ||
+        !chunkFlag_.ensure(occ.chunkTotal) || !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) ||
+        !chunkList_.ensure((size_t) occ.chunkTotal * 4)) {
+        return fail(kErrOutOfMemory, "device allocation failed (occupancy path, setup buffers)");
+    }
+    occ.chunkFlag = chunkFlag_.as<uint8_t>();
+    occ.chunkSlot = chunkSlot_.as<uint32_t>();
+    occ.chunkList = chunkList_.as<uint32_t>();
+    O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, occ.chunkTotal, stream));
+
+    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), dCounters, stream);
+    launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
+                        &dCounters->leaves, stream);
+    launchOccupancyAssignChunks(occ, dCounters, stream);
+    st.kernelLaunches += 5;
+    O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
+
+    const unsigned long long leafTotal = hostCounters_->leaves;
+    const unsigned long long candidateBound = hostCounters_->candidateVoxels;
+    const unsigned long long bigLeaves = hostCounters_->bigLeaves, bigBoxes = hostCounters_->bigBoxes;
+    occ.activeChunks = (uint32_t) hostCounters_->activeTiles;
+    if (leafTotal >= (1ull << 32) || bigBoxes >= (1ull << 32) || bigLeaves >= (1ull << 24)) {
+        return fail(kErrTooLarge, "more than 2^32-1 leaves or boxes in this slab");
+    }
+    st.occupancyPath = true;
+    if (leafTotal == 0) {
+        st.counters = *hostCounters_;
+        return kErrOk;
+    }
+
+    // Output capacity: every voxel needs a candidate, and a chunk emits at most 64^3 (8 times fewer when downscaled).
+    const unsigned long long perChunk =
+        (unsigned long long) kChunkEdge * kChunkEdge * kChunkEdge / (params.supersampling == 2 ? 8 : 1);
+    unsigned long long capacity = std::min(candidateBound, occ.activeChunks * perChunk);
+    capacity = std::max<unsigned long long>(capacity, 1);
+    // Queue of SAT-undecided voxels: a fraction of the candidates in practice (~5 %); sized at a quarter of the bound and
+    // grown to the need (one rerun) in the rare case that is not enough.
+    unsigned long long queueCapacity =
+        std::max<unsigned long long>(std::min<unsigned long long>(candidateBound, 1ull << 20), candidateBound / 4);
+
+    const size_t bitmapBytes = (size_t) occ.activeChunks * kChunkWords * 8;
+    if (bitmapBytes > tileBits_.size()) {
+        size_t freeBytes = 0, totalBytes = 0;
+        O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+        if (bitmapBytes > (freeBytes + tileBits_.size()) / 2) {
+            return kOccupancyFallback;  // e.g. a dense 8192^3 job: the caller takes the weighted path
         }
     }
+    if (!tileBits_.ensure(bitmapBytes) || !leaves_.ensure((size_t) leafTotal * sizeof(LeafRecord)) ||
+        !occQueue_.ensure((size_t) queueCapacity * sizeof(uint4)) ||
+        !bigLeaves_.ensure((size_t) std::max<unsigned long long>(bigLeaves, 1) * sizeof(uint2))) {
+        return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
+    }
+    if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
+        size_t freeBytes = 0, totalBytes = 0;
+        O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+        const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
+        capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
+    }
+    if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+        return fail(kErrOutOfMemory, "device allocation failed (voxel output)");
+    }
+    occ.bits = tileBits_.as<unsigned long long>();
+    occ.queue = occQueue_.as<uint4>();
+    occ.queueCapacity = queueCapacity;
+    occ.bigLeaves = bigLeaves_.as<uint2>();
+    occ.bigCapacity = (uint32_t) bigLeaves;
+
+    launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, stream);
+    ++st.kernelLaunches;
+    O2V_CUDA(cudaEventRecord(evSetup_, stream));
+
+    VoxelizeArgs args{};
+    args.grid = grid;
+    args.leaves = leaves_.as<LeafRecord>();
+    args.mesh = mesh;
+    args.out = out_.as<VoxelRecord>();
+    args.outCapacity = capacity;
+    args.counters = dCounters;
+    args.occ = occ;
+    args.variant = params.variant < 0 ? 0 : params.variant;
+    args.prefilter = params.prefilter;
+
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
+        O2V_CUDA(cudaMemsetAsync(occ.bits, 0, bitmapBytes, stream));
+        O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
+        launchOccupancyClassify(args, leafTotal, (uint32_t) bigLeaves, bigBoxes, smCount_, stream);
+        O2V_CUDA(cudaEventRecord(evClipStart_, stream));
+        launchOccupancyClip(args, smCount_, stream);
+        O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
+        launchOccupancyExpand(args, smCount_, stream);
+        O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
+        const int launched = 3 + (bigLeaves != 0 ? 1 : 0);
+        st.voxelizeLaunches += launched;
+        st.kernelLaunches += launched;
+        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        O2V_CUDA(cudaGetLastError());
+        const bool queueOverflow = hostCounters_->survivors > queueCapacity;
+        if (hostCounters_->outputOverflow == 0 && !queueOverflow) {
+            break;
+        }
+        if (attempt == 2) {
+            return fail(kErrOutOfMemory, "voxel output does not fit device memory");
+        }
+        if (queueOverflow) {
+            // what is queued depends on which bits were already visible: leave head-room, capped by the true bound
+            queueCapacity = std::min(candidateBound, hostCounters_->survivors * 2 + (1ull << 20));
+            if (!occQueue_.ensure((size_t) queueCapacity * sizeof(uint4))) {
+                return fail(kErrOutOfMemory, "device allocation failed (occupancy queue, grown)");
+            }
+            args.occ.queue = occQueue_.as<uint4>();
+            args.occ.queueCapacity = queueCapacity;
+        }
+        else {  // the exact voxel count is known now
+            capacity = hostCounters_->voxels;
+            if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+                return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
+            }
+            args.out = out_.as<VoxelRecord>();
+            args.outCapacity = capacity;
+        }
+        RunCounters reset = *hostCounters_;
+        reset.survivors = 0;
+        reset.voxels = 0;
+        reset.outputOverflow = 0;
+        *hostCountersInit_ = reset;
+        O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        memset(hostCountersInit_, 0, sizeof(RunCounters));
+        for (int i = 0; i < 3; ++i) {
+            hostCountersInit_->boundsMinBits[i] = 0xffffffffu;
+        }
+    }
+
+    hostCounters_->clipCalls = hostCounters_->survivors;  // every queued voxel is (at most) one exact clip
+    st.counters = *hostCounters_;
+    st.outCapacity = capacity;
+    voxelCount_ = hostCounters_->voxels;
+    cudaEventElapsedTime(&st.msTotal, evStart_, evVoxEnd_);
+    cudaEventElapsedTime(&st.msSetup, evStart_, evSetup_);
+    cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
+    cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evClipStart_);
+    cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
     return kErrOk;
 }
 

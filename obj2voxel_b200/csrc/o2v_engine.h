@@ -92,6 +92,11 @@ public:
 private:
     Engine() = default;
     int fail(int code, const std::string &message);
+    /// The occupancy-only pipeline (o2v_occupancy.cu) for an all-MATERIALLESS mesh; kOccupancyFallback if its bitmaps do
+    /// not fit device memory (the caller then runs the weighted pipeline).
+    int voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid, cudaStream_t stream,
+                          RunStats &st);
+    static constexpr int kOccupancyFallback = 1;
 
     int device_ = 0;
     int smCount_ = 0;
@@ -110,7 +115,7 @@ private:
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
-    DeviceBuffer tileSlot_, tileBits_, occQueue_;  // occupancy-only path
+    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

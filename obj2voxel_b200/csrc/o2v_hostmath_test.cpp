@@ -82,10 +82,13 @@ void o2vt_combine(float acc[4], const float incoming[4], int blend)
     acc[3] = c.b;
 }
 
-/// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through classifyVoxel (o2v_sat.cuh) and
-/// through the reference semantics (plane-distance cull + exact clip, o2v_exact.cuh) and counts disagreements.
-/// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts the reference hits
-/// (must be 0), [6] `certain` verdicts the reference does not hit (must be 0), [7] leaves skipped (AABB too large).
+/// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through the two SAT users of the kernels
+///   * prefilterPass with tile-relative constants (weighted path: o2v_sparse.cu / o2v_kernels.cu),
+///   * classifyVoxel with constants relative to the leaf's box — or to its 16^3 sub-boxes when the box holds more than
+///     4096 voxels — exactly as o2v_occupancy.cu stages them,
+/// and through the reference semantics (plane-distance cull + exact clip, o2v_exact.cuh), and counts disagreements.
+/// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts (either user) the
+/// reference hits (must be 0), [6] `certain` verdicts the reference does not hit (must be 0), [7] leaves skipped.
 void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVolume, unsigned long long out[8])
 {
     for (int i = 0; i < 8; ++i) {
@@ -104,36 +107,42 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
         Tri<false> tri;
         memcpy(tri.v, v, sizeof tri.v);
         const uint32_t flags = leafFlagsOf(v);
-        for (uint32_t tz = lo[2] / 8; tz <= (hi[2] - 1) / 8; ++tz) {
-            for (uint32_t ty = lo[1] / 8; ty <= (hi[1] - 1) / 8; ++ty) {
-                for (uint32_t tx = lo[0] / 8; tx <= (hi[0] - 1) / 8; ++tx) {
-                    const float origin[3] = {(float) (tx * 8), (float) (ty * 8), (float) (tz * 8)};
-                    LeafStage s;
-                    memcpy(s.v, v, sizeof s.v);
-                    s.flags = flags;
-                    buildPrefilter(s, origin);
-                    LeafCertain c;
-                    buildCertain(c, s, origin);
-                    for (uint32_t z = tz * 8 > lo[2] ? tz * 8 : lo[2]; z < hi[2] && z < tz * 8 + 8; ++z) {
-                        for (uint32_t y = ty * 8 > lo[1] ? ty * 8 : lo[1]; y < hi[1] && y < ty * 8 + 8; ++y) {
-                            for (uint32_t x = tx * 8 > lo[0] ? tx * 8 : lo[0]; x < hi[0] && x < tx * 8 + 8; ++x) {
-                                const int verdict = classifyVoxel(s, c, (float) (x - tx * 8), (float) (y - ty * 8),
-                                                                  (float) (z - tz * 8));
-                                const bool pass = prefilterPass(s, (float) (x - tx * 8), (float) (y - ty * 8),
-                                                                (float) (z - tz * 8));
-                                const bool hit = !planeDistanceCulled(v, x, y, z) &&
-                                                 clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
-                                ++out[0];
-                                ++out[1 + verdict];
-                                out[4] += hit ? 1 : 0;
-                                out[5] += ((verdict == kSatMiss || !pass) && hit) ? 1 : 0;
-                                out[6] += (verdict == kSatCertain && !hit) ? 1 : 0;
-                                if (pass != (verdict != kSatMiss)) {
-                                    out[5] += 1000000;  // the two forms of the conservative test must agree
-                                }
-                            }
-                        }
+        const uint32_t boxEdge = volume > 4096 ? 16u : 0xffffffffu;  // o2v_occupancy.cu: kOccBigVolume, kOccBoxEdge
+        for (uint32_t z = lo[2]; z < hi[2]; ++z) {
+            for (uint32_t y = lo[1]; y < hi[1]; ++y) {
+                for (uint32_t x = lo[0]; x < hi[0]; ++x) {
+                    // weighted path: constants relative to the voxel's 8^3 tile
+                    const float tileOrigin[3] = {(float) (x & ~7u), (float) (y & ~7u), (float) (z & ~7u)};
+                    LeafStage ts;
+                    memcpy(ts.v, v, sizeof ts.v);
+                    ts.flags = flags;
+                    buildPrefilter(ts, tileOrigin);
+                    const bool pass = prefilterPass(ts, (float) (x & 7u), (float) (y & 7u), (float) (z & 7u));
+                    // occupancy path: constants relative to the leaf's box or 16^3 sub-box
+                    uint32_t bo[3] = {lo[0], lo[1], lo[2]};
+                    if (boxEdge != 0xffffffffu) {
+                        bo[0] += (x - lo[0]) / boxEdge * boxEdge;
+                        bo[1] += (y - lo[1]) / boxEdge * boxEdge;
+                        bo[2] += (z - lo[2]) / boxEdge * boxEdge;
                     }
+                    const float boxOrigin[3] = {(float) bo[0], (float) bo[1], (float) bo[2]};
+                    LeafStage bs;
+                    memcpy(bs.v, v, sizeof bs.v);
+                    bs.flags = flags;
+                    buildPrefilter(bs, boxOrigin);
+                    PairSat sat;
+                    buildPairSat(sat, bs, boxOrigin);
+                    const int verdict = (flags & kLeafNoPrefilter) != 0
+                                            ? (int) kSatUncertain
+                                            : classifyVoxel(sat, (float) (x - bo[0]), (float) (y - bo[1]),
+                                                            (float) (z - bo[2]));
+                    const bool hit =
+                        !planeDistanceCulled(v, x, y, z) && clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
+                    ++out[0];
+                    ++out[1 + verdict];
+                    out[4] += hit ? 1 : 0;
+                    out[5] += ((verdict == kSatMiss || !pass) && hit) ? 1 : 0;
+                    out[6] += (verdict == kSatCertain && !hit) ? 1 : 0;
                 }
             }
         }

@@ -72,66 +72,6 @@ __global__ void finishBoundsKernel(RunCounters *counters)
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// triangle setup shared by the count and emit passes
-
-template <bool UV>
-__device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridView &grid, unsigned long long i,
-                                             Tri<UV> &t, float &area)
-{
-    const float *src = mesh.verts + i * 9;
-    float in[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        in[k] = __ldg(src + k);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        affineApply(grid.xf, in + k * 3, t.v + k * 3);  // applyMeshTransform, src/obj2voxel.cpp:202-209
-    }
-    if (UV) {
-        const float *uv = mesh.uvs + i * 6;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            t.t[k] = __ldg(uv + k);
-        }
-    }
-    area = triArea(t.v);
-    // A negative voxel-space coordinate wraps the reference's float -> u32 cast to a huge chunkMin (triangle.hpp:91-95,
-    // obj2voxel.cpp:211-219; formally UB), so the triangle lands in no chunk: dropped as a whole.
-    bool negative = false;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        negative |= floorf(min3(t.v[a], t.v[3 + a], t.v[6 + a])) < 0.0f;
-    }
-    // weight 0 never reaches the voxel map (voxelization.cpp:466); non-finite input is a contract violation
-    return area > 0.0f && area < INFINITY && !negative;
-}
-
-/// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
-template <bool UV, typename Visit>
-__device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit)
-{
-    uint32_t rlo[3], rhi[3];
-    triVoxelBounds(root.v, rlo, rhi);
-    if (rhi[2] <= grid.slabZ0 || rlo[2] >= grid.slabZ1) {
-        return true;  // midpoints stay inside the parent's AABB, so no leaf can reach the slab
-    }
-    return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
-        uint32_t lo[3], hi[3];
-        triVoxelBounds(leaf.v, lo, hi);
-        // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
-        hi[0] = min(hi[0], grid.gridExtent);
-        hi[1] = min(hi[1], grid.gridExtent);
-        lo[2] = max(lo[2], grid.slabZ0);
-        hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
-        if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
-            return;
-        }
-        visit(leaf, lo, hi);
-    });
-}
-
 __device__ __forceinline__ uint32_t localTileId(const GridView &grid, uint32_t tx, uint32_t ty, uint32_t tz)
 {
     return ((tz - grid.slabTileZ0) * grid.tilesPerAxis + ty) * grid.tilesPerAxis + tx;
@@ -173,15 +113,9 @@ countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount
         }
         leafCount[i] = leaves;
     }
-    if (candidates != 0) {
-        atomicAdd(&counters->candidateVoxels, candidates);
-    }
-    if (dropped != 0) {
-        atomicAdd(&counters->droppedTriangles, dropped);
-    }
-    if (overflow != 0) {
-        atomicAdd(&counters->depthOverflow, overflow);
-    }
+    warpTally(&counters->candidateVoxels, candidates);
+    warpTally(&counters->droppedTriangles, dropped);
+    warpTally(&counters->depthOverflow, overflow);
 }
 
 template <bool UV>
@@ -375,8 +309,7 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
                                          const uint32_t *__restrict__ tileStart, uint32_t tileTotal,
                                          uint32_t *__restrict__ allTiles, uint32_t *__restrict__ longTiles,
                                          uint32_t *__restrict__ heavyTiles, LightTile *__restrict__ lightTiles,
-                                         LightTile *__restrict__ bigLightTiles, uint32_t *__restrict__ tileSlot,
-                                         RunCounters *counters)
+                                         LightTile *__restrict__ bigLightTiles, RunCounters *counters)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = i < tileTotal ? tileCount[i] : 0u;
@@ -450,11 +383,7 @@ __global__ void compactActiveTilesKernel(const uint32_t *__restrict__ tileCount,
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (count != 0) {
-            const uint32_t slot = (uint32_t) base + __popc(anyBallot & below);
-            allTiles[slot] = i;
-            if (tileSlot != nullptr) {
-                tileSlot[i] = slot;
-            }
+            allTiles[base + __popc(anyBallot & below)] = i;
         }
     }
 }
@@ -799,15 +728,15 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, LightTile *bigLightTiles, uint32_t *tileSlot,
-                              RunCounters *counters, cudaStream_t stream)
+                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
+                              cudaStream_t stream)
 {
     if (tileTotal == 0) {
         return;
     }
     compactActiveTilesKernel<<<(tileTotal + 255) / 256, 256, 0, stream>>>(tileCount, tileCandidates, tileStart,
                                                                           tileTotal, allTiles, longTiles, heavyTiles,
-                                                                          lightTiles, bigLightTiles, tileSlot, counters);
+                                                                          lightTiles, bigLightTiles, counters);
 }
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,

@@ -83,6 +83,10 @@ struct RunCounters {
     unsigned int boundsMaxBits[3];
     unsigned int tileCursor;
     unsigned int pad;
+    // occupancy-only path
+    unsigned long long bigLeaves;       // leaves with more than kOccBigVolume candidate voxels
+    unsigned long long bigBoxes;        // their 16^3 boxes
+    unsigned long long bigTicket;       // emit pass: (table row << 40) | first box, handed out by one atomic
 };
 
 /// Descriptor of a light tile: everything the warp needs in one 16-byte load.
@@ -121,7 +125,7 @@ void launchExclusiveScan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *
 /// Splits the non-empty tiles into light descriptors and the heavy id list (order irrelevant: tiles are independent).
 void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCandidates, const uint32_t *tileStart,
                               uint32_t tileTotal, uint32_t *allTiles, uint32_t *longTiles, uint32_t *heavyTiles,
-                              LightTile *lightTiles, LightTile *bigLightTiles, uint32_t *tileSlot, RunCounters *counters,
+                              LightTile *lightTiles, LightTile *bigLightTiles, RunCounters *counters,
                               cudaStream_t stream);
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
@@ -144,14 +148,26 @@ struct SparseView {
     float2 *uvs;                     // per survivor (textured meshes only)
 };
 
+constexpr uint32_t kChunkEdge = 64;     // voxels per chunk edge: the unit the occupancy bitmaps are allocated in
+constexpr uint32_t kChunkWords = 4096;  // 64-bit words of one chunk bitmap: 512 tiles x 8 layers (32 KB)
+constexpr uint32_t kOccBigVolume = 4096;  // leaves with more candidate voxels are classified box by box ...
+constexpr uint32_t kOccBoxEdge = 16;      // ... in 16^3 boxes
+
 /// Buffers of the occupancy-only path (o2v_occupancy.cu): meshes whose every triangle is MATERIALLESS voxelize white
 /// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
-/// occupancy has to be decided — an order-independent OR.
+/// occupancy has to be decided — an order-independent OR into per-chunk bitmaps.
 struct OccupancyView {
-    const uint32_t *tileSlot;        // per tile: its index in TileWork::allTiles = its bitmap slot
-    unsigned long long *tileBits;    // 8 words per slot: bit (x + 8 y) of word z = voxel (x, y, z) of the tile is occupied
-    uint2 *queue;                    // {pair index, tile-local voxel} of the voxels the SAT could not decide
+    uint8_t *chunkFlag;              // per 64^3 chunk of the slab: some leaf's box reaches it
+    uint32_t *chunkSlot;             // per chunk: index of its bitmap
+    uint32_t *chunkList;             // per bitmap: its chunk
+    uint32_t chunksPerAxis, chunkZ0, chunkTotal;  // chunk id = cx + C * (cy + C * (cz - chunkZ0))
+    uint32_t activeChunks;           // bitmaps in use (host copy of the device count)
+    unsigned long long *bits;        // kChunkWords per bitmap: word = tile (x | y << 3 | z << 6) * 8 + layer z,
+                                     // bit (x + 8 y) = voxel (x, y, z) of that tile is occupied
+    uint4 *queue;                    // {leaf, x | y << 16, z, -} of the voxels the SAT could not decide
     unsigned long long queueCapacity;
+    uint2 *bigLeaves;                // {leaf, first box} of the leaves with more than kOccBigVolume candidates
+    uint32_t bigCapacity;
 };
 
 struct VoxelizeArgs {
@@ -185,11 +201,16 @@ void launchSparseSurvivors(const VoxelizeArgs &args, bool write, cudaStream_t st
 void launchSparseClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 
-/// Occupancy-only path for the same light tiles (see OccupancyView): (1) thread per (leaf, tile) pair classifies the
-/// pair's candidate voxels with the three-way SAT of o2v_sat.cuh — `certain` voxels are OR-ed into the tile bitmap,
-/// `uncertain` ones are queued —, (2) the exact clip decides the queued voxels, (3) thread per tile expands the bitmap
-/// (optionally 2x downscaled) into Voxel32 records.
-void launchOccupancyClassify(const VoxelizeArgs &args, cudaStream_t stream);
+/// Occupancy-only path (see OccupancyView and the header of o2v_occupancy.cu): count / emit leaves per triangle, classify
+/// every candidate voxel with the three-way SAT of o2v_sat.cuh (`certain` -> bitmap, `uncertain` -> queue), exact clip
+/// for the queue, bitmap -> Voxel32 records.
+void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
+                          RunCounters *counters, cudaStream_t stream);
+void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
+void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream);
+void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, uint32_t bigCount,
+                             unsigned long long boxTotal, int smCount, cudaStream_t stream);
 void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchOccupancyExpand(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 

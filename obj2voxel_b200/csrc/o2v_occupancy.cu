@@ -4,26 +4,63 @@
 // _colored — SURVEY fact 8) voxelizes to 0xFFFFFFFF wherever a voxel is occupied: colorAt_f returns white
 // (src/triangle.hpp:186), BLEND of equal colours is (w1 + w2) / (w1 + w2) = 1 exactly, MAX keeps one of two whites, the
 // 2x downscale combines whites.  The weights — the only thing the fold order and the piece count feed — never reach the
-// output, so the result is the set { voxel : some leaf's exact clip has >= 1 piece }, an order-independent OR:
+// output, so the result is the set { voxel : some leaf's exact clip has >= 1 piece }, an order-independent OR.  No tile
+// lists, no sort, no fold:
 //
-//   classify  thread = candidate voxel     three-way SAT (o2v_sat.cuh): `certain` -> atomicOr into the tile's 512-bit
-//                                          bitmap, `uncertain` -> queue entry (unless the bitmap already decides it)
-//   clip      persistent lanes             the bit-exact six-plane clip (WarpClipper) for queued voxels only
-//   expand    thread = tile                bitmap (OR-reduced 2x2x2 when supersampling) -> compacted Voxel32 records
+//   count     thread = triangle           subdivision DFS (exact) -> leaf count, candidate total, touched 64^3 chunks
+//   emit      thread = triangle           LeafRecord per leaf; leaves with more than 4096 candidates also enter the
+//                                          big-leaf table (their box is cut into 16^3 boxes)
+//   classify  thread = candidate voxel    block = 128 leaves (or one 16^3 box): SAT constants staged in shared memory, the
+//                                          batch's candidates as ONE flat index space (balanced whatever the box sizes),
+//                                          three-way SAT (o2v_sat.cuh): `certain` -> warp-aggregated atomicOr into the
+//                                          chunk bitmap, `uncertain` -> queue (unless the bitmap already decides it)
+//   clip      persistent lanes            the bit-exact six-plane clip (WarpClipper) for queued voxels only
+//   expand    thread = tile               bitmap (OR-reduced 2x2x2 when supersampling) -> compacted Voxel32 records
 //
 // Exactness: `miss` and `certain` are proofs about the reference's result (o2v_sat.cuh header; fuzzed by
-// tests/test_sat_classifier.py), everything else runs the reference arithmetic.  Tiles above kLightMaxCandidates keep
-// the block-per-tile kernel.  prefilter = 0 sends every candidate through the exact clip (validation).
+// tests/test_sat_classifier.py), everything else runs the reference arithmetic.  prefilter = 0 sends every candidate
+// through the exact clip (validation).
 #include "o2v_device.cuh"
 
 namespace o2v {
 
 namespace {
 
-constexpr int kOccPairThreads = 128;
+constexpr int kOccSetupThreads = 128;
+constexpr int kOccBatch = 128;          // leaves per classify block = threads per block
 constexpr int kOccClipThreads = 128;
 constexpr int kOccExpandThreads = 128;
 constexpr int kOccRefillThreshold = 8;
+constexpr uint32_t kOccMaybeCap = 2048;  // undecided voxels a block buffers before filtering them against the bitmap
+
+// ---------------------------------------------------------------------------------------------------------------------
+// addressing
+
+/// Clips a leaf's voxel AABB to the chunk grid and this rank's slab (the candidate set of voxelizeSubTriangle,
+/// src/voxelization.cpp:440-447, restricted to the voxels this rank owns).  false if nothing is left.
+__device__ __forceinline__ bool leafBoxInSlab(const float *v, const GridView &grid, uint32_t lo[3], uint32_t hi[3])
+{
+    triVoxelBounds(v, lo, hi);
+    // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
+    hi[0] = min(hi[0], grid.gridExtent);
+    hi[1] = min(hi[1], grid.gridExtent);
+    lo[2] = max(lo[2], grid.slabZ0);
+    hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
+    return lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2];
+}
+
+/// Index of the 64-bit bitmap word (layer z of the voxel's tile) and the voxel's bit in it.
+__device__ __forceinline__ size_t bitmapWord(const OccupancyView &occ, uint32_t x, uint32_t y, uint32_t z)
+{
+    const uint32_t chunk = (x >> 6) + occ.chunksPerAxis * ((y >> 6) + occ.chunksPerAxis * ((z >> 6) - occ.chunkZ0));
+    const uint32_t tileLocal = ((x >> 3) & 7u) | (((y >> 3) & 7u) << 3) | (((z >> 3) & 7u) << 6);
+    return (size_t) __ldg(occ.chunkSlot + chunk) * kChunkWords + tileLocal * kTileEdge + (z & 7u);
+}
+
+__device__ __forceinline__ unsigned long long bitmapBit(uint32_t x, uint32_t y)
+{
+    return 1ull << ((x & 7u) + 8u * (y & 7u));
+}
 
 /// Bits of `m` (layout x + 8 y) smeared over their 2x2 xy blocks: the footprint of the parents that already have a child.
 __device__ __forceinline__ unsigned long long smear2x2(unsigned long long m)
@@ -34,195 +71,305 @@ __device__ __forceinline__ unsigned long long smear2x2(unsigned long long m)
     return evenY | (evenY << 8);
 }
 
-/// Per-pair SAT constants staged in shared memory.  43 words: an odd stride, so the staging threads (one pair each) write
-/// without bank conflicts; in the flat phase the lanes of a warp read the same one or two pairs (broadcast).
-struct PairSat {
-    float plane[4];
-    float planeLimit, planeSure;
-    float edge[27];
-    float lo[3], hi[3];
-    uint32_t flags;
-    uint32_t box;               // tile-local AABB as in LeafStage::box; 0 = pair not on this path
-    uint32_t magicX, magicXY;   // n / d == (n * magic) >> 16 for n < 512, d = dx resp. dx * dy (<= 64)
+/// true if the bitmap already decides voxel (x, y, z): its bit is set or — when downscaling — its parent has a child.
+__device__ __forceinline__ bool alreadyDecided(const OccupancyView &occ, bool downscale, uint32_t x, uint32_t y,
+                                               uint32_t z)
+{
+    const size_t word = bitmapWord(occ, x, y, z);
+    unsigned long long known = __ldcg(occ.bits + word);
+    if (downscale) {
+        known = smear2x2(known | __ldcg(occ.bits + (word ^ 1u)));  // z ^ 1 is the neighbouring word of the same tile
+    }
+    return (known & bitmapBit(x, y)) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// count / emit: thread per triangle
+
+__device__ __forceinline__ uint32_t boxCountOf(const uint32_t *lo, const uint32_t *hi)
+{
+    return ((hi[0] - lo[0] + kOccBoxEdge - 1) / kOccBoxEdge) * ((hi[1] - lo[1] + kOccBoxEdge - 1) / kOccBoxEdge) *
+           ((hi[2] - lo[2] + kOccBoxEdge - 1) / kOccBoxEdge);
+}
+
+__global__ void __launch_bounds__(kOccSetupThreads)
+occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ leafCount,
+                     RunCounters *counters)
+{
+    unsigned long long candidates = 0, dropped = 0, overflow = 0, bigLeaves = 0, bigBoxes = 0;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
+        Tri<false> root;
+        float area;
+        uint32_t leaves = 0;
+        if (loadTriangle<false>(mesh, grid, i, root, area)) {
+            const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &, const uint32_t *lo,
+                                                                   const uint32_t *hi) {
+                ++leaves;
+                const unsigned long long volume =
+                    (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+                candidates += volume;
+                if (volume > kOccBigVolume) {
+                    ++bigLeaves;
+                    bigBoxes += boxCountOf(lo, hi);
+                }
+                for (uint32_t cz = lo[2] >> 6; cz <= (hi[2] - 1) >> 6; ++cz) {
+                    for (uint32_t cy = lo[1] >> 6; cy <= (hi[1] - 1) >> 6; ++cy) {
+                        for (uint32_t cx = lo[0] >> 6; cx <= (hi[0] - 1) >> 6; ++cx) {
+                            occ.chunkFlag[cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0))] = 1;
+                        }
+                    }
+                }
+            });
+            overflow += ok ? 0 : 1;
+        }
+        else {
+            ++dropped;
+        }
+        leafCount[i] = leaves;
+    }
+    warpTally(&counters->candidateVoxels, candidates);
+    warpTally(&counters->droppedTriangles, dropped);
+    warpTally(&counters->depthOverflow, overflow);
+    warpTally(&counters->bigLeaves, bigLeaves);
+    warpTally(&counters->bigBoxes, bigBoxes);
+}
+
+__global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *counters)
+{
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool touched = chunk < occ.chunkTotal && occ.chunkFlag[chunk] != 0;
+    const unsigned int ballot = __ballot_sync(0xffffffffu, touched);
+    if (ballot == 0) {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        base = atomicAdd(&counters->activeTiles, (unsigned long long) __popc(ballot));  // here: active chunks
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (touched) {
+        const uint32_t slot = (uint32_t) base + __popc(ballot & ((1u << lane) - 1u));
+        occ.chunkSlot[chunk] = slot;
+        occ.chunkList[slot] = chunk;
+    }
+}
+
+__global__ void __launch_bounds__(kOccSetupThreads)
+occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ leafOffset,
+                    LeafRecord *__restrict__ leaves, RunCounters *counters)
+{
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
+        Tri<false> root;
+        float area;
+        if (!loadTriangle<false>(mesh, grid, i, root, area)) {
+            continue;
+        }
+        uint32_t index = leafOffset[i];
+        traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
+            LeafRecord rec;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                rec.v[k] = leaf.v[k];
+            }
+            rec.tri = static_cast<uint32_t>(i);
+            rec.area = area;
+            rec.flags = leafFlagsOf(leaf.v);
+            leaves[index] = rec;
+            const unsigned long long volume = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+            if (volume > kOccBigVolume) {
+                // one atomic hands out the table row (high 24 bits) and the first box number (low 40 bits) together, so
+                // the rows are sorted by first box: the box kernel finds its leaf by binary search
+                const uint32_t boxes = boxCountOf(lo, hi);
+                const unsigned long long ticket = atomicAdd(&counters->bigTicket, (1ull << 40) | boxes);
+                const uint32_t row = (uint32_t) (ticket >> 40);
+                if (row < occ.bigCapacity) {
+                    occ.bigLeaves[row] = make_uint2(index, (uint32_t) (ticket & ((1ull << 40) - 1ull)));
+                }
+            }
+            ++index;
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// classify: thread per candidate voxel
+
+/// Batch entry in shared memory: the SAT constants plus where the entry's box sits.  56 words, 16-byte aligned.
+struct alignas(16) BatchEntry {
+    PairSat sat;
+    uint32_t leaf;                // leaf index (queue entries name it)
+    uint32_t x0, y0, z0;          // box min corner, voxel space
+    uint32_t dx, dxdy;            // box extent in x, in x * y
+    uint32_t magicX, magicXY;     // n / d == __umulhi(n, magic) for d > 1, n * d <= 2^24 (d == 1: n itself)
 };
 
-constexpr int kOccAccWords = 33;  // per pair: sure[8][2] | maybe[8][2] 32-bit halves of the layer masks, +1 pad word
+struct ClassifyShared {
+    BatchEntry entry[kOccBatch];
+    uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' candidate counts
+    uint32_t maybe[kOccMaybeCap];     // (entry << 12) | candidate index in its box; top bit: survived the filter
+    uint32_t warpSums[kOccBatch / 32];
+    uint32_t maybeCount;
+    unsigned long long queueBase;
+};
 
-/// One block = kOccPairThreads consecutive (leaf, tile) pairs.
-///   stage    thread = pair        leaf -> SAT constants in shared memory; block-wide scan of the pairs' candidate counts
-///   classify thread = candidate   the batch's candidate voxels as one flat index space (perfectly balanced: a pair has
-///                                 1 .. 512 candidates), verdict bits OR-ed into the pair's layer masks in shared memory
-///   flush    thread = pair        `certain` masks -> global tile bitmap (one 64-bit atomicOr per layer), `uncertain` ones
-///                                 filtered by what the bitmap already shows, then appended to the queue (one global
-///                                 atomic per block)
-__global__ void __launch_bounds__(kOccPairThreads)
-occupancyClassifyKernel(const VoxelizeArgs args)
+__device__ __forceinline__ uint32_t magicOf(uint32_t d)
 {
-    __shared__ PairSat sat[kOccPairThreads];
-    __shared__ uint32_t acc[kOccPairThreads * kOccAccWords];
-    __shared__ uint32_t prefix[kOccPairThreads + 1];
-    __shared__ uint32_t warpSums[kOccPairThreads / 32];
-    __shared__ unsigned long long queueBase;
+    return d > 1u ? (uint32_t) ((1ull << 32) / d) + 1u : 0u;
+}
 
-    const SparseView &sp = args.sparse;
+__device__ __forceinline__ uint32_t divideBy(uint32_t n, uint32_t d, uint32_t magic)
+{
+    return d > 1u ? __umulhi(n, magic) : n;
+}
+
+/// Fills one batch entry for `leaf` restricted to the box [lo, hi).  Returns the number of candidates (0 = skip).
+__device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, uint32_t leafIndex, const uint32_t lo[3],
+                                                    const uint32_t hi[3], LeafStage &s)
+{
+    const float origin[3] = {(float) lo[0], (float) lo[1], (float) lo[2]};
+    buildPrefilter(s, origin);
+    buildPairSat(e.sat, s, origin);
+    e.leaf = leafIndex;
+    e.x0 = lo[0];
+    e.y0 = lo[1];
+    e.z0 = lo[2];
+    e.dx = hi[0] - lo[0];
+    e.dxdy = e.dx * (hi[1] - lo[1]);
+    e.magicX = magicOf(e.dx);
+    e.magicXY = magicOf(e.dxdy);
+    return e.dxdy * (hi[2] - lo[2]);
+}
+
+__device__ __forceinline__ void loadLeafVertices(LeafStage &s, const LeafRecord *leaves, uint32_t leafIndex)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(leaves + leafIndex);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
+    s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
+    s.v[8] = c.x;
+    s.flags = __float_as_uint(c.w);
+}
+
+__device__ __forceinline__ void candidateVoxel(const BatchEntry &e, uint32_t local, uint32_t &x, uint32_t &y,
+                                               uint32_t &z)
+{
+    const uint32_t zi = divideBy(local, e.dxdy, e.magicXY);
+    const uint32_t inLayer = local - zi * e.dxdy;
+    const uint32_t yi = divideBy(inLayer, e.dx, e.magicX);
+    x = e.x0 + (inLayer - yi * e.dx);
+    y = e.y0 + yi;
+    z = e.z0 + zi;
+}
+
+/// The block-wide part shared by the leaf-batch and the box kernels.  sh.entry[0 .. count) are staged and
+/// sh.prefix[0 .. kOccBatch] holds the exclusive scan of their candidate counts (entries >= count contribute 0).
+/// `noSat[p]` (bit p of a per-entry flag kept in entry.sat.planeLimit < 0) marks kLeafNoPrefilter leaves.
+__device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const VoxelizeArgs &args)
+{
     const OccupancyView &occ = args.occ;
     const unsigned int full = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool downscale = args.grid.supersampling == 2;
-    const uint32_t pair = blockIdx.x * kOccPairThreads + tid;
+    const uint32_t total = sh.prefix[kOccBatch];
+    uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
 
-    // ---- stage ----
-    uint32_t volume = 0, tile = 0;
-    {
-        PairSat &mine = sat[tid];
-        mine.box = 0;
-        bool active = pair < sp.pairCount;
-        if (active) {
-            tile = sp.pairTile[pair];
-            active = sp.tileCandidates[tile] <= kLightMaxCandidates;  // heavy tiles: block-per-tile kernel
+    // ---- verdict per candidate; block-uniform trip count ----
+    for (uint32_t base = 0; base < total; base += kOccBatch) {
+        const uint32_t i = base + tid;
+        int verdict = kSatMiss;
+        uint32_t p = 0, local = 0, x = 0, y = 0, z = 0;
+        if (i < total) {
+#pragma unroll
+            for (uint32_t step = kOccBatch / 2; step > 0; step >>= 1) {  // last entry with prefix[p] <= i
+                p += sh.prefix[p + step] <= i ? step : 0u;
+            }
+            const BatchEntry &e = sh.entry[p];
+            local = i - sh.prefix[p];
+            candidateVoxel(e, local, x, y, z);
+            // planeLimit < 0 marks a leaf whose normal is too noisy for the SAT (kLeafNoPrefilter): all undecided
+            verdict = (args.prefilter && e.sat.planeLimit >= 0.0f)
+                          ? classifyVoxel(e.sat, (float) (x - e.x0), (float) (y - e.y0), (float) (z - e.z0))
+                          : (int) kSatUncertain;
         }
-        if (active) {
-            uint32_t origin[3];
-            tileOriginOf(args.grid, tile, origin);
-            LeafStage s;
-            stageLeaf<false>(s, args, args.work.tileList[pair], origin);
-            const float originF[3] = {(float) origin[0], (float) origin[1], (float) origin[2]};
-            LeafCertain c;
-            buildCertain(c, s, originF);
-            const uint32_t dx = ((s.box >> 12) & 15u) - (s.box & 15u), dy = ((s.box >> 16) & 15u) - ((s.box >> 4) & 15u),
-                           dz = ((s.box >> 20) & 15u) - ((s.box >> 8) & 15u);
-            volume = dx * dy * dz;
-            if (volume != 0) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    mine.plane[k] = s.plane[k];
-                }
-                mine.planeLimit = s.planeLimit;
-                mine.planeSure = c.planeSure;
-#pragma unroll
-                for (int k = 0; k < 27; ++k) {
-                    mine.edge[k] = s.edge[k];
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    mine.lo[k] = c.lo[k];
-                    mine.hi[k] = c.hi[k];
-                }
-                mine.flags = s.flags;
-                mine.box = s.box;
-                mine.magicX = (65536u + dx - 1u) / dx;
-                mine.magicXY = (65536u + dx * dy - 1u) / (dx * dy);
+        __syncwarp(full);
+        const unsigned int certain = __ballot_sync(full, verdict == kSatCertain);
+        if (verdict == kSatCertain) {
+            // lanes that hit the same 32-bit half word (4 rows of one tile layer) merge their bits: one atomic per group
+            const size_t half = bitmapWord(occ, x, y, z) * 2u + ((y & 7u) >> 2);
+            const uint32_t bit = 1u << ((x & 7u) + 8u * (y & 3u));
+            const unsigned int peers = __match_any_sync(certain, (unsigned long long) half);
+            const uint32_t merged = __reduce_or_sync(peers, bit);
+            if (lane == (uint32_t) __ffs(peers) - 1u) {
+                atomicOr(bits32 + half, merged);
             }
         }
-#pragma unroll
-        for (int k = 0; k < kOccAccWords - 1; ++k) {
-            acc[tid * kOccAccWords + k] = 0;
-        }
-    }
-    uint32_t inclusive = volume;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(full, inclusive, o);
-        inclusive += lane >= (uint32_t) o ? up : 0u;
-    }
-    if (lane == 31) {
-        warpSums[warp] = inclusive;
-    }
-    __syncthreads();
-    uint32_t warpBase = 0;
-    for (uint32_t w = 0; w < warp; ++w) {
-        warpBase += warpSums[w];
-    }
-    prefix[tid + 1] = warpBase + inclusive;
-    if (tid == 0) {
-        prefix[0] = 0;
-    }
-    __syncthreads();
-    const uint32_t total = prefix[kOccPairThreads];
-
-    // ---- classify ----
-    for (uint32_t i = tid; i < total; i += kOccPairThreads) {
-        uint32_t p = 0;  // last pair with prefix[p] <= i
-#pragma unroll
-        for (uint32_t step = kOccPairThreads / 2; step > 0; step >>= 1) {
-            p += prefix[p + step] <= i ? step : 0u;
-        }
-        const PairSat &s = sat[p];
-        const uint32_t local = i - prefix[p];
-        const uint32_t x0 = s.box & 15u, y0 = (s.box >> 4) & 15u, z0 = (s.box >> 8) & 15u;
-        const uint32_t dx = ((s.box >> 12) & 15u) - x0, dy = ((s.box >> 16) & 15u) - y0;
-        const uint32_t zi = (local * s.magicXY) >> 16;
-        const uint32_t inLayer = local - zi * dx * dy;
-        const uint32_t yi = (inLayer * s.magicX) >> 16;
-        const uint32_t x = x0 + (inLayer - yi * dx), y = y0 + yi, z = z0 + zi;
-        const int verdict = args.prefilter ? classifyVoxel(s, s, (float) x, (float) y, (float) z) : kSatUncertain;
-        if (verdict != kSatMiss) {
-            // word = layer z, half y / 4; bit = x + 8 (y % 4)
-            atomicOr(&acc[p * kOccAccWords + (verdict == kSatCertain ? 0u : 16u) + z * 2u + (y >> 2)],
-                     1u << (x + 8u * (y & 3u)));
+        const unsigned int undecided = __ballot_sync(full, verdict == kSatUncertain);
+        if (undecided != 0) {
+            uint32_t slot = 0;
+            if (lane == 0) {
+                slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(undecided));
+            }
+            slot = __shfl_sync(full, slot, 0) + __popc(undecided & ((1u << lane) - 1u));
+            if (verdict == kSatUncertain) {
+                if (slot < kOccMaybeCap) {
+                    sh.maybe[slot] = (p << 12) | local;
+                }
+                else {  // buffer full (dense batch): straight to the queue, unfiltered
+                    const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
+                    if (index < occ.queueCapacity) {
+                        occ.queue[index] = make_uint4(sh.entry[p].leaf, x | (y << 16), z, 0u);
+                    }
+                }
+            }
         }
     }
     __syncthreads();
 
-    // ---- flush ----
+    // ---- filter the undecided voxels by what the bitmap shows now (this block's own `certain` bits included) ----
+    const uint32_t buffered = min(sh.maybeCount, kOccMaybeCap);
     uint32_t count = 0;
-    if (volume != 0) {
-        unsigned long long *bits = occ.tileBits + (size_t) occ.tileSlot[tile] * kTileEdge;
-        uint32_t *mine = acc + tid * kOccAccWords;
-        const uint32_t z0 = (sat[tid].box >> 8) & 15u, z1 = (sat[tid].box >> 20) & 15u;
-        for (uint32_t z = z0; z < z1; ++z) {
-            const unsigned long long sure = mine[z * 2] | ((unsigned long long) mine[z * 2 + 1] << 32);
-            unsigned long long maybe = mine[16 + z * 2] | ((unsigned long long) mine[16 + z * 2 + 1] << 32);
-            unsigned long long known = sure;
-            if (sure != 0) {
-                known |= atomicOr(bits + z, sure);
-            }
-            else if (maybe != 0) {
-                known = __ldcg(bits + z);
-            }
-            if (downscale && maybe != 0) {
-                // a parent that already has a child needs no further children
-                known = smear2x2(known | __ldcg(bits + (z ^ 1u)));
-            }
-            maybe &= ~known;  // already decided by this or another leaf (a stale read only costs a redundant clip)
-            mine[16 + z * 2] = (uint32_t) maybe;
-            mine[16 + z * 2 + 1] = (uint32_t) (maybe >> 32);
-            count += (uint32_t) __popcll(maybe);
+    for (uint32_t k = tid; k < buffered; k += kOccBatch) {
+        const uint32_t m = sh.maybe[k];
+        uint32_t x, y, z;
+        candidateVoxel(sh.entry[m >> 12], m & 4095u, x, y, z);
+        if (!alreadyDecided(occ, downscale, x, y, z)) {  // a stale read only costs a redundant clip
+            sh.maybe[k] = m | 0x80000000u;
+            ++count;
         }
     }
-    inclusive = count;
+    uint32_t inclusive = count;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t up = __shfl_up_sync(full, inclusive, o);
         inclusive += lane >= (uint32_t) o ? up : 0u;
     }
-    __syncthreads();  // warpSums is reused
     if (lane == 31) {
-        warpSums[warp] = inclusive;
+        sh.warpSums[warp] = inclusive;
     }
     __syncthreads();
-    uint32_t blockTotal = 0;
-    warpBase = 0;
-    for (uint32_t w = 0; w < kOccPairThreads / 32; ++w) {
-        warpBase += w < warp ? warpSums[w] : 0u;
-        blockTotal += warpSums[w];
+    uint32_t blockTotal = 0, warpBase = 0;
+    for (uint32_t w = 0; w < kOccBatch / 32; ++w) {
+        warpBase += w < warp ? sh.warpSums[w] : 0u;
+        blockTotal += sh.warpSums[w];
     }
-    if (blockTotal == 0) {
-        return;  // block-uniform
-    }
-    if (tid == 0) {
-        queueBase = atomicAdd(&args.counters->survivors, (unsigned long long) blockTotal);
-    }
-    __syncthreads();
-    if (count != 0) {
-        unsigned long long index = queueBase + warpBase + (inclusive - count);
-        const uint32_t *mine = acc + tid * kOccAccWords;
-        const uint32_t z0 = (sat[tid].box >> 8) & 15u, z1 = (sat[tid].box >> 20) & 15u;
-        for (uint32_t z = z0; z < z1; ++z) {
-            unsigned long long maybe = mine[16 + z * 2] | ((unsigned long long) mine[16 + z * 2 + 1] << 32);
-            while (maybe != 0) {
-                const uint32_t b = (uint32_t) __ffsll((long long) maybe) - 1u;
-                maybe &= maybe - 1ull;
+    if (blockTotal != 0) {  // block-uniform
+        if (tid == 0) {
+            sh.queueBase = atomicAdd(&args.counters->survivors, (unsigned long long) blockTotal);
+        }
+        __syncthreads();
+        unsigned long long index = sh.queueBase + warpBase + (inclusive - count);
+        for (uint32_t k = tid; k < buffered; k += kOccBatch) {
+            const uint32_t m = sh.maybe[k];
+            if ((m & 0x80000000u) != 0) {
+                uint32_t x, y, z;
+                const BatchEntry &e = sh.entry[(m >> 12) & 0x7ffffu];
+                candidateVoxel(e, m & 4095u, x, y, z);
                 if (index < occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
-                    occ.queue[index] = make_uint2(pair, (z << 6) | b);
+                    occ.queue[index] = make_uint4(e.leaf, x | (y << 16), z, 0u);
                 }
                 ++index;
             }
@@ -230,11 +377,109 @@ occupancyClassifyKernel(const VoxelizeArgs args)
     }
 }
 
+/// One block = kOccBatch consecutive leaves (big leaves are left to the box kernel).
+__global__ void __launch_bounds__(kOccBatch)
+occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
+{
+    __shared__ ClassifyShared sh;
+    const unsigned int full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t leafIndex = blockIdx.x * kOccBatch + tid;
+
+    uint32_t volume = 0;
+    if (leafIndex < leafTotal) {
+        LeafStage s;
+        loadLeafVertices(s, args.leaves, leafIndex);
+        uint32_t lo[3], hi[3];
+        if (leafBoxInSlab(s.v, args.grid, lo, hi)) {
+            const unsigned long long v64 = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+            if (v64 <= kOccBigVolume) {
+                volume = stageBatchEntry(sh.entry[tid], leafIndex, lo, hi, s);
+                if ((s.flags & kLeafNoPrefilter) != 0) {
+                    sh.entry[tid].sat.planeLimit = -1.0f;
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        sh.maybeCount = 0;
+        sh.prefix[0] = 0;
+    }
+    uint32_t inclusive = volume;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(full, inclusive, o);
+        inclusive += lane >= (uint32_t) o ? up : 0u;
+    }
+    if (lane == 31) {
+        sh.warpSums[warp] = inclusive;
+    }
+    __syncthreads();
+    uint32_t warpBase = 0;
+    for (uint32_t w = 0; w < warp; ++w) {
+        warpBase += sh.warpSums[w];
+    }
+    sh.prefix[tid + 1] = warpBase + inclusive;
+    __syncthreads();
+    if (sh.prefix[kOccBatch] == 0) {
+        return;
+    }
+    classifyBatch(sh, args);
+}
+
+/// Persistent blocks over the 16^3 boxes of the big leaves (axis-aligned triangles the reference does not subdivide).
+__global__ void __launch_bounds__(kOccBatch)
+occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigned long long boxTotal)
+{
+    __shared__ ClassifyShared sh;
+    const uint32_t tid = threadIdx.x;
+    for (unsigned long long box = blockIdx.x; box < boxTotal; box += gridDim.x) {
+        __syncthreads();  // the previous round is done with the shared state
+        if (tid == 0) {
+            // last table row whose first box is <= box (rows are sorted by first box, see occupancyEmitKernel)
+            uint32_t lo = 0, hi = bigCount;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (args.occ.bigLeaves[mid].y <= box) {
+                    lo = mid;
+                }
+                else {
+                    hi = mid;
+                }
+            }
+            const uint2 row = args.occ.bigLeaves[lo];
+            LeafStage s;
+            loadLeafVertices(s, args.leaves, row.x);
+            uint32_t leafLo[3], leafHi[3];
+            leafBoxInSlab(s.v, args.grid, leafLo, leafHi);
+            const uint32_t nbx = (leafHi[0] - leafLo[0] + kOccBoxEdge - 1) / kOccBoxEdge;
+            const uint32_t nby = (leafHi[1] - leafLo[1] + kOccBoxEdge - 1) / kOccBoxEdge;
+            const uint32_t b = (uint32_t) (box - row.y);
+            const uint32_t bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+            uint32_t lo3[3] = {leafLo[0] + bx * kOccBoxEdge, leafLo[1] + by * kOccBoxEdge, leafLo[2] + bz * kOccBoxEdge};
+            uint32_t hi3[3] = {min(lo3[0] + kOccBoxEdge, leafHi[0]), min(lo3[1] + kOccBoxEdge, leafHi[1]),
+                               min(lo3[2] + kOccBoxEdge, leafHi[2])};
+            const uint32_t volume = stageBatchEntry(sh.entry[0], row.x, lo3, hi3, s);
+            if ((s.flags & kLeafNoPrefilter) != 0) {
+                sh.entry[0].sat.planeLimit = -1.0f;
+            }
+            sh.maybeCount = 0;
+            sh.prefix[0] = 0;
+            for (uint32_t k = 1; k <= kOccBatch; ++k) {
+                sh.prefix[k] = volume;
+            }
+        }
+        __syncthreads();
+        classifyBatch(sh, args);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// clip: the exact six-plane clip for the queued voxels
+
 /// Same persistent-lane scheme as sparseClipKernel (o2v_sparse.cu), fed from the queue; a surviving piece sets the bit.
 __global__ void __launch_bounds__(kOccClipThreads)
 occupancyClipKernel(const VoxelizeArgs args)
 {
-    const SparseView &sp = args.sparse;
     const OccupancyView &occ = args.occ;
     const unsigned int full = 0xffffffffu;
     const bool downscale = args.grid.supersampling == 2;
@@ -276,35 +521,22 @@ occupancyClipKernel(const VoxelizeArgs args)
                 }
                 const unsigned long long e = cursor + __popc(idle & below);
                 if (e < end) {
-                    const uint2 entry = occ.queue[e];
-                    const uint32_t pair = entry.x;
-                    const uint32_t tile = __ldg(sp.pairTile + pair);
-                    const uint32_t z = entry.y >> 6, xy = entry.y & 63u;
-                    unsigned long long *layer = occ.tileBits + (size_t) __ldg(occ.tileSlot + tile) * kTileEdge + z;
-                    const unsigned long long mine = 1ull << xy;
-                    unsigned long long known = __ldcg(layer);
-                    if (downscale) {
-                        known = smear2x2(known | __ldcg(occ.tileBits + (size_t) __ldg(occ.tileSlot + tile) * kTileEdge +
-                                                        (z ^ 1u)));
-                    }
-                    if ((known & mine) == 0) {
-                        const uint32_t leafIndex = __ldg(args.work.tileList + pair);
-                        uint32_t origin[3];
-                        tileOriginOf(args.grid, tile, origin);
-                        const float4 *src = reinterpret_cast<const float4 *>(args.leaves + leafIndex);
+                    const uint4 entry = occ.queue[e];
+                    const uint32_t x = entry.y & 0xffffu, y = entry.y >> 16, z = entry.z;
+                    if (!alreadyDecided(occ, downscale, x, y, z)) {
+                        const float4 *src = reinterpret_cast<const float4 *>(args.leaves + entry.x);
                         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
                         Tri<false> leaf;
                         leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
                         leaf.v[4] = b.x; leaf.v[5] = b.y; leaf.v[6] = b.z; leaf.v[7] = b.w;
                         leaf.v[8] = c.x;
-                        clipper.begin(leaf, origin[0] + (xy & 7u), origin[1] + (xy >> 3), origin[2] + z, c.z);
-                        if ((__float_as_uint(c.w) & kLeafNeedsCull) != 0 &&
-                            planeDistanceCulled(leaf.v, clipper.px, clipper.py, clipper.pz)) {
+                        clipper.begin(leaf, x, y, z, c.z);
+                        if ((__float_as_uint(c.w) & kLeafNeedsCull) != 0 && planeDistanceCulled(leaf.v, x, y, z)) {
                             clipper.done = true;  // voxelization.cpp:451-458 (slivers only)
                         }
                         hasEntry = true;
-                        word = layer;
-                        bit = mine;
+                        word = occ.bits + bitmapWord(occ, x, y, z);
+                        bit = bitmapBit(x, y);
                     }
                 }
             }
@@ -317,6 +549,9 @@ occupancyClipKernel(const VoxelizeArgs args)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// expand: thread per tile of every active chunk
+
 __global__ void __launch_bounds__(kOccExpandThreads)
 occupancyExpandKernel(const VoxelizeArgs args)
 {
@@ -324,28 +559,31 @@ occupancyExpandKernel(const VoxelizeArgs args)
     const unsigned int full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
     const bool downscale = args.grid.supersampling == 2;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const unsigned long long tiles = (unsigned long long) occ.activeChunks * (kChunkWords / kTileEdge);
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
 
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < args.work.allCount; base += stride) {
-        const uint32_t slot = base + lane;
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < tiles;
+         base += stride) {
+        const unsigned long long t = base + lane;
         unsigned long long m[kTileEdge];
 #pragma unroll
         for (int z = 0; z < (int) kTileEdge; ++z) {
             m[z] = 0;
         }
         uint32_t origin[3] = {0, 0, 0};
-        if (slot < args.work.allCount) {
-            const uint32_t tile = args.work.allTiles[slot];
-            if (args.sparse.tileCandidates[tile] <= kLightMaxCandidates) {
-                tileOriginOf(args.grid, tile, origin);
-                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(occ.tileBits + (size_t) slot * kTileEdge);
+        if (t < tiles) {
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(occ.bits + t * kTileEdge);
 #pragma unroll
-                for (int k = 0; k < (int) kTileEdge / 2; ++k) {
-                    const ulonglong2 w = src[k];
-                    m[2 * k] = w.x;
-                    m[2 * k + 1] = w.y;
-                }
+            for (int k = 0; k < (int) kTileEdge / 2; ++k) {
+                const ulonglong2 w = src[k];
+                m[2 * k] = w.x;
+                m[2 * k + 1] = w.y;
             }
+            const uint32_t chunk = occ.chunkList[t >> 9], tileLocal = (uint32_t) t & 511u;
+            const uint32_t C = occ.chunksPerAxis;
+            origin[0] = (chunk % C) * kChunkEdge + (tileLocal & 7u) * kTileEdge;
+            origin[1] = ((chunk / C) % C) * kChunkEdge + ((tileLocal >> 3) & 7u) * kTileEdge;
+            origin[2] = (chunk / (C * C) + occ.chunkZ0) * kChunkEdge + (tileLocal >> 6) * kTileEdge;
         }
         if (downscale) {
             // parent (qx, qy, qz) = OR of its 8 children; kept at bit (2 qx + 16 qy) of word qz
@@ -420,15 +658,45 @@ unsigned occupancyPersistentBlocks(Kernel kernel, int threads, int smCount)
     return (unsigned) smCount * (unsigned) perSm;  // a multiple of the SM count
 }
 
+unsigned setupBlocks(unsigned long long n)
+{
+    unsigned long long blocks = (n + kOccSetupThreads - 1) / kOccSetupThreads;
+    blocks = blocks < 1 ? 1 : blocks;
+    return (unsigned) (blocks < 148ull * 64 ? blocks : 148ull * 64);
+}
+
 }  // namespace
 
-void launchOccupancyClassify(const VoxelizeArgs &args, cudaStream_t stream)
+void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
+                          RunCounters *counters, cudaStream_t stream)
 {
-    if (args.sparse.pairCount == 0) {
-        return;
+    occupancyCountKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, leafCount, counters);
+}
+
+void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream)
+{
+    occupancyAssignChunksKernel<<<(occ.chunkTotal + 255) / 256, 256, 0, stream>>>(occ, counters);
+}
+
+void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream)
+{
+    occupancyEmitKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, leafOffset, leaves,
+                                                                                   counters);
+}
+
+void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, uint32_t bigCount,
+                             unsigned long long boxTotal, int smCount, cudaStream_t stream)
+{
+    if (leafTotal != 0) {
+        const unsigned blocks = (unsigned) ((leafTotal + kOccBatch - 1) / kOccBatch);
+        occupancyClassifyKernel<<<blocks, kOccBatch, 0, stream>>>(args, (uint32_t) leafTotal);
     }
-    const unsigned blocks = (args.sparse.pairCount + kOccPairThreads - 1) / kOccPairThreads;
-    occupancyClassifyKernel<<<blocks, kOccPairThreads, 0, stream>>>(args);
+    if (bigCount != 0 && boxTotal != 0) {
+        unsigned long long blocks = occupancyPersistentBlocks(occupancyClassifyBoxesKernel, kOccBatch, smCount);
+        blocks = blocks < boxTotal ? blocks : boxTotal;
+        occupancyClassifyBoxesKernel<<<(unsigned) blocks, kOccBatch, 0, stream>>>(args, bigCount, boxTotal);
+    }
 }
 
 void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
@@ -440,13 +708,15 @@ void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t str
 
 void launchOccupancyExpand(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
 {
-    if (args.work.allCount == 0) {
+    if (args.occ.activeChunks == 0) {
         return;
     }
-    unsigned blocks = occupancyPersistentBlocks(occupancyExpandKernel, kOccExpandThreads, smCount);
-    const unsigned needed = (args.work.allCount + kOccExpandThreads - 1) / kOccExpandThreads;
+    unsigned long long blocks = occupancyPersistentBlocks(occupancyExpandKernel, kOccExpandThreads, smCount);
+    const unsigned long long needed =
+        ((unsigned long long) args.occ.activeChunks * (kChunkWords / kTileEdge) + kOccExpandThreads - 1) /
+        kOccExpandThreads;
     blocks = blocks < needed ? blocks : needed;
-    occupancyExpandKernel<<<blocks, kOccExpandThreads, 0, stream>>>(args);
+    occupancyExpandKernel<<<(unsigned) blocks, kOccExpandThreads, 0, stream>>>(args);
 }
 
 }  // namespace o2v

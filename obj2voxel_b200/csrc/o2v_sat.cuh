@@ -109,57 +109,77 @@ O2V_UNROLL
     return true;
 }
 
-/// Extra per-leaf constants of the three-way classification (kept apart from LeafStage, whose size is tuned for the
-/// shared-memory staging of the heavy-tile kernel).
-struct LeafCertain {
-    float planeSure;       // (0.5 - kCertainMargin) * |n|_1
-    float lo[3], hi[3];    // tile-local float AABB of the leaf
+enum SatVerdict : int { kSatMiss = 0, kSatUncertain = 1, kSatCertain = 2 };
+
+/// One edge function of the SAT with both thresholds: inside the inflated box iff a * qa + b * qb + c >= 0, inside the
+/// shrunk box iff that value >= k, k = (|a| + |b|) * (kPrefilterMargin + kCertainMargin) (critical corner moved from the
+/// inflated to the shrunk box).
+struct alignas(16) SatEdge {
+    float a, b, c, k;
 };
 
-O2V_HD void buildCertain(LeafCertain &c, const LeafStage &s, const float origin[3])
+/// Everything the three-way classification of one leaf against the unit voxels of a box needs, relative to the box's
+/// min corner (`origin`): 48 floats, 16-byte aligned (twelve 128-bit shared-memory loads per candidate voxel).
+struct alignas(16) PairSat {
+    float plane[4];        // n . q + d at the voxel centre, q = voxel min corner - origin
+    float planeLimit;      // (0.5 + kPrefilterMargin) * |n|_1
+    float planeSure;       // (0.5 - kCertainMargin) * |n|_1
+    float lo[3], hi[3];    // origin-relative float AABB of the leaf (box-normal axes of the SAT)
+    SatEdge edge[9];
+};
+
+/// Builds the constants from a leaf staged with buildPrefilter(s, origin).
+O2V_HD void buildPairSat(PairSat &out, const LeafStage &s, const float origin[3])
 {
-    c.planeSure = (0.5f - kCertainMargin) * (fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]));
+    const float norm1 = fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]);
+O2V_UNROLL
+    for (int k = 0; k < 4; ++k) {
+        out.plane[k] = s.plane[k];
+    }
+    out.planeLimit = s.planeLimit;
+    out.planeSure = (0.5f - kCertainMargin) * norm1;
 O2V_UNROLL
     for (int a = 0; a < 3; ++a) {
-        c.lo[a] = fminf(fminf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
-        c.hi[a] = fmaxf(fmaxf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+        out.lo[a] = fminf(fminf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+        out.hi[a] = fmaxf(fmaxf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+    }
+    const float shift = kPrefilterMargin + kCertainMargin;
+O2V_UNROLL
+    for (int k = 0; k < 9; ++k) {
+        out.edge[k].a = s.edge[k * 3];
+        out.edge[k].b = s.edge[k * 3 + 1];
+        out.edge[k].c = s.edge[k * 3 + 2];
+        out.edge[k].k = (fabsf(s.edge[k * 3]) + fabsf(s.edge[k * 3 + 1])) * shift;
     }
 }
 
-enum SatVerdict : int { kSatMiss = 0, kSatUncertain = 1, kSatCertain = 2 };
-
-/// Three-way verdict for the voxel whose tile-local min corner is (lx, ly, lz).  Leaves with kLeafNoPrefilter are never
-/// `miss` and never `certain`.  Any NaN makes the comparisons fail towards `uncertain`.
-/// S provides plane[4], planeLimit, edge[27], flags (LeafStage or a compact copy); C provides planeSure, lo[3], hi[3].
-template <typename S, typename C>
-O2V_HD int classifyVoxel(const S &s, const C &c, float lx, float ly, float lz)
+/// Three-way verdict for the voxel whose min corner is origin + (lx, ly, lz).  Leaves flagged kLeafNoPrefilter must not
+/// be classified (they are `uncertain` throughout: their normal is too noisy for the plane test).  Any NaN makes the
+/// comparisons fail towards `uncertain` or `miss` only where `miss` is proven by a comparison that held.
+O2V_HD int classifyVoxel(const PairSat &s, float lx, float ly, float lz)
 {
-    if ((s.flags & kLeafNoPrefilter) != 0) {
-        return kSatUncertain;
-    }
     const float dist = fabsf(s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3]);
     if (dist > s.planeLimit) {
         return kSatMiss;
     }
-    bool sure = dist <= c.planeSure;
+    bool sure = dist <= s.planeSure;
     const float q[3] = {lx, ly, lz};
-    const float shift = kPrefilterMargin + kCertainMargin;  // inflated -> shrunk critical corner: (|A| + |B|) * shift
 O2V_UNROLL
     for (int proj = 0; proj < 3; ++proj) {
         const float qa = q[proj], qb = q[(proj + 1) % 3];
 O2V_UNROLL
         for (int i = 0; i < 3; ++i) {
-            const float *e = s.edge + (proj * 3 + i) * 3;
-            const float value = e[0] * qa + e[1] * qb + e[2];
+            const SatEdge e = s.edge[proj * 3 + i];
+            const float value = e.a * qa + e.b * qb + e.c;
             if (value < 0.0f) {
                 return kSatMiss;
             }
-            sure = sure && value >= (fabsf(e[0]) + fabsf(e[1])) * shift;
+            sure = sure && value >= e.k;
         }
     }
 O2V_UNROLL
     for (int a = 0; a < 3; ++a) {  // box normals against the shrunk box [q + margin, q + 1 - margin]
-        sure = sure && (q[a] + kCertainMargin <= c.hi[a]) && (q[a] + 1.0f - kCertainMargin >= c.lo[a]);
+        sure = sure && (q[a] + kCertainMargin <= s.hi[a]) && (q[a] + 1.0f - kCertainMargin >= s.lo[a]);
     }
     return sure ? kSatCertain : kSatUncertain;
 }
