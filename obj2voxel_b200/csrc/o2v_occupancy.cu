@@ -27,11 +27,12 @@ namespace o2v {
 namespace {
 
 constexpr int kOccSetupThreads = 128;
-constexpr int kOccBatch = 128;          // leaves per classify block = threads per block
+constexpr int kOccBatch = 64;           // leaves per classify block
+constexpr int kOccThreads = 128;        // threads per classify block (two candidates' worth of lanes per staged leaf)
 constexpr int kOccClipThreads = 128;
 constexpr int kOccExpandThreads = 128;
 constexpr int kOccRefillThreshold = 8;
-constexpr uint32_t kOccMaybeCap = 2048;  // undecided voxels a block buffers before filtering them against the bitmap
+constexpr uint32_t kOccMaybeCap = 1024;  // undecided voxels a block buffers before filtering them against the bitmap
 
 // ---------------------------------------------------------------------------------------------------------------------
 // addressing
@@ -206,13 +207,17 @@ struct alignas(16) BatchEntry {
     uint32_t x0, y0, z0;          // box min corner, voxel space
     uint32_t dx, dxdy;            // box extent in x, in x * y
     uint32_t magicX, magicXY;     // n / d == __umulhi(n, magic) for d > 1, n * d <= 2^24 (d == 1: n itself)
+    uint32_t slot;                // bitmap of the box's chunk, or kNoSlot if the box spans several chunks
+    uint32_t pad[3];
 };
+
+constexpr uint32_t kNoSlot = 0xffffffffu;
 
 struct ClassifyShared {
     BatchEntry entry[kOccBatch];
     uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' candidate counts
     uint32_t maybe[kOccMaybeCap];     // (entry << 12) | candidate index in its box; top bit: survived the filter
-    uint32_t warpSums[kOccBatch / 32];
+    uint32_t warpSums[kOccThreads / 32];
     uint32_t maybeCount;
     unsigned long long queueBase;
 };
@@ -227,10 +232,26 @@ __device__ __forceinline__ uint32_t divideBy(uint32_t n, uint32_t d, uint32_t ma
     return d > 1u ? __umulhi(n, magic) : n;
 }
 
-/// Fills one batch entry for `leaf` restricted to the box [lo, hi).  Returns the number of candidates (0 = skip).
-__device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, uint32_t leafIndex, const uint32_t lo[3],
-                                                    const uint32_t hi[3], LeafStage &s)
+/// Bitmap word of voxel (x, y, z) for an entry: the chunk lookup is skipped when the entry's box lies in one chunk.
+__device__ __forceinline__ size_t entryWord(const OccupancyView &occ, const BatchEntry &e, uint32_t x, uint32_t y,
+                                            uint32_t z)
 {
+    if (e.slot == kNoSlot) {
+        return bitmapWord(occ, x, y, z);
+    }
+    const uint32_t tileLocal = ((x >> 3) & 7u) | (((y >> 3) & 7u) << 3) | (((z >> 3) & 7u) << 6);
+    return (size_t) e.slot * kChunkWords + tileLocal * kTileEdge + (z & 7u);
+}
+
+/// Fills one batch entry for `leaf` restricted to the box [lo, hi).  Returns the number of candidates (0 = skip).
+__device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, const OccupancyView &occ, uint32_t leafIndex,
+                                                    const uint32_t lo[3], const uint32_t hi[3], LeafStage &s)
+{
+    const bool oneChunk = (lo[0] >> 6) == ((hi[0] - 1) >> 6) && (lo[1] >> 6) == ((hi[1] - 1) >> 6) &&
+                          (lo[2] >> 6) == ((hi[2] - 1) >> 6);
+    e.slot = oneChunk ? __ldg(occ.chunkSlot + (lo[0] >> 6) +
+                              occ.chunksPerAxis * ((lo[1] >> 6) + occ.chunksPerAxis * ((lo[2] >> 6) - occ.chunkZ0)))
+                      : kNoSlot;
     const float origin[3] = {(float) lo[0], (float) lo[1], (float) lo[2]};
     buildPrefilter(s, origin);
     buildPairSat(e.sat, s, origin);
@@ -279,7 +300,7 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
     uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
 
     // ---- verdict per candidate; block-uniform trip count ----
-    for (uint32_t base = 0; base < total; base += kOccBatch) {
+    for (uint32_t base = 0; base < total; base += kOccThreads) {
         const uint32_t i = base + tid;
         int verdict = kSatMiss;
         uint32_t p = 0, local = 0, x = 0, y = 0, z = 0;
@@ -296,17 +317,11 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
                           ? classifyVoxel(e.sat, (float) (x - e.x0), (float) (y - e.y0), (float) (z - e.z0))
                           : (int) kSatUncertain;
         }
-        __syncwarp(full);
-        const unsigned int certain = __ballot_sync(full, verdict == kSatCertain);
         if (verdict == kSatCertain) {
-            // lanes that hit the same 32-bit half word (4 rows of one tile layer) merge their bits: one atomic per group
-            const size_t half = bitmapWord(occ, x, y, z) * 2u + ((y & 7u) >> 2);
-            const uint32_t bit = 1u << ((x & 7u) + 8u * (y & 3u));
-            const unsigned int peers = __match_any_sync(certain, (unsigned long long) half);
-            const uint32_t merged = __reduce_or_sync(peers, bit);
-            if (lane == (uint32_t) __ffs(peers) - 1u) {
-                atomicOr(bits32 + half, merged);
-            }
+            // one RED per lane on the 32-bit half word (4 rows of one tile layer): the lanes of a warp that hit the same
+            // 32-byte sector travel as one request, and nothing waits for the result
+            const size_t half = entryWord(occ, sh.entry[p], x, y, z) * 2u + ((y & 7u) >> 2);
+            atomicOr(bits32 + half, 1u << ((x & 7u) + 8u * (y & 3u)));
         }
         const unsigned int undecided = __ballot_sync(full, verdict == kSatUncertain);
         if (undecided != 0) {
@@ -333,11 +348,16 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
     // ---- filter the undecided voxels by what the bitmap shows now (this block's own `certain` bits included) ----
     const uint32_t buffered = min(sh.maybeCount, kOccMaybeCap);
     uint32_t count = 0;
-    for (uint32_t k = tid; k < buffered; k += kOccBatch) {
+    for (uint32_t k = tid; k < buffered; k += kOccThreads) {
         const uint32_t m = sh.maybe[k];
         uint32_t x, y, z;
         candidateVoxel(sh.entry[m >> 12], m & 4095u, x, y, z);
-        if (!alreadyDecided(occ, downscale, x, y, z)) {  // a stale read only costs a redundant clip
+        const size_t word = entryWord(occ, sh.entry[m >> 12], x, y, z);
+        unsigned long long known = __ldcg(occ.bits + word);
+        if (downscale) {
+            known = smear2x2(known | __ldcg(occ.bits + (word ^ 1u)));
+        }
+        if ((known & bitmapBit(x, y)) == 0) {  // a stale read only costs a redundant clip
             sh.maybe[k] = m | 0x80000000u;
             ++count;
         }
@@ -352,7 +372,7 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
     }
     __syncthreads();
     uint32_t blockTotal = 0, warpBase = 0;
-    for (uint32_t w = 0; w < kOccBatch / 32; ++w) {
+    for (uint32_t w = 0; w < kOccThreads / 32; ++w) {
         warpBase += w < warp ? sh.warpSums[w] : 0u;
         blockTotal += sh.warpSums[w];
     }
@@ -362,7 +382,7 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
         }
         __syncthreads();
         unsigned long long index = sh.queueBase + warpBase + (inclusive - count);
-        for (uint32_t k = tid; k < buffered; k += kOccBatch) {
+        for (uint32_t k = tid; k < buffered; k += kOccThreads) {
             const uint32_t m = sh.maybe[k];
             if ((m & 0x80000000u) != 0) {
                 uint32_t x, y, z;
@@ -378,7 +398,7 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
 }
 
 /// One block = kOccBatch consecutive leaves (big leaves are left to the box kernel).
-__global__ void __launch_bounds__(kOccBatch)
+__global__ void __launch_bounds__(kOccThreads)
 occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
 {
     __shared__ ClassifyShared sh;
@@ -387,14 +407,14 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
     const uint32_t leafIndex = blockIdx.x * kOccBatch + tid;
 
     uint32_t volume = 0;
-    if (leafIndex < leafTotal) {
+    if (tid < kOccBatch && leafIndex < leafTotal) {
         LeafStage s;
         loadLeafVertices(s, args.leaves, leafIndex);
         uint32_t lo[3], hi[3];
         if (leafBoxInSlab(s.v, args.grid, lo, hi)) {
             const unsigned long long v64 = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
             if (v64 <= kOccBigVolume) {
-                volume = stageBatchEntry(sh.entry[tid], leafIndex, lo, hi, s);
+                volume = stageBatchEntry(sh.entry[tid], args.occ, leafIndex, lo, hi, s);
                 if ((s.flags & kLeafNoPrefilter) != 0) {
                     sh.entry[tid].sat.planeLimit = -1.0f;
                 }
@@ -418,7 +438,9 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
     for (uint32_t w = 0; w < warp; ++w) {
         warpBase += sh.warpSums[w];
     }
-    sh.prefix[tid + 1] = warpBase + inclusive;
+    if (tid < kOccBatch) {
+        sh.prefix[tid + 1] = warpBase + inclusive;
+    }
     __syncthreads();
     if (sh.prefix[kOccBatch] == 0) {
         return;
@@ -427,7 +449,7 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
 }
 
 /// Persistent blocks over the 16^3 boxes of the big leaves (axis-aligned triangles the reference does not subdivide).
-__global__ void __launch_bounds__(kOccBatch)
+__global__ void __launch_bounds__(kOccThreads)
 occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigned long long boxTotal)
 {
     __shared__ ClassifyShared sh;
@@ -458,7 +480,7 @@ occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigne
             uint32_t lo3[3] = {leafLo[0] + bx * kOccBoxEdge, leafLo[1] + by * kOccBoxEdge, leafLo[2] + bz * kOccBoxEdge};
             uint32_t hi3[3] = {min(lo3[0] + kOccBoxEdge, leafHi[0]), min(lo3[1] + kOccBoxEdge, leafHi[1]),
                                min(lo3[2] + kOccBoxEdge, leafHi[2])};
-            const uint32_t volume = stageBatchEntry(sh.entry[0], row.x, lo3, hi3, s);
+            const uint32_t volume = stageBatchEntry(sh.entry[0], args.occ, row.x, lo3, hi3, s);
             if ((s.flags & kLeafNoPrefilter) != 0) {
                 sh.entry[0].sat.planeLimit = -1.0f;
             }
@@ -690,12 +712,12 @@ void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTo
 {
     if (leafTotal != 0) {
         const unsigned blocks = (unsigned) ((leafTotal + kOccBatch - 1) / kOccBatch);
-        occupancyClassifyKernel<<<blocks, kOccBatch, 0, stream>>>(args, (uint32_t) leafTotal);
+        occupancyClassifyKernel<<<blocks, kOccThreads, 0, stream>>>(args, (uint32_t) leafTotal);
     }
     if (bigCount != 0 && boxTotal != 0) {
-        unsigned long long blocks = occupancyPersistentBlocks(occupancyClassifyBoxesKernel, kOccBatch, smCount);
+        unsigned long long blocks = occupancyPersistentBlocks(occupancyClassifyBoxesKernel, kOccThreads, smCount);
         blocks = blocks < boxTotal ? blocks : boxTotal;
-        occupancyClassifyBoxesKernel<<<(unsigned) blocks, kOccBatch, 0, stream>>>(args, bigCount, boxTotal);
+        occupancyClassifyBoxesKernel<<<(unsigned) blocks, kOccThreads, 0, stream>>>(args, bigCount, boxTotal);
     }
 }
 
