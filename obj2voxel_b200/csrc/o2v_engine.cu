@@ -2,6 +2,7 @@
 #include "o2v_engine.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -215,6 +216,9 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
             return rc;
         }
         // the chunk bitmaps do not fit: fold weights like for any other mesh (same result)
+        st = RunStats();
+        memcpy(st.transform, grid.xf, sizeof st.transform);
+        occupancy = false;
         O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
     }
 
@@ -482,6 +486,11 @@ int Engine::voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, 
         std::max<unsigned long long>(std::min<unsigned long long>(candidateBound, 1ull << 20), candidateBound / 4);
 
     const size_t bitmapBytes = (size_t) occ.activeChunks * kChunkWords * 8;
+    if (const char *env = getenv("O2V_B200_OCCUPANCY_MAX_BYTES")) {  // test hook for the fallback below
+        if (bitmapBytes > strtoull(env, nullptr, 10)) {
+            return kOccupancyFallback;
+        }
+    }
     if (bitmapBytes > tileBits_.size()) {
         size_t freeBytes = 0, totalBytes = 0;
         O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));

@@ -16,7 +16,13 @@ cases = [
      dict(uvs=meshes.random_uvs(2000) * 3 - 1, textures=[(meshes.random_texture(32, 16, 3), 1)])),
 ]
 for verts, kw, extra in cases:
-    v, st = eng.voxelize_host(verts, o2v.make_params(**kw), **extra)
-    print(len(v), st["light_tiles"], st["heavy_tiles"], flush=True)
+    for occ in (1, 0):  # all-white meshes: occupancy-only pipeline, then the weighted one; textured: weighted twice
+        v, st = eng.voxelize_host(verts, o2v.make_params(occupancy_path=occ, **kw), **extra)
+        print(len(v), st["occupancy_path"], st["light_tiles"], st["heavy_tiles"], st["survivors"], flush=True)
+# occupancy pipeline without its SAT shortcuts (queue growth + rerun) and on a Z-slab
+v, st = eng.voxelize_host(meshes.random_triangles(3000, 0.03), o2v.make_params(resolution=128, prefilter=0, bounds=meshes.UNIT_BOUNDS))
+print(len(v), st["occupancy_path"], st["survivors"], flush=True)
+v, st = eng.voxelize_host(meshes.random_triangles(3000, 0.03), o2v.make_params(resolution=64, supersampling=2, slab=(40, 104), bounds=meshes.UNIT_BOUNDS))
+print(len(v), st["occupancy_path"], st["survivors"], flush=True)
 eng.close()
 print("sanitize run done")

@@ -19,8 +19,14 @@ PATH = os.path.join(GOLDEN_DIR, "full_size_checksums.json")
 CHECKSUMS = json.load(open(PATH)) if os.path.exists(PATH) else {}
 
 
-@pytest.mark.parametrize("name", sorted(CHECKSUMS))
-def test_full_size_config_matches_reference_checksum(engine, name):
+CASES = [(name, path) for name in sorted(CHECKSUMS) for path in ("default", "weighted")
+         if not (path == "weighted" and name == "cfg3")]  # cfg3 is textured: its default already is the weighted path
+
+
+@pytest.mark.parametrize("name,path", CASES)
+def test_full_size_config_matches_reference_checksum(engine, name, path):
+    """`default` = what a caller gets (the occupancy-only path for the all-white cfg2 / cfg4 / cfg5); `weighted` = the same
+    input with every weight folded in reference order."""
     import torch
 
     import bench
@@ -37,8 +43,10 @@ def test_full_size_config_matches_reference_checksum(engine, name):
     assert verts.shape[0] == ref["triangles"]
     textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(dev), o2v.UV_WRAP)] if uvs is not None else []
     params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"],
-                             strategy=cfg["strategy"], bounds=cfg["bounds"])
-    engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
+                             strategy=cfg["strategy"], bounds=cfg["bounds"],
+                             occupancy_path=0 if path == "weighted" else 1)
+    stats = engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
+    assert bool(stats["occupancy_path"]) == (path == "default" and uvs is None)
     del verts, uvs
     assert engine.result_count() == ref["voxels"]
     v = engine.result_tensor().to(torch.int64)

@@ -247,6 +247,61 @@ def test_supersampling_pre_downscale_equals_double_resolution(engine):  # SURVEY
     assert np.array_equal(got, g["api_voxels"])
 
 
+# ---- occupancy-only path: the pieces the fixtures above do not reach --------------------------------------------------
+
+def test_unit_cube_r256_golden_count_and_big_leaf_boxes(engine):
+    """SURVEY §8c golden: unit cube at 256 -> 390,152 voxels.  Its 12 axis-aligned triangles are not subdivided: 65,536+
+    candidates each, classified box by box (16^3) on the occupancy-only path and by the heavy-tile kernel otherwise."""
+    for occ in (1, 0):
+        got, stats = engine.voxelize_host(meshes.unit_cube(), o2v.make_params(resolution=256, occupancy_path=occ))
+        assert bool(stats["occupancy_path"]) == bool(occ)
+        assert len(got) == 390152 and np.all(got[:, 3] == 0xFFFFFFFF)
+        s = o2v.sort_voxels(got)
+        on_face = (s[:, :3] == 0).any(axis=1) | (s[:, :3] == 255).any(axis=1)
+        assert on_face.all()
+
+
+def test_occupancy_slab_union_equals_whole(engine):
+    """Z-slabs that are multiples of 8 but not of the 64-voxel bitmap chunks; supersampled and not."""
+    v = meshes.random_triangles(150000, 0.006, seed=77)
+    b = [-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]
+    for res, ss, cuts in ((256, 1, (0, 72, 200, 256)), (128, 2, (0, 8, 136, 256))):
+        whole, stats = engine.voxelize_host(v, o2v.make_params(resolution=res, supersampling=ss, bounds=b))
+        assert stats["occupancy_path"]
+        weighted, _ = engine.voxelize_host(v, o2v.make_params(resolution=res, supersampling=ss, bounds=b,
+                                                              occupancy_path=0))
+        assert checksum(whole) == checksum(weighted)
+        parts = []
+        for z0, z1 in zip(cuts[:-1], cuts[1:]):
+            part, _ = engine.voxelize_host(v, o2v.make_params(resolution=res, supersampling=ss, bounds=b,
+                                                              slab=(z0, z1)))
+            assert len(part) == 0 or (part[:, 2].min() >= z0 // ss and part[:, 2].max() < -(-z1 // ss))
+            parts.append(part)
+        assert checksum(np.concatenate(parts)) == checksum(whole)
+
+
+def test_occupancy_queue_overflow_reruns_with_a_larger_queue(engine):
+    """prefilter = 0 queues every candidate voxel: more than the initial queue (a quarter of the candidates), so the
+    engine must grow it and rerun — same records."""
+    v = meshes.random_triangles(80000, 0.01, seed=5)
+    b = [-0.02, -0.02, -0.02, 1.02, 1.02, 1.02]
+    fast, fs = engine.voxelize_host(v, o2v.make_params(resolution=256, bounds=b))
+    slow, ss = engine.voxelize_host(v, o2v.make_params(resolution=256, bounds=b, prefilter=0))
+    assert fs["occupancy_path"] and ss["occupancy_path"]
+    assert ss["clip_calls"] > 4 * fs["clip_calls"] and ss["candidate_voxels"] > (1 << 21)
+    assert checksum(fast) == checksum(slow)
+
+
+def test_occupancy_falls_back_when_the_bitmaps_do_not_fit(engine, monkeypatch):
+    v = meshes.random_triangles(20000, 0.01, seed=6)
+    b = [-0.02, -0.02, -0.02, 1.02, 1.02, 1.02]
+    want, ws = engine.voxelize_host(v, o2v.make_params(resolution=128, bounds=b))
+    monkeypatch.setenv("O2V_B200_OCCUPANCY_MAX_BYTES", "1000")
+    got, gs = engine.voxelize_host(v, o2v.make_params(resolution=128, bounds=b))
+    assert ws["occupancy_path"] and not gs["occupancy_path"]
+    assert checksum(got) == checksum(want)
+
+
 # ---- properties at BASELINE sizes (no oracle needed) ---------------------------------------------------------------
 
 def checksum(voxels):
