@@ -6,6 +6,9 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <unordered_map>
 
 namespace o2v {
 
@@ -225,6 +228,309 @@ private:
     bool finalized_ = false;
 };
 
+// ---- palette formats: QEF (text) and VOX (MagicaVoxel) -------------------------------------------------------------
+//
+// Like the reference's VoxelioVoxelSink (src/io.cpp:524-636) these formats need the whole palette before the first byte
+// can be written: every voxel is buffered, colours are indexed in first-seen order (Palette32::insert,
+// voxelio/include/voxelio/palette.hpp:74-80), and finalize() writes the file.  File layouts follow
+// voxelio/src/format/qef.cpp:212-295 and voxelio/src/format/vox.cpp:828-1080 (version 150, 256^3 models, one nTRN + nSHP
+// per model under a single nGRP, no LAYR chunk, RGBA chunk last).  Deviation, stated: when a VOX needs more than 255
+// colours the reference reduces its palette with a randomly seeded k-means (voxelio/src/palette.cpp); here the reduction
+// is a deterministic median cut (each colour maps to the mean of its box) — the same contract, other representatives.
+
+struct PaletteBuilder {
+    std::vector<uint32_t> colors;  // index -> argb
+    std::unordered_map<uint32_t, uint32_t> indexOf;
+
+    uint32_t insert(uint32_t argb)
+    {
+        auto found = indexOf.find(argb);
+        if (found != indexOf.end()) {
+            return found->second;
+        }
+        const uint32_t index = (uint32_t) colors.size();
+        indexOf.emplace(argb, index);
+        colors.push_back(argb);
+        return index;
+    }
+};
+
+/// Median cut of `colors` (argb) into at most `limit` boxes; returns per input colour the index of its box and fills
+/// `representatives` with the channel-wise mean of each box.
+std::vector<uint32_t> medianCut(const std::vector<uint32_t> &colors, size_t limit, std::vector<uint32_t> *representatives)
+{
+    struct Box {
+        std::vector<uint32_t> members;  // indices into colors
+    };
+    auto channel = [&](uint32_t index, int c) { return (int) ((colors[index] >> (8 * c)) & 255u); };
+    auto widest = [&](const Box &box, int *axis) {
+        int best = -1;
+        for (int c = 0; c < 4; ++c) {
+            int lo = 255, hi = 0;
+            for (uint32_t m : box.members) {
+                lo = std::min(lo, channel(m, c));
+                hi = std::max(hi, channel(m, c));
+            }
+            if (hi - lo > best) {
+                best = hi - lo;
+                *axis = c;
+            }
+        }
+        return best;
+    };
+    std::vector<Box> boxes(1);
+    boxes[0].members.resize(colors.size());
+    for (uint32_t i = 0; i < colors.size(); ++i) {
+        boxes[0].members[i] = i;
+    }
+    while (boxes.size() < limit) {
+        size_t pick = boxes.size();
+        int pickRange = 0, pickAxis = 0;
+        for (size_t b = 0; b < boxes.size(); ++b) {
+            int axis = 0;
+            const int range = boxes[b].members.size() > 1 ? widest(boxes[b], &axis) : 0;
+            if (range > pickRange) {
+                pick = b;
+                pickRange = range;
+                pickAxis = axis;
+            }
+        }
+        if (pick == boxes.size()) {
+            break;  // every box holds one colour (or identical colours)
+        }
+        std::vector<uint32_t> &m = boxes[pick].members;
+        std::sort(m.begin(), m.end(), [&](uint32_t a, uint32_t b) {
+            const int ca = channel(a, pickAxis), cb = channel(b, pickAxis);
+            return ca != cb ? ca < cb : a < b;
+        });
+        Box upper;
+        upper.members.assign(m.begin() + (long) (m.size() / 2), m.end());
+        m.resize(m.size() / 2);
+        boxes.push_back(std::move(upper));
+    }
+    std::vector<uint32_t> mapping(colors.size(), 0);
+    representatives->clear();
+    for (size_t b = 0; b < boxes.size(); ++b) {
+        uint64_t sum[4] = {0, 0, 0, 0};
+        for (uint32_t m : boxes[b].members) {
+            for (int c = 0; c < 4; ++c) {
+                sum[c] += (uint64_t) channel(m, c);
+            }
+            mapping[m] = (uint32_t) b;
+        }
+        uint32_t mean = 0;
+        const uint64_t n = std::max<uint64_t>(boxes[b].members.size(), 1);
+        for (int c = 0; c < 4; ++c) {
+            mean |= (uint32_t) ((sum[c] + n / 2) / n) << (8 * c);
+        }
+        representatives->push_back(mean);
+    }
+    return mapping;
+}
+
+/// voxelio stringifyFractionRpad (src/stringify.cpp:9-38): truncated decimal expansion, right-padded with zeros.
+std::string fractionRpad(uint32_t num, uint32_t den, unsigned precision)
+{
+    std::string result = std::to_string(num / den);
+    num %= den;
+    result.push_back('.');
+    for (unsigned i = 0; i < precision; ++i) {
+        num *= 10;
+        result.push_back((char) ('0' + num / den));
+        num %= den;
+    }
+    return result;
+}
+
+class PaletteSink final : public VoxelSink {
+public:
+    PaletteSink(FileFormat format, FILE *file, uint32_t resolution)
+        : format_{format}, stream_{file}, resolution_{resolution}
+    {
+    }
+
+    bool write(uint32_t *quads, size_t count) override
+    {
+        voxels_.insert(voxels_.end(), quads, quads + count * 4);
+        for (size_t i = 0; i < count; ++i) {
+            palette_.insert(quads[i * 4 + 3]);
+        }
+        return stream_.good();
+    }
+
+    void finalize() override
+    {
+        if (finalized_) {
+            return;
+        }
+        finalized_ = true;
+        if (format_ == FileFormat::QEF) {
+            writeQef();
+        }
+        else {
+            writeVox();
+        }
+        stream_.flush();
+        voxels_.clear();
+        voxels_.shrink_to_fit();
+    }
+
+    bool good() const override { return stream_.good() && !failed_; }
+    size_t voxelsWritten() const override { return finalized_ ? written_ : voxels_.size() / 4; }
+    const std::vector<uint8_t> *memory() const override { return stream_.memory(); }
+
+private:
+    void text(const std::string &s) { stream_.write(s.data(), s.size()); }
+    void u32le(uint32_t v) { stream_.write(&v, 4); }  // little-endian host (x86-64 / aarch64)
+    void fourcc(const char *id) { stream_.write(id, 4); }
+    void vstring(const std::string &s)
+    {
+        u32le((uint32_t) s.size());
+        text(s);
+    }
+    void chunkHeader(const char *id, uint32_t selfSize, uint32_t childSize = 0)
+    {
+        fourcc(id);
+        u32le(selfSize);
+        u32le(childSize);
+    }
+
+    void writeQef()
+    {
+        const size_t count = voxels_.size() / 4;
+        text("Qubicle Exchange Format\nVersion 0.2\nwww.minddesk.com\n");
+        text(std::to_string(resolution_) + ' ' + std::to_string(resolution_) + ' ' + std::to_string(resolution_) + '\n');
+        text(std::to_string(palette_.colors.size()) + '\n');
+        for (uint32_t argb : palette_.colors) {
+            text(fractionRpad((argb >> 16) & 255u, 255u, 4) + ' ' + fractionRpad((argb >> 8) & 255u, 255u, 4) + ' ' +
+                 fractionRpad(argb & 255u, 255u, 4) + '\n');
+        }
+        std::string block;
+        for (size_t i = 0; i < count; ++i) {
+            const uint32_t *q = voxels_.data() + i * 4;
+            // the reference rejects positions outside [0, resolution] (qef.cpp:297-312): WRITE_ERROR_POSITION_OUT_OF_BOUNDS
+            if ((int32_t) q[0] < 0 || (int32_t) q[1] < 0 || (int32_t) q[2] < 0 || q[0] > resolution_ ||
+                q[1] > resolution_ || q[2] > resolution_) {
+                failed_ = true;
+                break;
+            }
+            block += std::to_string((int32_t) q[0]) + ' ' + std::to_string((int32_t) q[1]) + ' ' +
+                     std::to_string((int32_t) q[2]) + ' ' + std::to_string(palette_.indexOf[q[3]]) + '\n';
+            if (block.size() > (1u << 20)) {
+                text(block);
+                block.clear();
+            }
+            ++written_;
+        }
+        text(block);
+    }
+
+    void nodeTransform(uint32_t id, uint32_t child, const int32_t t[3])
+    {
+        const std::string translation = std::to_string(t[0]) + ' ' + std::to_string(t[1]) + ' ' + std::to_string(t[2]);
+        chunkHeader("nTRN", 11 * 4 + 2 + 1 + 2 + (uint32_t) translation.size());
+        u32le(id);
+        u32le(0);            // node attributes: empty dict
+        u32le(child);
+        u32le(0xffffffffu);  // reserved id, must be -1
+        u32le(0);            // layer
+        u32le(1);            // frames, must be 1
+        u32le(2);            // frame dict
+        vstring("_r");
+        vstring("4");        // identity rotation
+        vstring("_t");
+        vstring(translation);
+    }
+
+    void writeVox()
+    {
+        const size_t count = voxels_.size() / 4;
+        // palette: at most 255 usable entries (index 0 is reserved)
+        std::vector<uint32_t> reduced = palette_.colors;
+        std::vector<uint32_t> mapping(palette_.colors.size());
+        for (uint32_t i = 0; i < mapping.size(); ++i) {
+            mapping[i] = i;
+        }
+        if (palette_.colors.size() > 255) {
+            logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, "Reducing palette from " + std::to_string(palette_.colors.size()) +
+                                                      " to 255 colors ...");
+            mapping = medianCut(palette_.colors, 255, &reduced);
+        }
+        // models: 256^3 chunks in ascending (x, y, z) order
+        std::map<std::array<int32_t, 3>, std::vector<uint32_t>> models;
+        for (size_t i = 0; i < count; ++i) {
+            const uint32_t *q = voxels_.data() + i * 4;
+            const int32_t p[3] = {(int32_t) q[0], (int32_t) q[1], (int32_t) q[2]};
+            std::array<int32_t, 3> key;
+            uint32_t xyzi = 0;
+            for (int a = 0; a < 3; ++a) {
+                key[(size_t) a] = p[a] >= 0 ? p[a] / 256 : -((255 - p[a]) / 256);  // floor division
+                xyzi |= (uint32_t) (p[a] - key[(size_t) a] * 256) << (8 * a);      // bytes x, y, z, i in file order
+            }
+            xyzi |= (mapping[palette_.indexOf[q[3]]] + 1u) << 24;
+            models[key].push_back(xyzi);
+            ++written_;
+        }
+
+        text("VOX ");
+        u32le(150);
+        chunkHeader("MAIN", 0, 0);  // child size patched below
+        for (const auto &model : models) {
+            chunkHeader("SIZE", 12);
+            u32le(256);
+            u32le(256);
+            u32le(256);
+            chunkHeader("XYZI", (uint32_t) (model.second.size() + 1) * 4);
+            u32le((uint32_t) model.second.size());
+            stream_.write(model.second.data(), model.second.size() * 4);
+        }
+        const int32_t zero[3] = {0, 0, 0};
+        nodeTransform(0, 1, zero);
+        chunkHeader("nGRP", (3 + (uint32_t) models.size()) * 4);
+        u32le(1);
+        u32le(0);
+        u32le((uint32_t) models.size());
+        for (uint32_t k = 0; k < models.size(); ++k) {
+            u32le(2 + 2 * k);
+        }
+        uint32_t k = 0;
+        for (const auto &model : models) {
+            const int32_t t[3] = {model.first[0] * 256 + 128, model.first[1] * 256 + 128, model.first[2] * 256 + 128};
+            nodeTransform(2 + 2 * k, 3 + 2 * k, t);
+            chunkHeader("nSHP", 5 * 4);
+            u32le(3 + 2 * k);
+            u32le(0);
+            u32le(1);
+            u32le(k);
+            u32le(0);
+            ++k;
+        }
+        chunkHeader("RGBA", 1024);
+        uint8_t rgba[1024];
+        memset(rgba, 0, sizeof rgba);
+        for (size_t i = 0; i < reduced.size() && i < 255; ++i) {  // RGBA entry i is palette index i + 1
+            rgba[i * 4 + 0] = (uint8_t) (reduced[i] >> 16);
+            rgba[i * 4 + 1] = (uint8_t) (reduced[i] >> 8);
+            rgba[i * 4 + 2] = (uint8_t) reduced[i];
+            rgba[i * 4 + 3] = (uint8_t) (reduced[i] >> 24);
+        }
+        stream_.write(rgba, sizeof rgba);
+        const size_t end = stream_.position();
+        stream_.seek(16);
+        u32le((uint32_t) (end - 20));
+        stream_.seek(end);
+    }
+
+    FileFormat format_;
+    ByteStream stream_;
+    uint32_t resolution_;
+    std::vector<uint32_t> voxels_;
+    PaletteBuilder palette_;
+    size_t written_ = 0;
+    bool finalized_ = false;
+    bool failed_ = false;
+};
+
 }  // namespace
 
 std::unique_ptr<VoxelSink> makeCallbackSink(obj2voxel_voxel_callback *callback, void *data)
@@ -232,10 +538,11 @@ std::unique_ptr<VoxelSink> makeCallbackSink(obj2voxel_voxel_callback *callback, 
     return std::unique_ptr<VoxelSink>(new CallbackSink{callback, data});
 }
 
-std::unique_ptr<VoxelSink> makeFormatSink(FileFormat format, const char *path, uint32_t, std::string *error)
+std::unique_ptr<VoxelSink> makeFormatSink(FileFormat format, const char *path, uint32_t resolution, std::string *error)
 {
-    if (format != FileFormat::VL32 && format != FileFormat::PLY && format != FileFormat::XYZRGB) {
-        *error = "only the streamable voxel formats vl32, ply and xyzrgb are implemented (palette formats qef/vox are not)";
+    const bool palette = format == FileFormat::QEF || format == FileFormat::VOX;
+    if (!palette && format != FileFormat::VL32 && format != FileFormat::PLY && format != FileFormat::XYZRGB) {
+        *error = "not a voxel output format (supported: vl32, ply, xyzrgb, qef, vox)";
         return nullptr;
     }
     FILE *file = nullptr;
@@ -245,6 +552,9 @@ std::unique_ptr<VoxelSink> makeFormatSink(FileFormat format, const char *path, u
             *error = std::string("cannot open \"") + path + "\" for writing";
             return nullptr;
         }
+    }
+    if (palette) {
+        return std::unique_ptr<VoxelSink>(new PaletteSink{format, file, resolution});
     }
     return std::unique_ptr<VoxelSink>(new FormatSink{format, file});
 }

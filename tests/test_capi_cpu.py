@@ -2,6 +2,7 @@
 checks, error codes, textures, worker bookkeeping, sinks) behaves like the reference's — all without a compute call."""
 import os
 import re
+import subprocess
 import threading
 import time
 
@@ -151,6 +152,34 @@ def test_no_cpu_fallback_without_a_device():
     assert inst.collected().shape == (0, 4)
     inst.free()
     lib.obj2voxel_set_log_level(_lib.LOG_INFO)
+
+
+def test_cli_argument_handling_without_a_device(tmp_path):
+    """obj2voxel-b200 (reference CLI flags, src/main.cpp:264-380): help / version / incomplete and invalid arguments; with
+    no GPU in this container a complete job fails with OBJ2VOXEL_ERR_DEVICE instead of falling back to a CPU path."""
+    exe = os.path.join(ROOT, "obj2voxel_b200", "obj2voxel-b200")
+
+    def run(*argv):
+        return subprocess.run([exe, *argv], capture_output=True, text=True, timeout=120)
+
+    r = run("-h")
+    assert r.returncode == 1 and "Usage: obj2voxel-b200" in r.stdout and "--strat=[max|blend]" in r.stdout
+    assert run("--80").stdout.splitlines() and max(len(x) for x in run("--80").stdout.splitlines()) <= 81
+    r = run("-V")
+    assert r.returncode == 0 and "===== obj2voxel =====" in r.stdout and "1.3.5-dev" in r.stdout
+    assert run("in.stl", "out.vl32").returncode == 1            # -r is required
+    assert run("in.stl", "-r", "16").returncode == 1            # OUTPUT_FILE is required
+    assert run("in.stl", "out.vl32", "-r", "16", "-s", "mean").returncode == 1
+    assert run("in.stl", "out.vl32", "-r", "16", "--bogus").returncode == 1
+    r = run("in.stl", "out.vl32", "-r", "16", "-p", "xxz")
+    assert r.returncode == 1 and "Invalid combination of permutation chars" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        stl = tmp_path / "t.stl"
+        stl.write_bytes(b" " * 80 + (1).to_bytes(4, "little") + b"\0" * 12 +
+                        np.array([0, 0, 0, 0, 0, 1, 1, 0, 0], np.float32).tobytes() + b"\0\0")
+        r = run(str(stl), str(tmp_path / "t.vl32"), "-r", "16")
+        assert r.returncode == 8, r.stdout + r.stderr       # OBJ2VOXEL_ERR_DEVICE
 
 
 def test_product_never_references_the_oracle():

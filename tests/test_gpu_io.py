@@ -1,5 +1,6 @@
 """GPU (-m gpu): the I/O adapters either side of the hot path through the reference API:
-binary STL and OBJ(+MTL) input files, VL32 / PLY / XYZRGB output (file and memory)."""
+binary STL and OBJ(+MTL) input files, VL32 / PLY / XYZRGB / QEF / VOX output (file and memory), and the CLI."""
+import os
 import struct
 
 import numpy as np
@@ -87,12 +88,150 @@ def test_vl32_ply_xyzrgb_outputs_agree(tmp_path):
     assert len(rows) == len(want) and np.all(rows[:, 3:] == 255)
 
 
-def test_palette_formats_report_open_output_error(tmp_path):
-    o2v.load().obj2voxel_set_log_level(_lib.LOG_SILENT)
-    stl = str(tmp_path / "cube.stl")
-    write_binary_stl(stl, meshes.unit_cube())
-    assert run_file_job(stl, 16, out=str(tmp_path / "cube.qef"))["err"] == _lib.ERR_IO_OPEN_OUTPUT
-    o2v.load().obj2voxel_set_log_level(_lib.LOG_INFO)
+def parse_qef(path):
+    """Qubicle Exchange Format as the reference writes it (voxelio/src/format/qef.cpp:212-295)."""
+    lines = open(path).read().split("\n")
+    assert lines[:3] == ["Qubicle Exchange Format", "Version 0.2", "www.minddesk.com"]
+    dims = [int(x) for x in lines[3].split()]
+    n_colors = int(lines[4])
+    palette = []
+    for line in lines[5:5 + n_colors]:
+        parts = line.split()
+        assert all(len(x.split(".")[1]) == 4 for x in parts)  # stringifyFractionRpad(channel, 255, 4)
+        palette.append([float(x) for x in parts])
+    rows = np.array([[int(x) for x in line.split()] for line in lines[5 + n_colors:] if line], dtype=np.int64)
+    return dims, np.array(palette), rows
+
+
+def parse_vox(path):
+    """MagicaVoxel 150 as the reference writes it (voxelio/src/format/vox.cpp:828-1080): returns (voxels (n, 4) with
+    the palette index in column 3, palette (256, 4) RGBA with entry i = index i + 1, number of models)."""
+    data = open(path, "rb").read()
+    assert data[:4] == b"VOX " and struct.unpack_from("<I", data, 4)[0] == 150
+    assert data[8:12] == b"MAIN"
+    self_size, child_size = struct.unpack_from("<II", data, 12)
+    assert self_size == 0 and child_size == len(data) - 20
+    pos, models, translations, palette = 20, [], [], None
+    while pos < len(data):
+        cid = data[pos:pos + 4]
+        size, children = struct.unpack_from("<II", data, pos + 4)
+        body = data[pos + 12:pos + 12 + size]
+        if cid == b"SIZE":
+            assert struct.unpack("<III", body) == (256, 256, 256)
+        elif cid == b"XYZI":
+            n = struct.unpack_from("<I", body, 0)[0]
+            models.append(np.frombuffer(body[4:4 + 4 * n], dtype=np.uint8).reshape(-1, 4).astype(np.int64))
+        elif cid == b"nTRN":
+            node_id = struct.unpack_from("<I", body, 0)[0]
+            tail = body[body.rindex(b"_t") + 2:]
+            length = struct.unpack_from("<I", tail, 0)[0]
+            if node_id >= 2:
+                translations.append([int(x) for x in tail[4:4 + length].decode().split()])
+        elif cid == b"RGBA":
+            palette = np.frombuffer(body, dtype=np.uint8).reshape(256, 4)
+        else:
+            assert cid in (b"nGRP", b"nSHP"), cid
+        pos += 12 + size + children
+    assert len(models) == len(translations) and palette is not None
+    voxels = []
+    for m, t in zip(models, translations):
+        world = m.copy()
+        world[:, :3] += np.array(t) - 128  # the transform node carries the model centre
+        voxels.append(world)
+    return np.concatenate(voxels), palette, len(models)
+
+
+def test_qef_and_vox_outputs(tmp_path):
+    """Palette formats: a two-colour OBJ at resolution 300 (> 256: two VOX models per axis)."""
+    (tmp_path / "m.mtl").write_text("newmtl red\nKd 1 0 0\nnewmtl teal\nKd 0 0.5 0.5\n")
+    obj = tmp_path / "m.obj"
+    obj.write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\n"
+                   "usemtl red\nf 1 2 3 4\nusemtl teal\nf 1 2 6 5\n")
+    res = 300
+    want = run_file_job(str(obj), res)["voxels"]
+    assert len(want) > 100000 and set(np.unique(want[:, 3]).tolist()) >= {0xFFFF0000, 0xFF007F7F}
+
+    qef = str(tmp_path / "m.qef")
+    assert run_file_job(str(obj), res, out=qef)["err"] == o2v.ERR_OK
+    dims, palette, rows = parse_qef(qef)
+    assert dims == [res, res, res] and len(rows) == len(want)
+    rgb = (np.floor(palette[rows[:, 3]] * 255 + 0.5)).astype(np.int64)  # 4 truncated decimals round back exactly
+    argb = 0xFF000000 | (rgb[:, 0] << 16) | (rgb[:, 1] << 8) | rgb[:, 2]
+    got = o2v.sort_voxels(np.concatenate([rows[:, :3], argb[:, None]], axis=1).astype(np.uint32))
+    assert np.array_equal(got, want)
+
+    vox = str(tmp_path / "m.vox")
+    assert run_file_job(str(obj), res, out=vox)["err"] == o2v.ERR_OK
+    voxels, rgba, n_models = parse_vox(vox)
+    assert n_models > 1 and voxels[:, 3].min() >= 1  # palette index 0 is reserved
+    colour = rgba[voxels[:, 3] - 1].astype(np.int64)
+    argb = (colour[:, 3] << 24) | (colour[:, 0] << 16) | (colour[:, 1] << 8) | colour[:, 2]
+    got = o2v.sort_voxels(np.concatenate([voxels[:, :3], argb[:, None]], axis=1).astype(np.uint32))
+    assert np.array_equal(got, want)
+
+
+def test_vox_palette_reduction_keeps_positions(tmp_path):
+    """More than 255 colours: positions stay exact, colours move to at most 255 representatives close to the originals."""
+    n = 1500
+    v = meshes.random_triangles(n, 0.04, seed=3)
+    uv = meshes.random_uvs(n, seed=4)
+    tex = o2v.Texture(meshes.random_texture(64, 64, 3, seed=9), wrap=o2v.UV_WRAP)
+
+    def job(out):
+        inst = o2v.Instance()
+        inst.set_input_callback(v, uvs=uv, texture=tex)
+        if out is None:
+            inst.set_output_callback()
+        else:
+            inst.set_output_file(out, None)
+        inst.set_resolution(64)
+        inst.set_color_strategy(1)
+        inst.set_mesh_boundaries([0, 0, 0, 1, 1, 1])
+        err = inst.voxelize()
+        voxels = inst.collected()
+        inst.free()
+        assert err == o2v.ERR_OK
+        return voxels
+
+    want = job(None)
+    assert len(np.unique(want[:, 3])) > 255
+    vox = str(tmp_path / "t.vox")
+    job(vox)
+    voxels, rgba, _ = parse_vox(vox)
+    order = np.lexsort((voxels[:, 2], voxels[:, 1], voxels[:, 0]))
+    voxels = voxels[order]
+    assert np.array_equal(voxels[:, :3], want[:, :3].astype(np.int64))
+    assert len(np.unique(voxels[:, 3])) <= 255
+    colour = rgba[voxels[:, 3] - 1].astype(np.int64)
+    orig = np.stack([(want[:, 3] >> 16) & 255, (want[:, 3] >> 8) & 255, want[:, 3] & 255], axis=1).astype(np.int64)
+    assert np.abs(colour[:, :3] - orig).mean() < 24  # median cut of ~64^3 random colours into 255 boxes
+
+
+def test_cli_matches_the_api(tmp_path):
+    """obj2voxel-b200 with the reference CLI's flags (src/main.cpp:264-380): -r, -s, -u, -p, -o, exit status."""
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "obj2voxel_b200", "obj2voxel-b200")
+    tris = meshes.lumpy_sphere(20, 21) * np.float32([1.0, 0.6, 0.3] * 3)
+    stl = str(tmp_path / "s.stl")
+    write_binary_stl(stl, tris)
+    out = str(tmp_path / "s.vl32")
+    r = subprocess.run([exe, stl, out, "-r", "48", "-s", "blend", "-u", "-p", "zXy", "-j", "2"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = o2v.sort_voxels(np.fromfile(out, dtype=">u4").reshape(-1, 4).astype(np.uint32))
+    # -p zXy: output x = input z, output y = -input x, output z = input y
+    want = oracle.voxelize(tris, 48, strategy=1, supersampling=2, unit=[0, 0, 1, -1, 0, 0, 0, 1, 0])["voxels"]
+    assert np.array_equal(got, want)
+    # explicit output format on an extension-less path, long flags
+    out2 = str(tmp_path / "noext")
+    r = subprocess.run([exe, stl, out2, "--res=16", "-oxyzrgb"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and len(open(out2).read().splitlines()) == len(oracle.voxelize(tris, 16)["voxels"])
+    # failures surface in the exit status (stated deviation from the reference, which always exits 0)
+    r = subprocess.run([exe, str(tmp_path / "missing.stl"), out, "-r", "16"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == _lib.ERR_IO_OPEN_INPUT
 
 
 def test_obj_with_materials(tmp_path):
