@@ -30,26 +30,14 @@ __device__ __forceinline__ void tileOriginOf(const GridView &grid, uint32_t tile
 // ---------------------------------------------------------------------------------------------------------------------
 // triangle setup shared by the count and emit passes
 
+/// Transforms the model-space triangle `in` (applyMeshTransform, src/obj2voxel.cpp:202-209) and computes its area.
+/// false: the triangle contributes nothing (zero area, non-finite, or a negative voxel-space coordinate).
 template <bool UV>
-__device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridView &grid, unsigned long long i,
-                                             Tri<UV> &t, float &area)
+__device__ __forceinline__ bool setupTriangle(const GridView &grid, const float in[9], Tri<UV> &t, float &area)
 {
-    const float *src = mesh.verts + i * 9;
-    float in[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        in[k] = __ldg(src + k);
-    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        affineApply(grid.xf, in + k * 3, t.v + k * 3);  // applyMeshTransform, src/obj2voxel.cpp:202-209
-    }
-    if (UV) {
-        const float *uv = mesh.uvs + i * 6;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            t.t[k] = __ldg(uv + k);
-        }
+        affineApply(grid.xf, in + k * 3, t.v + k * 3);
     }
     area = triArea(t.v);
     // A negative voxel-space coordinate wraps the reference's float -> u32 cast to a huge chunkMin (triangle.hpp:91-95,
@@ -61,6 +49,136 @@ __device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridVie
     }
     // weight 0 never reaches the voxel map (voxelization.cpp:466); non-finite input is a contract violation
     return area > 0.0f && area < INFINITY && !negative;
+}
+
+template <bool UV>
+__device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridView &grid, unsigned long long i,
+                                             Tri<UV> &t, float &area)
+{
+    const float *src = mesh.verts + i * 9;
+    float in[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        in[k] = __ldg(src + k);
+    }
+    if (UV) {
+        const float *uv = mesh.uvs + i * 6;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            t.t[k] = __ldg(uv + k);
+        }
+    }
+    return setupTriangle<UV>(grid, in, t, area);
+}
+
+/// true if the voxel z range of the model-space triangle `in` provably misses this rank's slab: the decision of
+/// traverseLeaves' root test, taken from the three transformed z coordinates alone (same arithmetic as affineApply).
+/// Triangles with a negative z are kept: the count pass drops and counts them.
+__device__ __forceinline__ bool triangleMissesSlab(const GridView &grid, const float in[9])
+{
+    const float *m = grid.xf;
+    float z[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        z[k] = xadd(dot3(m[6], m[7], m[8], in[k * 3], in[k * 3 + 1], in[k * 3 + 2]), m[11]);
+    }
+    const float zlo = floorf(min3(z[0], z[1], z[2])), zhi = floorf(max3(z[0], z[1], z[2]));
+    return zlo >= 0.0f && (toU32(zhi) + 1u <= grid.slabZ0 || toU32(zlo) >= grid.slabZ1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// triangle batches through shared memory: bulk-async copies (the TMA engine, no tensor map needed for a 1-D run)
+
+__device__ __forceinline__ uint32_t sharedAddress(const void *p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbarrierInit(unsigned long long *bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sharedAddress(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+/// Arms `bar` with the byte count and starts the copy global -> shared; src, dst and bytes are multiples of 16.
+__device__ __forceinline__ void bulkLoad(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic accesses of dst come first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sharedAddress(bar)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sharedAddress(dst)),
+                 "l"(src), "r"(bytes), "r"(sharedAddress(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbarrierWait(unsigned long long *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred done;\n"
+        "WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+        "@!done bra WAIT;\n"
+        "}\n" ::"r"(sharedAddress(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int kThreads>
+struct TriangleBatch {
+    alignas(128) float v[kThreads * 9];
+    alignas(8) unsigned long long bar;
+};
+
+/// Calls visit(i, in, valid) from every thread of the block, once per batch of kThreads triangles of the contiguous array
+/// verts[9 * count] (grid-stride over batches): `in` = the nine model-space floats of triangle i, valid = false for the
+/// threads beyond the end of the ragged last batch (so that visit may use block-wide barriers).  Thread 0 starts the bulk copy of the
+/// block's next batch as soon as the current one sits in registers, so the copy runs under the visit.  Batches the bulk
+/// copy cannot take (array not 16-byte aligned; the ragged last batch) are loaded by the block.
+template <int kThreads, typename Visit>
+__device__ __forceinline__ void streamTriangles(const float *verts, unsigned long long count,
+                                                TriangleBatch<kThreads> &sh, Visit &&visit)
+{
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long batches = (count + kThreads - 1) / kThreads;
+    const bool aligned = (reinterpret_cast<unsigned long long>(verts) & 15ull) == 0;
+    constexpr uint32_t kBatchBytes = kThreads * 9 * sizeof(float);
+    static_assert(kBatchBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
+    if (tid == 0) {
+        mbarrierInit(&sh.bar, 1);
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    unsigned long long b = blockIdx.x;
+    if (tid == 0 && b < batches && aligned && (b + 1) * kThreads <= count) {
+        bulkLoad(sh.v, verts + b * kThreads * 9, kBatchBytes, &sh.bar);
+    }
+    for (; b < batches; b += gridDim.x) {
+        const unsigned long long first = b * kThreads;
+        const uint32_t n = (uint32_t) (count - first < (unsigned long long) kThreads ? count - first : kThreads);
+        if (aligned && n == (uint32_t) kThreads) {
+            mbarrierWait(&sh.bar, parity);
+            parity ^= 1u;
+        }
+        else {
+            for (uint32_t k = tid; k < n * 9u; k += kThreads) {
+                sh.v[k] = __ldg(verts + first * 9 + k);
+            }
+            __syncthreads();
+        }
+        float in[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            in[k] = sh.v[tid * 9 + k];  // stride 9 words: conflict-free
+        }
+        __syncthreads();  // the batch sits in registers: its buffer is free again
+        const unsigned long long next = b + gridDim.x;
+        if (tid == 0 && next < batches && aligned && (next + 1) * kThreads <= count) {
+            bulkLoad(sh.v, verts + next * kThreads * 9, kBatchBytes, &sh.bar);
+        }
+        visit(first + tid, in, tid < n);
+    }
 }
 
 /// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.

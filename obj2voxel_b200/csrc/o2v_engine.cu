@@ -432,10 +432,30 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     return kErrOk;
 }
 
-int Engine::voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid,
+int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params, const GridView &grid,
                               cudaStream_t stream, RunStats &st)
 {
     RunCounters *dCounters = counters_.as<RunCounters>();
+    MeshView mesh = meshIn;
+    if (grid.slabZ0 != 0 || grid.slabZ1 < grid.gridExtent) {
+        // One rank of several: keep only the triangles whose z range can reach the slab (one streaming pass over the
+        // mesh); everything after works on that share.
+        if (!slabVerts_.ensure((size_t) meshIn.count * 9 * sizeof(float))) {
+            return fail(kErrOutOfMemory, "device allocation failed (occupancy path, slab triangles)");
+        }
+        launchOccupancySlabFilter(meshIn, grid, slabVerts_.as<float>(), dCounters, stream);
+        ++st.kernelLaunches;
+        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        O2V_CUDA(cudaGetLastError());
+        mesh.verts = slabVerts_.as<float>();
+        mesh.count = hostCounters_->slabTriangles;
+        if (mesh.count == 0) {
+            st.occupancyPath = true;
+            st.counters = *hostCounters_;
+            return kErrOk;
+        }
+    }
     const size_t n = (size_t) mesh.count;
 
     OccupancyView occ{};
@@ -444,14 +464,14 @@ int Engine::voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, 
     const uint32_t chunkRows = (grid.slabZ1 + kChunkEdge - 1) / kChunkEdge - occ.chunkZ0;
     occ.chunkTotal = occ.chunksPerAxis * occ.chunksPerAxis * chunkRows;  // <= 128^3
     if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !scratch_.ensure(scanScratchElems(n) * 4) ||
-        !chunkFlag_.ensure(occ.chunkTotal) || !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) ||
+        !chunkFlag_.ensure(((size_t) occ.chunkTotal + 31) / 32 * 4) || !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) ||
         !chunkList_.ensure((size_t) occ.chunkTotal * 4)) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path, setup buffers)");
     }
-    occ.chunkFlag = chunkFlag_.as<uint8_t>();
+    occ.chunkFlag = chunkFlag_.as<uint32_t>();
     occ.chunkSlot = chunkSlot_.as<uint32_t>();
     occ.chunkList = chunkList_.as<uint32_t>();
-    O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, occ.chunkTotal, stream));
+    O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, ((size_t) occ.chunkTotal + 31) / 32 * 4, stream));
 
     launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), dCounters, stream);
     launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),

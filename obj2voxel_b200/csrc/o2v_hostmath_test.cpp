@@ -84,7 +84,7 @@ void o2vt_combine(float acc[4], const float incoming[4], int blend)
 
 /// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through the two SAT users of the kernels
 ///   * prefilterPass with tile-relative constants (weighted path: o2v_sparse.cu / o2v_kernels.cu),
-///   * classifyVoxel with constants relative to the leaf's box — or to its 16^3 sub-boxes when the box holds more than
+///   * buildRowSat / rowSpanMisses / classifyInRow (and classifyVoxel) with constants relative to the leaf's box — or to its 16^3 sub-boxes when the box holds more than
 ///     4096 voxels — exactly as o2v_occupancy.cu stages them,
 /// and through the reference semantics (plane-distance cull + exact clip, o2v_exact.cuh), and counts disagreements.
 /// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts (either user) the
@@ -132,10 +132,24 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
                     buildPrefilter(bs, boxOrigin);
                     PairSat sat;
                     buildPairSat(sat, bs, boxOrigin);
-                    const int verdict = (flags & kLeafNoPrefilter) != 0
-                                            ? (int) kSatUncertain
-                                            : classifyVoxel(sat, (float) (x - bo[0]), (float) (y - bo[1]),
-                                                            (float) (z - bo[2]));
+                    // as the classify kernel does it: the row's 8-aligned x segment is tested as a whole first
+                    const uint32_t boxHiX = boxEdge != 0xffffffffu && bo[0] + boxEdge < hi[0] ? bo[0] + boxEdge : hi[0];
+                    const uint32_t segFirst = (x & ~7u) > bo[0] ? (x & ~7u) : bo[0];
+                    const uint32_t segLast = ((x & ~7u) + 8u < boxHiX ? (x & ~7u) + 8u : boxHiX) - 1u;
+                    RowSat row;
+                    buildRowSat(sat, (float) (y - bo[1]), (float) (z - bo[2]), row);
+                    int verdict = kSatUncertain;
+                    if ((flags & kLeafNoPrefilter) == 0) {
+                        const float spanFirst = (float) (segFirst - bo[0]), spanLast = (float) (segLast - bo[0]);
+                        verdict = (rowPlaneSpanMisses(sat, row, spanFirst, spanLast) ||
+                                   rowSpanMisses(sat, row, spanFirst, spanLast))
+                                      ? (int) kSatMiss
+                                      : classifyInRow(sat, row, (float) (x - bo[0]));
+                        if (verdict != classifyVoxel(sat, (float) (x - bo[0]), (float) (y - bo[1]),
+                                                     (float) (z - bo[2]))) {
+                            ++out[5];  // the segment test must never reject what the voxel's own test accepts
+                        }
+                    }
                     const bool hit =
                         !planeDistanceCulled(v, x, y, z) && clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
                     ++out[0];

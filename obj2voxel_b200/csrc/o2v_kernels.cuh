@@ -87,6 +87,7 @@ struct RunCounters {
     unsigned long long bigLeaves;       // leaves with more than kOccBigVolume candidate voxels
     unsigned long long bigBoxes;        // their 16^3 boxes
     unsigned long long bigTicket;       // emit pass: (table row << 40) | first box, handed out by one atomic
+    unsigned long long slabTriangles;   // triangles the slab filter kept (only when the slab is a part of the grid)
 };
 
 /// Descriptor of a light tile: everything the warp needs in one 16-byte load.
@@ -157,7 +158,7 @@ constexpr uint32_t kOccBoxEdge = 16;      // ... in 16^3 boxes
 /// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
 /// occupancy has to be decided — an order-independent OR into per-chunk bitmaps.
 struct OccupancyView {
-    uint8_t *chunkFlag;              // per 64^3 chunk of the slab: some leaf's box reaches it
+    uint32_t *chunkFlag;             // one bit per 64^3 chunk of the slab: some leaf's box reaches it
     uint32_t *chunkSlot;             // per chunk: index of its bitmap
     uint32_t *chunkList;             // per bitmap: its chunk
     uint32_t chunksPerAxis, chunkZ0, chunkTotal;  // chunk id = cx + C * (cy + C * (cz - chunkZ0))
@@ -204,6 +205,8 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 /// Occupancy-only path (see OccupancyView and the header of o2v_occupancy.cu): count / emit leaves per triangle, classify
 /// every candidate voxel with the three-way SAT of o2v_sat.cuh (`certain` -> bitmap, `uncertain` -> queue), exact clip
 /// for the queue, bitmap -> Voxel32 records.
+void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
+                               cudaStream_t stream);
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
                           RunCounters *counters, cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);

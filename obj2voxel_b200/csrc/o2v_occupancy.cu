@@ -93,18 +93,94 @@ __device__ __forceinline__ uint32_t boxCountOf(const uint32_t *lo, const uint32_
            ((hi[2] - lo[2] + kOccBoxEdge - 1) / kOccBoxEdge);
 }
 
+/// Only when the rank's slab is a part of the grid: copies the triangles whose z range can reach the slab into a dense
+/// array, so that the count and emit passes neither read nor diverge on the others (with N ranks, (N - 1) / N of the
+/// mesh).  A block collects what it keeps in shared memory and appends it to the array kOccSetupThreads or more
+/// triangles at a time: one atomic and one coalesced copy per append.  The order of the array is arbitrary; the
+/// occupancy result is an OR, order-free.
+__global__ void __launch_bounds__(kOccSetupThreads)
+occupancySlabFilterKernel(MeshView mesh, GridView grid, float *__restrict__ kept, RunCounters *counters)
+{
+    __shared__ TriangleBatch<kOccSetupThreads> batch;
+    __shared__ float keep[2 * kOccSetupThreads * 9];
+    __shared__ uint32_t warpCount[kOccSetupThreads / 32];
+    __shared__ unsigned long long appendAt;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t held = 0;  // block-uniform: triangles waiting in `keep`, < kOccSetupThreads between batches
+
+    auto append = [&]() {  // all threads; `held` is block-uniform
+        if (tid == 0) {
+            appendAt = atomicAdd(&counters->slabTriangles, (unsigned long long) held);
+        }
+        __syncthreads();
+        float *dst = kept + appendAt * 9;
+        for (uint32_t k = tid; k < held * 9u; k += kOccSetupThreads) {
+            dst[k] = keep[k];
+        }
+        __syncthreads();
+        held = 0;
+    };
+
+    streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
+                                      [&](unsigned long long, const float in[9], bool valid) {
+        const bool mine = valid && !triangleMissesSlab(grid, in);
+        const unsigned int votes = __ballot_sync(0xffffffffu, mine);
+        if (lane == 0) {
+            warpCount[warp] = (uint32_t) __popc(votes);
+        }
+        __syncthreads();
+        uint32_t slot = held + (uint32_t) __popc(votes & ((1u << lane) - 1u)), added = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kOccSetupThreads / 32; ++w) {
+            slot += w < warp ? warpCount[w] : 0u;
+            added += warpCount[w];
+        }
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                keep[slot * 9 + k] = in[k];  // stride 9 words: conflict-free
+            }
+        }
+        __syncthreads();
+        held += added;
+        if (held >= (uint32_t) kOccSetupThreads) {
+            append();
+        }
+    });
+    if (held != 0) {
+        append();
+    }
+}
+
+constexpr uint32_t kOccBlockChunkWords = 2048;  // chunk bits a block collects in shared memory: 65536 chunks (8 KB)
+
 __global__ void __launch_bounds__(kOccSetupThreads)
 occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ leafCount,
                      RunCounters *counters)
 {
+    __shared__ TriangleBatch<kOccSetupThreads> batch;
+    // Millions of leaves mark a few thousand chunks: up to 65536 chunks per slab (any grid up to 2560^3, and slabs of
+    // larger ones) a block ORs its marks into shared memory and publishes each word once when it is done, so that the
+    // hot words see a few reads per block instead of a read per leaf.
+    __shared__ uint32_t chunkBits[kOccBlockChunkWords];
+    const uint32_t chunkWords = (occ.chunkTotal + 31u) / 32u;
+    const bool collect = chunkWords <= kOccBlockChunkWords;
+    if (collect) {
+        for (uint32_t w = threadIdx.x; w < chunkWords; w += kOccSetupThreads) {
+            chunkBits[w] = 0;
+        }
+    }
+    // (streamTriangles starts with a barrier)
     unsigned long long candidates = 0, dropped = 0, overflow = 0, bigLeaves = 0, bigBoxes = 0;
-    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
-         i += stride) {
+    streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
+                                      [&](unsigned long long i, const float in[9], bool valid) {
+        if (!valid) {
+            return;
+        }
         Tri<false> root;
         float area;
         uint32_t leaves = 0;
-        if (loadTriangle<false>(mesh, grid, i, root, area)) {
+        if (setupTriangle<false>(grid, in, root, area)) {
             const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &, const uint32_t *lo,
                                                                    const uint32_t *hi) {
                 ++leaves;
@@ -118,7 +194,16 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
                 for (uint32_t cz = lo[2] >> 6; cz <= (hi[2] - 1) >> 6; ++cz) {
                     for (uint32_t cy = lo[1] >> 6; cy <= (hi[1] - 1) >> 6; ++cy) {
                         for (uint32_t cx = lo[0] >> 6; cx <= (hi[0] - 1) >> 6; ++cx) {
-                            occ.chunkFlag[cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0))] = 1;
+                            const uint32_t chunk = cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0));
+                            const uint32_t bit = 1u << (chunk & 31u);
+                            if (collect) {
+                                if ((chunkBits[chunk >> 5] & bit) == 0) {
+                                    atomicOr(&chunkBits[chunk >> 5], bit);
+                                }
+                            }
+                            else if ((__ldcg(occ.chunkFlag + (chunk >> 5)) & bit) == 0) {  // look before the atomic
+                                atomicOr(occ.chunkFlag + (chunk >> 5), bit);
+                            }
                         }
                     }
                 }
@@ -129,6 +214,15 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
             ++dropped;
         }
         leafCount[i] = leaves;
+    });
+    if (collect) {
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < chunkWords; w += kOccSetupThreads) {
+            const uint32_t marks = chunkBits[w];
+            if (marks != 0 && (marks & ~__ldcg(occ.chunkFlag + w)) != 0) {
+                atomicOr(occ.chunkFlag + w, marks);
+            }
+        }
     }
     warpTally(&counters->candidateVoxels, candidates);
     warpTally(&counters->droppedTriangles, dropped);
@@ -140,7 +234,7 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
 __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *counters)
 {
     const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool touched = chunk < occ.chunkTotal && occ.chunkFlag[chunk] != 0;
+    const bool touched = chunk < occ.chunkTotal && ((occ.chunkFlag[chunk >> 5] >> (chunk & 31u)) & 1u) != 0;
     const unsigned int ballot = __ballot_sync(0xffffffffu, touched);
     if (ballot == 0) {
         return;
@@ -162,13 +256,13 @@ __global__ void __launch_bounds__(kOccSetupThreads)
 occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ leafOffset,
                     LeafRecord *__restrict__ leaves, RunCounters *counters)
 {
-    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
-         i += stride) {
+    __shared__ TriangleBatch<kOccSetupThreads> batch;
+    streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
+                                      [&](unsigned long long i, const float in[9], bool valid) {
         Tri<false> root;
         float area;
-        if (!loadTriangle<false>(mesh, grid, i, root, area)) {
-            continue;
+        if (!valid || !setupTriangle<false>(grid, in, root, area)) {
+            return;
         }
         uint32_t index = leafOffset[i];
         traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
@@ -177,7 +271,7 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
             for (int k = 0; k < 9; ++k) {
                 rec.v[k] = leaf.v[k];
             }
-            rec.tri = static_cast<uint32_t>(i);
+            rec.tri = static_cast<uint32_t>(i);  // position in the array this pass reads (not used on this path)
             rec.area = area;
             rec.flags = leafFlagsOf(leaf.v);
             leaves[index] = rec;
@@ -194,29 +288,32 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
             }
             ++index;
         });
-    }
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // classify: thread per candidate voxel
 
-/// Batch entry in shared memory: the SAT constants plus where the entry's box sits.  56 words, 16-byte aligned.
+/// Batch entry in shared memory: the SAT constants plus where the entry's box sits.  The unit of work is a *row
+/// segment*: the voxels of one row (fixed y, z) of the box that share a tile column (x >> 3) — at most 8 voxels, all in
+/// one 32-bit half of one bitmap word.  60 words, 16-byte aligned.
 struct alignas(16) BatchEntry {
     PairSat sat;
     uint32_t leaf;                // leaf index (queue entries name it)
     uint32_t x0, y0, z0;          // box min corner, voxel space
-    uint32_t dx, dxdy;            // box extent in x, in x * y
-    uint32_t magicX, magicXY;     // n / d == __umulhi(n, magic) for d > 1, n * d <= 2^24 (d == 1: n itself)
+    uint32_t dx;                  // box extent in x
+    uint32_t segs, segsDy;        // segments per row, per layer (= segs * extent in y)
+    uint32_t magicSegs, magicSegsDy;  // n / d == __umulhi(n, magic) for d > 1, n * d <= 2^24 (d == 1: n itself)
     uint32_t slot;                // bitmap of the box's chunk, or kNoSlot if the box spans several chunks
-    uint32_t pad[3];
+    uint32_t pad[2];
 };
 
 constexpr uint32_t kNoSlot = 0xffffffffu;
 
 struct ClassifyShared {
     BatchEntry entry[kOccBatch];
-    uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' candidate counts
-    uint32_t maybe[kOccMaybeCap];     // (entry << 12) | candidate index in its box; top bit: survived the filter
+    uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' row-segment counts
+    uint32_t maybe[kOccMaybeCap];     // undecided voxels: entry << 15 | segment << 3 | x & 7; top bit: survived the filter
     uint32_t warpSums[kOccThreads / 32];
     uint32_t maybeCount;
     unsigned long long queueBase;
@@ -243,7 +340,8 @@ __device__ __forceinline__ size_t entryWord(const OccupancyView &occ, const Batc
     return (size_t) e.slot * kChunkWords + tileLocal * kTileEdge + (z & 7u);
 }
 
-/// Fills one batch entry for `leaf` restricted to the box [lo, hi).  Returns the number of candidates (0 = skip).
+/// Fills one batch entry for `leaf` restricted to the box [lo, hi) (at most kOccBigVolume voxels).  Returns the number
+/// of row segments (0 = skip).
 __device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, const OccupancyView &occ, uint32_t leafIndex,
                                                     const uint32_t lo[3], const uint32_t hi[3], LeafStage &s)
 {
@@ -260,10 +358,11 @@ __device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, const Occupan
     e.y0 = lo[1];
     e.z0 = lo[2];
     e.dx = hi[0] - lo[0];
-    e.dxdy = e.dx * (hi[1] - lo[1]);
-    e.magicX = magicOf(e.dx);
-    e.magicXY = magicOf(e.dxdy);
-    return e.dxdy * (hi[2] - lo[2]);
+    e.segs = ((hi[0] - 1u) >> 3) - (lo[0] >> 3) + 1u;
+    e.segsDy = e.segs * (hi[1] - lo[1]);
+    e.magicSegs = magicOf(e.segs);
+    e.magicSegsDy = magicOf(e.segsDy);
+    return e.segsDy * (hi[2] - lo[2]);
 }
 
 __device__ __forceinline__ void loadLeafVertices(LeafStage &s, const LeafRecord *leaves, uint32_t leafIndex)
@@ -276,13 +375,24 @@ __device__ __forceinline__ void loadLeafVertices(LeafStage &s, const LeafRecord 
     s.flags = __float_as_uint(c.w);
 }
 
-__device__ __forceinline__ void candidateVoxel(const BatchEntry &e, uint32_t local, uint32_t &x, uint32_t &y,
-                                               uint32_t &z)
+/// Row (yi, zi, box-relative) and voxel range [xs, xe) (absolute x) of row segment `unit` of an entry.
+__device__ __forceinline__ void segmentOf(const BatchEntry &e, uint32_t unit, uint32_t &yi, uint32_t &zi, uint32_t &xs,
+                                          uint32_t &xe)
 {
-    const uint32_t zi = divideBy(local, e.dxdy, e.magicXY);
-    const uint32_t inLayer = local - zi * e.dxdy;
-    const uint32_t yi = divideBy(inLayer, e.dx, e.magicX);
-    x = e.x0 + (inLayer - yi * e.dx);
+    zi = divideBy(unit, e.segsDy, e.magicSegsDy);
+    const uint32_t inLayer = unit - zi * e.segsDy;
+    yi = divideBy(inLayer, e.segs, e.magicSegs);
+    const uint32_t column = (e.x0 >> 3) + (inLayer - yi * e.segs);
+    xs = max(e.x0, column << 3);
+    xe = min(e.x0 + e.dx, (column + 1u) << 3);
+}
+
+/// Voxel named by an entry of ClassifyShared::maybe.
+__device__ __forceinline__ void maybeVoxel(const BatchEntry &e, uint32_t m, uint32_t &x, uint32_t &y, uint32_t &z)
+{
+    uint32_t yi, zi, xs, xe;
+    segmentOf(e, (m >> 3) & 4095u, yi, zi, xs, xe);
+    x = (xs & ~7u) | (m & 7u);
     y = e.y0 + yi;
     z = e.z0 + zi;
 }
@@ -299,47 +409,72 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
     const uint32_t total = sh.prefix[kOccBatch];
     uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
 
-    // ---- verdict per candidate; block-uniform trip count ----
-    for (uint32_t base = 0; base < total; base += kOccThreads) {
-        const uint32_t i = base + tid;
-        int verdict = kSatMiss;
-        uint32_t p = 0, local = 0, x = 0, y = 0, z = 0;
+    // ---- verdicts: lane = row segment, the flat segment space of the batch shared out warp by warp.  The row tests
+    // (o2v_sat.cuh: yz edge functions, the plane at both ends of the segment) skip most segments of a thin triangle in a
+    // fat box; the others walk their <= 8 voxels with one multiply-add per axis and voxel. ----
+    for (uint32_t base = warp * 32u; base < total; base += kOccThreads) {  // warp-uniform trip count
+        const uint32_t i = base + lane;
+        uint32_t sure = 0, open = 0, p = 0, code = 0, x8 = 0, y = 0, z = 0;  // bit x & 7: certain / undecided
         if (i < total) {
 #pragma unroll
             for (uint32_t step = kOccBatch / 2; step > 0; step >>= 1) {  // last entry with prefix[p] <= i
                 p += sh.prefix[p + step] <= i ? step : 0u;
             }
             const BatchEntry &e = sh.entry[p];
-            local = i - sh.prefix[p];
-            candidateVoxel(e, local, x, y, z);
+            const uint32_t unit = i - sh.prefix[p];
+            code = (p << 15) | (unit << 3);
+            uint32_t yi, zi, xs, xe;
+            segmentOf(e, unit, yi, zi, xs, xe);
+            x8 = xs & ~7u;
+            y = e.y0 + yi;
+            z = e.z0 + zi;
             // planeLimit < 0 marks a leaf whose normal is too noisy for the SAT (kLeafNoPrefilter): all undecided
-            verdict = (args.prefilter && e.sat.planeLimit >= 0.0f)
-                          ? classifyVoxel(e.sat, (float) (x - e.x0), (float) (y - e.y0), (float) (z - e.z0))
-                          : (int) kSatUncertain;
-        }
-        if (verdict == kSatCertain) {
-            // one RED per lane on the 32-bit half word (4 rows of one tile layer): the lanes of a warp that hit the same
-            // 32-byte sector travel as one request, and nothing waits for the result
-            const size_t half = entryWord(occ, sh.entry[p], x, y, z) * 2u + ((y & 7u) >> 2);
-            atomicOr(bits32 + half, 1u << ((x & 7u) + 8u * (y & 3u)));
-        }
-        const unsigned int undecided = __ballot_sync(full, verdict == kSatUncertain);
-        if (undecided != 0) {
-            uint32_t slot = 0;
-            if (lane == 0) {
-                slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(undecided));
+            if (args.prefilter && e.sat.planeLimit >= 0.0f) {
+                RowSat row;
+                buildRowSat(e.sat, (float) yi, (float) zi, row);
+                if (!rowPlaneSpanMisses(e.sat, row, (float) (xs - e.x0), (float) (xe - 1u - e.x0))) {
+                    for (uint32_t x = xs; x < xe; ++x) {
+                        const int verdict = classifyInRow(e.sat, row, (float) (x - e.x0));
+                        sure |= verdict == kSatCertain ? 1u << (x & 7u) : 0u;
+                        open |= verdict == kSatUncertain ? 1u << (x & 7u) : 0u;
+                    }
+                }
             }
-            slot = __shfl_sync(full, slot, 0) + __popc(undecided & ((1u << lane) - 1u));
-            if (verdict == kSatUncertain) {
+            else {
+                open = ((1u << (xe - x8)) - 1u) & ~((1u << (xs - x8)) - 1u);
+            }
+        }
+        if (sure != 0) {
+            // one RED per segment on its 32-bit half word (4 rows of one tile layer); nothing waits for the result
+            const size_t half = entryWord(occ, sh.entry[p], x8, y, z) * 2u + ((y & 7u) >> 2);
+            atomicOr(bits32 + half, sure << (8u * (y & 3u)));
+        }
+        if (__any_sync(full, open != 0)) {
+            const uint32_t count = (uint32_t) __popc(open);
+            uint32_t inclusive = count;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(full, inclusive, o);
+                inclusive += lane >= (uint32_t) o ? up : 0u;
+            }
+            uint32_t slot = 0;
+            if (lane == 31) {
+                slot = atomicAdd(&sh.maybeCount, inclusive);
+            }
+            slot = __shfl_sync(full, slot, 31) + inclusive - count;
+            while (open != 0) {
+                const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
+                open &= open - 1u;
                 if (slot < kOccMaybeCap) {
-                    sh.maybe[slot] = (p << 12) | local;
+                    sh.maybe[slot] = code | bit;
                 }
                 else {  // buffer full (dense batch): straight to the queue, unfiltered
                     const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
                     if (index < occ.queueCapacity) {
-                        occ.queue[index] = make_uint4(sh.entry[p].leaf, x | (y << 16), z, 0u);
+                        occ.queue[index] = make_uint4(sh.entry[p].leaf, (x8 | bit) | (y << 16), z, 0u);
                     }
                 }
+                ++slot;
             }
         }
     }
@@ -351,8 +486,8 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
     for (uint32_t k = tid; k < buffered; k += kOccThreads) {
         const uint32_t m = sh.maybe[k];
         uint32_t x, y, z;
-        candidateVoxel(sh.entry[m >> 12], m & 4095u, x, y, z);
-        const size_t word = entryWord(occ, sh.entry[m >> 12], x, y, z);
+        maybeVoxel(sh.entry[m >> 15], m, x, y, z);
+        const size_t word = entryWord(occ, sh.entry[m >> 15], x, y, z);
         unsigned long long known = __ldcg(occ.bits + word);
         if (downscale) {
             known = smear2x2(known | __ldcg(occ.bits + (word ^ 1u)));
@@ -386,8 +521,8 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
             const uint32_t m = sh.maybe[k];
             if ((m & 0x80000000u) != 0) {
                 uint32_t x, y, z;
-                const BatchEntry &e = sh.entry[(m >> 12) & 0x7ffffu];
-                candidateVoxel(e, m & 4095u, x, y, z);
+                const BatchEntry &e = sh.entry[(m >> 15) & 0xffffu];
+                maybeVoxel(e, m, x, y, z);
                 if (index < occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
                     occ.queue[index] = make_uint4(e.leaf, x | (y << 16), z, 0u);
                 }
@@ -574,15 +709,54 @@ occupancyClipKernel(const VoxelizeArgs args)
 // ---------------------------------------------------------------------------------------------------------------------
 // expand: thread per tile of every active chunk
 
+/// Position of the r-th (0-based) set bit of w; r < popcount(w).
+__device__ __forceinline__ uint32_t selectBit64(unsigned long long w, uint32_t r)
+{
+    uint32_t word = (uint32_t) w, pos = 0;
+    const uint32_t inLow = (uint32_t) __popc(word);
+    if (r >= inLow) {
+        r -= inLow;
+        word = (uint32_t) (w >> 32);
+        pos = 32;
+    }
+#pragma unroll
+    for (uint32_t step = 16; step > 0; step >>= 1) {
+        const uint32_t c = (uint32_t) __popc(word & ((1u << step) - 1u));
+        const bool up = r >= c;
+        r -= up ? c : 0u;
+        word = up ? word >> step : word;
+        pos += up ? step : 0u;
+    }
+    return pos;
+}
+
+/// What the record-writing lanes need to know about one of the warp's 32 tiles.
+struct alignas(16) ExpandTile {
+    uint32_t first;         // records of the warp's earlier tiles
+    uint16_t origin[3];     // output-space min corner
+    uint16_t wordFirst[9];  // records of the tile's earlier layers; [8] = the tile's total
+};
+
+struct ExpandShared {
+    unsigned long long mask[kOccExpandThreads / 32][kTileEdge][32];  // [layer][tile]: conflict-free to fill
+    ExpandTile tile[kOccExpandThreads / 32][32];
+};
+
+/// Two steps per warp and 32 tiles: (1) lane = tile: load the 8 layer words, fold 2x2x2 when downscaling, count;
+/// (2) lane = output record: records are numbered across the warp's tiles, record j finds its tile, layer and bit by
+/// rank/select in shared memory — all lanes busy whatever the fill of the tiles, and a warp stores 512 contiguous bytes.
 __global__ void __launch_bounds__(kOccExpandThreads)
 occupancyExpandKernel(const VoxelizeArgs args)
 {
+    __shared__ ExpandShared sh;
     const OccupancyView &occ = args.occ;
     const unsigned int full = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const bool downscale = args.grid.supersampling == 2;
+    const uint32_t shift = downscale ? 1u : 0u;
     const unsigned long long tiles = (unsigned long long) occ.activeChunks * (kChunkWords / kTileEdge);
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    unsigned long long overflow = 0;
 
     for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < tiles;
          base += stride) {
@@ -597,15 +771,10 @@ occupancyExpandKernel(const VoxelizeArgs args)
             const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(occ.bits + t * kTileEdge);
 #pragma unroll
             for (int k = 0; k < (int) kTileEdge / 2; ++k) {
-                const ulonglong2 w = src[k];
+                const ulonglong2 w = __ldcs(src + k);  // read once
                 m[2 * k] = w.x;
                 m[2 * k + 1] = w.y;
             }
-            const uint32_t chunk = occ.chunkList[t >> 9], tileLocal = (uint32_t) t & 511u;
-            const uint32_t C = occ.chunksPerAxis;
-            origin[0] = (chunk % C) * kChunkEdge + (tileLocal & 7u) * kTileEdge;
-            origin[1] = ((chunk / C) % C) * kChunkEdge + ((tileLocal >> 3) & 7u) * kTileEdge;
-            origin[2] = (chunk / (C * C) + occ.chunkZ0) * kChunkEdge + (tileLocal >> 6) * kTileEdge;
         }
         if (downscale) {
             // parent (qx, qy, qz) = OR of its 8 children; kept at bit (2 qx + 16 qy) of word qz
@@ -620,15 +789,15 @@ occupancyExpandKernel(const VoxelizeArgs args)
             for (int q = (int) kTileEdge / 2; q < (int) kTileEdge; ++q) {
                 m[q] = 0;
             }
-            origin[0] >>= 1;
-            origin[1] >>= 1;
-            origin[2] >>= 1;
         }
         uint32_t count = 0;
+        uint16_t wordFirst[kTileEdge + 1];
 #pragma unroll
         for (int z = 0; z < (int) kTileEdge; ++z) {
+            wordFirst[z] = (uint16_t) count;
             count += (uint32_t) __popcll(m[z]);
         }
+        wordFirst[kTileEdge] = (uint16_t) count;
         uint32_t inclusive = count;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(full, inclusive, o);
@@ -638,36 +807,64 @@ occupancyExpandKernel(const VoxelizeArgs args)
         if (warpCount == 0) {
             continue;
         }
+        if (count != 0) {
+            const uint32_t chunk = occ.chunkList[t >> 9], tileLocal = (uint32_t) t & 511u;
+            const uint32_t C = occ.chunksPerAxis;
+            origin[0] = ((chunk % C) * kChunkEdge + (tileLocal & 7u) * kTileEdge) >> shift;
+            origin[1] = (((chunk / C) % C) * kChunkEdge + ((tileLocal >> 3) & 7u) * kTileEdge) >> shift;
+            origin[2] = ((chunk / (C * C) + occ.chunkZ0) * kChunkEdge + (tileLocal >> 6) * kTileEdge) >> shift;
+        }
+        __syncwarp();  // the previous round's readers are done
+        ExpandTile &mine = sh.tile[warp][lane];
+        mine.first = inclusive - count;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mine.origin[a] = (uint16_t) origin[a];
+        }
+#pragma unroll
+        for (int z = 0; z <= (int) kTileEdge; ++z) {
+            mine.wordFirst[z] = wordFirst[z];
+        }
+#pragma unroll
+        for (int z = 0; z < (int) kTileEdge; ++z) {
+            sh.mask[warp][z][lane] = m[z];
+        }
         unsigned long long index = 0;
         if (lane == 31) {
             index = atomicAdd(&args.counters->voxels, (unsigned long long) warpCount);
         }
-        index = __shfl_sync(full, index, 31) + (inclusive - count);
-        unsigned long long overflow = 0;
-        const uint32_t shift = downscale ? 1u : 0u;
+        index = __shfl_sync(full, index, 31);
+        __syncwarp();
+
+        for (uint32_t j = lane; j < warpCount; j += 32u) {
+            uint32_t tile = 0;
 #pragma unroll
-        for (int z = 0; z < (int) kTileEdge; ++z) {
-            unsigned long long w = m[z];
-            while (w != 0) {
-                const uint32_t b = (uint32_t) __ffsll((long long) w) - 1u;
-                w &= w - 1ull;
-                if (index < args.outCapacity) {
-                    VoxelRecord rec;
-                    rec.x = (int32_t) (origin[0] + ((b & 7u) >> shift));
-                    rec.y = (int32_t) (origin[1] + ((b >> 3) >> shift));
-                    rec.z = (int32_t) (origin[2] + (uint32_t) z);
-                    rec.argb = 0xFFFFFFFFu;  // quantizeArgb(1, 1, 1)
-                    *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
-                }
-                else {
-                    ++overflow;
-                }
-                ++index;
+            for (uint32_t step = 16; step > 0; step >>= 1) {  // last tile with first <= j (empty tiles share a first)
+                tile += sh.tile[warp][tile + step].first <= j ? step : 0u;
+            }
+            const ExpandTile &info = sh.tile[warp][tile];
+            const uint32_t r = j - info.first;
+            uint32_t z = 0;
+#pragma unroll
+            for (uint32_t step = kTileEdge / 2; step > 0; step >>= 1) {  // last layer with wordFirst <= r
+                z += info.wordFirst[z + step] <= r ? step : 0u;
+            }
+            const uint32_t b = selectBit64(sh.mask[warp][z][tile], r - info.wordFirst[z]);
+            if (index + j < args.outCapacity) {
+                VoxelRecord rec;
+                rec.x = (int32_t) (info.origin[0] + ((b & 7u) >> shift));
+                rec.y = (int32_t) (info.origin[1] + ((b >> 3) >> shift));
+                rec.z = (int32_t) (info.origin[2] + z);
+                rec.argb = 0xFFFFFFFFu;  // quantizeArgb(1, 1, 1)
+                __stcs(reinterpret_cast<int4 *>(args.out + index + j), *reinterpret_cast<const int4 *>(&rec));
+            }
+            else {
+                ++overflow;
             }
         }
-        if (overflow != 0) {
-            atomicAdd(&args.counters->outputOverflow, overflow);
-        }
+    }
+    if (overflow != 0) {
+        atomicAdd(&args.counters->outputOverflow, overflow);
     }
 }
 
@@ -684,10 +881,16 @@ unsigned setupBlocks(unsigned long long n)
 {
     unsigned long long blocks = (n + kOccSetupThreads - 1) / kOccSetupThreads;
     blocks = blocks < 1 ? 1 : blocks;
-    return (unsigned) (blocks < 148ull * 64 ? blocks : 148ull * 64);
+    return (unsigned) (blocks < 148ull * 10 ? blocks : 148ull * 10);  // persistent: the next batch loads under this one
 }
 
 }  // namespace
+
+void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
+                               cudaStream_t stream)
+{
+    occupancySlabFilterKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, kept, counters);
+}
 
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
                           RunCounters *counters, cudaStream_t stream)

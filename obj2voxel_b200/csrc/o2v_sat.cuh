@@ -119,7 +119,7 @@ struct alignas(16) SatEdge {
 };
 
 /// Everything the three-way classification of one leaf against the unit voxels of a box needs, relative to the box's
-/// min corner (`origin`): 48 floats, 16-byte aligned (twelve 128-bit shared-memory loads per candidate voxel).
+/// min corner (`origin`): 48 floats, 16-byte aligned (128-bit shared-memory loads).
 struct alignas(16) PairSat {
     float plane[4];        // n . q + d at the voxel centre, q = voxel min corner - origin
     float planeLimit;      // (0.5 + kPrefilterMargin) * |n|_1
@@ -153,35 +153,86 @@ O2V_UNROLL
     }
 }
 
+/// The SAT along one row of voxels (fixed y and z, x running): every axis is linear in x, so the y/z part of each of
+/// the thirteen axes is evaluated once per row and a voxel costs one multiply-add per axis.
+struct RowSat {
+    float planeRow;    // n.y * ly + n.z * lz + d:       signed plane value = n.x * lx + planeRow
+    float xyBase[3];   // e.b * ly + e.c (xy projection): value = e.a * lx + xyBase
+    float zxBase[3];   // e.a * lz + e.c (zx projection): value = e.b * lx + zxBase
+    bool miss;         // a yz edge function is negative: no voxel of the row can be hit
+    bool sure;         // the yz edge functions and the y / z box normals allow `certain`
+};
+
+O2V_HD void buildRowSat(const PairSat &s, float ly, float lz, RowSat &r)
+{
+    r.planeRow = s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
+    r.miss = false;
+    r.sure = (ly + kCertainMargin <= s.hi[1]) && (ly + 1.0f - kCertainMargin >= s.lo[1]) &&
+             (lz + kCertainMargin <= s.hi[2]) && (lz + 1.0f - kCertainMargin >= s.lo[2]);
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        r.xyBase[i] = s.edge[i].b * ly + s.edge[i].c;
+        const SatEdge e = s.edge[3 + i];
+        const float value = e.a * ly + e.b * lz + e.c;
+        r.miss = r.miss || value < 0.0f;
+        r.sure = r.sure && value >= e.k;
+        r.zxBase[i] = s.edge[6 + i].a * lz + s.edge[6 + i].c;
+    }
+}
+
+/// true only if every voxel lx in [lxFirst, lxLast] of the row is a `miss`: the row's yz edges say so, or one of the
+/// seven axes that vary with x is beyond its threshold at both ends on the same side (each is a monotone function of
+/// lx, in floating point too).  A NaN compares false: not a miss.
+O2V_HD bool rowSpanMisses(const PairSat &s, const RowSat &r, float lxFirst, float lxLast)
+{
+    const float d0 = s.plane[0] * lxFirst + r.planeRow, d1 = s.plane[0] * lxLast + r.planeRow;
+    bool miss = r.miss || (d0 > s.planeLimit && d1 > s.planeLimit) || (d0 < -s.planeLimit && d1 < -s.planeLimit);
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const float a = s.edge[i].a, b = s.edge[6 + i].b;
+        miss = miss || (a * lxFirst + r.xyBase[i] < 0.0f && a * lxLast + r.xyBase[i] < 0.0f);
+        miss = miss || (b * lxFirst + r.zxBase[i] < 0.0f && b * lxLast + r.zxBase[i] < 0.0f);
+    }
+    return miss;
+}
+
+/// The cheap part of rowSpanMisses: the row's yz edges and the plane at both ends of the span.
+O2V_HD bool rowPlaneSpanMisses(const PairSat &s, const RowSat &r, float lxFirst, float lxLast)
+{
+    const float d0 = s.plane[0] * lxFirst + r.planeRow, d1 = s.plane[0] * lxLast + r.planeRow;
+    return r.miss || (d0 > s.planeLimit && d1 > s.planeLimit) || (d0 < -s.planeLimit && d1 < -s.planeLimit);
+}
+
+/// Three-way verdict for voxel lx of a row that is not RowSat::miss.
+O2V_HD int classifyInRow(const PairSat &s, const RowSat &r, float lx)
+{
+    const float dist = fabsf(s.plane[0] * lx + r.planeRow);
+    bool miss = dist > s.planeLimit;
+    bool sure = r.sure && dist <= s.planeSure && (lx + kCertainMargin <= s.hi[0]) &&
+                (lx + 1.0f - kCertainMargin >= s.lo[0]);
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const float xy = s.edge[i].a * lx + r.xyBase[i];
+        miss = miss || xy < 0.0f;
+        sure = sure && xy >= s.edge[i].k;
+        const float zx = s.edge[6 + i].b * lx + r.zxBase[i];
+        miss = miss || zx < 0.0f;
+        sure = sure && zx >= s.edge[6 + i].k;
+    }
+    return miss ? kSatMiss : (sure ? kSatCertain : kSatUncertain);
+}
+
 /// Three-way verdict for the voxel whose min corner is origin + (lx, ly, lz).  Leaves flagged kLeafNoPrefilter must not
 /// be classified (they are `uncertain` throughout: their normal is too noisy for the plane test).  Any NaN makes the
 /// comparisons fail towards `uncertain` or `miss` only where `miss` is proven by a comparison that held.
 O2V_HD int classifyVoxel(const PairSat &s, float lx, float ly, float lz)
 {
-    const float dist = fabsf(s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3]);
-    if (dist > s.planeLimit) {
+    RowSat r;
+    buildRowSat(s, ly, lz, r);
+    if (r.miss || rowSpanMisses(s, r, lx, lx)) {
         return kSatMiss;
     }
-    bool sure = dist <= s.planeSure;
-    const float q[3] = {lx, ly, lz};
-O2V_UNROLL
-    for (int proj = 0; proj < 3; ++proj) {
-        const float qa = q[proj], qb = q[(proj + 1) % 3];
-O2V_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            const SatEdge e = s.edge[proj * 3 + i];
-            const float value = e.a * qa + e.b * qb + e.c;
-            if (value < 0.0f) {
-                return kSatMiss;
-            }
-            sure = sure && value >= e.k;
-        }
-    }
-O2V_UNROLL
-    for (int a = 0; a < 3; ++a) {  // box normals against the shrunk box [q + margin, q + 1 - margin]
-        sure = sure && (q[a] + kCertainMargin <= s.hi[a]) && (q[a] + 1.0f - kCertainMargin >= s.lo[a]);
-    }
-    return sure ? kSatCertain : kSatUncertain;
+    return classifyInRow(s, r, lx);
 }
 
 }  // namespace o2v
