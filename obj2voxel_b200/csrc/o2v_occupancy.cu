@@ -449,19 +449,9 @@ __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const Voxelize
             const size_t half = entryWord(occ, sh.entry[p], x8, y, z) * 2u + ((y & 7u) >> 2);
             atomicOr(bits32 + half, sure << (8u * (y & 3u)));
         }
-        if (__any_sync(full, open != 0)) {
-            const uint32_t count = (uint32_t) __popc(open);
-            uint32_t inclusive = count;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t up = __shfl_up_sync(full, inclusive, o);
-                inclusive += lane >= (uint32_t) o ? up : 0u;
-            }
-            uint32_t slot = 0;
-            if (lane == 31) {
-                slot = atomicAdd(&sh.maybeCount, inclusive);
-            }
-            slot = __shfl_sync(full, slot, 31) + inclusive - count;
+        if (open != 0) {
+            // undecided voxels are rare (a few per warp round): each lane reserves its own slots
+            uint32_t slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(open));
             while (open != 0) {
                 const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
                 open &= open - 1u;
