@@ -170,6 +170,36 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->reserved = 0.0f;
 }
 
+/// Totals of a job that ran as several z parts (every voxel, leaf and clip belongs to exactly one part; a dropped
+/// triangle may be seen by several parts: the largest count is reported).
+void accumulateStats(RunStats &total, const RunStats &part)
+{
+    RunCounters &t = total.counters;
+    const RunCounters &p = part.counters;
+    t.voxels += p.voxels;
+    t.leaves += p.leaves;
+    t.pairs += p.pairs;
+    t.activeTiles += p.activeTiles;
+    t.candidateVoxels += p.candidateVoxels;
+    t.clipCalls += p.clipCalls;
+    t.contributions += p.contributions;
+    t.droppedTriangles = std::max(t.droppedTriangles, p.droppedTriangles);
+    t.depthOverflow = std::max(t.depthOverflow, p.depthOverflow);
+    t.lightTiles += p.lightTiles;
+    t.bigLightTiles += p.bigLightTiles;
+    t.heavyTiles += p.heavyTiles;
+    t.survivors += p.survivors;
+    total.outCapacity = std::max(total.outCapacity, part.outCapacity);
+    total.msTotal += part.msTotal;
+    total.msSetup += part.msSetup;
+    total.msVoxelize += part.msVoxelize;
+    total.msClip += part.msClip;
+    total.msClassify += part.msClassify;
+    total.kernelLaunches += part.kernelLaunches;
+    total.voxelizeLaunches += part.voxelizeLaunches;
+    total.occupancyPath = total.occupancyPath && part.occupancyPath;
+}
+
 EngineParams paramsFromC(const o2v_b200_params &p)
 {
     EngineParams e;
@@ -462,59 +492,162 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
         cudaStreamSynchronize(stream);
         const double msUpload = msSince(tJob);
         const auto tRun = std::chrono::steady_clock::now();
-        const int rc = engine->voxelize(uploaded.view, uploaded.textureViews.data(),
-                                        (uint32_t) uploaded.textureViews.size(), params, stream, &stats);
-        const double msRun = msSince(tRun);
-        const auto tSink = std::chrono::steady_clock::now();
-        if (rc != 0) {
-            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed on the device: " + engine->lastError());
+
+        // ---- plan: a big job runs as up to four z sub-slabs of whole 64-voxel chunk rows, so that the download of one
+        // part (PCIe, the longest leg of a host-to-host job) runs under the kernels of the next.  Every voxel belongs to
+        // exactly one part: same records, part by part. ----
+        const uint32_t sampleRes = inst.outputResolution * inst.supersampling;
+        const uint32_t gridExtent = (sampleRes + 63u) / 64u * 64u;
+        uint32_t jobZ0 = inst.slabZ0, jobZ1 = inst.slabZ1;
+        if (jobZ0 == 0 && jobZ1 == 0) {
+            jobZ1 = gridExtent;
+        }
+        jobZ1 = std::min(jobZ1, gridExtent);
+        const uint32_t row0 = jobZ0 / 64u, row1 = (jobZ1 + 63u) / 64u;
+        uint32_t parts = (mesh.count >= (1ull << 20) && row1 > row0 + 1u) ? std::min(4u, row1 - row0) : 1u;
+        if (const char *env = getenv("O2V_B200_PIPELINE_PARTS")) {
+            parts = std::max(1u, std::min((uint32_t) atoi(env), std::max(1u, row1 - row0)));
+        }
+        auto partBound = [&](uint32_t k) {
+            const uint32_t z = (row0 + (uint32_t) ((unsigned long long) (row1 - row0) * k / parts)) * 64u;
+            return std::min(std::max(z, jobZ0), jobZ1);
+        };
+
+        cudaStream_t copyStream = nullptr;
+        cudaEvent_t copied[2] = {nullptr, nullptr};
+        if (cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming) != cudaSuccess) {
+            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, std::string("cudaStreamCreate failed: ") +
+                                                      cudaGetErrorString(cudaGetLastError()));
             return OBJ2VOXEL_ERR_DEVICE;
         }
-        statsToC(stats, &inst.stats);
+        struct CopyGuard {
+            cudaStream_t s;
+            cudaEvent_t *e;
+            ~CopyGuard()
+            {
+                cudaStreamSynchronize(s);
+                cudaStreamDestroy(s);
+                cudaEventDestroy(e[0]);
+                cudaEventDestroy(e[1]);
+            }
+        } copyGuard{copyStream, copied};
 
-        // ---- sink: stream the compacted Voxel32 records back through two pinned staging buffers; the D2H copy of batch
-        // k+1 overlaps the sink call of batch k ----
-        const unsigned long long total = engine->voxelCount();
-        const size_t batch = 1u << 21;  // 32 MiB of records per sink call
-        const auto *deviceRecords = reinterpret_cast<const unsigned char *>(engine->deviceVoxels());
-        uint32_t *staging[2] = {nullptr, nullptr};
-        std::vector<uint32_t> pageable;
-        if (total != 0) {
-            staging[0] = static_cast<uint32_t *>(engine->pinnedStaging(0, batch * 16));
-            staging[1] = static_cast<uint32_t *>(engine->pinnedStaging(1, batch * 16));
+        const size_t batch = 1u << 21;  // records per sink call (32 MiB)
+        bool sinkOk = true, deviceOk = true;
+        double msKernels = 0;
+        bool firstPart = true;
+
+        // What is still on its way to the sink: a part whose records are being copied into pinned buffer `slot`.
+        struct Pending {
+            bool active = false;
+            int slot = 0;
+            uint32_t *records = nullptr;
+            unsigned long long count = 0;
+        } pending;
+        auto deliver = [&](Pending &p) {  // waits for the copy, then hands the records to the sink batch by batch
+            if (!p.active) {
+                return;
+            }
+            p.active = false;
+            deviceOk = deviceOk && cudaEventSynchronize(copied[p.slot]) == cudaSuccess;
+            for (unsigned long long done = 0; done < p.count && sinkOk && deviceOk; done += batch) {
+                sinkOk = inst.sink->write(p.records + done * 4, (size_t) std::min<unsigned long long>(batch, p.count - done));
+            }
+        };
+        // Fallback for a part whose records do not fit a pinned buffer: two 32 MiB staging buffers, the copy of batch
+        // k+1 under the sink call of batch k (also the whole story of a job that runs as one part).
+        auto streamOut = [&](const unsigned char *deviceRecords, unsigned long long total) {
+            uint32_t *staging[2] = {static_cast<uint32_t *>(engine->pinnedStaging(0, batch * 16)),
+                                    static_cast<uint32_t *>(engine->pinnedStaging(1, batch * 16))};
+            std::vector<uint32_t> pageable;
             if (staging[0] == nullptr || staging[1] == nullptr) {  // pinned memory exhausted: plain host memory still works
                 pageable.resize(batch * 4 * 2);
                 staging[0] = pageable.data();
                 staging[1] = pageable.data() + batch * 4;
             }
-        }
-        cudaEvent_t copied[2] = {nullptr, nullptr};
-        cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming);
-        auto startCopy = [&](unsigned long long done, int slot) -> bool {
-            const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
-            return cudaMemcpyAsync(staging[slot], deviceRecords + done * 16, count * 16, cudaMemcpyDeviceToHost, stream) ==
-                       cudaSuccess &&
-                   cudaEventRecord(copied[slot], stream) == cudaSuccess;
+            auto startCopy = [&](unsigned long long done, int slot) -> bool {
+                const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
+                return cudaMemcpyAsync(staging[slot], deviceRecords + done * 16, count * 16, cudaMemcpyDeviceToHost,
+                                       copyStream) == cudaSuccess &&
+                       cudaEventRecord(copied[slot], copyStream) == cudaSuccess;
+            };
+            int slot = 0;
+            deviceOk = deviceOk && startCopy(0, 0);
+            for (unsigned long long done = 0; done < total && sinkOk && deviceOk; done += batch, slot ^= 1) {
+                const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
+                if (done + batch < total) {
+                    deviceOk = startCopy(done + batch, slot ^ 1);
+                }
+                deviceOk = deviceOk && cudaEventSynchronize(copied[slot]) == cudaSuccess;
+                if (deviceOk) {
+                    sinkOk = inst.sink->write(staging[slot], count);
+                }
+            }
+            cudaStreamSynchronize(copyStream);
         };
-        bool sinkOk = true, deviceOk = true;
-        int slot = 0;
-        if (total != 0) {
-            deviceOk = startCopy(0, 0);
-        }
-        for (unsigned long long done = 0; done < total && sinkOk && deviceOk; done += batch, slot ^= 1) {
-            const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
-            if (done + batch < total) {
-                deviceOk = startCopy(done + batch, slot ^ 1);
+
+        for (uint32_t k = 0; k < parts && sinkOk && deviceOk; ++k) {
+            EngineParams partParams = params;
+            if (parts > 1) {
+                partParams.slabZ0 = partBound(k);
+                partParams.slabZ1 = partBound(k + 1);
+                if (partParams.slabZ0 >= partParams.slabZ1) {
+                    continue;
+                }
             }
-            deviceOk = deviceOk && cudaEventSynchronize(copied[slot]) == cudaSuccess;
-            if (deviceOk) {
-                sinkOk = inst.sink->write(staging[slot], count);
+            RunStats partStats;
+            const int rc = engine->voxelize(uploaded.view, uploaded.textureViews.data(),
+                                            (uint32_t) uploaded.textureViews.size(), partParams, stream, &partStats);
+            if (rc != 0) {
+                logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed on the device: " + engine->lastError());
+                return OBJ2VOXEL_ERR_DEVICE;
             }
+            msKernels += partStats.msTotal;
+            if (firstPart) {
+                stats = partStats;
+                firstPart = false;
+            }
+            else {
+                accumulateStats(stats, partStats);
+            }
+            const unsigned long long total = engine->voxelCount();
+            const auto *deviceRecords = reinterpret_cast<const unsigned char *>(engine->deviceVoxels());
+            if (parts == 1) {
+                if (total != 0) {
+                    streamOut(deviceRecords, total);
+                }
+                break;
+            }
+            // this part's records start their way to the host before the previous part is handed to the sink, and stay
+            // in their device buffer while the next part writes the other one
+            const int slot = (int) (k & 1u);
+            uint32_t *host = total != 0 && total * 16 <= (1ull << 30)
+                                 ? static_cast<uint32_t *>(engine->pinnedStaging(slot, (size_t) total * 16))
+                                 : nullptr;
+            Pending mine;
+            if (host != nullptr) {
+                deviceOk = deviceOk &&
+                           cudaMemcpyAsync(host, deviceRecords, (size_t) total * 16, cudaMemcpyDeviceToHost, copyStream) ==
+                               cudaSuccess &&
+                           cudaEventRecord(copied[slot], copyStream) == cudaSuccess;
+                mine.active = true;
+                mine.slot = slot;
+                mine.records = host;
+                mine.count = total;
+            }
+            deliver(pending);
+            if (host == nullptr && total != 0) {
+                streamOut(deviceRecords, total);  // too big to pin in one piece (or pinning failed)
+            }
+            pending = mine;
+            engine->swapOutputBuffers();
         }
-        cudaStreamSynchronize(stream);
-        cudaEventDestroy(copied[0]);
-        cudaEventDestroy(copied[1]);
+        deliver(pending);
+        cudaStreamSynchronize(copyStream);
+        const double msRun = msSince(tRun);
+        statsToC(stats, &inst.stats);
         if (!deviceOk) {
             logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR,
                        std::string("voxel download failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -525,8 +658,8 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
             return OBJ2VOXEL_ERR_IO_ERROR_DURING_VOXEL_WRITE;
         }
         char timing[160];
-        snprintf(timing, sizeof timing, "timing: upload %.2f ms, device run %.2f ms (kernels %.2f), download+sink %.2f ms",
-                 msUpload, msRun, stats.msTotal, msSince(tSink));
+        snprintf(timing, sizeof timing, "timing: upload %.2f ms, %u part(s): kernels %.2f ms, run + download + sink %.2f ms",
+                 msUpload, parts, msKernels, msRun);
         logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, timing);
     }
 

@@ -81,7 +81,8 @@ Engine *Engine::create(int device, std::string *error)
     e->device_ = device;
     e->smCount_ = prop.multiProcessorCount;
     e->totalMemory_ = prop.totalGlobalMem;
-    bool ok = cudaMallocHost(&e->hostCounters_, sizeof(RunCounters)) == cudaSuccess;
+    bool ok = cudaHostAlloc(&e->hostCounters_, sizeof(RunCounters), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer(&e->hostCountersDevice_, e->hostCounters_, 0) == cudaSuccess;
     ok = ok && cudaMallocHost(&e->hostCountersInit_, sizeof(RunCounters)) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evStart_) == cudaSuccess && cudaEventCreate(&e->evSetup_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evVoxStart_) == cudaSuccess && cudaEventCreate(&e->evVoxEnd_) == cudaSuccess;
@@ -180,7 +181,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         launchBounds(mesh, dCounters, stream);
         launchFinishBounds(dCounters, stream);
         st.kernelLaunches += 2;
-        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        launchPublishCounters(dCounters, hostCountersDevice_, stream);
+        ++st.kernelLaunches;
         O2V_CUDA(cudaStreamSynchronize(stream));
         memcpy(meshMin, hostCounters_->boundsMin, sizeof meshMin);
         memcpy(meshMax, hostCounters_->boundsMax, sizeof meshMax);
@@ -254,7 +256,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
                              allTiles_.as<uint32_t>(), longTiles_.as<uint32_t>(), activeTiles_.as<uint32_t>(),
                              lightTiles_.as<LightTile>(), bigLightTiles_.as<LightTile>(), dCounters, stream);
     st.kernelLaunches += 8;
-    O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+    launchPublishCounters(dCounters, hostCountersDevice_, stream);
+    ++st.kernelLaunches;
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
@@ -355,7 +358,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         st.kernelLaunches += 4;
         unsigned long long entryCapacity = candidateBound;
         if (!boundAffordable) {
-            O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+            launchPublishCounters(dCounters, hostCountersDevice_, stream);
+            ++st.kernelLaunches;
             O2V_CUDA(cudaStreamSynchronize(stream));
             O2V_CUDA(cudaGetLastError());
             entryCapacity = hostCounters_->survivors;
@@ -388,7 +392,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         const int launched = (sparseActive ? 4 : 0) + (args.work.activeCount != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
-        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        launchPublishCounters(dCounters, hostCountersDevice_, stream);
+        ++st.kernelLaunches;
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
         if (hostCounters_->outputOverflow == 0) {
@@ -445,7 +450,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         }
         launchOccupancySlabFilter(meshIn, grid, slabVerts_.as<float>(), dCounters, stream);
         ++st.kernelLaunches;
-        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        launchPublishCounters(dCounters, hostCountersDevice_, stream);
+        ++st.kernelLaunches;
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
         mesh.verts = slabVerts_.as<float>();
@@ -478,7 +484,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
                         &dCounters->leaves, stream);
     launchOccupancyAssignChunks(occ, dCounters, stream);
     st.kernelLaunches += 5;
-    O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+    launchPublishCounters(dCounters, hostCountersDevice_, stream);
+    ++st.kernelLaunches;
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
@@ -566,7 +573,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         const int launched = 3 + (bigLeaves != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
-        O2V_CUDA(cudaMemcpyAsync(hostCounters_, dCounters, sizeof(RunCounters), cudaMemcpyDeviceToHost, stream));
+        launchPublishCounters(dCounters, hostCountersDevice_, stream);
+        ++st.kernelLaunches;
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
         const bool queueOverflow = hostCounters_->survivors > queueCapacity;

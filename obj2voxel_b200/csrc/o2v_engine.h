@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "o2v_kernels.cuh"
@@ -59,6 +60,11 @@ public:
         return static_cast<T *>(ptr_);
     }
     size_t size() const { return size_; }
+    void swap(DeviceBuffer &other)
+    {
+        std::swap(ptr_, other.ptr_);
+        std::swap(size_, other.size_);
+    }
 
 private:
     void *ptr_ = nullptr;
@@ -83,6 +89,10 @@ public:
     unsigned long long voxelCount() const { return voxelCount_; }
     const std::string &lastError() const { return error_; }
 
+    /// Two output buffers: after the swap the result of the last run stays where it is (the caller keeps the pointer
+    /// it got from deviceVoxels) while the next run writes the other buffer.
+    void swapOutputBuffers() { out_.swap(outSpare_); }
+
     /// Copies the result of the last run to host memory (count * 16 bytes) on `stream` and synchronises it.
     int download(void *hostDst, cudaStream_t stream);
 
@@ -106,14 +116,15 @@ private:
 
     void *staging_[2] = {nullptr, nullptr};  // pinned, for host sinks
     size_t stagingBytes_[2] = {0, 0};
-    RunCounters *hostCounters_ = nullptr;  // pinned
+    RunCounters *hostCounters_ = nullptr;  // pinned + mapped: the device publishes the counters into it
+    RunCounters *hostCountersDevice_ = nullptr;  // its device-side address
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
     cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr;
 
     DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
-    DeviceBuffer leaves_, leafUvs_, tileList_, out_, textures_;
+    DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
     DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_;  // occupancy-only path
 };

@@ -687,6 +687,24 @@ void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stre
     boundsKernel<<<gridFor(vertices, 256, 148 * 8), 256, 0, stream>>>(mesh.verts, vertices, counters);
 }
 
+/// The counters reach the host through a store from the SM into mapped pinned memory, not through a copy engine: a
+/// 300-byte read-back must not queue behind a multi-hundred-megabyte download that another stream has in flight.
+__global__ void publishCountersKernel(const RunCounters *__restrict__ counters, RunCounters *hostMapped)
+{
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(counters);
+    volatile unsigned long long *dst = reinterpret_cast<volatile unsigned long long *>(hostMapped);
+    for (unsigned k = threadIdx.x; k < sizeof(RunCounters) / sizeof(unsigned long long); k += blockDim.x) {
+        dst[k] = src[k];
+    }
+    __threadfence_system();
+}
+
+void launchPublishCounters(const RunCounters *counters, RunCounters *hostMapped, cudaStream_t stream)
+{
+    static_assert(sizeof(RunCounters) % sizeof(unsigned long long) == 0, "copied as 64-bit words");
+    publishCountersKernel<<<1, 64, 0, stream>>>(counters, hostMapped);
+}
+
 void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
 {
     finishBoundsKernel<<<1, 32, 0, stream>>>(counters);

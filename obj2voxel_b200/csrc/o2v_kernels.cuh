@@ -114,6 +114,7 @@ struct TileWork {
 
 void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stream);
 void launchFinishBounds(RunCounters *counters, cudaStream_t stream);
+void launchPublishCounters(const RunCounters *counters, RunCounters *hostMapped, cudaStream_t stream);
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
                        uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream);

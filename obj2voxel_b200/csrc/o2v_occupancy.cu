@@ -27,8 +27,14 @@ namespace o2v {
 namespace {
 
 constexpr int kOccSetupThreads = 128;
-constexpr int kOccBatch = 64;           // leaves per classify block
-constexpr int kOccThreads = 128;        // threads per classify block (two candidates' worth of lanes per staged leaf)
+#ifndef O2V_OCC_BATCH
+#define O2V_OCC_BATCH 64
+#endif
+#ifndef O2V_OCC_THREADS
+#define O2V_OCC_THREADS 128
+#endif
+constexpr int kOccBatch = O2V_OCC_BATCH;      // leaves per classify block
+constexpr int kOccThreads = O2V_OCC_THREADS;  // threads per classify block
 constexpr int kOccClipThreads = 128;
 constexpr int kOccExpandThreads = 128;
 constexpr int kOccRefillThreshold = 8;

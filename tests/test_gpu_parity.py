@@ -101,6 +101,31 @@ def test_empty_model_is_ok_and_empty():  # src/obj2voxel.cpp:590-594
     assert err == o2v.ERR_OK and len(voxels) == 0
 
 
+@pytest.mark.parametrize("textured", [False, True])
+@pytest.mark.parametrize("parts", [2, 4, 7])
+def test_job_in_z_parts_equals_job_in_one_piece(monkeypatch, parts, textured):
+    """obj2voxel_voxelize() runs big jobs as z sub-slabs so that the download of one part overlaps the kernels of the
+    next (o2v_capi.cpp); forced here on a small mesh: the sink must receive exactly the same records (both pipelines),
+    and the oracle's."""
+    verts = meshes.random_triangles(4000, 0.03, seed=11)
+    kw = dict(strategy=o2v.BLEND_STRATEGY, bounds=meshes.UNIT_BOUNDS)
+    okw = dict(strategy=o2v.BLEND_STRATEGY, bounds=meshes.UNIT_BOUNDS)
+    if textured:
+        uvs = meshes.random_uvs(4000, seed=12)
+        pixels = meshes.random_texture(32, 16, 3)
+        kw.update(uvs=uvs, texture=o2v.Texture(pixels, wrap=o2v.UV_WRAP))
+        okw.update(uvs=uvs, texture=dict(pixels=pixels, wrap=o2v.UV_WRAP))
+    monkeypatch.setenv("O2V_B200_PIPELINE_PARTS", "1")
+    err, whole = run_instance(verts, 200, **kw)
+    assert err == o2v.ERR_OK
+    monkeypatch.setenv("O2V_B200_PIPELINE_PARTS", str(parts))
+    err, pieces = run_instance(verts, 200, **kw)
+    assert err == o2v.ERR_OK
+    whole, pieces = o2v.sort_voxels(whole), o2v.sort_voxels(pieces)
+    assert np.array_equal(whole, pieces)
+    assert np.array_equal(whole, oracle.voxelize(verts, 200, **okw)["voxels"])
+
+
 def test_colored_triangles_voxelize_white_like_the_reference():  # SURVEY fact 8
     inst = o2v.Instance()
     inst.set_input_callback(meshes.single_triangle(), colors=np.array([[1.0, 0.0, 0.0]], np.float32))
@@ -367,3 +392,40 @@ def test_device_resident_path_equals_host_path(engine):
     dev = engine.result_tensor().cpu().numpy().view(np.uint32)
     assert checksum(dev) == checksum(host)
     assert np.array_equal(o2v.sort_voxels(engine.download()), o2v.sort_voxels(host))
+
+
+def test_triangle_array_that_is_not_16_byte_aligned(engine):
+    """The count / emit / slab-filter passes stream triangle batches with bulk-async copies, which need 16-byte aligned
+    source addresses; an array that is only 4-byte aligned (a view one float into a buffer) takes the block-load path and
+    must give the same records — whole grid and slab (the slab filter reads it too)."""
+    import torch
+
+    v = meshes.random_triangles(30001, 0.01, seed=5)  # ragged last batch as well
+    params = o2v.make_params(resolution=256, bounds=[-0.02, -0.02, -0.02, 1.02, 1.02, 1.02])
+    want = o2v.sort_voxels(engine.voxelize_host(v, params)[0])
+    buf = torch.zeros(v.size + 1, dtype=torch.float32, device="cuda")
+    buf[1:] = torch.from_numpy(v).cuda().reshape(-1)
+    shifted = buf[1:].view(-1, 9)
+    assert shifted.data_ptr() % 16 == 4
+    engine.voxelize_device(shifted, params)
+    assert np.array_equal(o2v.sort_voxels(engine.download()), want)
+    parts = []
+    for slab in ((0, 64), (64, 256)):
+        engine.voxelize_device(shifted, o2v.make_params(resolution=256, bounds=[-0.02, -0.02, -0.02, 1.02, 1.02, 1.02],
+                                                        slab=slab))
+        parts.append(engine.download())
+    assert np.array_equal(o2v.sort_voxels(np.concatenate(parts)), want)
+
+
+def test_more_chunks_than_a_block_collects(engine):
+    """Above 65536 chunks per slab (grids beyond 2560^3) the count pass marks chunks in global memory instead of per
+    block; 2688^3 = 42^3 = 74088 chunks, a few thousand small triangles: occupancy path vs weighted path vs oracle."""
+    v = meshes.random_triangles(3000, 0.002, seed=9)
+    kw = dict(resolution=2688, bounds=meshes.UNIT_BOUNDS)
+    got, stats = engine.voxelize_host(v, o2v.make_params(**kw))
+    assert stats["occupancy_path"]
+    weighted, wstats = engine.voxelize_host(v, o2v.make_params(occupancy_path=0, **kw))
+    assert not wstats["occupancy_path"]
+    got = o2v.sort_voxels(got)
+    assert np.array_equal(got, o2v.sort_voxels(weighted))
+    assert np.array_equal(got, oracle.voxelize(v, 2688, bounds=meshes.UNIT_BOUNDS)["voxels"])
