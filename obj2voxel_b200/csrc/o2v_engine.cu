@@ -471,25 +471,26 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     occ.chunkTotal = occ.chunksPerAxis * occ.chunksPerAxis * chunkRows;  // <= 128^3
     if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !scratch_.ensure(scanScratchElems(n) * 4) ||
         !chunkFlag_.ensure(((size_t) occ.chunkTotal + 31) / 32 * 4) || !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) ||
-        !chunkList_.ensure((size_t) occ.chunkTotal * 4)) {
+        !chunkList_.ensure((size_t) occ.chunkTotal * 4) || !leaves_.ensure(n * sizeof(LeafRecord))) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path, setup buffers)");
     }
     occ.chunkFlag = chunkFlag_.as<uint32_t>();
     occ.chunkSlot = chunkSlot_.as<uint32_t>();
     occ.chunkList = chunkList_.as<uint32_t>();
+    occ.firstLeaves = (uint32_t) n;
     O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, ((size_t) occ.chunkTotal + 31) / 32 * 4, stream));
 
-    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), dCounters, stream);
-    launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
-                        &dCounters->leaves, stream);
+    // the one pass over the triangles: statistics, chunk marks, and the first leaf of triangle i into leaf slot i
+    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, stream);
     launchOccupancyAssignChunks(occ, dCounters, stream);
-    st.kernelLaunches += 5;
+    st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
     ++st.kernelLaunches;
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
-    const unsigned long long leafTotal = hostCounters_->leaves;
+    const unsigned long long extraLeaves = hostCounters_->extraLeaves;
+    const unsigned long long leafTotal = hostCounters_->leaves == 0 ? 0 : n + extraLeaves;  // leaf slots
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
     const unsigned long long bigLeaves = hostCounters_->bigLeaves, bigBoxes = hostCounters_->bigBoxes;
     occ.activeChunks = (uint32_t) hostCounters_->activeTiles;
@@ -525,7 +526,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
             return kOccupancyFallback;  // e.g. a dense 8192^3 job: the caller takes the weighted path
         }
     }
-    if (!tileBits_.ensure(bitmapBytes) || !leaves_.ensure((size_t) leafTotal * sizeof(LeafRecord)) ||
+    if (!tileBits_.ensure(bitmapBytes) ||
+        !extraLeaves_.ensure((size_t) std::max<unsigned long long>(extraLeaves, 1) * sizeof(LeafRecord)) ||
         !occQueue_.ensure((size_t) queueCapacity * sizeof(uint4)) ||
         !bigLeaves_.ensure((size_t) std::max<unsigned long long>(bigLeaves, 1) * sizeof(uint2))) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
@@ -545,8 +547,15 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     occ.bigLeaves = bigLeaves_.as<uint2>();
     occ.bigCapacity = (uint32_t) bigLeaves;
 
-    launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, stream);
-    ++st.kernelLaunches;
+    occ.extraLeaves = extraLeaves_.as<LeafRecord>();
+    if (extraLeaves != 0 || bigLeaves != 0) {
+        // second pass, only when some triangle subdivides or some leaf is big (axis-aligned triangles)
+        launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
+                            &dCounters->scanTotal, stream);
+        launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), extraLeaves_.as<LeafRecord>(), dCounters,
+                            stream);
+        st.kernelLaunches += 4;
+    }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));
 
     VoxelizeArgs args{};

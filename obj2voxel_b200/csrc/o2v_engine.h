@@ -126,7 +126,7 @@ private:
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
-    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_;  // occupancy-only path
+    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_, extraLeaves_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

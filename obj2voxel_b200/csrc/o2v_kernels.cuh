@@ -88,6 +88,8 @@ struct RunCounters {
     unsigned long long bigBoxes;        // their 16^3 boxes
     unsigned long long bigTicket;       // emit pass: (table row << 40) | first box, handed out by one atomic
     unsigned long long slabTriangles;   // triangles the slab filter kept (only when the slab is a part of the grid)
+    unsigned long long extraLeaves;     // leaves beyond the first of their triangle (the emit pass writes those)
+    unsigned long long scanTotal;       // total of the exclusive scan over the per-triangle extra-leaf counts
 };
 
 /// Descriptor of a light tile: everything the warp needs in one 16-byte load.
@@ -154,6 +156,7 @@ constexpr uint32_t kChunkEdge = 64;     // voxels per chunk edge: the unit the o
 constexpr uint32_t kChunkWords = 4096;  // 64-bit words of one chunk bitmap: 512 tiles x 8 layers (32 KB)
 constexpr uint32_t kOccBigVolume = 4096;  // leaves with more candidate voxels are classified box by box ...
 constexpr uint32_t kOccBoxEdge = 16;      // ... in 16^3 boxes
+constexpr uint32_t kLeafEmpty = 4u;       // LeafRecord::flags on this path: the triangle of this slot has no leaf in the slab
 
 /// Buffers of the occupancy-only path (o2v_occupancy.cu): meshes whose every triangle is MATERIALLESS voxelize white
 /// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
@@ -168,6 +171,8 @@ struct OccupancyView {
                                      // bit (x + 8 y) = voxel (x, y, z) of that tile is occupied
     uint4 *queue;                    // {leaf, x | y << 16, z, -} of the voxels the SAT could not decide
     unsigned long long queueCapacity;
+    const LeafRecord *extraLeaves;   // leaf firstLeaves + k: the leaves beyond the first of their triangle
+    uint32_t firstLeaves;            // = triangles: leaf i < firstLeaves is the first leaf of triangle i (VoxelizeArgs::leaves)
     uint2 *bigLeaves;                // {leaf, first box} of the leaves with more than kOccBigVolume candidates
     uint32_t bigCapacity;
 };
@@ -208,8 +213,8 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 /// for the queue, bitmap -> Voxel32 records.
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
                                cudaStream_t stream);
-void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
-                          RunCounters *counters, cudaStream_t stream);
+void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
+                          LeafRecord *firstLeaves, RunCounters *counters, cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
                          const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream);

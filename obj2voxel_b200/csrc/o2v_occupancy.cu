@@ -160,9 +160,12 @@ occupancySlabFilterKernel(MeshView mesh, GridView grid, float *__restrict__ kept
 
 constexpr uint32_t kOccBlockChunkWords = 2048;  // chunk bits a block collects in shared memory: 65536 chunks (8 KB)
 
+/// The one pass every triangle takes: transform, subdivision DFS, statistics, chunk marks — and the triangle's first leaf
+/// goes straight into leaf slot i, so that a mesh whose triangles are all leaves themselves (anything fine relative to
+/// the grid) needs no second pass.  extraCount[i] = the triangle's leaves beyond the first.
 __global__ void __launch_bounds__(kOccSetupThreads)
-occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ leafCount,
-                     RunCounters *counters)
+occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ extraCount,
+                     LeafRecord *__restrict__ firstLeaves, RunCounters *counters)
 {
     __shared__ TriangleBatch<kOccSetupThreads> batch;
     // Millions of leaves mark a few thousand chunks: up to 65536 chunks per slab (any grid up to 2560^3, and slabs of
@@ -177,7 +180,8 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
         }
     }
     // (streamTriangles starts with a barrier)
-    unsigned long long candidates = 0, dropped = 0, overflow = 0, bigLeaves = 0, bigBoxes = 0;
+    unsigned long long candidates = 0, dropped = 0, overflow = 0, bigLeaves = 0, bigBoxes = 0, leafTally = 0,
+                       extraTally = 0;
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
                                       [&](unsigned long long i, const float in[9], bool valid) {
         if (!valid) {
@@ -187,8 +191,19 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
         float area;
         uint32_t leaves = 0;
         if (setupTriangle<false>(grid, in, root, area)) {
-            const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &, const uint32_t *lo,
+            const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo,
                                                                    const uint32_t *hi) {
+                if (leaves == 0) {
+                    LeafRecord rec;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        rec.v[k] = leaf.v[k];
+                    }
+                    rec.tri = static_cast<uint32_t>(i);  // position in the array this pass reads (unused on this path)
+                    rec.area = area;
+                    rec.flags = leafFlagsOf(leaf.v);
+                    firstLeaves[i] = rec;
+                }
                 ++leaves;
                 const unsigned long long volume =
                     (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
@@ -219,7 +234,12 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
         else {
             ++dropped;
         }
-        leafCount[i] = leaves;
+        if (leaves == 0) {  // only the flags of an empty slot are ever read
+            reinterpret_cast<float4 *>(firstLeaves + i)[2] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kLeafEmpty));
+        }
+        extraCount[i] = leaves > 1u ? leaves - 1u : 0u;
+        leafTally += leaves;
+        extraTally += leaves > 1u ? leaves - 1u : 0u;
     });
     if (collect) {
         __syncthreads();
@@ -230,6 +250,8 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
             }
         }
     }
+    warpTally(&counters->leaves, leafTally);
+    warpTally(&counters->extraLeaves, extraTally);
     warpTally(&counters->candidateVoxels, candidates);
     warpTally(&counters->droppedTriangles, dropped);
     warpTally(&counters->depthOverflow, overflow);
@@ -258,9 +280,12 @@ __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *coun
     }
 }
 
+/// Second pass, only for meshes that need it (some triangle subdivides, or some leaf is big): writes the leaves beyond
+/// the first of each triangle to extraLeaves[extraOffset[i] ...] (leaf index firstLeaves + that) and enters the leaves
+/// with more than kOccBigVolume candidates — first leaves included — into the big-leaf table.
 __global__ void __launch_bounds__(kOccSetupThreads)
-occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ leafOffset,
-                    LeafRecord *__restrict__ leaves, RunCounters *counters)
+occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ extraOffset,
+                    LeafRecord *__restrict__ extraLeaves, RunCounters *counters)
 {
     __shared__ TriangleBatch<kOccSetupThreads> batch;
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
@@ -270,17 +295,21 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
         if (!valid || !setupTriangle<false>(grid, in, root, area)) {
             return;
         }
-        uint32_t index = leafOffset[i];
+        uint32_t seen = 0;
+        const uint32_t extraAt = extraOffset[i];
         traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
-            LeafRecord rec;
+            const uint32_t index = seen == 0 ? static_cast<uint32_t>(i) : occ.firstLeaves + extraAt + (seen - 1u);
+            if (seen != 0) {
+                LeafRecord rec;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                rec.v[k] = leaf.v[k];
+                for (int k = 0; k < 9; ++k) {
+                    rec.v[k] = leaf.v[k];
+                }
+                rec.tri = static_cast<uint32_t>(i);
+                rec.area = area;
+                rec.flags = leafFlagsOf(leaf.v);
+                extraLeaves[extraAt + (seen - 1u)] = rec;
             }
-            rec.tri = static_cast<uint32_t>(i);  // position in the array this pass reads (not used on this path)
-            rec.area = area;
-            rec.flags = leafFlagsOf(leaf.v);
-            leaves[index] = rec;
             const unsigned long long volume = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
             if (volume > kOccBigVolume) {
                 // one atomic hands out the table row (high 24 bits) and the first box number (low 40 bits) together, so
@@ -292,7 +321,7 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
                     occ.bigLeaves[row] = make_uint2(index, (uint32_t) (ticket & ((1ull << 40) - 1ull)));
                 }
             }
-            ++index;
+            ++seen;
         });
     });
 }
@@ -371,9 +400,15 @@ __device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, const Occupan
     return e.segsDy * (hi[2] - lo[2]);
 }
 
-__device__ __forceinline__ void loadLeafVertices(LeafStage &s, const LeafRecord *leaves, uint32_t leafIndex)
+/// Leaf `index`: slots below firstLeaves hold the first leaf of triangle `index`, the others follow in extraLeaves.
+__device__ __forceinline__ const LeafRecord *leafAt(const VoxelizeArgs &args, uint32_t index)
 {
-    const float4 *src = reinterpret_cast<const float4 *>(leaves + leafIndex);
+    return index < args.occ.firstLeaves ? args.leaves + index : args.occ.extraLeaves + (index - args.occ.firstLeaves);
+}
+
+__device__ __forceinline__ void loadLeafVertices(LeafStage &s, const VoxelizeArgs &args, uint32_t leafIndex)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(leafAt(args, leafIndex));
     const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
     s.v[0] = a.x; s.v[1] = a.y; s.v[2] = a.z; s.v[3] = a.w;
     s.v[4] = b.x; s.v[5] = b.y; s.v[6] = b.z; s.v[7] = b.w;
@@ -540,9 +575,9 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
     uint32_t volume = 0;
     if (tid < kOccBatch && leafIndex < leafTotal) {
         LeafStage s;
-        loadLeafVertices(s, args.leaves, leafIndex);
+        loadLeafVertices(s, args, leafIndex);
         uint32_t lo[3], hi[3];
-        if (leafBoxInSlab(s.v, args.grid, lo, hi)) {
+        if ((s.flags & kLeafEmpty) == 0 && leafBoxInSlab(s.v, args.grid, lo, hi)) {
             const unsigned long long v64 = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
             if (v64 <= kOccBigVolume) {
                 volume = stageBatchEntry(sh.entry[tid], args.occ, leafIndex, lo, hi, s);
@@ -601,7 +636,7 @@ occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigne
             }
             const uint2 row = args.occ.bigLeaves[lo];
             LeafStage s;
-            loadLeafVertices(s, args.leaves, row.x);
+            loadLeafVertices(s, args, row.x);
             uint32_t leafLo[3], leafHi[3];
             leafBoxInSlab(s.v, args.grid, leafLo, leafHi);
             const uint32_t nbx = (leafHi[0] - leafLo[0] + kOccBoxEdge - 1) / kOccBoxEdge;
@@ -677,7 +712,7 @@ occupancyClipKernel(const VoxelizeArgs args)
                     const uint4 entry = occ.queue[e];
                     const uint32_t x = entry.y & 0xffffu, y = entry.y >> 16, z = entry.z;
                     if (!alreadyDecided(occ, downscale, x, y, z)) {
-                        const float4 *src = reinterpret_cast<const float4 *>(args.leaves + entry.x);
+                        const float4 *src = reinterpret_cast<const float4 *>(leafAt(args, entry.x));
                         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
                         Tri<false> leaf;
                         leaf.v[0] = a.x; leaf.v[1] = a.y; leaf.v[2] = a.z; leaf.v[3] = a.w;
@@ -888,10 +923,11 @@ void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float
     occupancySlabFilterKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, kept, counters);
 }
 
-void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *leafCount,
-                          RunCounters *counters, cudaStream_t stream)
+void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
+                          LeafRecord *firstLeaves, RunCounters *counters, cudaStream_t stream)
 {
-    occupancyCountKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, leafCount, counters);
+    occupancyCountKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, extraCount,
+                                                                                    firstLeaves, counters);
 }
 
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream)
