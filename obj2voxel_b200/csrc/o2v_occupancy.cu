@@ -356,7 +356,8 @@ struct ClassifyShared {
 
 __device__ __forceinline__ uint32_t magicOf(uint32_t d)
 {
-    return d > 1u ? (uint32_t) ((1ull << 32) / d) + 1u : 0u;
+    // floor(2^32 / d) + 1 for d that do not divide 2^32, 2^32 / d (exact quotients) for those that do; 32-bit division
+    return d > 1u ? 0xffffffffu / d + 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t divideBy(uint32_t n, uint32_t d, uint32_t magic)

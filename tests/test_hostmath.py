@@ -126,3 +126,12 @@ def test_texture_lookup_quantize_combine(shim):
     assert acc.tolist() == pytest.approx([2.0, 0.1, 0.2, 0.3])
     shim.o2vt_combine(acc.ctypes.data_as(fp), np.array([6.0, 0.5, 0.6, 0.7], np.float32).ctypes.data_as(fp), 1)
     assert acc[0] == 8.0 and acc[1] == np.float32((np.float32(6.0) * np.float32(0.5) + np.float32(2.0) * np.float32(0.1)) / np.float32(8.0))
+
+
+def test_magic_division_of_the_classify_kernel_is_exact():
+    """o2v_occupancy.cu decodes a row-segment number with n / d == __umulhi(n, 0xffffffff / d + 1) (magicOf /
+    divideBy); d <= 4096 (kOccBigVolume) and n * d <= 2^24 there: exhaustive over that range."""
+    for d in range(2, 4097):
+        magic = (0xFFFFFFFF // d + 1) & 0xFFFFFFFF
+        n = np.arange(0, (1 << 24) // d + 1, dtype=np.uint64)
+        assert np.array_equal((n * np.uint64(magic)) >> np.uint64(32), n // np.uint64(d)), d
