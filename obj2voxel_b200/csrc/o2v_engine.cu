@@ -573,7 +573,10 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
         O2V_CUDA(cudaMemsetAsync(occ.bits, 0, bitmapBytes, stream));
         O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
-        launchOccupancyClassify(args, leafTotal, (uint32_t) bigLeaves, bigBoxes, smCount_, stream);
+        // variant 1 / 2 force the block-per-batch / the thread-per-leaf classifier (tests: both must agree)
+        const bool microLeaves = args.variant == 2 ||
+                                 (args.variant != 1 && candidateBound <= kOccDirectCandidates * hostCounters_->leaves);
+        launchOccupancyClassify(args, leafTotal, microLeaves, (uint32_t) bigLeaves, bigBoxes, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evClipStart_, stream));
         launchOccupancyClip(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evClipEnd_, stream));

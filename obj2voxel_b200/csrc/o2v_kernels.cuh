@@ -156,6 +156,7 @@ constexpr uint32_t kChunkEdge = 64;     // voxels per chunk edge: the unit the o
 constexpr uint32_t kChunkWords = 4096;  // 64-bit words of one chunk bitmap: 512 tiles x 8 layers (32 KB)
 constexpr uint32_t kOccBigVolume = 4096;  // leaves with more candidate voxels are classified box by box ...
 constexpr uint32_t kOccBoxEdge = 16;      // ... in 16^3 boxes
+constexpr uint32_t kOccDirectCandidates = 8;  // see launchOccupancyClassify
 constexpr uint32_t kLeafEmpty = 4u;       // LeafRecord::flags on this path: the triangle of this slot has no leaf in the slab
 
 /// Buffers of the occupancy-only path (o2v_occupancy.cu): meshes whose every triangle is MATERIALLESS voxelize white
@@ -218,7 +219,9 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
                          const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream);
-void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, uint32_t bigCount,
+/// microLeaves: the mesh averages at most kOccDirectCandidates candidate voxels per leaf — classified thread = leaf
+/// (occupancyClassifyDirectKernel) instead of block = 64 leaves.
+void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,
                              unsigned long long boxTotal, int smCount, cudaStream_t stream);
 void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchOccupancyExpand(const VoxelizeArgs &args, int smCount, cudaStream_t stream);

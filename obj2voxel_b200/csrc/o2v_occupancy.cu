@@ -7,15 +7,23 @@
 // output, so the result is the set { voxel : some leaf's exact clip has >= 1 piece }, an order-independent OR.  No tile
 // lists, no sort, no fold:
 //
-//   count     thread = triangle           subdivision DFS (exact) -> leaf count, candidate total, touched 64^3 chunks
-//   emit      thread = triangle           LeafRecord per leaf; leaves with more than 4096 candidates also enter the
-//                                          big-leaf table (their box is cut into 16^3 boxes)
-//   classify  thread = candidate voxel    block = 128 leaves (or one 16^3 box): SAT constants staged in shared memory, the
-//                                          batch's candidates as ONE flat index space (balanced whatever the box sizes),
-//                                          three-way SAT (o2v_sat.cuh): `certain` -> warp-aggregated atomicOr into the
+//   filter    thread = triangle           only for a rank that owns a part of the grid: the triangles whose z range can
+//                                          reach the slab, copied into a dense array (everything below reads that)
+//   count     thread = triangle           transform, subdivision DFS (exact), statistics, touched 64^3 chunks — and the
+//                                          triangle's first leaf goes straight into leaf slot i
+//   emit      thread = triangle           only if some triangle subdivides or some leaf is big: the other leaves; leaves
+//                                          with more than 4096 candidates enter the big-leaf table (16^3 boxes)
+//   classify  thread = row segment        block = 64 leaves (or one 16^3 box): SAT constants staged in shared memory, the
+//                                          batch's row segments (<= 8 voxels of one row in one tile column) as ONE flat
+//                                          index space (balanced whatever the box sizes); three-way SAT per voxel with one
+//                                          multiply-add per axis (o2v_sat.cuh): `certain` -> one RED per segment into the
 //                                          chunk bitmap, `uncertain` -> queue (unless the bitmap already decides it)
 //   clip      persistent lanes            the bit-exact six-plane clip (WarpClipper) for queued voxels only
-//   expand    thread = tile               bitmap (OR-reduced 2x2x2 when supersampling) -> compacted Voxel32 records
+//   expand    lane = tile, then = record  bitmap (OR-reduced 2x2x2 when supersampling) -> compacted Voxel32 records,
+//                                          rank / select in shared memory so that a warp stores 512 contiguous bytes
+//
+// filter, count and emit stream the triangle array through shared memory with bulk-async copies (cp.async.bulk + mbarrier,
+// the TMA engine: streamTriangles in o2v_device.cuh).
 //
 // Exactness: `miss` and `certain` are proofs about the reference's result (o2v_sat.cuh header; fuzzed by
 // tests/test_sat_classifier.py), everything else runs the reference arithmetic.  prefilter = 0 sends every candidate
@@ -615,6 +623,144 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
     classifyBatch(sh, args);
 }
 
+constexpr int kOccDirectThreads = 128;
+constexpr uint32_t kOccDirectMaybeCap = 1024;
+
+struct DirectShared {
+    uint4 maybe[kOccDirectMaybeCap];  // undecided voxels as queue entries; .w = 1: survived the filter
+    uint32_t warpSums[kOccDirectThreads / 32];
+    uint32_t maybeCount;
+    unsigned long long queueBase;
+};
+
+/// Thread = leaf, for meshes of micro-triangles (on average at most kOccDirectCandidates candidate voxels per leaf:
+/// BASELINE config 5).  Sharing a leaf's few voxels out over a block costs more than testing them: the SAT constants
+/// stay in registers and the thread walks its own rows.  Same verdict functions, same bitmap and queue as
+/// occupancyClassifyKernel; big leaves are left to the box kernel.
+__global__ void __launch_bounds__(kOccDirectThreads)
+occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
+{
+    __shared__ DirectShared sh;
+    const OccupancyView &occ = args.occ;
+    const unsigned int full = 0xffffffffu;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool downscale = args.grid.supersampling == 2;
+    uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
+    if (tid == 0) {
+        sh.maybeCount = 0;
+    }
+    __syncthreads();
+
+    const uint32_t leafIndex = blockIdx.x * kOccDirectThreads + tid;
+    if (leafIndex < leafTotal) {
+        LeafStage s;
+        loadLeafVertices(s, args, leafIndex);
+        uint32_t lo[3], hi[3];
+        if ((s.flags & kLeafEmpty) == 0 && leafBoxInSlab(s.v, args.grid, lo, hi) &&
+            (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) <= kOccBigVolume) {
+            const bool oneChunk = (lo[0] >> 6) == ((hi[0] - 1) >> 6) && (lo[1] >> 6) == ((hi[1] - 1) >> 6) &&
+                                  (lo[2] >> 6) == ((hi[2] - 1) >> 6);
+            BatchEntry where;  // only .slot is used (entryWord)
+            where.slot = oneChunk ? __ldg(occ.chunkSlot + (lo[0] >> 6) +
+                                          occ.chunksPerAxis * ((lo[1] >> 6) + occ.chunksPerAxis * ((lo[2] >> 6) - occ.chunkZ0)))
+                                  : kNoSlot;
+            const float origin[3] = {(float) lo[0], (float) lo[1], (float) lo[2]};
+            buildPrefilter(s, origin);
+            PairSat sat;
+            buildPairSat(sat, s, origin);
+            // a leaf whose normal is too noisy for the SAT (kLeafNoPrefilter): all undecided
+            const bool useSat = args.prefilter && (s.flags & kLeafNoPrefilter) == 0;
+            for (uint32_t z = lo[2]; z < hi[2]; ++z) {
+                for (uint32_t y = lo[1]; y < hi[1]; ++y) {
+                    RowSat row;
+                    buildRowSat(sat, (float) (y - lo[1]), (float) (z - lo[2]), row);
+                    for (uint32_t x8 = lo[0] & ~7u; x8 < hi[0]; x8 += 8u) {
+                        const uint32_t xs = max(lo[0], x8), xe = min(hi[0], x8 + 8u);
+                        uint32_t sure = 0, open = 0;  // bit x & 7: certain / undecided
+                        if (!useSat) {
+                            open = ((1u << (xe - x8)) - 1u) & ~((1u << (xs - x8)) - 1u);
+                        }
+                        else if (!rowPlaneSpanMisses(sat, row, (float) (xs - lo[0]), (float) (xe - 1u - lo[0]))) {
+                            for (uint32_t x = xs; x < xe; ++x) {
+                                const int verdict = classifyInRow(sat, row, (float) (x - lo[0]));
+                                sure |= verdict == kSatCertain ? 1u << (x & 7u) : 0u;
+                                open |= verdict == kSatUncertain ? 1u << (x & 7u) : 0u;
+                            }
+                        }
+                        if (sure != 0) {
+                            const size_t half = entryWord(occ, where, x8, y, z) * 2u + ((y & 7u) >> 2);
+                            atomicOr(bits32 + half, sure << (8u * (y & 3u)));
+                        }
+                        if (open != 0) {
+                            uint32_t slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(open));
+                            while (open != 0) {
+                                const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
+                                open &= open - 1u;
+                                const uint4 entry = make_uint4(leafIndex, (x8 | bit) | (y << 16), z, 0u);
+                                if (slot < kOccDirectMaybeCap) {
+                                    sh.maybe[slot] = entry;
+                                }
+                                else {  // buffer full: straight to the queue, unfiltered
+                                    const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
+                                    if (index < occ.queueCapacity) {
+                                        occ.queue[index] = entry;
+                                    }
+                                }
+                                ++slot;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- filter the undecided voxels by what the bitmap shows now, then one reservation in the queue per block ----
+    const uint32_t buffered = min(sh.maybeCount, kOccDirectMaybeCap);
+    if (buffered == 0) {
+        return;
+    }
+    uint32_t count = 0;
+    for (uint32_t k = tid; k < buffered; k += kOccDirectThreads) {
+        const uint4 m = sh.maybe[k];
+        if (!alreadyDecided(occ, downscale, m.y & 0xffffu, m.y >> 16, m.z)) {  // a stale read only costs a redundant clip
+            sh.maybe[k].w = 1u;
+            ++count;
+        }
+    }
+    uint32_t inclusive = count;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(full, inclusive, o);
+        inclusive += lane >= (uint32_t) o ? up : 0u;
+    }
+    if (lane == 31) {
+        sh.warpSums[warp] = inclusive;
+    }
+    __syncthreads();
+    uint32_t blockTotal = 0, warpBase = 0;
+    for (uint32_t w = 0; w < kOccDirectThreads / 32; ++w) {
+        warpBase += w < warp ? sh.warpSums[w] : 0u;
+        blockTotal += sh.warpSums[w];
+    }
+    if (blockTotal != 0) {  // block-uniform
+        if (tid == 0) {
+            sh.queueBase = atomicAdd(&args.counters->survivors, (unsigned long long) blockTotal);
+        }
+        __syncthreads();
+        unsigned long long index = sh.queueBase + warpBase + (inclusive - count);
+        for (uint32_t k = tid; k < buffered; k += kOccDirectThreads) {
+            const uint4 m = sh.maybe[k];
+            if (m.w != 0) {
+                if (index < occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
+                    occ.queue[index] = make_uint4(m.x, m.y, m.z, 0u);
+                }
+                ++index;
+            }
+        }
+    }
+}
+
 /// Persistent blocks over the 16^3 boxes of the big leaves (axis-aligned triangles the reference does not subdivide).
 __global__ void __launch_bounds__(kOccThreads)
 occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigned long long boxTotal)
@@ -943,10 +1089,14 @@ void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const Occup
                                                                                    counters);
 }
 
-void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, uint32_t bigCount,
+void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,
                              unsigned long long boxTotal, int smCount, cudaStream_t stream)
 {
-    if (leafTotal != 0) {
+    if (leafTotal != 0 && microLeaves) {
+        const unsigned blocks = (unsigned) ((leafTotal + kOccDirectThreads - 1) / kOccDirectThreads);
+        occupancyClassifyDirectKernel<<<blocks, kOccDirectThreads, 0, stream>>>(args, (uint32_t) leafTotal);
+    }
+    else if (leafTotal != 0) {
         const unsigned blocks = (unsigned) ((leafTotal + kOccBatch - 1) / kOccBatch);
         occupancyClassifyKernel<<<blocks, kOccThreads, 0, stream>>>(args, (uint32_t) leafTotal);
     }

@@ -429,3 +429,17 @@ def test_more_chunks_than_a_block_collects(engine):
     got = o2v.sort_voxels(got)
     assert np.array_equal(got, o2v.sort_voxels(weighted))
     assert np.array_equal(got, oracle.voxelize(v, 2688, bounds=meshes.UNIT_BOUNDS)["voxels"])
+
+
+@pytest.mark.parametrize("extent,resolution,supersampling", [(0.0005, 512, 1), (0.02, 128, 1), (0.004, 128, 2)])
+def test_both_classifiers_agree_with_the_oracle(engine, extent, resolution, supersampling):
+    """The occupancy pipeline classifies block = 64 leaves (variant 1) or, for meshes of micro-triangles, thread = leaf
+    (variant 2; the engine picks by the average number of candidate voxels per leaf).  Forced both ways on micro and on
+    ordinary triangles (big axis-aligned leaves ride along): identical records, the oracle's."""
+    v = np.concatenate([meshes.random_triangles(20000, extent, seed=31), meshes.unit_cube() * np.float32(0.9) + np.float32(0.05)])
+    kw = dict(resolution=resolution, supersampling=supersampling, bounds=meshes.UNIT_BOUNDS)
+    want = oracle.voxelize(v, resolution, supersampling=supersampling, bounds=meshes.UNIT_BOUNDS)["voxels"]
+    for variant in (1, 2):
+        got, stats = engine.voxelize_host(v, o2v.make_params(variant=variant, **kw))
+        assert stats["occupancy_path"]
+        assert np.array_equal(o2v.sort_voxels(got), want), variant
