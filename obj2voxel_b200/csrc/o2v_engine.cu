@@ -448,7 +448,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         if (!slabVerts_.ensure((size_t) meshIn.count * 9 * sizeof(float))) {
             return fail(kErrOutOfMemory, "device allocation failed (occupancy path, slab triangles)");
         }
-        launchOccupancySlabFilter(meshIn, grid, slabVerts_.as<float>(), dCounters, stream);
+        launchOccupancySlabFilter(meshIn, grid, slabVerts_.as<float>(), dCounters, smCount_, stream);
         ++st.kernelLaunches;
         launchPublishCounters(dCounters, hostCountersDevice_, stream);
         ++st.kernelLaunches;
@@ -481,7 +481,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, ((size_t) occ.chunkTotal + 31) / 32 * 4, stream));
 
     // the one pass over the triangles: statistics, chunk marks, and the first leaf of triangle i into leaf slot i
-    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, stream);
+    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, smCount_,
+                         stream);
     launchOccupancyAssignChunks(occ, dCounters, stream);
     st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
@@ -553,7 +554,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                             &dCounters->scanTotal, stream);
         launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), extraLeaves_.as<LeafRecord>(), dCounters,
-                            stream);
+                            smCount_, stream);
         st.kernelLaunches += 4;
     }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));

@@ -213,12 +213,13 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 /// every candidate voxel with the three-way SAT of o2v_sat.cuh (`certain` -> bitmap, `uncertain` -> queue), exact clip
 /// for the queue, bitmap -> Voxel32 records.
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
-                               cudaStream_t stream);
+                               int smCount, cudaStream_t stream);
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, cudaStream_t stream);
+                          LeafRecord *firstLeaves, RunCounters *counters, int smCount, cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream);
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,
+                         cudaStream_t stream);
 /// microLeaves: the mesh averages at most kOccDirectCandidates candidate voxels per leaf — classified thread = leaf
 /// (occupancyClassifyDirectKernel) instead of block = 64 leaves.
 void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,

@@ -1055,26 +1055,31 @@ unsigned occupancyPersistentBlocks(Kernel kernel, int threads, int smCount)
     return (unsigned) smCount * (unsigned) perSm;  // a multiple of the SM count
 }
 
-unsigned setupBlocks(unsigned long long n)
+/// Persistent grid of the triangle passes: as many blocks as are resident at once (a multiple of the SM count; no tail
+/// wave, since a block's batches are dealt round-robin), fewer if there are fewer batches.
+template <typename Kernel>
+unsigned setupBlocks(Kernel kernel, unsigned long long n, int smCount)
 {
-    unsigned long long blocks = (n + kOccSetupThreads - 1) / kOccSetupThreads;
-    blocks = blocks < 1 ? 1 : blocks;
-    return (unsigned) (blocks < 148ull * 10 ? blocks : 148ull * 10);  // persistent: the next batch loads under this one
+    unsigned long long batches = (n + kOccSetupThreads - 1) / kOccSetupThreads;
+    batches = batches < 1 ? 1 : batches;
+    const unsigned long long resident = occupancyPersistentBlocks(kernel, kOccSetupThreads, smCount);
+    return (unsigned) (batches < resident ? batches : resident);
 }
 
 }  // namespace
 
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
-                               cudaStream_t stream)
+                               int smCount, cudaStream_t stream)
 {
-    occupancySlabFilterKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, kept, counters);
+    occupancySlabFilterKernel<<<setupBlocks(occupancySlabFilterKernel, mesh.count, smCount), kOccSetupThreads, 0,
+                                stream>>>(mesh, grid, kept, counters);
 }
 
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, cudaStream_t stream)
+                          LeafRecord *firstLeaves, RunCounters *counters, int smCount, cudaStream_t stream)
 {
-    occupancyCountKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, extraCount,
-                                                                                    firstLeaves, counters);
+    occupancyCountKernel<<<setupBlocks(occupancyCountKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
+        mesh, grid, occ, extraCount, firstLeaves, counters);
 }
 
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream)
@@ -1083,10 +1088,11 @@ void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters
 }
 
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, cudaStream_t stream)
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,
+                         cudaStream_t stream)
 {
-    occupancyEmitKernel<<<setupBlocks(mesh.count), kOccSetupThreads, 0, stream>>>(mesh, grid, occ, leafOffset, leaves,
-                                                                                   counters);
+    occupancyEmitKernel<<<setupBlocks(occupancyEmitKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
+        mesh, grid, occ, leafOffset, leaves, counters);
 }
 
 void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,
