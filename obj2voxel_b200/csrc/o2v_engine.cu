@@ -442,47 +442,39 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
 {
     RunCounters *dCounters = counters_.as<RunCounters>();
     MeshView mesh = meshIn;
-    if (grid.slabZ0 != 0 || grid.slabZ1 < grid.gridExtent) {
+    const bool partOfGrid = grid.slabZ0 != 0 || grid.slabZ1 < grid.gridExtent;
+    if (partOfGrid) {
         // One rank of several: keep only the triangles whose z range can reach the slab (one streaming pass over the
-        // mesh); everything after works on that share.
+        // mesh); everything after works on that share.  How many were kept stays on the device until the count pass is
+        // through as well (mesh.count is their upper bound until then).
         if (!slabVerts_.ensure((size_t) meshIn.count * 9 * sizeof(float))) {
             return fail(kErrOutOfMemory, "device allocation failed (occupancy path, slab triangles)");
         }
         launchOccupancySlabFilter(meshIn, grid, slabVerts_.as<float>(), dCounters, smCount_, stream);
         ++st.kernelLaunches;
-        launchPublishCounters(dCounters, hostCountersDevice_, stream);
-        ++st.kernelLaunches;
-        O2V_CUDA(cudaStreamSynchronize(stream));
-        O2V_CUDA(cudaGetLastError());
         mesh.verts = slabVerts_.as<float>();
-        mesh.count = hostCounters_->slabTriangles;
-        if (mesh.count == 0) {
-            st.occupancyPath = true;
-            st.counters = *hostCounters_;
-            return kErrOk;
-        }
     }
-    const size_t n = (size_t) mesh.count;
+    const size_t nBound = (size_t) mesh.count;  // = meshIn.count
 
     OccupancyView occ{};
     occ.chunksPerAxis = grid.gridExtent / kChunkEdge;
     occ.chunkZ0 = grid.slabZ0 / kChunkEdge;
     const uint32_t chunkRows = (grid.slabZ1 + kChunkEdge - 1) / kChunkEdge - occ.chunkZ0;
     occ.chunkTotal = occ.chunksPerAxis * occ.chunksPerAxis * chunkRows;  // <= 128^3
-    if (!leafCount_.ensure(n * 4) || !leafOffset_.ensure(n * 4) || !scratch_.ensure(scanScratchElems(n) * 4) ||
-        !chunkFlag_.ensure(((size_t) occ.chunkTotal + 31) / 32 * 4) || !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) ||
-        !chunkList_.ensure((size_t) occ.chunkTotal * 4) || !leaves_.ensure(n * sizeof(LeafRecord))) {
+    if (!leafCount_.ensure(nBound * 4) || !leafOffset_.ensure(nBound * 4) ||
+        !scratch_.ensure(scanScratchElems(nBound) * 4) || !chunkFlag_.ensure(((size_t) occ.chunkTotal + 31) / 32 * 4) ||
+        !chunkSlot_.ensure((size_t) occ.chunkTotal * 4) || !chunkList_.ensure((size_t) occ.chunkTotal * 4) ||
+        !leaves_.ensure(nBound * sizeof(LeafRecord))) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path, setup buffers)");
     }
     occ.chunkFlag = chunkFlag_.as<uint32_t>();
     occ.chunkSlot = chunkSlot_.as<uint32_t>();
     occ.chunkList = chunkList_.as<uint32_t>();
-    occ.firstLeaves = (uint32_t) n;
     O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, ((size_t) occ.chunkTotal + 31) / 32 * 4, stream));
 
     // the one pass over the triangles: statistics, chunk marks, and the first leaf of triangle i into leaf slot i
-    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, smCount_,
-                         stream);
+    launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, partOfGrid,
+                         smCount_, stream);
     launchOccupancyAssignChunks(occ, dCounters, stream);
     st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
@@ -490,6 +482,11 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
+    if (partOfGrid) {
+        mesh.count = hostCounters_->slabTriangles;
+    }
+    const size_t n = (size_t) mesh.count;  // triangles the passes work on = first-leaf slots
+    occ.firstLeaves = (uint32_t) n;
     const unsigned long long extraLeaves = hostCounters_->extraLeaves;
     const unsigned long long leafTotal = hostCounters_->leaves == 0 ? 0 : n + extraLeaves;  // leaf slots
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;

@@ -215,7 +215,8 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
                                int smCount, cudaStream_t stream);
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, int smCount, cudaStream_t stream);
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, int smCount,
+                          cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
                          const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,

@@ -173,8 +173,12 @@ constexpr uint32_t kOccBlockChunkWords = 2048;  // chunk bits a block collects i
 /// the grid) needs no second pass.  extraCount[i] = the triangle's leaves beyond the first.
 __global__ void __launch_bounds__(kOccSetupThreads)
 occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ extraCount,
-                     LeafRecord *__restrict__ firstLeaves, RunCounters *counters)
+                     LeafRecord *__restrict__ firstLeaves, RunCounters *counters, bool countFromFilter)
 {
+    if (countFromFilter) {
+        // the array is what the slab filter kept: its length is still on the device (no host round trip in between)
+        mesh.count = counters->slabTriangles;
+    }
     __shared__ TriangleBatch<kOccSetupThreads> batch;
     // Millions of leaves mark a few thousand chunks: up to 65536 chunks per slab (any grid up to 2560^3, and slabs of
     // larger ones) a block ORs its marks into shared memory and publishes each word once when it is done, so that the
@@ -1076,10 +1080,12 @@ void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float
 }
 
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, int smCount, cudaStream_t stream)
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, int smCount,
+                          cudaStream_t stream)
 {
+    // countFromFilter: mesh.count is only an upper bound (the grid is sized by it; blocks without a batch leave at once)
     occupancyCountKernel<<<setupBlocks(occupancyCountKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
-        mesh, grid, occ, extraCount, firstLeaves, counters);
+        mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
 }
 
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream)
