@@ -395,7 +395,8 @@ def run_ours(args, cfg, workload):
             if step > 0:
                 e2e_times.append(dt)
                 e2e_voxels = received["n"]
-        e2e_api = "obj2voxel_b200_set_input_triangles + obj2voxel_voxelize + voxel callback"
+        e2e_api = ("obj2voxel_b200_set_input_triangles + obj2voxel_voxelize + voxel callback (the job runs in 4 z parts: "
+                   "the download of one under the kernels of the next)")
     else:
         per_rank = -(-n_tri // world)
         lo, hi = min(rank * per_rank, n_tri), min((rank + 1) * per_rank, n_tri)

@@ -1,6 +1,7 @@
 """Turns gpurun_out/ ncu outputs into the committed summaries under profiles/ (run here, no GPU needed).
   python scripts/summarize_profiles.py launches <launches.csv> <out.md> "<title>"
   python scripts/summarize_profiles.py raw <report.ncu-rep> <out.md> "<title>"
+  python scripts/summarize_profiles.py traffic <report.ncu-rep> <out.json> <workload>
 """
 import collections
 import csv
@@ -47,17 +48,38 @@ def launches(path, out, title):
 def raw(rep, out, title):
     text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(text.splitlines()))
-    hdr = rows[0]
+    hdr, units = rows[0], dict(zip(rows[0], rows[1]))
     with open(out, "w") as f:
         f.write("# %s\n\nSource: `ncu --set full --clock-control none --import-source on`, read with `ncu -i … --page raw --csv`.\n\n" % title)
         for vals in rows[2:]:
             d = dict(zip(hdr, vals))
-            f.write("## %s\n\n| metric | value |\n|---|---|\n" % d.get("Kernel Name", "?").split("(")[0])
+            f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % d.get("Kernel Name", "?").split("(")[0])
             for k in KEYS:
                 if k in d and d[k] != "":
-                    f.write("| %s | %s |\n" % (k, d[k]))
+                    f.write("| %s | %s | %s |\n" % (k, d[k], units.get(k, "")))
             f.write("\n")
 
 
+def traffic(rep, out, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of every kernel in the report -> JSON for bench.py."""
+    import json
+
+    text = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(text.splitlines()))
+    hdr, units = rows[0], dict(zip(rows[0], rows[1]))
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    kernels = {}
+    for vals in rows[2:]:
+        d = dict(zip(hdr, vals))
+        name = d.get("Kernel Name", "?").split("(")[0].split("::")[-1]
+        total = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(d[k].replace(",", "")) * scale[units[k]]
+        kernels[name] = {"dram_bytes_per_launch": int(total), "gpu_time_ms": float(d["gpu__time_duration.sum"]) *
+                         {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units["gpu__time_duration.sum"]]}
+    json.dump({"workload": workload, "source": rep.split("/")[-1] + " (ncu --set full, one launch per kernel)",
+               "kernels": kernels}, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])
+    {"launches": launches, "raw": raw, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])
