@@ -14,6 +14,7 @@ cases = [
     (meshes.random_triangles(6000, 0.02, seed=23) * np.float32(0.1), dict(resolution=32, strategy=1, bounds=[0, 0, 0, 1, 1, 1]), {}),  # heavy tiles, long lists
     (meshes.random_triangles(2000, 0.03), dict(resolution=128, strategy=1, bounds=meshes.UNIT_BOUNDS),
      dict(uvs=meshes.random_uvs(2000) * 3 - 1, textures=[(meshes.random_texture(32, 16, 3), 1)])),
+    (meshes.random_triangles(5000, 0.002, seed=4), dict(resolution=128, bounds=meshes.UNIT_BOUNDS), {}),  # micro-triangles: thread-per-leaf classifier
 ]
 for verts, kw, extra in cases:
     for occ in (1, 0):  # all-white meshes: occupancy-only pipeline, then the weighted one; textured: weighted twice
