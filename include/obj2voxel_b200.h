@@ -39,7 +39,8 @@ typedef struct o2v_b200_params {
     float bounds[6];            /* min xyz, max xyz */
     int32_t unit_transform[9];  /* row-major */
     uint32_t slab_z0, slab_z1;  /* owned sample-space z range [z0, z1), multiples of 8; 0,0 = the whole grid */
-    int32_t variant;            /* kernel variant, -1 = default */
+    int32_t variant;            /* kernel A/B switch, -1 = default (occupancy-only path: 1 / 2 force the block-per-batch /
+                                 * thread-per-leaf classifier; both give the same records) */
     int32_t prefilter;          /* 1 = conservative SAT prefilter on (default); 0 = off (validation only) */
     int32_t occupancy_path;     /* 1 (default) = meshes whose every triangle is MATERIALLESS (output colour is white
                                  * whatever the weights, reference src/triangle.hpp:186) take the occupancy-only path;
@@ -119,7 +120,10 @@ void obj2voxel_b200_set_input_triangles(obj2voxel_instance *instance, const floa
                                         size_t count, obj2voxel_texture *texture);
 /* Restrict the job to a Z-slab of the sample grid (multiples of 8). */
 void obj2voxel_b200_set_slab(obj2voxel_instance *instance, uint32_t z0, uint32_t z1);
-/* Statistics of the last obj2voxel_voxelize() on this instance. */
+/* Statistics of the last obj2voxel_voxelize() on this instance.  A big job (>= 2^20 triangles) runs as up to four z parts
+ * so that the download of one part overlaps the kernels of the next (O2V_B200_PIPELINE_PARTS overrides the number): the
+ * counts and the device times are then sums over the parts (dropped_triangles: the largest of the parts), and the sink /
+ * voxel callback receives the parts one after the other. */
 void obj2voxel_b200_get_stats(obj2voxel_instance *instance, o2v_b200_stats *out_stats);
 
 #ifdef __cplusplus
