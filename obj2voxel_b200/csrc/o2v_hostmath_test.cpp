@@ -163,4 +163,148 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
     }
 }
 
+
+// ---- study of two leads for the classify kernel, CPU only: nothing below is used by a kernel ----
+
+namespace {
+
+/// Every edge function divided by its `certain` threshold: miss <=> value < 0, sure <=> value >= 1, so that the six (plus
+/// three) values of a voxel reduce to one minimum.  A degenerate edge (a = b = 0: value = c everywhere) becomes the
+/// constant 1 (c >= 0), -1 (c < 0) or 0.5 (NaN: neither verdict).
+struct ScaledSat {
+    float a[9], b[9], c[9];
+};
+
+void buildScaledSat(ScaledSat &out, const PairSat &s)
+{
+    for (int k = 0; k < 9; ++k) {
+        const SatEdge e = s.edge[k];
+        if (e.k > 0.0f) {
+            out.a[k] = e.a / e.k;
+            out.b[k] = e.b / e.k;
+            out.c[k] = e.c / e.k;
+        }
+        else {
+            out.a[k] = out.b[k] = 0.0f;
+            out.c[k] = e.c < 0.0f ? -1.0f : (e.c >= 0.0f ? 1.0f : 0.5f);
+        }
+    }
+}
+
+int classifyScaled(const PairSat &s, const ScaledSat &t, float lx, float ly, float lz, float certainMargin)
+{
+    const float dist = fabsf(s.plane[0] * lx + s.plane[1] * ly + s.plane[2] * lz + s.plane[3]);
+    const float q[3] = {lx, ly, lz};
+    float least = 2.0f;
+    for (int proj = 0; proj < 3; ++proj) {
+        const float qa = q[proj], qb = q[(proj + 1) % 3];
+        for (int i = 0; i < 3; ++i) {
+            const int k = proj * 3 + i;
+            least = fminf(least, t.a[k] * qa + t.b[k] * qb + t.c[k]);
+        }
+    }
+    if (dist > s.planeLimit || least < 0.0f) {
+        return kSatMiss;
+    }
+    bool sure = least >= 1.0f && dist <= s.planeSure;
+    for (int a = 0; a < 3; ++a) {
+        sure = sure && (q[a] + certainMargin <= s.hi[a]) && (q[a] + 1.0f - certainMargin >= s.lo[a]);
+    }
+    return sure ? kSatCertain : kSatUncertain;
+}
+
+/// buildPairSat with the `certain` shrink as a parameter (the header's is the constant kCertainMargin).
+void buildPairSatWith(PairSat &out, const LeafStage &s, const float origin[3], float certainMargin)
+{
+    buildPairSat(out, s, origin);
+    const float norm1 = fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]);
+    out.planeSure = (0.5f - certainMargin) * norm1;
+    const float shift = kPrefilterMargin + certainMargin;
+    for (int k = 0; k < 9; ++k) {
+        out.edge[k].k = (fabsf(s.edge[k * 3]) + fabsf(s.edge[k * 3 + 1])) * shift;
+    }
+}
+
+}  // namespace
+
+/// The sweep of o2vt_classify_fuzz with the `certain` shrink given at run time and, if scaled != 0, the scaled-minimum
+/// form of the edge tests.  out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts
+/// the reference hits, [6] `certain` verdicts the reference does not hit, [7] leaves skipped.
+void o2vt_classify_study(const float *leaves, size_t n, unsigned long long maxVolume, float certainMargin, int scaled,
+                         unsigned long long out[8])
+{
+    for (int i = 0; i < 8; ++i) {
+        out[i] = 0;
+    }
+    for (size_t l = 0; l < n; ++l) {
+        const float *v = leaves + l * 9;
+        uint32_t lo[3], hi[3];
+        triVoxelBounds(v, lo, hi);
+        const unsigned long long volume =
+            (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (unsigned long long) (hi[2] - lo[2]);
+        if (!(triArea(v) > 0.0f) || volume > maxVolume) {
+            ++out[7];
+            continue;
+        }
+        Tri<false> tri;
+        memcpy(tri.v, v, sizeof tri.v);
+        const uint32_t flags = leafFlagsOf(v);
+        const uint32_t boxEdge = volume > 4096 ? 16u : 0xffffffffu;
+        for (uint32_t z = lo[2]; z < hi[2]; ++z) {
+            for (uint32_t y = lo[1]; y < hi[1]; ++y) {
+                for (uint32_t x = lo[0]; x < hi[0]; ++x) {
+                    uint32_t bo[3] = {lo[0], lo[1], lo[2]};
+                    if (boxEdge != 0xffffffffu) {
+                        bo[0] += (x - lo[0]) / boxEdge * boxEdge;
+                        bo[1] += (y - lo[1]) / boxEdge * boxEdge;
+                        bo[2] += (z - lo[2]) / boxEdge * boxEdge;
+                    }
+                    const float boxOrigin[3] = {(float) bo[0], (float) bo[1], (float) bo[2]};
+                    LeafStage bs;
+                    memcpy(bs.v, v, sizeof bs.v);
+                    bs.flags = flags;
+                    buildPrefilter(bs, boxOrigin);
+                    PairSat sat;
+                    buildPairSatWith(sat, bs, boxOrigin, certainMargin);
+                    int verdict = kSatUncertain;
+                    if ((flags & kLeafNoPrefilter) == 0) {
+                        const float lx = (float) (x - bo[0]), ly = (float) (y - bo[1]), lz = (float) (z - bo[2]);
+                        if (scaled != 0) {
+                            ScaledSat t;
+                            buildScaledSat(t, sat);
+                            verdict = classifyScaled(sat, t, lx, ly, lz, certainMargin);
+                        }
+                        else {  // the header's form with the run-time margin in the box-normal tests
+                            verdict = classifyVoxel(sat, lx, ly, lz);
+                            if (verdict != kSatMiss) {
+                                const float q[3] = {lx, ly, lz};
+                                bool sure = fabsf(sat.plane[0] * lx + sat.plane[1] * ly + sat.plane[2] * lz + sat.plane[3]) <=
+                                            sat.planeSure;
+                                for (int k = 0; k < 9; ++k) {
+                                    const int proj = k / 3;
+                                    const float value = sat.edge[k].a * q[proj] + sat.edge[k].b * q[(proj + 1) % 3] +
+                                                        sat.edge[k].c;
+                                    sure = sure && value >= sat.edge[k].k;
+                                }
+                                for (int a = 0; a < 3; ++a) {
+                                    sure = sure && (q[a] + certainMargin <= sat.hi[a]) &&
+                                           (q[a] + 1.0f - certainMargin >= sat.lo[a]);
+                                }
+                                verdict = sure ? kSatCertain : kSatUncertain;
+                            }
+                        }
+                    }
+                    const bool hit =
+                        !planeDistanceCulled(v, x, y, z) && clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
+                    ++out[0];
+                    ++out[1 + verdict];
+                    out[4] += hit ? 1 : 0;
+                    out[5] += (verdict == kSatMiss && hit) ? 1 : 0;
+                    out[6] += (verdict == kSatCertain && !hit) ? 1 : 0;
+                }
+            }
+        }
+    }
+}
+
 }  // extern "C"
