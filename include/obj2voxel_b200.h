@@ -112,6 +112,14 @@ int o2v_b200_voxelize_host(o2v_b200_engine *engine, const o2v_b200_params *param
                            const o2v_b200_texture *textures, uint32_t texture_count, uint32_t *out_voxels,
                            uint64_t out_capacity, uint64_t *out_count, o2v_b200_stats *out_stats);
 
+/* How obj2voxel_voxelize() would cut a job into z parts (see obj2voxel_b200_get_stats below): returns the number of parts
+ * and writes parts + 1 ascending bounds (at most bounds_capacity) — part k covers sample-space z in
+ * [out_bounds[k], out_bounds[k + 1]); inner bounds are multiples of 64 (the reference's chunk rows,
+ * src/obj2voxel.cpp:245-252).  requested_parts > 0 forces the number (as O2V_B200_PIPELINE_PARTS does), <= 0 applies the
+ * default rule.  Pure host arithmetic: no device needed. */
+uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint32_t slab_z1, uint64_t triangles,
+                             int32_t requested_parts, uint32_t *out_bounds, uint32_t bounds_capacity);
+
 /* ---- additive setters on the reference-compatible instance ------------------------------------------------------- */
 
 /* Bulk input: count triangles as 9 floats each (+ 6 uv floats each and a texture when textured).  The arrays are not

@@ -76,7 +76,7 @@ ADDITIVE_SYMBOLS = [
     "o2v_b200_engine_create", "o2v_b200_engine_destroy", "o2v_b200_last_error", "o2v_b200_sm_count",
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
     "o2v_b200_result_download", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
-    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats",
+    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts",
 ]
 
 
@@ -147,6 +147,7 @@ def load():
         "obj2voxel_b200_set_input_triangles": (None, [vp, fp, fp, sz, vp]),
         "obj2voxel_b200_set_slab": (None, [vp, u32, u32]),
         "obj2voxel_b200_get_stats": (None, [vp, C.POINTER(Stats)]),
+        "o2v_b200_plan_parts": (u32, [u32, u32, u32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), u32]),
     }
     for name, (restype, argtypes) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -170,6 +170,34 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->reserved = 0.0f;
 }
 
+constexpr uint32_t kMaxJobParts = 128;  // a part is at least one 64-voxel chunk row; sample resolution <= 8192
+
+/// How obj2voxel_voxelize() cuts a job into z parts (bounds[0 .. parts], ascending, inner bounds multiples of 64; the
+/// parts tile [z0, z1) clipped to the chunk grid).  requested > 0 forces the number of parts (at most one per chunk row),
+/// otherwise jobs of at least 2^20 triangles run in up to four parts and smaller ones in one.
+uint32_t planJobParts(uint32_t sampleRes, uint32_t slabZ0, uint32_t slabZ1, unsigned long long triangles, int requested,
+                      uint32_t *bounds)
+{
+    const uint32_t gridExtent = (sampleRes + 63u) / 64u * 64u;
+    uint32_t jobZ0 = slabZ0, jobZ1 = slabZ1;
+    if (jobZ0 == 0 && jobZ1 == 0) {
+        jobZ1 = gridExtent;
+    }
+    jobZ1 = std::min(jobZ1, gridExtent);
+    jobZ0 = std::min(jobZ0, jobZ1);
+    const uint32_t row0 = jobZ0 / 64u, row1 = std::max((jobZ1 + 63u) / 64u, row0 + 1u);
+    const uint32_t rows = row1 - row0;
+    uint32_t parts = (triangles >= (1ull << 20) && rows > 1u) ? std::min(4u, rows) : 1u;
+    if (requested > 0) {
+        parts = std::min(std::min((uint32_t) requested, rows), kMaxJobParts);
+    }
+    for (uint32_t k = 0; k <= parts; ++k) {
+        const uint32_t z = (row0 + (uint32_t) ((unsigned long long) rows * k / parts)) * 64u;
+        bounds[k] = std::min(std::max(z, jobZ0), jobZ1);
+    }
+    return parts;
+}
+
 /// Totals of a job that ran as several z parts (every voxel, leaf and clip belongs to exactly one part; a dropped
 /// triangle may be seen by several parts: the largest count is reported).
 void accumulateStats(RunStats &total, const RunStats &part)
@@ -496,22 +524,11 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
         // ---- plan: a big job runs as up to four z sub-slabs of whole 64-voxel chunk rows, so that the download of one
         // part (PCIe, the longest leg of a host-to-host job) runs under the kernels of the next.  Every voxel belongs to
         // exactly one part: same records, part by part. ----
-        const uint32_t sampleRes = inst.outputResolution * inst.supersampling;
-        const uint32_t gridExtent = (sampleRes + 63u) / 64u * 64u;
-        uint32_t jobZ0 = inst.slabZ0, jobZ1 = inst.slabZ1;
-        if (jobZ0 == 0 && jobZ1 == 0) {
-            jobZ1 = gridExtent;
-        }
-        jobZ1 = std::min(jobZ1, gridExtent);
-        const uint32_t row0 = jobZ0 / 64u, row1 = (jobZ1 + 63u) / 64u;
-        uint32_t parts = (mesh.count >= (1ull << 20) && row1 > row0 + 1u) ? std::min(4u, row1 - row0) : 1u;
-        if (const char *env = getenv("O2V_B200_PIPELINE_PARTS")) {
-            parts = std::max(1u, std::min((uint32_t) atoi(env), std::max(1u, row1 - row0)));
-        }
-        auto partBound = [&](uint32_t k) {
-            const uint32_t z = (row0 + (uint32_t) ((unsigned long long) (row1 - row0) * k / parts)) * 64u;
-            return std::min(std::max(z, jobZ0), jobZ1);
-        };
+        uint32_t partBounds[kMaxJobParts + 1];
+        const char *partsEnv = getenv("O2V_B200_PIPELINE_PARTS");
+        const uint32_t parts = planJobParts(inst.outputResolution * inst.supersampling, inst.slabZ0, inst.slabZ1, mesh.count,
+                                            partsEnv != nullptr ? atoi(partsEnv) : 0, partBounds);
+        auto partBound = [&](uint32_t k) { return partBounds[k]; };
 
         cudaStream_t copyStream = nullptr;
         cudaEvent_t copied[2] = {nullptr, nullptr};
@@ -1100,6 +1117,17 @@ const void *o2v_b200_result_device(const o2v_b200_engine *engine)
 uint64_t o2v_b200_result_count(const o2v_b200_engine *engine)
 {
     return engine->engine->voxelCount();
+}
+
+uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint32_t slab_z1, uint64_t triangles,
+                             int32_t requested_parts, uint32_t *out_bounds, uint32_t bounds_capacity)
+{
+    uint32_t bounds[kMaxJobParts + 1];
+    const uint32_t parts = planJobParts(sample_resolution, slab_z0, slab_z1, triangles, requested_parts, bounds);
+    for (uint32_t k = 0; k <= parts && k < bounds_capacity; ++k) {
+        out_bounds[k] = bounds[k];
+    }
+    return parts;
 }
 
 int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda_stream)

@@ -1,5 +1,6 @@
 """CPU: the C-ABI shared library loads, exports every symbol include/*.h declares, and its host-side logic (argument
 checks, error codes, textures, worker bookkeeping, sinks) behaves like the reference's — all without a compute call."""
+import ctypes as C
 import os
 import re
 import subprocess
@@ -195,3 +196,42 @@ def test_product_never_references_the_oracle():
                     continue
                 assert "liboracle" not in text and "o2v_oracle" not in text and "from oracle" not in text and \
                     "import oracle" not in text, os.path.join(dirpath, f)
+
+
+def plan_parts(sample_res, z0, z1, triangles, requested):
+    lib = o2v.load()
+    out = (C.c_uint32 * 130)()
+    n = lib.o2v_b200_plan_parts(sample_res, z0, z1, triangles, requested, out, 130)
+    return n, [int(out[k]) for k in range(n + 1)]
+
+
+def test_job_part_plan_tiles_the_slab_in_whole_chunk_rows():
+    """How obj2voxel_voxelize() cuts a big job into z parts (download of one part under the kernels of the next): the
+    parts must tile the job's z range exactly, without empty parts, with inner bounds on the reference's 64-voxel chunk
+    rows (src/obj2voxel.cpp:245-252) — every voxel then belongs to exactly one part."""
+    # default rule: small jobs in one part, big ones in up to four
+    assert plan_parts(2048, 0, 0, 1000, 0) == (1, [0, 2048])
+    assert plan_parts(2048, 0, 0, 10_000_000, 0) == (4, [0, 512, 1024, 1536, 2048])
+    assert plan_parts(100, 0, 0, 10_000_000, 0) == (2, [0, 64, 128])        # 2 chunk rows: at most one part per row
+    assert plan_parts(64, 0, 0, 10_000_000, 0) == (1, [0, 64])
+    assert plan_parts(2048, 0, 0, 10_000_000, -3) == (4, [0, 512, 1024, 1536, 2048])
+    # forced count, capped by the number of chunk rows; a slab that is not chunk-aligned keeps its own ends
+    assert plan_parts(200, 0, 0, 10, 7) == (4, [0, 64, 128, 192, 256])
+    assert plan_parts(2048, 1024, 1280, 10, 2) == (2, [1024, 1152, 1280])
+    assert plan_parts(2048, 40, 104, 10, 8) == (2, [40, 64, 104])
+    assert plan_parts(2048, 8, 48, 10_000_000, 0) == (1, [8, 48])
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        res = int(rng.integers(1, 8193))
+        grid = (res + 63) // 64 * 64
+        if rng.random() < 0.5:
+            z0, z1 = 0, 0
+            lo, hi = 0, grid
+        else:
+            z0 = int(rng.integers(0, grid // 8)) * 8
+            z1 = int(rng.integers(z0 // 8 + 1, grid // 8 + 1)) * 8
+            lo, hi = z0, z1
+        n, b = plan_parts(res, z0, z1, int(rng.integers(0, 1 << 24)), int(rng.integers(-2, 200)))
+        assert 1 <= n <= 128 and b[0] == lo and b[-1] == hi
+        assert all(b[k] < b[k + 1] for k in range(n)), (res, z0, z1, b)
+        assert all(x % 64 == 0 for x in b[1:-1])
