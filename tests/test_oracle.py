@@ -125,3 +125,30 @@ def test_oracle_matches_live_reference_fuzz():
         b = oracle.voxelize(v, res, uvs=uv, texture=tex, strategy=strategy)
         assert np.array_equal(a["xyz"], b["xyz"])
         assert np.array_equal(a["wrgb"].view(np.uint32), b["wrgb"].view(np.uint32))
+
+
+@pytest.mark.skipif(not refharness.available(), reason="oracle/_ref is only built where /root/reference exists")
+@pytest.mark.parametrize("extent,resolution,supersampling", [(0.0005, 512, 1), (0.02, 128, 1), (0.004, 128, 2),
+                                                              (0.002, 4096, 1), (0.002, 2688, 1)])
+def test_oracle_matches_live_reference_on_the_inputs_of_the_gpu_classifier_tests(extent, resolution, supersampling):
+    """The GPU tests of the two occupancy classifiers, of the job parts and of the > 65536-chunk grid compare against the
+    oracle on micro-triangles, ordinary triangles with big axis-aligned leaves, 2x supersampling and a 2688^3 grid
+    (tests/test_gpu_parity.py); here the oracle itself is pinned on the same inputs against the reference built from
+    /root/reference (public API; the patched build where the down-scaling matters).  2688 = 42 chunks per axis is not a
+    power of two: there the reference never dispatches the chunks whose Morton index is >= 42^3 (SURVEY B2,
+    src/obj2voxel.cpp:503-505) while the oracle and the product cover the whole grid — the reference's voxels must be
+    exactly the oracle's voxels inside the chunks it dispatched; 4096 pins the same input on a power-of-two grid."""
+    big = resolution > 2048
+    v = meshes.random_triangles(3000 if big else 20000, extent, seed=9 if big else 31)
+    if not big:
+        v = np.concatenate([v, meshes.unit_cube() * np.float32(0.9) + np.float32(0.05)])
+    want = refharness.run_api(v, resolution, supersampling=supersampling, bounds=meshes.UNIT_BOUNDS,
+                              patched_downscale=supersampling > 1)["voxels"]
+    got = oracle.voxelize(v, resolution, supersampling=supersampling, bounds=meshes.UNIT_BOUNDS)["voxels"]
+    chunks = (resolution * supersampling + 63) // 64
+    if chunks & (chunks - 1) != 0:
+        c = got[:, :3] // (64 // supersampling)
+        morton = np.array([oracle.ileave3(int(x), int(y), int(z)) for x, y, z in c.tolist()], dtype=np.uint64)
+        assert len(got) > len(want) > 0
+        got = got[morton < np.uint64(chunks) ** 3]
+    assert np.array_equal(got, want)
