@@ -138,6 +138,27 @@ def workload_spec(name):
     return cfg
 
 
+def config_dict(workload, cfg, n_tri, world):
+    """`config` of the JSON line — the same dict from both arms (ours and --impl reference) for a given workload and N."""
+    tri_bytes = 64 if cfg.get("textured") else 36
+    return {"workload": workload, "description": WORKLOADS[workload], "triangles": int(n_tri),
+            "resolution": cfg["resolution"], "supersampling": cfg["supersampling"],
+            "strategy": "blend" if cfg["strategy"] else "max",
+            "partition": "whole grid on one GPU" if world == 1 else
+                         "%d Z-slabs of whole 64-voxel chunk rows, one per GPU (strong scaling)" % world,
+            "l2": "inputs (%d MB of triangles) exceed the 126 MB L2; no explicit flush" % (n_tri * tri_bytes // 1000000)}
+
+
+def golden_checksums():
+    """Voxel count + order-independent record hash of the UNMODIFIED reference's output per workload
+    (tests/golden/full_size_checksums.json, written by tests/golden/make_full_size_checksums.py from oracle/_ref)."""
+    path = os.path.join(ROOT, "tests", "golden", "full_size_checksums.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
 def host_mesh(cfg, count=None):
     from obj2voxel_b200 import meshes
 
@@ -226,7 +247,10 @@ def run_reference_arm(args, cfg, workload):
         "impl": "reference", "metric": "triangles_per_second", "value": value, "unit": "Mtri/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "description": WORKLOADS[workload]},
+        "config": config_dict(workload, cfg, total, args.gpus),
+        "sample": "each step: the first %d of the %d triangles at resolution %d x supersampling 1 (the reference's "
+                  "downscale is broken, BASELINE.md section 3: same work per triangle without it)" %
+                  (sample, total, cfg["resolution"] * cfg["supersampling"]),
         "mvoxel_per_s": voxels / mean / 1e6,
         "cpu_baseline": {"value": value, "unit": "Mtri/s", "cores": workers, "kind": kind,
                          "sample": "each step: first %d of %d triangles of the workload through obj2voxel_voxelize() "
@@ -240,6 +264,136 @@ def run_reference_arm(args, cfg, workload):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
+
+class Leg:
+    """One workload on this rank's GPU: mesh resident in HBM (generated in place; with N > 1 ranks on the occupancy-only
+    path the rank keeps only the triangles that can reach its Z-slab — distributed once at ingest, outside any timed
+    region), parameters, and the reference's checksum to compare with."""
+
+    def __init__(self, engine, name, cfg, rank, world, device, broadcast=False):
+        import torch
+        import torch.distributed as dist
+
+        import obj2voxel_b200 as o2v
+        from obj2voxel_b200 import meshes, slabs
+
+        self.engine, self.name, self.cfg, self.rank, self.world, self.device = engine, name, cfg, rank, world, device
+        if cfg["kind"] == "sphere":
+            verts = torch.from_numpy(meshes.lumpy_sphere()).to(device)
+            uvs = None
+        elif broadcast and world > 1:
+            # the ingest rank owns the mesh and broadcasts it once (NCCL over NVLink)
+            n = cfg["n"]
+            if rank == 0:
+                verts = meshes.random_triangles_torch(n, cfg["extent"], seed=1, device=device)
+            else:
+                verts = torch.empty((n, 9), dtype=torch.float32, device=device)
+            uvs = None
+            if cfg.get("textured"):
+                uvs = meshes.random_uvs_torch(n, seed=2, device=device) if rank == 0 else \
+                    torch.empty((n, 6), dtype=torch.float32, device=device)
+            slabs.broadcast_mesh([verts, uvs], src=0)
+        else:
+            verts = meshes.random_triangles_torch(cfg["n"], cfg["extent"], seed=1, device=device)
+            uvs = meshes.random_uvs_torch(cfg["n"], seed=2, device=device) if cfg.get("textured") else None
+        self.n_tri = int(verts.shape[0])
+        self.textures = []
+        if uvs is not None:
+            self.textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(device), o2v.UV_WRAP)]
+        S = cfg["resolution"] * cfg["supersampling"]
+        self.bounds = slabs.equal_slabs(S, world)
+        z0, z1 = slabs.my_slab(self.bounds, rank)
+        self.empty = world > 1 and z0 == z1  # more ranks than rows: this rank owns nothing (and must not pass (0, 0))
+        kw = dict(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
+                  bounds=cfg["bounds"])
+        self.kw = kw
+        self.full_verts, self.full_uvs = verts, uvs
+        self.verts, self.uvs = verts, uvs
+        self.params = o2v.make_params(slab=(z0, z1) if world > 1 else None, **kw)
+        self.distributed_once = False
+        if world > 1 and uvs is None and not self.empty and cfg["bounds"] is not None:
+            # z-binned distribution: this rank keeps what can reach its slab (o2v_b200_filter_slab)
+            self.verts = engine.filter_slab(verts, self.params)
+            self.params = o2v.make_params(slab=(z0, z1), slab_filtered=1, **kw)
+            self.distributed_once = True
+        self.tri_bytes = 64 if uvs is not None else 36
+
+    def step(self, params=None):
+        if self.empty:
+            return None
+        return self.engine.voxelize_device(self.verts, params or self.params, uvs=self.uvs, textures=self.textures)
+
+    def result_check(self):
+        """(voxel count, record hash) of the last step on this rank, hash computed on the device."""
+        if self.empty:
+            return 0, 0
+        return self.engine.result_count(), self.engine.result_hash()
+
+
+def gather_check(leg, golden, dist_on):
+    """Sums the per-rank voxel counts and record hashes (mod 2^64) and compares with the reference's."""
+    import torch
+    import torch.distributed as dist
+
+    count, h = leg.result_check()
+    parts = [(count, h)]
+    if dist_on:
+        t = torch.tensor([count, h - (1 << 64) if h >= (1 << 63) else h], dtype=torch.int64, device=leg.device)
+        out = [torch.empty_like(t) for _ in range(leg.world)]
+        dist.all_gather(out, t)
+        parts = [(int(o[0].item()), int(o[1].item()) & ((1 << 64) - 1)) for o in out]
+    total = sum(p[0] for p in parts)
+    digest = sum(p[1] for p in parts) & ((1 << 64) - 1)
+    ref = golden.get(leg.name)
+    ok = None
+    if ref is not None and "hash64" in ref:
+        ok = bool(total == ref["voxels"] and digest == ref["hash64"])
+    return total, digest, ok
+
+
+def time_leg(leg, steps, warmup, sync_all, params=None):
+    """Device-resident steps: CUDA events on the stream the kernels run on; returns (elapsed ms over `steps`, last stats,
+    per-step kernel timings)."""
+    import torch
+
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = None
+    for _ in range(warmup):
+        stats = leg.step(params)
+    sync_all()
+    rows = []
+    start.record()
+    for _ in range(steps):
+        stats = leg.step(params)
+        if stats is not None:
+            rows.append(stats)
+    stop.record()
+    sync_all()
+    return start.elapsed_time(stop), stats, rows
+
+
+def side_config(engine, name, rank, world, device, sync_all, golden, steps):
+    """One of BASELINE.json's other named configs, measured like the headline (device-resident, max over ranks) and
+    checked against the reference's checksum; reported under `configs`, never as the headline."""
+    import torch
+    import torch.distributed as dist
+
+    cfg = workload_spec(name)
+    leg = Leg(engine, name, cfg, rank, world, device)
+    elapsed, stats, _rows = time_leg(leg, steps, 3, sync_all)
+    total, digest, ok = gather_check(leg, golden, world > 1)
+    t = torch.tensor([elapsed], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    out = {"mtri_per_s": leg.n_tri / (ms * 1e-3) / 1e6, "mvoxel_per_s": total / (ms * 1e-3) / 1e6, "ms_per_step": ms,
+           "triangles": leg.n_tri, "voxels": total, "hash64": digest, "hash_ok": ok, "steps": steps,
+           "path": "occupancy-only" if (stats is not None and stats["occupancy_path"]) else "weighted fold",
+           "config": config_dict(name, cfg, leg.n_tri, world)}
+    del leg
+    torch.cuda.empty_cache()
+    return out
+
 
 def run_ours(args, cfg, workload):
     import torch
@@ -256,103 +410,152 @@ def run_ours(args, cfg, workload):
         dist.init_process_group("nccl", device_id=device)
 
     engine = o2v.Engine(local)  # raises without a GPU: there is no fallback
-    S = cfg["resolution"] * cfg["supersampling"]
-
-    # ---- inputs resident in HBM; the ingest rank broadcasts the triangle array once (not timed) ----
-    if cfg["kind"] == "sphere":
-        verts = torch.from_numpy(meshes.lumpy_sphere()).to(device)
-        uvs = None
-    else:
-        n = cfg["n"]
-        if rank == 0:
-            verts = meshes.random_triangles_torch(n, cfg["extent"], seed=1, device=device)
-            uvs = meshes.random_uvs_torch(n, seed=2, device=device) if cfg.get("textured") else None
-        else:
-            verts = torch.empty((n, 9), dtype=torch.float32, device=device)
-            uvs = torch.empty((n, 6), dtype=torch.float32, device=device) if cfg.get("textured") else None
-        if distributed:
-            slabs.broadcast_mesh([verts, uvs], src=0)
-    n_tri = verts.shape[0]
-    textures = []
-    if uvs is not None:
-        textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(device), o2v.UV_WRAP)]
-
-    bounds = slabs.equal_slabs(S, world)
-    z0, z1 = slabs.my_slab(bounds, rank)
-    params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"],
-                             strategy=cfg["strategy"], bounds=cfg["bounds"], slab=(z0, z1) if distributed else None)
+    golden = golden_checksums()
 
     def sync_all():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    # ---- inputs resident in HBM; the ingest rank broadcasts the triangle array once, every rank keeps its slab's
+    # triangles (not timed) ----
+    leg = Leg(engine, workload, cfg, rank, world, device, broadcast=True)
+    n_tri = leg.n_tri
+    uvs = leg.uvs
+
     # ---- device-resident steps ----
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stats = None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()  # started before the warm-up (nvidia-smi takes a while to come up); samples are windowed
-    for _ in range(args.warmup):
-        stats = engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
-    sync_all()
+    time_leg(leg, 0, args.warmup, sync_all)
     sampler.mark()
-    kernel_ms, setup_ms, clip_ms, classify_ms, launches = [], [], [], [], 0
-    start.record()
-    for _ in range(args.steps):
-        stats = engine.voxelize_device(verts, params, uvs=uvs, textures=textures)
-        kernel_ms.append(stats["ms_voxelize"])
-        clip_ms.append(stats["ms_clip"])
-        classify_ms.append(stats["ms_classify"])
-        setup_ms.append(stats["ms_setup"])
-        launches += stats["kernel_launches"]
-    stop.record()
-    sync_all()
-    elapsed_ms = start.elapsed_time(stop)
+    elapsed_ms, stats, rows = time_leg(leg, args.steps, 0, sync_all)
     clocks = sampler.stop() if rank == 0 else None
+    if stats is None:  # a rank without rows
+        stats = {k: 0 for k in ("voxels", "contributions", "clip_calls", "leaves", "light_tiles", "heavy_tiles",
+                                "occupancy_path", "slab_triangles")}
+    kernel_ms = [r["ms_voxelize"] for r in rows] or [0.0]
+    setup_ms = [r["ms_setup"] for r in rows] or [0.0]
+    clip_ms = [r["ms_clip"] for r in rows] or [0.0]
+    classify_ms = [r["ms_classify"] for r in rows] or [0.0]
+    launches = sum(r["kernel_launches"] for r in rows)
     occupancy_path = bool(stats["occupancy_path"])
+    voxels, digest, hash_ok = gather_check(leg, golden, distributed)
+    if hash_ok is False:
+        raise RuntimeError("%s: %d voxels, record hash %d differ from the reference's (%s)" %
+                           (workload, voxels, digest, golden.get(workload)))
 
     # The same workload with the occupancy-only path switched off (weights and colours folded for every voxel): what a
     # coloured / textured mesh of this shape costs.  Reported beside the headline, not as the headline.
     weighted = None
     if occupancy_path and not distributed:
-        wparams = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"],
-                                  strategy=cfg["strategy"], bounds=cfg["bounds"], occupancy_path=0)
-        for _ in range(2):
-            wstats = engine.voxelize_device(verts, wparams, uvs=uvs, textures=textures)
-        sync_all()
+        wparams = o2v.make_params(occupancy_path=0, **leg.kw)
         wsteps = max(1, min(args.steps, 5))
-        wstart, wstop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        wstart.record()
-        for _ in range(wsteps):
-            wstats = engine.voxelize_device(verts, wparams, uvs=uvs, textures=textures)
-        wstop.record()
-        sync_all()
-        wms = wstart.elapsed_time(wstop) / wsteps
-        if wstats["voxels"] != stats["voxels"]:
-            raise RuntimeError("weighted path emitted %d voxels, occupancy path %d" % (wstats["voxels"], stats["voxels"]))
+        wms, wstats, _ = time_leg(leg, wsteps, 2, sync_all, params=wparams)
+        wms /= wsteps
+        wcount, wdigest = leg.result_check()
+        if wcount != voxels or wdigest != digest:
+            raise RuntimeError("weighted path: %d voxels / hash %d, occupancy path %d / %d" %
+                               (wcount, wdigest, voxels, digest))
         weighted = {"value": n_tri / (wms * 1e-3) / 1e6, "unit": "Mtri/s", "ms_per_step": wms,
                     "clip_calls": wstats["clip_calls"], "contributions": wstats["contributions"],
-                    "ms_clip_kernel": wstats["ms_clip"],
+                    "ms_clip_kernel": wstats["ms_clip"], "hash_ok": hash_ok,
                     "note": "same workload with occupancy_path=0: every (triangle, voxel) weight folded in reference "
-                            "order (what coloured / textured meshes cost); identical output"}
-        launches += 0  # not part of the timed region above
+                            "order (what coloured / textured meshes cost); identical records (same hash)"}
 
-    counts = [stats["voxels"], stats["contributions"], stats["clip_calls"], stats["leaves"], launches]
+    counts = [stats["contributions"], stats["clip_calls"], stats["leaves"], launches]
     tile_split = (stats["light_tiles"], stats["heavy_tiles"])
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         counts = slabs.allreduce_counts(counts, device)
     elapsed_ms = float(t.item())
-    voxels, contributions, clip_calls, leaves, launches = counts
+    contributions, clip_calls, leaves, launches = counts
     ms_per_step = elapsed_ms / args.steps
+    rank_tri = int(stats["slab_triangles"]) if occupancy_path else n_tri
+    rank_voxels = int(stats["voxels"])
 
     # ---- end to end with HOST buffers (H2D + kernels + D2H inside the timed region) ----
-    # N = 1: the reference-facing C API (obj2voxel instance, bulk input, voxel callback).
-    # N > 1: every rank uploads its 1/N share of the host triangle array from pinned memory, the shares are all-gathered
-    #        over NVLink (the "triangles broadcast once" of the slab scheme; no voxel data is exchanged), each rank
-    #        voxelizes its Z-slab through the Engine API and downloads its own voxels into pinned host memory.
+    e2e = run_e2e(args, cfg, leg, engine, rank, world, device, sync_all, voxels, golden)
+
+    # ---- BASELINE.json's other named configs, same measurement, each checked against the reference's checksum ----
+    leg_bounds = leg.bounds
+    del leg
+    torch.cuda.empty_cache()
+    side = {}
+    side_steps = max(1, min(args.steps, 5))
+    for name in ("cfg2", "cfg3", "cfg5"):
+        if name != workload and os.environ.get("O2V_BENCH_SIDE", "1") != "0":
+            side[name] = side_config(engine, name, rank, world, device, sync_all, golden, side_steps)
+
+    if rank == 0:
+        peak, peak_source = measured_peak()
+        tri_bytes = 64 if uvs is not None else 36  # SURVEY §8d: algorithmic read per triangle
+        # dominant kernel of the step, by its live CUDA-event duration: the SAT classification kernel on the occupancy-only
+        # path, the exact clip otherwise; one launch processes this rank's whole slab
+        k_ms = float(np.mean(kernel_ms))
+        c_ms = float(np.mean(clip_ms))
+        f_ms = float(np.mean(classify_ms))
+        dominant, d_ms = ("occupancyClassifyKernel", f_ms) if f_ms > c_ms else \
+            ("occupancyClipKernel" if occupancy_path else "sparseClipKernel", c_ms)
+        # algorithmic bytes of ONE launch on THIS rank: its slab's triangles (what the z-binned ingest left it) and the
+        # voxels it emits
+        alg_bytes = 16 * rank_voxels + tri_bytes * rank_tri
+        achieved = alg_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
+        traffic = profiled_traffic(workload, dominant) if world == 1 else None
+        baseline = cpu_baseline(cfg) if world == 1 else None
+        line = {
+            "metric": "triangles_per_second", "value": n_tri / (ms_per_step * 1e-3) / 1e6, "unit": "Mtri/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(workload, cfg, n_tri, world),
+            "slab_bounds": leg_bounds if distributed else None,
+            "mvoxel_per_s": voxels / (ms_per_step * 1e-3) / 1e6, "voxels": voxels, "hash64": digest, "hash_ok": hash_ok,
+            "contributions": contributions,
+            "clip_calls": clip_calls, "leaves": leaves, "light_tiles_rank0": tile_split[0],
+            "heavy_tiles_rank0": tile_split[1],
+            "ms_setup_rank0": float(np.mean(setup_ms)), "ms_voxelize_rank0": k_ms, "ms_clip_kernel_rank0": c_ms,
+            "ms_classify_kernel_rank0": f_ms,
+            "path": "occupancy-only (every triangle MATERIALLESS: output colour is white whatever the weights)"
+                    if occupancy_path else "weighted fold",
+            "hbm_write_gbs": 16 * voxels / (ms_per_step * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_source, "rank0_triangles": rank_tri, "rank0_voxels": rank_voxels,
+                         "note": "rank 0: algorithmic bytes = 16 B x its voxels + %d B x its slab's triangles per launch / "
+                                 "CUDA-event duration of its dominant kernel; traffic is an ncu capture at N = 1 only"
+                                 % tri_bytes},
+            "e2e": e2e,
+            "configs": side,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if weighted is not None:
+            line["weighted_path"] = weighted
+        if baseline is not None:
+            line["cpu_baseline"] = baseline
+        print(json.dumps(line), flush=True)
+    engine.close()
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, cfg, leg, engine, rank, world, device, sync_all, voxels, golden):
+    """End to end with HOST buffers.
+    N = 1: the reference-facing C API (obj2voxel instance, bulk input, voxel callback).
+    N > 1: every rank uploads its 1/N share of the host triangle array from pinned memory, the shares are all-gathered
+           over NVLink, each rank voxelizes its Z-slab through the Engine API and downloads its own voxels into pinned
+           host memory."""
+    import torch
+    import torch.distributed as dist
+
+    import obj2voxel_b200 as o2v
+    from obj2voxel_b200 import meshes, slabs
+
+    distributed = world > 1
+    verts, uvs, n_tri = leg.full_verts, leg.full_uvs, leg.n_tri
     pinned_verts = torch.empty(verts.shape, dtype=verts.dtype, pin_memory=True)
     pinned_verts.copy_(verts)
     host_verts = pinned_verts.numpy()
@@ -398,6 +601,7 @@ def run_ours(args, cfg, workload):
         e2e_api = ("obj2voxel_b200_set_input_triangles + obj2voxel_voxelize + voxel callback (the job runs in 4 z parts: "
                    "the download of one under the kernels of the next)")
     else:
+        params = o2v.make_params(slab=slabs.my_slab(leg.bounds, rank), **leg.kw)
         per_rank = -(-n_tri // world)
         lo, hi = min(rank * per_rank, n_tri), min((rank + 1) * per_rank, n_tri)
         share_v = torch.zeros((per_rank, 9), dtype=torch.float32, device=device)
@@ -406,7 +610,8 @@ def run_ours(args, cfg, workload):
         if uvs is not None:
             share_u = torch.zeros((per_rank, 6), dtype=torch.float32, device=device)
             full_u = torch.empty((per_rank * world, 6), dtype=torch.float32, device=device)
-        out_pinned = torch.empty((max(int(stats["voxels"] * 1.1) + 1024, 1), 4), dtype=torch.int32, pin_memory=True)
+        out_pinned = torch.empty((max(int(engine.result_count() * 1.1) + 1024, 1), 4), dtype=torch.int32,
+                                 pin_memory=True)
         out_np = out_pinned.numpy().view(np.uint32)
         stream = torch.cuda.current_stream(device).cuda_stream
         for step in range(1 + e2e_steps):
@@ -417,9 +622,11 @@ def run_ours(args, cfg, workload):
             if uvs is not None:
                 share_u[: hi - lo].copy_(pinned_uvs[lo:hi], non_blocking=True)
                 dist.all_gather_into_tensor(full_u, share_u)
-            st = engine.voxelize_device(full_v[:n_tri], params, uvs=None if uvs is None else full_u[:n_tri],
-                                        textures=textures)
-            got = engine.download(out=out_np, stream=stream)
+            got = []
+            if not leg.empty:
+                engine.voxelize_device(full_v[:n_tri], params, uvs=None if uvs is None else full_u[:n_tri],
+                                       textures=leg.textures)
+                got = engine.download(out=out_np, stream=stream)
             torch.cuda.synchronize(device)
             dt = time.perf_counter() - t0
             if step > 0:
@@ -435,62 +642,9 @@ def run_ours(args, cfg, workload):
     e2e_seconds = float(e2e_t.item())
     if e2e_counts[0] != voxels:
         raise RuntimeError("e2e voxel count %d != device-resident count %d" % (e2e_counts[0], voxels))
-
-    if rank == 0:
-        peak, peak_source = measured_peak()
-        tri_bytes = 64 if uvs is not None else 36  # SURVEY §8d: algorithmic read per triangle
-        # dominant kernel of the step, by its live CUDA-event duration: the SAT classification kernel on the occupancy-only
-        # path, the exact clip otherwise; one launch processes this rank's whole slab
-        k_ms = float(np.mean(kernel_ms))
-        c_ms = float(np.mean(clip_ms))
-        f_ms = float(np.mean(classify_ms))
-        dominant, d_ms = ("occupancyClassifyKernel", f_ms) if f_ms > c_ms else \
-            ("occupancyClipKernel" if occupancy_path else "sparseClipKernel", c_ms)
-        alg_bytes = 16 * stats["voxels"] + tri_bytes * n_tri
-        achieved = alg_bytes / (d_ms * 1e-3) / 1e9 if d_ms > 0 else 0.0
-        traffic = profiled_traffic(workload, dominant)
-        baseline = cpu_baseline(cfg) if world == 1 else None
-        line = {
-            "metric": "triangles_per_second", "value": n_tri / (ms_per_step * 1e-3) / 1e6, "unit": "Mtri/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "description": WORKLOADS[workload], "triangles": n_tri,
-                       "resolution": cfg["resolution"], "supersampling": cfg["supersampling"],
-                       "strategy": "blend" if cfg["strategy"] else "max",
-                       "partition": "z-slabs %s" % bounds if distributed else "single GPU, whole grid",
-                       "l2": "inputs (%d MB of triangles) exceed the 126 MB L2; no explicit flush" %
-                             (n_tri * tri_bytes // 1000000)},
-            "mvoxel_per_s": voxels / (ms_per_step * 1e-3) / 1e6, "voxels": voxels, "contributions": contributions,
-            "clip_calls": clip_calls, "leaves": leaves, "light_tiles_rank0": tile_split[0],
-            "heavy_tiles_rank0": tile_split[1],
-            "ms_setup_rank0": float(np.mean(setup_ms)), "ms_voxelize_rank0": k_ms, "ms_clip_kernel_rank0": c_ms,
-            "ms_classify_kernel_rank0": f_ms,
-            "path": "occupancy-only (every triangle MATERIALLESS: output colour is white whatever the weights)"
-                    if occupancy_path else "weighted fold",
-            "hbm_write_gbs": 16 * stats["voxels"] / (ms_per_step * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic // world) if traffic else None,
-                         "peak_source": peak_source,
-                         "note": "algorithmic bytes = 16 B x voxels + %d B x triangles per launch / CUDA-event duration of "
-                                 "the dominant kernel; the kernel is bound by instruction issue / latency of the "
-                                 "triangle-box predicates, not by HBM — see DESIGN.md section 4" % tri_bytes},
-            "e2e": {"value": n_tri / e2e_seconds / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_seconds * 1e3,
-                    "h2d_bytes_per_step": int(n_tri * tri_bytes), "d2h_bytes_per_step": int(16 * voxels),
-                    "api": e2e_api},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        if weighted is not None:
-            line["weighted_path"] = weighted
-        if baseline is not None:
-            line["cpu_baseline"] = baseline
-        print(json.dumps(line), flush=True)
-    engine.close()
-    if distributed:
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    return {"value": n_tri / e2e_seconds / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_seconds * 1e3,
+            "h2d_bytes_per_step": int(n_tri * leg.tri_bytes), "d2h_bytes_per_step": int(16 * voxels),
+            "api": e2e_api}
 
 
 def main():

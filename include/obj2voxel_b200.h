@@ -42,6 +42,8 @@ typedef struct o2v_b200_params {
     int32_t variant;            /* kernel A/B switch, -1 = default (occupancy-only path: 1 / 2 force the block-per-batch /
                                  * thread-per-leaf classifier; both give the same records) */
     int32_t prefilter;          /* 1 = conservative SAT prefilter on (default); 0 = off (validation only) */
+    int32_t slab_filtered;      /* 1 = mesh is the output of o2v_b200_filter_slab() for this very slab: the step skips
+                                 * its own filter pass (multi-GPU ingest distributes triangles by z range once) */
     int32_t occupancy_path;     /* 1 (default) = meshes whose every triangle is MATERIALLESS (output colour is white
                                  * whatever the weights, reference src/triangle.hpp:186) take the occupancy-only path;
                                  * 0 = always fold weights and colours (validation / measurement) */
@@ -85,6 +87,8 @@ typedef struct o2v_b200_stats {
     int32_t occupancy_path;     /* 1 = this run took the occupancy-only path (survivors = voxels the SAT left undecided) */
     float ms_classify;          /* occupancy-only path: duration of the SAT classification kernel, CUDA events */
     float reserved;
+    uint64_t slab_triangles;    /* occupancy-only path: triangles the step worked on (all of them, or what the slab filter
+                                 * kept on a rank / job part that owns a part of the grid) */
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */
@@ -104,6 +108,20 @@ int o2v_b200_voxelize_device(o2v_b200_engine *engine, const o2v_b200_params *par
 const void *o2v_b200_result_device(const o2v_b200_engine *engine);
 uint64_t o2v_b200_result_count(const o2v_b200_engine *engine);
 int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda_stream);
+
+/* Multi-GPU ingest on the occupancy-only path (all-MATERIALLESS meshes): copies the triangles of the DEVICE mesh whose z
+ * range can reach the slab [slab_z0, slab_z1) of `params` into an engine-owned dense device array (*out_kept: 9 floats
+ * per triangle, arbitrary order, valid until the next call).  Voxelizing that array with slab_filtered = 1 gives the
+ * slab's records without touching the rest of the mesh again — the "triangles distributed once" of the Z-slab scheme
+ * (the reference re-tests every triangle against every chunk it might touch: src/obj2voxel.cpp:211-243). */
+int o2v_b200_filter_slab(o2v_b200_engine *engine, const o2v_b200_params *params, const o2v_b200_mesh *mesh,
+                         void *cuda_stream, const float **out_kept, uint64_t *out_count);
+
+/* Order-independent 64-bit checksum of the last run's records, computed on the device: the sum mod 2^64 over the records
+ * of splitmix64_finalise((x + (y << 21) + (z << 42)) ^ (argb * 0x9E3779B97F4A7C15)).  Z-slabs / job parts / ranks add their
+ * sums; the total equals the same sum over the reference's output (voxelio Voxel32 list, src/io.cpp:638-653) whatever the
+ * order, so a multi-GPU job is verified without gathering records. */
+int o2v_b200_result_hash(o2v_b200_engine *engine, void *cuda_stream, uint64_t *out_hash);
 
 /* Host-buffer convenience: uploads the mesh (and textures), runs, downloads up to out_capacity records into out_voxels
  * (4 u32 each).  *out_count receives the number of voxels produced (may exceed out_capacity: then nothing past the

@@ -28,7 +28,7 @@ class Params(C.Structure):
     _fields_ = [("resolution", C.c_uint32), ("supersampling", C.c_uint32), ("strategy", C.c_uint32),
                 ("bounds_known", C.c_uint32), ("bounds", C.c_float * 6), ("unit_transform", C.c_int32 * 9),
                 ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("variant", C.c_int32), ("prefilter", C.c_int32),
-                ("occupancy_path", C.c_int32)]
+                ("slab_filtered", C.c_int32), ("occupancy_path", C.c_int32)]
 
 
 class Mesh(C.Structure):
@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("transform", C.c_float * 12), ("kernel_launches", C.c_int32), ("voxelize_launches", C.c_int32),
                 ("light_tiles", C.c_uint64), ("heavy_tiles", C.c_uint64), ("survivors", C.c_uint64),
                 ("ms_clip", C.c_float), ("occupancy_path", C.c_int32),
-                ("ms_classify", C.c_float), ("reserved", C.c_float)]
+                ("ms_classify", C.c_float), ("reserved", C.c_float), ("slab_triangles", C.c_uint64)]
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "transform"}
@@ -76,7 +76,7 @@ ADDITIVE_SYMBOLS = [
     "o2v_b200_engine_create", "o2v_b200_engine_destroy", "o2v_b200_last_error", "o2v_b200_sm_count",
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
     "o2v_b200_result_download", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
-    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts",
+    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab",
 ]
 
 
@@ -141,6 +141,9 @@ def load():
         "o2v_b200_result_device": (vp, [vp]),
         "o2v_b200_result_count": (C.c_uint64, [vp]),
         "o2v_b200_result_download": (C.c_int, [vp, vp, vp]),
+        "o2v_b200_result_hash": (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
+        "o2v_b200_filter_slab": (C.c_int, [vp, C.POINTER(Params), C.POINTER(Mesh), vp, C.POINTER(vp),
+                                           C.POINTER(C.c_uint64)]),
         "o2v_b200_voxelize_host": (C.c_int, [vp, C.POINTER(Params), C.POINTER(Mesh), C.POINTER(Texture), u32,
                                              C.POINTER(C.c_uint32), C.c_uint64, C.POINTER(C.c_uint64),
                                              C.POINTER(Stats)]),

@@ -208,7 +208,7 @@ def sort_voxels(voxels):
 
 
 def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None, unit=None, slab=None, variant=-1,
-                prefilter=1, occupancy_path=1):
+                prefilter=1, occupancy_path=1, slab_filtered=0):
     p = Params()
     _lib.load().o2v_b200_default_params(C.byref(p))
     p.resolution = resolution
@@ -224,6 +224,7 @@ def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None,
     p.variant = variant
     p.prefilter = prefilter
     p.occupancy_path = occupancy_path
+    p.slab_filtered = slab_filtered
     return p
 
 
@@ -301,6 +302,40 @@ class Engine:
                                          "data": (int(self._lib.o2v_b200_result_device(self.handle)), False),
                                          "version": 2}
         return torch.as_tensor(view, device="cuda:%d" % self.device)
+
+    def filter_slab(self, verts, params, stream=None):
+        """Multi-GPU ingest (o2v_b200_filter_slab): the triangles of the CUDA tensor `verts` whose z range can reach the
+        slab of `params`, as a new (k, 9) CUDA tensor (copied out of the engine-owned array), arbitrary order."""
+        import torch
+
+        assert verts.is_cuda and verts.is_contiguous() and verts.dtype == torch.float32
+        mesh = Mesh(verts.data_ptr(), None, None, None, None, verts.numel() // 9)
+        if stream is None:
+            stream = torch.cuda.current_stream(verts.device).cuda_stream
+        kept, count = C.c_void_p(), C.c_uint64()
+        rc = self._lib.o2v_b200_filter_slab(self.handle, C.byref(params), C.byref(mesh), C.c_void_p(stream),
+                                            C.byref(kept), C.byref(count))
+        if rc != 0:
+            raise DeviceError("o2v_b200_filter_slab failed (%d): %s" % (rc, self._lib.o2v_b200_last_error().decode()))
+        n = int(count.value)
+        if n == 0:
+            return torch.zeros((0, 9), dtype=torch.float32, device=verts.device)
+
+        class _View:
+            pass
+
+        view = _View()
+        view.__cuda_array_interface__ = {"shape": (n, 9), "typestr": "<f4", "data": (int(kept.value), False),
+                                         "version": 2}
+        return torch.as_tensor(view, device=verts.device).clone()
+
+    def result_hash(self, stream=None):
+        """Order-independent 64-bit checksum of the last result, computed on the device (meshes.record_hash on the host)."""
+        h = C.c_uint64()
+        rc = self._lib.o2v_b200_result_hash(self.handle, C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise DeviceError(self._lib.o2v_b200_last_error().decode())
+        return int(h.value)
 
     def download(self, out=None, stream=None):
         """Copies the last result to host memory: numpy (n, 4) uint32."""

@@ -168,6 +168,7 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->occupancy_path = in.occupancyPath ? 1 : 0;
     out->ms_classify = in.msClassify;
     out->reserved = 0.0f;
+    out->slab_triangles = in.slabTriangles;
 }
 
 constexpr uint32_t kMaxJobParts = 128;  // a part is at least one 64-voxel chunk row; sample resolution <= 8192
@@ -244,6 +245,7 @@ EngineParams paramsFromC(const o2v_b200_params &p)
     e.variant = p.variant;
     e.prefilter = p.prefilter;
     e.occupancyPath = p.occupancy_path;
+    e.slabFiltered = p.slab_filtered != 0;
     return e;
 }
 
@@ -1136,6 +1138,33 @@ int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda
     if (rc != 0) {
         gLastError = engine->engine->lastError();
     }
+    return rc;
+}
+
+int o2v_b200_filter_slab(o2v_b200_engine *engine, const o2v_b200_params *params, const o2v_b200_mesh *mesh,
+                         void *cuda_stream, const float **out_kept, uint64_t *out_count)
+{
+    MeshView view{};
+    view.verts = mesh->verts;
+    view.count = mesh->count;
+    unsigned long long count = 0;
+    const int rc = engine->engine->filterSlab(view, paramsFromC(*params), static_cast<cudaStream_t>(cuda_stream),
+                                              out_kept, &count);
+    if (rc != 0) {
+        gLastError = engine->engine->lastError();
+    }
+    *out_count = count;
+    return rc;
+}
+
+int o2v_b200_result_hash(o2v_b200_engine *engine, void *cuda_stream, uint64_t *out_hash)
+{
+    unsigned long long hash = 0;
+    const int rc = engine->engine->resultHash(static_cast<cudaStream_t>(cuda_stream), &hash);
+    if (rc != 0) {
+        gLastError = engine->engine->lastError();
+    }
+    *out_hash = hash;
     return rc;
 }
 

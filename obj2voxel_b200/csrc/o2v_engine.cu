@@ -132,6 +132,53 @@ int Engine::fail(int code, const std::string &message)
     return code;
 }
 
+/// Bounds (given or computed on the device), the exact mesh transform and this run's slab: everything of GridView.
+int Engine::setupGrid(const MeshView &mesh, const EngineParams &params, cudaStream_t stream, RunStats &st, GridView &grid,
+                      bool *emptySlab)
+{
+    RunCounters *dCounters = counters_.as<RunCounters>();
+    const uint32_t S = params.resolution * params.supersampling;
+    // ---- bounds + transform (src/obj2voxel.cpp:475-482) ----
+    float meshMin[3], meshMax[3];
+    if (params.boundsKnown) {
+        memcpy(meshMin, params.bounds, sizeof meshMin);
+        memcpy(meshMax, params.bounds + 3, sizeof meshMax);
+    }
+    else {
+        launchBounds(mesh, dCounters, stream);
+        launchFinishBounds(dCounters, stream);
+        st.kernelLaunches += 2;
+        launchPublishCounters(dCounters, hostCountersDevice_, stream);
+        ++st.kernelLaunches;
+        O2V_CUDA(cudaStreamSynchronize(stream));
+        memcpy(meshMin, hostCounters_->boundsMin, sizeof meshMin);
+        memcpy(meshMax, hostCounters_->boundsMax, sizeof meshMax);
+    }
+
+    computeMeshTransform(meshMin, meshMax, S, params.unitTransform, grid.xf);
+    memcpy(st.transform, grid.xf, sizeof st.transform);
+    grid.sampleRes = S;
+    grid.gridExtent = (S + 63u) / 64u * 64u;
+    grid.tilesPerAxis = grid.gridExtent / kTileEdge;
+    const uint32_t gridZ = (S + 63u) / 64u * 64u;
+    uint32_t z0 = params.slabZ0, z1 = params.slabZ1;
+    if (z0 == 0 && z1 == 0) {
+        z1 = gridZ;
+    }
+    z1 = std::min(z1, gridZ);
+    if (z0 % kTileEdge != 0 || z1 % kTileEdge != 0 || z0 > z1) {
+        return fail(kErrBadParams, "slab bounds must be multiples of 8 with z0 <= z1");
+    }
+    grid.slabZ0 = z0;
+    grid.slabZ1 = z1;
+    grid.slabTileZ0 = z0 / kTileEdge;
+    grid.slabTileZCount = (z1 - z0) / kTileEdge;
+    grid.supersampling = params.supersampling;
+    grid.strategy = params.strategy;
+    *emptySlab = grid.slabTileZCount == 0;
+    return kErrOk;
+}
+
 int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
                      const EngineParams &params, cudaStream_t stream, RunStats *stats)
 {
@@ -171,45 +218,12 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         return kErrOk;  // src/obj2voxel.cpp:590-594: empty model, empty output
     }
 
-    // ---- bounds + transform (src/obj2voxel.cpp:475-482) ----
-    float meshMin[3], meshMax[3];
-    if (params.boundsKnown) {
-        memcpy(meshMin, params.bounds, sizeof meshMin);
-        memcpy(meshMax, params.bounds + 3, sizeof meshMax);
-    }
-    else {
-        launchBounds(mesh, dCounters, stream);
-        launchFinishBounds(dCounters, stream);
-        st.kernelLaunches += 2;
-        launchPublishCounters(dCounters, hostCountersDevice_, stream);
-        ++st.kernelLaunches;
-        O2V_CUDA(cudaStreamSynchronize(stream));
-        memcpy(meshMin, hostCounters_->boundsMin, sizeof meshMin);
-        memcpy(meshMax, hostCounters_->boundsMax, sizeof meshMax);
-    }
-
     GridView grid;
-    computeMeshTransform(meshMin, meshMax, S, params.unitTransform, grid.xf);
-    memcpy(st.transform, grid.xf, sizeof st.transform);
-    grid.sampleRes = S;
-    grid.gridExtent = (S + 63u) / 64u * 64u;
-    grid.tilesPerAxis = grid.gridExtent / kTileEdge;
-    const uint32_t gridZ = grid.gridExtent;
-    uint32_t z0 = params.slabZ0, z1 = params.slabZ1;
-    if (z0 == 0 && z1 == 0) {
-        z1 = gridZ;
+    bool emptySlab = false;
+    if (const int rc = setupGrid(mesh, params, stream, st, grid, &emptySlab)) {
+        return rc;
     }
-    z1 = std::min(z1, gridZ);
-    if (z0 % kTileEdge != 0 || z1 % kTileEdge != 0 || z0 > z1) {
-        return fail(kErrBadParams, "slab bounds must be multiples of 8 with z0 <= z1");
-    }
-    grid.slabZ0 = z0;
-    grid.slabZ1 = z1;
-    grid.slabTileZ0 = z0 / kTileEdge;
-    grid.slabTileZCount = (z1 - z0) / kTileEdge;
-    grid.supersampling = params.supersampling;
-    grid.strategy = params.strategy;
-    if (grid.slabTileZCount == 0) {
+    if (emptySlab) {
         return kErrOk;
     }
     if (occupancy) {
@@ -442,7 +456,9 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
 {
     RunCounters *dCounters = counters_.as<RunCounters>();
     MeshView mesh = meshIn;
-    const bool partOfGrid = grid.slabZ0 != 0 || grid.slabZ1 < grid.gridExtent;
+    // slabFiltered: the caller's array already is what filterSlab() keeps for this slab (multi-GPU ingest distributes the
+    // triangles by z range once; a step then never touches the rest of the mesh)
+    const bool partOfGrid = (grid.slabZ0 != 0 || grid.slabZ1 < grid.gridExtent) && !params.slabFiltered;
     if (partOfGrid) {
         // One rank of several: keep only the triangles whose z range can reach the slab (one streaming pass over the
         // mesh); everything after works on that share.  How many were kept stays on the device until the count pass is
@@ -485,6 +501,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     if (partOfGrid) {
         mesh.count = hostCounters_->slabTriangles;
     }
+    st.slabTriangles = mesh.count;
     const size_t n = (size_t) mesh.count;  // triangles the passes work on = first-leaf slots
     occ.firstLeaves = (uint32_t) n;
     const unsigned long long extraLeaves = hostCounters_->extraLeaves;
@@ -633,6 +650,59 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
     cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evClipStart_);
     cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
+    return kErrOk;
+}
+
+int Engine::filterSlab(const MeshView &mesh, const EngineParams &params, cudaStream_t stream, const float **kept,
+                       unsigned long long *keptCount)
+{
+    error_.clear();
+    *kept = nullptr;
+    *keptCount = 0;
+    if (params.resolution == 0 || params.supersampling == 0 || params.supersampling > 2 ||
+        (unsigned long long) params.resolution * params.supersampling > 8192ull) {
+        return fail(kErrBadParams, "resolution must be > 0 (sample resolution <= 8192), supersampling 1 or 2");
+    }
+    O2V_CUDA(cudaSetDevice(device_));
+    RunCounters *dCounters = counters_.as<RunCounters>();
+    O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+    if (mesh.count == 0) {
+        return kErrOk;
+    }
+    RunStats st;
+    GridView grid;
+    bool emptySlab = false;
+    if (const int rc = setupGrid(mesh, params, stream, st, grid, &emptySlab)) {
+        return rc;
+    }
+    if (emptySlab) {
+        return kErrOk;
+    }
+    if (!slabKept_.ensure((size_t) mesh.count * 9 * sizeof(float))) {
+        return fail(kErrOutOfMemory, "device allocation failed (slab triangles)");
+    }
+    launchOccupancySlabFilter(mesh, grid, slabKept_.as<float>(), dCounters, smCount_, stream);
+    launchPublishCounters(dCounters, hostCountersDevice_, stream);
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
+    *kept = slabKept_.as<float>();
+    *keptCount = hostCounters_->slabTriangles;
+    return kErrOk;
+}
+
+int Engine::resultHash(cudaStream_t stream, unsigned long long *out)
+{
+    *out = 0;
+    O2V_CUDA(cudaSetDevice(device_));
+    if (!hash_.ensure(sizeof(unsigned long long))) {
+        return fail(kErrOutOfMemory, "device allocation failed (record hash)");
+    }
+    O2V_CUDA(cudaMemsetAsync(hash_.as<void>(), 0, sizeof(unsigned long long), stream));
+    if (voxelCount_ != 0) {
+        launchRecordHash(out_.as<VoxelRecord>(), voxelCount_, hash_.as<unsigned long long>(), smCount_, stream);
+    }
+    O2V_CUDA(cudaMemcpyAsync(out, hash_.as<void>(), sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
     return kErrOk;
 }
 

@@ -30,6 +30,7 @@ struct EngineParams {
     int variant = -1;                 // -1 = default kernel variant
     int prefilter = 1;
     int occupancyPath = 1;            // 1 = all-MATERIALLESS meshes take the occupancy-only path; 0 = always fold weights
+    bool slabFiltered = false;        // the mesh is the output of filterSlab() for this very slab: skip the filter pass
 };
 
 struct RunStats {
@@ -44,6 +45,7 @@ struct RunStats {
     int kernelLaunches = 0;
     unsigned long long outCapacity = 0;
     bool occupancyPath = false;  // this run took the occupancy-only path
+    unsigned long long slabTriangles = 0;  // occupancy-only path: triangles the passes worked on (= kept by the slab filter)
 };
 
 class DeviceBuffer {
@@ -96,6 +98,16 @@ public:
     /// Copies the result of the last run to host memory (count * 16 bytes) on `stream` and synchronises it.
     int download(void *hostDst, cudaStream_t stream);
 
+    /// The ingest step of a multi-GPU job on the occupancy-only path: copies the triangles of `mesh` whose z range can
+    /// reach the slab of `params` into an engine-owned dense array (*kept, valid until the next filterSlab).  A later
+    /// voxelize() on that array with EngineParams::slabFiltered never reads the rest of the mesh.  Order is arbitrary.
+    int filterSlab(const MeshView &mesh, const EngineParams &params, cudaStream_t stream, const float **kept,
+                   unsigned long long *keptCount);
+
+    /// Order-independent 64-bit checksum of the last run's records, computed on the device (see launchRecordHash):
+    /// parts of a job and ranks of a multi-GPU job add theirs, and the sum is comparable with the reference's.
+    int resultHash(cudaStream_t stream, unsigned long long *out);
+
     /// Engine-owned pinned host buffer `slot` (0 or 1) of at least `bytes` (grow-only); nullptr if pinning fails.
     void *pinnedStaging(int slot, size_t bytes);
 
@@ -104,6 +116,8 @@ private:
     int fail(int code, const std::string &message);
     /// The occupancy-only pipeline (o2v_occupancy.cu) for an all-MATERIALLESS mesh; kOccupancyFallback if its bitmaps do
     /// not fit device memory (the caller then runs the weighted pipeline).
+    int setupGrid(const MeshView &mesh, const EngineParams &params, cudaStream_t stream, RunStats &st, GridView &grid,
+                  bool *emptySlab);
     int voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid, cudaStream_t stream,
                           RunStats &st);
     static constexpr int kOccupancyFallback = 1;
@@ -122,11 +136,11 @@ private:
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
     cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr;
 
-    DeviceBuffer counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
+    DeviceBuffer hash_, counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
-    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_, extraLeaves_;  // occupancy-only path
+    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_, slabKept_, extraLeaves_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

@@ -705,6 +705,38 @@ void launchPublishCounters(const RunCounters *counters, RunCounters *hostMapped,
     publishCountersKernel<<<1, 64, 0, stream>>>(counters, hostMapped);
 }
 
+/// Order-independent checksum of a record set: sum mod 2^64 of the splitmix64 finaliser of
+/// x + (y << 21) + (z << 42) xor argb * 0x9E3779B97F4A7C15 (obj2voxel_b200/meshes.py record_hash is the host twin).
+__global__ void __launch_bounds__(256)
+recordHashKernel(const VoxelRecord *__restrict__ records, unsigned long long count, unsigned long long *sum)
+{
+    unsigned long long local = 0;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const int4 r = __ldcs(reinterpret_cast<const int4 *>(records + i));
+        unsigned long long k = (unsigned long long) (uint32_t) r.x + ((unsigned long long) (uint32_t) r.y << 21) +
+                               ((unsigned long long) (uint32_t) r.z << 42);
+        k ^= (unsigned long long) (uint32_t) r.w * 0x9E3779B97F4A7C15ull;
+        k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ull;
+        k = (k ^ (k >> 27)) * 0x94D049BB133111EBull;
+        local += k ^ (k >> 31);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        local += __shfl_xor_sync(0xffffffffu, local, o);
+    }
+    if ((threadIdx.x & 31) == 0 && local != 0) {
+        atomicAdd(sum, local);
+    }
+}
+
+void launchRecordHash(const VoxelRecord *records, unsigned long long count, unsigned long long *sum, int smCount,
+                      cudaStream_t stream)
+{
+    unsigned long long blocks = (count + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > (unsigned long long) smCount * 8 ? (unsigned long long) smCount * 8 : blocks);
+    recordHashKernel<<<(unsigned) blocks, 256, 0, stream>>>(records, count, sum);
+}
+
 void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
 {
     finishBoundsKernel<<<1, 32, 0, stream>>>(counters);

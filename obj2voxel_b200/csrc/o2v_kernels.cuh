@@ -117,6 +117,9 @@ struct TileWork {
 void launchBounds(const MeshView &mesh, RunCounters *counters, cudaStream_t stream);
 void launchFinishBounds(RunCounters *counters, cudaStream_t stream);
 void launchPublishCounters(const RunCounters *counters, RunCounters *hostMapped, cudaStream_t stream);
+/// *sum += the order-independent 64-bit checksum of `count` records (o2v_kernels.cu: recordHashKernel).
+void launchRecordHash(const VoxelRecord *records, unsigned long long count, unsigned long long *sum, int smCount,
+                      cudaStream_t stream);
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
                        uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream);

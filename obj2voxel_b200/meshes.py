@@ -49,6 +49,21 @@ def uniform_torch(start, count, seed, device):
     return lsr(z, 40).to(torch.float32) * (2.0 ** -24)
 
 
+def record_hash(voxels):
+    """Order-independent 64-bit checksum of a set of (x, y, z, argb) records (any order, numpy (n, 4) uint32): the sum mod
+    2^64 of the splitmix64 finaliser of x + (y << 21) + (z << 42) xor argb * 0x9E3779B97F4A7C15.  The device computes the
+    same sum over an engine's result (o2v_b200_result_hash) and ranks add their parts, so a multi-GPU job is checked against
+    the reference without gathering a single record."""
+    v = np.asarray(voxels).reshape(-1, 4).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        k = v[:, 0] + (v[:, 1] << np.uint64(21)) + (v[:, 2] << np.uint64(42))
+        k = k ^ (v[:, 3] * np.uint64(_GOLDEN))
+        k = (k ^ (k >> np.uint64(30))) * np.uint64(_M1)
+        k = (k ^ (k >> np.uint64(27))) * np.uint64(_M2)
+        k = k ^ (k >> np.uint64(31))
+        return int(np.sum(k, dtype=np.uint64))
+
+
 def single_triangle():
     """cfg1: (0,0,0),(0,0,1),(1,0,0) — reference test/main.cpp:15-19."""
     return np.array([[0, 0, 0, 0, 0, 1, 1, 0, 0]], dtype=np.float32)

@@ -1,5 +1,6 @@
 """Runs the UNMODIFIED reference (oracle/_ref, built from /root/reference) on BASELINE.json's full-size configurations and
-records voxel count + CRC32 of the sorted (x, y, z, argb) list in tests/golden/full_size_checksums.json.  CPU only, takes
+records voxel count, CRC32 of the sorted (x, y, z, argb) list and the order-independent 64-bit record hash
+(meshes.record_hash: what bench.py all-reduces across ranks) in tests/golden/full_size_checksums.json.  CPU only, takes
 minutes to tens of minutes; run in the build container: `python tests/golden/make_full_size_checksums.py cfg2 cfg3 cfg4`.
 
 cfg4 uses supersampling 2: the reference build with the two-line downscale fix (oracle/downscale_fix.sed) is used; the mesh
@@ -36,7 +37,7 @@ def main():
         v = np.ascontiguousarray(r["voxels"])
         results[name] = dict(triangles=int(len(verts)), resolution=cfg["resolution"],
                              supersampling=cfg["supersampling"], strategy=cfg["strategy"], voxels=int(len(v)),
-                             crc32=int(zlib.crc32(v.tobytes())), reference_seconds=round(time.time() - t0, 1),
+                             crc32=int(zlib.crc32(v.tobytes())), hash64=meshes.record_hash(v), reference_seconds=round(time.time() - t0, 1),
                              reference="patched downscale" if cfg["supersampling"] == 2 else "unmodified")
         print(name, results[name], flush=True)
         json.dump(results, open(OUT, "w"), indent=1)
