@@ -89,6 +89,10 @@ typedef struct o2v_b200_stats {
     float reserved;
     uint64_t slab_triangles;    /* occupancy-only path: triangles the step worked on (all of them, or what the slab filter
                                  * kept on a rank / job part that owns a part of the grid) */
+    uint64_t undecided_ranges;  /* occupancy-only path: rows with voxels the SAT left undecided (their x runs are checked
+                                 * against the bitmap; `survivors` of them reach the exact clip) */
+    float ms_filter;            /* occupancy-only path: duration of that check (occupancyFilterQueueKernel) */
+    float ms_expand;            /* occupancy-only path: bitmap -> records (occupancyExpandKernel) */
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */

@@ -49,7 +49,8 @@ class Stats(C.Structure):
                 ("transform", C.c_float * 12), ("kernel_launches", C.c_int32), ("voxelize_launches", C.c_int32),
                 ("light_tiles", C.c_uint64), ("heavy_tiles", C.c_uint64), ("survivors", C.c_uint64),
                 ("ms_clip", C.c_float), ("occupancy_path", C.c_int32),
-                ("ms_classify", C.c_float), ("reserved", C.c_float), ("slab_triangles", C.c_uint64)]
+                ("ms_classify", C.c_float), ("reserved", C.c_float), ("slab_triangles", C.c_uint64),
+                ("undecided_ranges", C.c_uint64), ("ms_filter", C.c_float), ("ms_expand", C.c_float)]
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "transform"}

@@ -169,6 +169,9 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->ms_classify = in.msClassify;
     out->reserved = 0.0f;
     out->slab_triangles = in.slabTriangles;
+    out->undecided_ranges = in.counters.ranges;
+    out->ms_filter = in.msFilter;
+    out->ms_expand = in.msExpand;
 }
 
 constexpr uint32_t kMaxJobParts = 128;  // a part is at least one 64-voxel chunk row; sample resolution <= 8192
@@ -224,6 +227,9 @@ void accumulateStats(RunStats &total, const RunStats &part)
     total.msVoxelize += part.msVoxelize;
     total.msClip += part.msClip;
     total.msClassify += part.msClassify;
+    total.msExpand += part.msExpand;
+    total.msFilter += part.msFilter;
+    t.ranges += p.ranges;
     total.kernelLaunches += part.kernelLaunches;
     total.voxelizeLaunches += part.voxelizeLaunches;
     total.occupancyPath = total.occupancyPath && part.occupancyPath;

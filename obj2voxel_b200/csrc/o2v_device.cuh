@@ -190,6 +190,19 @@ __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridVi
     if (rhi[2] <= grid.slabZ0 || rlo[2] >= grid.slabZ1) {
         return true;  // midpoints stay inside the parent's AABB, so no leaf can reach the slab
     }
+    if ((rhi[0] - rlo[0]) * (rhi[1] - rlo[1]) * (rhi[2] - rlo[2]) < kSubdivisionVolumeLimit) {
+        // The triangle is its own single leaf whether or not it is axis-aligned (aligned: voxelized whole,
+        // voxelization.cpp:498-501; otherwise the subdivision pops it at once, :349-379): no normal, no square root, and
+        // the bounds are computed once.  Almost every triangle of a mesh that is fine relative to the grid ends here.
+        rhi[0] = min(rhi[0], grid.gridExtent);
+        rhi[1] = min(rhi[1], grid.gridExtent);
+        rlo[2] = max(rlo[2], grid.slabZ0);
+        rhi[2] = min(rhi[2], min(grid.slabZ1, grid.gridExtent));
+        if (rlo[0] < rhi[0] && rlo[1] < rhi[1] && rlo[2] < rhi[2]) {
+            visit(root, rlo, rhi);
+        }
+        return true;
+    }
     return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
         uint32_t lo[3], hi[3];
         triVoxelBounds(leaf.v, lo, hi);

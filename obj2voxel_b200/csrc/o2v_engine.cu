@@ -1,5 +1,6 @@
 // o2v::Engine — buffer management and kernel sequencing for one GPU (see o2v_engine.h).
 #include "o2v_engine.h"
+#include "o2v_sat.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -88,6 +89,7 @@ Engine *Engine::create(int device, std::string *error)
     ok = ok && cudaEventCreate(&e->evVoxStart_) == cudaSuccess && cudaEventCreate(&e->evVoxEnd_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evClipStart_) == cudaSuccess && cudaEventCreate(&e->evClipEnd_) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->evClassifyStart_) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->evFilterStart_) == cudaSuccess;
     ok = ok && e->counters_.ensure(sizeof(RunCounters));
     if (!ok) {
         if (error != nullptr) {
@@ -118,7 +120,7 @@ Engine::~Engine()
             cudaFreeHost(p);
         }
     }
-    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_, evClassifyStart_}) {
+    for (cudaEvent_t ev : {evStart_, evSetup_, evVoxStart_, evVoxEnd_, evClipStart_, evClipEnd_, evClassifyStart_, evFilterStart_}) {
         if (ev != nullptr) {
             cudaEventDestroy(ev);
         }
@@ -207,7 +209,6 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     if (mesh.count >= (1ull << 32)) {
         return fail(kErrTooLarge, "more than 2^32-1 triangles");
     }
-    const uint32_t S = (uint32_t) sampleRes64;
     O2V_CUDA(cudaSetDevice(device_));
 
     RunCounters *dCounters = counters_.as<RunCounters>();
@@ -473,9 +474,11 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     const size_t nBound = (size_t) mesh.count;  // = meshIn.count
 
     OccupancyView occ{};
-    occ.chunksPerAxis = grid.gridExtent / kChunkEdge;
-    occ.chunkZ0 = grid.slabZ0 / kChunkEdge;
-    const uint32_t chunkRows = (grid.slabZ1 + kChunkEdge - 1) / kChunkEdge - occ.chunkZ0;
+    // bitmaps in OUTPUT space: chunks of 64^3 output voxels (128^3 samples when downscaling)
+    occ.shift = params.supersampling == 2 ? 1u : 0u;
+    occ.chunksPerAxis = ((grid.gridExtent >> occ.shift) + kChunkEdge - 1) / kChunkEdge;
+    occ.chunkZ0 = (grid.slabZ0 >> occ.shift) / kChunkEdge;
+    const uint32_t chunkRows = ((grid.slabZ1 >> occ.shift) + kChunkEdge - 1) / kChunkEdge - occ.chunkZ0;
     occ.chunkTotal = occ.chunksPerAxis * occ.chunksPerAxis * chunkRows;  // <= 128^3
     if (!leafCount_.ensure(nBound * 4) || !leafOffset_.ensure(nBound * 4) ||
         !scratch_.ensure(scanScratchElems(nBound) * 4) || !chunkFlag_.ensure(((size_t) occ.chunkTotal + 31) / 32 * 4) ||
@@ -519,8 +522,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     }
 
     // Output capacity: every voxel needs a candidate, and a chunk emits at most 64^3 (8 times fewer when downscaled).
-    const unsigned long long perChunk =
-        (unsigned long long) kChunkEdge * kChunkEdge * kChunkEdge / (params.supersampling == 2 ? 8 : 1);
+    const unsigned long long perChunk = (unsigned long long) kChunkEdge * kChunkEdge * kChunkEdge;
     unsigned long long capacity = std::min(candidateBound, occ.activeChunks * perChunk);
     capacity = std::max<unsigned long long>(capacity, 1);
     // Queue of SAT-undecided voxels: a fraction of the candidates in practice (~5 %); sized at a quarter of the bound and
@@ -528,6 +530,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     unsigned long long queueCapacity =
         std::max<unsigned long long>(std::min<unsigned long long>(candidateBound, 1ull << 20), candidateBound / 4);
 
+    unsigned long long rangeCapacity = queueCapacity;  // one entry per row with undecided voxels
     const size_t bitmapBytes = (size_t) occ.activeChunks * kChunkWords * 8;
     if (const char *env = getenv("O2V_B200_OCCUPANCY_MAX_BYTES")) {  // test hook for the fallback below
         if (bitmapBytes > strtoull(env, nullptr, 10)) {
@@ -544,6 +547,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     if (!tileBits_.ensure(bitmapBytes) ||
         !extraLeaves_.ensure((size_t) std::max<unsigned long long>(extraLeaves, 1) * sizeof(LeafRecord)) ||
         !occQueue_.ensure((size_t) queueCapacity * sizeof(uint4)) ||
+        !occRanges_.ensure((size_t) rangeCapacity * sizeof(uint4)) ||
         !bigLeaves_.ensure((size_t) std::max<unsigned long long>(bigLeaves, 1) * sizeof(uint2))) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
     }
@@ -559,6 +563,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     occ.bits = tileBits_.as<unsigned long long>();
     occ.queue = occQueue_.as<uint4>();
     occ.queueCapacity = queueCapacity;
+    occ.ranges = occRanges_.as<uint4>();
+    occ.rangeCapacity = rangeCapacity;
     occ.bigLeaves = bigLeaves_.as<uint2>();
     occ.bigCapacity = (uint32_t) bigLeaves;
 
@@ -583,8 +589,9 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     args.occ = occ;
     args.variant = params.variant < 0 ? 0 : params.variant;
     args.prefilter = params.prefilter;
+    args.certainMargin = certainMarginFor(grid.sampleRes);
 
-    for (int attempt = 0; attempt < 3; ++attempt) {
+    for (int attempt = 0; attempt < 4; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
         O2V_CUDA(cudaMemsetAsync(occ.bits, 0, bitmapBytes, stream));
         O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
@@ -592,12 +599,14 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         const bool microLeaves = args.variant == 2 ||
                                  (args.variant != 1 && candidateBound <= kOccDirectCandidates * hostCounters_->leaves);
         launchOccupancyClassify(args, leafTotal, microLeaves, (uint32_t) bigLeaves, bigBoxes, smCount_, stream);
+        O2V_CUDA(cudaEventRecord(evFilterStart_, stream));
+        launchOccupancyFilterQueue(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evClipStart_, stream));
         launchOccupancyClip(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
         launchOccupancyExpand(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
-        const int launched = 3 + (bigLeaves != 0 ? 1 : 0);
+        const int launched = 4 + (bigLeaves != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
         st.kernelLaunches += launched;
         launchPublishCounters(dCounters, hostCountersDevice_, stream);
@@ -605,13 +614,22 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         O2V_CUDA(cudaStreamSynchronize(stream));
         O2V_CUDA(cudaGetLastError());
         const bool queueOverflow = hostCounters_->survivors > queueCapacity;
-        if (hostCounters_->outputOverflow == 0 && !queueOverflow) {
+        const bool rangeOverflow = hostCounters_->ranges > rangeCapacity;
+        if (hostCounters_->outputOverflow == 0 && !queueOverflow && !rangeOverflow) {
             break;
         }
-        if (attempt == 2) {
+        if (attempt == 3) {
             return fail(kErrOutOfMemory, "voxel output does not fit device memory");
         }
-        if (queueOverflow) {
+        if (rangeOverflow) {
+            rangeCapacity = hostCounters_->ranges;  // exact: the list does not depend on the order of execution
+            if (!occRanges_.ensure((size_t) rangeCapacity * sizeof(uint4))) {
+                return fail(kErrOutOfMemory, "device allocation failed (occupancy range list, grown)");
+            }
+            args.occ.ranges = occRanges_.as<uint4>();
+            args.occ.rangeCapacity = rangeCapacity;
+        }
+        else if (queueOverflow) {
             // what is queued depends on which bits were already visible: leave head-room, capped by the true bound
             queueCapacity = std::min(candidateBound, hostCounters_->survivors * 2 + (1ull << 20));
             if (!occQueue_.ensure((size_t) queueCapacity * sizeof(uint4))) {
@@ -630,6 +648,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         }
         RunCounters reset = *hostCounters_;
         reset.survivors = 0;
+        reset.ranges = 0;
         reset.voxels = 0;
         reset.outputOverflow = 0;
         *hostCountersInit_ = reset;
@@ -648,8 +667,10 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     cudaEventElapsedTime(&st.msTotal, evStart_, evVoxEnd_);
     cudaEventElapsedTime(&st.msSetup, evStart_, evSetup_);
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
-    cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evClipStart_);
+    cudaEventElapsedTime(&st.msClassify, evClassifyStart_, evFilterStart_);
+    cudaEventElapsedTime(&st.msFilter, evFilterStart_, evClipStart_);
     cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
+    cudaEventElapsedTime(&st.msExpand, evClipEnd_, evVoxEnd_);
     return kErrOk;
 }
 

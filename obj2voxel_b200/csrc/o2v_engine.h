@@ -41,6 +41,8 @@ struct RunStats {
     float msVoxelize = 0;  // clip + fold + heavy tiles
     float msClip = 0;      // the exact-clip kernel alone (sparseClipKernel / occupancyClipKernel)
     float msClassify = 0;  // occupancy-only path: the SAT classification kernel alone
+    float msFilter = 0;    // occupancy-only path: undecided ranges -> clip queue
+    float msExpand = 0;    // occupancy-only path: bitmap -> records
     int voxelizeLaunches = 0;
     int kernelLaunches = 0;
     unsigned long long outCapacity = 0;
@@ -134,13 +136,13 @@ private:
     RunCounters *hostCountersDevice_ = nullptr;  // its device-side address
     RunCounters *hostCountersInit_ = nullptr;  // pinned template
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
-    cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr;
+    cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr, evFilterStart_ = nullptr;
 
     DeviceBuffer hash_, counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
-    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, bigLeaves_, slabVerts_, slabKept_, extraLeaves_;  // occupancy-only path
+    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, occRanges_, bigLeaves_, slabVerts_, slabKept_, extraLeaves_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

@@ -82,16 +82,22 @@ void o2vt_combine(float acc[4], const float incoming[4], int blend)
     acc[3] = c.b;
 }
 
-/// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through the two SAT users of the kernels
+/// Sweeps every voxel of every leaf's AABB (leaves: n x 9 floats, voxel space) through the SAT users of the kernels
 ///   * prefilterPass with tile-relative constants (weighted path: o2v_sparse.cu / o2v_kernels.cu),
-///   * buildRowSat / rowSpanMisses / classifyInRow (and classifyVoxel) with constants relative to the leaf's box — or to its 16^3 sub-boxes when the box holds more than
-///     4096 voxels — exactly as o2v_occupancy.cu stages them,
+///   * buildRowSat / rowSpanMisses / classifyInRow (and classifyVoxel) with constants relative to the leaf's box — or to
+///     its 16^3 sub-boxes when the box holds more than 4096 voxels — exactly as the thread-per-leaf classifier of
+///     o2v_occupancy.cu stages them,
+///   * classifySpan (the row-interval form of the block classifier) with the same constants,
 /// and through the reference semantics (plane-distance cull + exact clip, o2v_exact.cuh), and counts disagreements.
-/// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts (either user) the
-/// reference hits (must be 0), [6] `certain` verdicts the reference does not hit (must be 0), [7] leaves skipped.
-void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVolume, unsigned long long out[8])
+/// certainMargin: the `certain` shrink (certainMarginFor(S) in the kernels).
+/// out: [0] pairs, [1] miss, [2] uncertain, [3] certain, [4] reference hits, [5] `miss` verdicts (either per-voxel user)
+/// the reference hits (must be 0), [6] `certain` verdicts the reference does not hit (must be 0), [7] leaves skipped,
+/// [8] span: miss, [9] span: uncertain, [10] span: certain, [11] span `miss` the reference hits (must be 0),
+/// [12] span `certain` the reference does not hit (must be 0), [13] voxels where span and per-voxel verdicts differ.
+void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVolume, float certainMargin,
+                        unsigned long long out[16])
 {
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < 16; ++i) {
         out[i] = 0;
     }
     for (size_t l = 0; l < n; ++l) {
@@ -110,6 +116,8 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
         const uint32_t boxEdge = volume > 4096 ? 16u : 0xffffffffu;  // o2v_occupancy.cu: kOccBigVolume, kOccBoxEdge
         for (uint32_t z = lo[2]; z < hi[2]; ++z) {
             for (uint32_t y = lo[1]; y < hi[1]; ++y) {
+                // span form: once per row and box
+                int spanVerdict[4096 + 16];
                 for (uint32_t x = lo[0]; x < hi[0]; ++x) {
                     // weighted path: constants relative to the voxel's 8^3 tile
                     const float tileOrigin[3] = {(float) (x & ~7u), (float) (y & ~7u), (float) (z & ~7u)};
@@ -131,14 +139,14 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
                     bs.flags = flags;
                     buildPrefilter(bs, boxOrigin);
                     PairSat sat;
-                    buildPairSat(sat, bs, boxOrigin);
-                    // as the classify kernel does it: the row's 8-aligned x segment is tested as a whole first
+                    buildPairSat(sat, bs, boxOrigin, certainMargin);
+                    // as the thread-per-leaf classifier does it: the row's 8-aligned x segment is tested as a whole first
                     const uint32_t boxHiX = boxEdge != 0xffffffffu && bo[0] + boxEdge < hi[0] ? bo[0] + boxEdge : hi[0];
                     const uint32_t segFirst = (x & ~7u) > bo[0] ? (x & ~7u) : bo[0];
                     const uint32_t segLast = ((x & ~7u) + 8u < boxHiX ? (x & ~7u) + 8u : boxHiX) - 1u;
                     RowSat row;
                     buildRowSat(sat, (float) (y - bo[1]), (float) (z - bo[2]), row);
-                    int verdict = kSatUncertain;
+                    int verdict = kSatUncertain, span = kSatUncertain;
                     if ((flags & kLeafNoPrefilter) == 0) {
                         const float spanFirst = (float) (segFirst - bo[0]), spanLast = (float) (segLast - bo[0]);
                         verdict = (rowPlaneSpanMisses(sat, row, spanFirst, spanLast) ||
@@ -149,6 +157,20 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
                                                      (float) (z - bo[2]))) {
                             ++out[5];  // the segment test must never reject what the voxel's own test accepts
                         }
+                        if (x == bo[0]) {  // first voxel of this box's row: solve the row
+                            SpanSat ss;
+                            buildSpanSat(ss, sat);
+                            int i0, i1, j0, j1;
+                            classifySpan(ss, (float) (y - bo[1]), (float) (z - bo[2]), (float) (boxHiX - 1u - bo[0]), i0, i1,
+                                         j0, j1);
+                            for (uint32_t xx = bo[0]; xx < boxHiX; ++xx) {
+                                const int lx = (int) (xx - bo[0]);
+                                spanVerdict[xx - lo[0]] = (lx < i0 || lx > i1) ? (int) kSatMiss
+                                                          : (lx >= j0 && lx <= j1) ? (int) kSatCertain
+                                                                                   : (int) kSatUncertain;
+                            }
+                        }
+                        span = spanVerdict[x - lo[0]];
                     }
                     const bool hit =
                         !planeDistanceCulled(v, x, y, z) && clipLeafInVoxel<false>(tri, x, y, z, 1.0f).pieces != 0;
@@ -157,6 +179,10 @@ void o2vt_classify_fuzz(const float *leaves, size_t n, unsigned long long maxVol
                     out[4] += hit ? 1 : 0;
                     out[5] += ((verdict == kSatMiss || !pass) && hit) ? 1 : 0;
                     out[6] += (verdict == kSatCertain && !hit) ? 1 : 0;
+                    ++out[8 + span];
+                    out[11] += (span == kSatMiss && hit) ? 1 : 0;
+                    out[12] += (span == kSatCertain && !hit) ? 1 : 0;
+                    out[13] += span != verdict ? 1 : 0;
                 }
             }
         }
@@ -208,7 +234,7 @@ int classifyScaled(const PairSat &s, const ScaledSat &t, float lx, float ly, flo
     }
     bool sure = least >= 1.0f && dist <= s.planeSure;
     for (int a = 0; a < 3; ++a) {
-        sure = sure && (q[a] + certainMargin <= s.hi[a]) && (q[a] + 1.0f - certainMargin >= s.lo[a]);
+        sure = sure && q[a] <= s.hi[a] && q[a] >= s.lo[a];
     }
     return sure ? kSatCertain : kSatUncertain;
 }
@@ -216,13 +242,7 @@ int classifyScaled(const PairSat &s, const ScaledSat &t, float lx, float ly, flo
 /// buildPairSat with the `certain` shrink as a parameter (the header's is the constant kCertainMargin).
 void buildPairSatWith(PairSat &out, const LeafStage &s, const float origin[3], float certainMargin)
 {
-    buildPairSat(out, s, origin);
-    const float norm1 = fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]);
-    out.planeSure = (0.5f - certainMargin) * norm1;
-    const float shift = kPrefilterMargin + certainMargin;
-    for (int k = 0; k < 9; ++k) {
-        out.edge[k].k = (fabsf(s.edge[k * 3]) + fabsf(s.edge[k * 3 + 1])) * shift;
-    }
+    buildPairSat(out, s, origin, certainMargin);
 }
 
 }  // namespace
@@ -287,8 +307,7 @@ void o2vt_classify_study(const float *leaves, size_t n, unsigned long long maxVo
                                     sure = sure && value >= sat.edge[k].k;
                                 }
                                 for (int a = 0; a < 3; ++a) {
-                                    sure = sure && (q[a] + certainMargin <= sat.hi[a]) &&
-                                           (q[a] + 1.0f - certainMargin >= sat.lo[a]);
+                                    sure = sure && q[a] <= sat.hi[a] && q[a] >= sat.lo[a];
                                 }
                                 verdict = sure ? kSatCertain : kSatUncertain;
                             }

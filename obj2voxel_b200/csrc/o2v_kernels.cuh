@@ -90,6 +90,7 @@ struct RunCounters {
     unsigned long long slabTriangles;   // triangles the slab filter kept (only when the slab is a part of the grid)
     unsigned long long extraLeaves;     // leaves beyond the first of their triangle (the emit pass writes those)
     unsigned long long scanTotal;       // total of the exclusive scan over the per-triangle extra-leaf counts
+    unsigned long long ranges;          // rows with voxels the SAT left undecided = entries of OccupancyView::ranges
 };
 
 /// Descriptor of a light tile: everything the warp needs in one 16-byte load.
@@ -166,14 +167,17 @@ constexpr uint32_t kLeafEmpty = 4u;       // LeafRecord::flags on this path: the
 /// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
 /// occupancy has to be decided — an order-independent OR into per-chunk bitmaps.
 struct OccupancyView {
-    uint32_t *chunkFlag;             // one bit per 64^3 chunk of the slab: some leaf's box reaches it
+    uint32_t *chunkFlag;             // one bit per chunk (64^3 OUTPUT voxels) of the slab: some leaf's box reaches it
     uint32_t *chunkSlot;             // per chunk: index of its bitmap
     uint32_t *chunkList;             // per bitmap: its chunk
-    uint32_t chunksPerAxis, chunkZ0, chunkTotal;  // chunk id = cx + C * (cy + C * (cz - chunkZ0))
+    uint32_t chunksPerAxis, chunkZ0, chunkTotal;  // chunk id = cx + C * (cy + C * (cz - chunkZ0)), OUTPUT space
+    uint32_t shift;                  // log2(supersampling): output voxel = sample voxel >> shift
     uint32_t activeChunks;           // bitmaps in use (host copy of the device count)
     unsigned long long *bits;        // kChunkWords per bitmap: word = tile (x | y << 3 | z << 6) * 8 + layer z,
-                                     // bit (x + 8 y) = voxel (x, y, z) of that tile is occupied
-    uint4 *queue;                    // {leaf, x | y << 16, z, -} of the voxels the SAT could not decide
+                                     // bit (x + 8 y) = OUTPUT voxel (x, y, z) of that tile is occupied
+    uint4 *ranges;                   // per row with undecided voxels: {leaf, x | y << 16, z | gap << 16, lenA | lenB << 16}
+    unsigned long long rangeCapacity;
+    uint4 *queue;                    // {leaf, x | y << 16, z, -} of the voxels neither the SAT nor the bitmap decided
     unsigned long long queueCapacity;
     const LeafRecord *extraLeaves;   // leaf firstLeaves + k: the leaves beyond the first of their triangle
     uint32_t firstLeaves;            // = triangles: leaf i < firstLeaves is the first leaf of triangle i (VoxelizeArgs::leaves)
@@ -200,6 +204,7 @@ struct VoxelizeArgs {
     OccupancyView occ;
     int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
+    float certainMargin;  // occupancy-only path: shrink of the voxel box for `certain` (certainMarginFor(sample resolution))
 };
 
 /// Heavy tiles: one 512-thread block per tile, thread = voxel.
@@ -228,6 +233,7 @@ void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const Occup
 /// (occupancyClassifyDirectKernel) instead of block = 64 leaves.
 void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,
                              unsigned long long boxTotal, int smCount, cudaStream_t stream);
+void launchOccupancyFilterQueue(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 void launchOccupancyExpand(const VoxelizeArgs &args, int smCount, cudaStream_t stream);
 

@@ -41,12 +41,19 @@ constexpr int kOccSetupThreads = 128;
 #ifndef O2V_OCC_THREADS
 #define O2V_OCC_THREADS 128
 #endif
+#ifndef O2V_OCC_MIN_BLOCKS
+#define O2V_OCC_MIN_BLOCKS 8
+#endif
 constexpr int kOccBatch = O2V_OCC_BATCH;      // leaves per classify block
 constexpr int kOccThreads = O2V_OCC_THREADS;  // threads per classify block
 constexpr int kOccClipThreads = 128;
 constexpr int kOccExpandThreads = 128;
 constexpr int kOccRefillThreshold = 8;
-constexpr uint32_t kOccMaybeCap = 1024;  // undecided voxels a block buffers before filtering them against the bitmap
+constexpr uint32_t kOccRangeCap = 128;     // undecided x ranges a block buffers before appending them to the range list
+constexpr uint32_t kOccOwnerCap = 2048;    // rows of a batch whose owner (batch entry) is looked up in a table
+constexpr int kOccFilterThreads = 256;
+constexpr uint32_t kFilterEntries = 4;     // range entries a filter thread handles per round (their probes overlap)
+constexpr uint32_t kFilterProbe = 2;       // voxels per run probed up front (ordinary runs are 1 - 2 long)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // addressing
@@ -64,38 +71,29 @@ __device__ __forceinline__ bool leafBoxInSlab(const float *v, const GridView &gr
     return lo[0] < hi[0] && lo[1] < hi[1] && lo[2] < hi[2];
 }
 
-/// Index of the 64-bit bitmap word (layer z of the voxel's tile) and the voxel's bit in it.
-__device__ __forceinline__ size_t bitmapWord(const OccupancyView &occ, uint32_t x, uint32_t y, uint32_t z)
+/// The bitmaps live in OUTPUT space: with 2x supersampling a sample voxel (x, y, z) sets the bit of its parent
+/// (x >> 1, y >> 1, z >> 1) — the downscale of an all-white model is the OR of the children, so the
+/// children never need bits of their own.  One eighth of the memory to clear, classify into and expand, and a bitmap
+/// that stays in L2 at 1024^3.
+/// Index of the 64-bit bitmap word (layer oz of the output voxel's tile) and the voxel's bit in it.
+__device__ __forceinline__ size_t bitmapWord(const OccupancyView &occ, uint32_t ox, uint32_t oy, uint32_t oz)
 {
-    const uint32_t chunk = (x >> 6) + occ.chunksPerAxis * ((y >> 6) + occ.chunksPerAxis * ((z >> 6) - occ.chunkZ0));
-    const uint32_t tileLocal = ((x >> 3) & 7u) | (((y >> 3) & 7u) << 3) | (((z >> 3) & 7u) << 6);
-    return (size_t) __ldg(occ.chunkSlot + chunk) * kChunkWords + tileLocal * kTileEdge + (z & 7u);
+    const uint32_t chunk = (ox >> 6) + occ.chunksPerAxis * ((oy >> 6) + occ.chunksPerAxis * ((oz >> 6) - occ.chunkZ0));
+    const uint32_t tileLocal = ((ox >> 3) & 7u) | (((oy >> 3) & 7u) << 3) | (((oz >> 3) & 7u) << 6);
+    return (size_t) __ldg(occ.chunkSlot + chunk) * kChunkWords + tileLocal * kTileEdge + (oz & 7u);
 }
 
-__device__ __forceinline__ unsigned long long bitmapBit(uint32_t x, uint32_t y)
+__device__ __forceinline__ unsigned long long bitmapBit(uint32_t ox, uint32_t oy)
 {
-    return 1ull << ((x & 7u) + 8u * (y & 7u));
+    return 1ull << ((ox & 7u) + 8u * (oy & 7u));
 }
 
-/// Bits of `m` (layout x + 8 y) smeared over their 2x2 xy blocks: the footprint of the parents that already have a child.
-__device__ __forceinline__ unsigned long long smear2x2(unsigned long long m)
+/// true if the bitmap already decides sample voxel (x, y, z): the bit of its output voxel is set (by this voxel or, when
+/// downscaling, by any of its siblings).
+__device__ __forceinline__ bool alreadyDecided(const OccupancyView &occ, uint32_t x, uint32_t y, uint32_t z)
 {
-    const unsigned long long evenX = (m | (m >> 1)) & 0x5555555555555555ull;
-    const unsigned long long pairX = evenX | (evenX << 1);
-    const unsigned long long evenY = (pairX | (pairX >> 8)) & 0x00ff00ff00ff00ffull;
-    return evenY | (evenY << 8);
-}
-
-/// true if the bitmap already decides voxel (x, y, z): its bit is set or — when downscaling — its parent has a child.
-__device__ __forceinline__ bool alreadyDecided(const OccupancyView &occ, bool downscale, uint32_t x, uint32_t y,
-                                               uint32_t z)
-{
-    const size_t word = bitmapWord(occ, x, y, z);
-    unsigned long long known = __ldcg(occ.bits + word);
-    if (downscale) {
-        known = smear2x2(known | __ldcg(occ.bits + (word ^ 1u)));  // z ^ 1 is the neighbouring word of the same tile
-    }
-    return (known & bitmapBit(x, y)) != 0;
+    const uint32_t ox = x >> occ.shift, oy = y >> occ.shift, oz = z >> occ.shift;
+    return (__ldcg(occ.bits + bitmapWord(occ, ox, oy, oz)) & bitmapBit(ox, oy)) != 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -224,18 +222,27 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
                     ++bigLeaves;
                     bigBoxes += boxCountOf(lo, hi);
                 }
-                for (uint32_t cz = lo[2] >> 6; cz <= (hi[2] - 1) >> 6; ++cz) {
-                    for (uint32_t cy = lo[1] >> 6; cy <= (hi[1] - 1) >> 6; ++cy) {
-                        for (uint32_t cx = lo[0] >> 6; cx <= (hi[0] - 1) >> 6; ++cx) {
-                            const uint32_t chunk = cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0));
-                            const uint32_t bit = 1u << (chunk & 31u);
-                            if (collect) {
-                                if ((chunkBits[chunk >> 5] & bit) == 0) {
-                                    atomicOr(&chunkBits[chunk >> 5], bit);
-                                }
-                            }
-                            else if ((__ldcg(occ.chunkFlag + (chunk >> 5)) & bit) == 0) {  // look before the atomic
-                                atomicOr(occ.chunkFlag + (chunk >> 5), bit);
+                const uint32_t cs = 6u + occ.shift;  // a chunk is 64^3 OUTPUT voxels
+                auto mark = [&](uint32_t cx, uint32_t cy, uint32_t cz) {
+                    const uint32_t chunk = cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0));
+                    const uint32_t bit = 1u << (chunk & 31u);
+                    if (collect) {
+                        if ((chunkBits[chunk >> 5] & bit) == 0) {
+                            atomicOr(&chunkBits[chunk >> 5], bit);
+                        }
+                    }
+                    else if ((__ldcg(occ.chunkFlag + (chunk >> 5)) & bit) == 0) {  // look before the atomic
+                        atomicOr(occ.chunkFlag + (chunk >> 5), bit);
+                    }
+                };
+                const uint32_t cx0 = lo[0] >> cs, cy0 = lo[1] >> cs, cz0 = lo[2] >> cs;
+                const uint32_t cx1 = (hi[0] - 1) >> cs, cy1 = (hi[1] - 1) >> cs, cz1 = (hi[2] - 1) >> cs;
+                mark(cx0, cy0, cz0);
+                if (cx0 != cx1 || cy0 != cy1 || cz0 != cz1) {  // rare: the box straddles a chunk boundary
+                    for (uint32_t cz = cz0; cz <= cz1; ++cz) {
+                        for (uint32_t cy = cy0; cy <= cy1; ++cy) {
+                            for (uint32_t cx = cx0; cx <= cx1; ++cx) {
+                                mark(cx, cy, cz);
                             }
                         }
                     }
@@ -339,31 +346,81 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// classify: thread per candidate voxel
+// classify: lane = row of a leaf's box
 
-/// Batch entry in shared memory: the SAT constants plus where the entry's box sits.  The unit of work is a *row
-/// segment*: the voxels of one row (fixed y, z) of the box that share a tile column (x >> 3) — at most 8 voxels, all in
-/// one 32-bit half of one bitmap word.  60 words, 16-byte aligned.
+/// Batch entry in shared memory: the row-interval SAT constants (o2v_sat.cuh, SpanSat) plus where the entry's box sits.
+/// The unit of work is a *row* of the box (fixed y, z): classifySpan solves the thirteen axes for the x interval that is
+/// not a `miss` and the sub-interval that is `certain`, so a row costs the same whatever its length and every lane of a
+/// warp does the same work.  84 words: lanes reading the same field of different entries with 128-bit loads hit distinct
+/// banks (84 mod 32 = 20).
 struct alignas(16) BatchEntry {
-    PairSat sat;
-    uint32_t leaf;                // leaf index (queue entries name it)
-    uint32_t x0, y0, z0;          // box min corner, voxel space
-    uint32_t dx;                  // box extent in x
-    uint32_t segs, segsDy;        // segments per row, per layer (= segs * extent in y)
-    uint32_t magicSegs, magicSegsDy;  // n / d == __umulhi(n, magic) for d > 1, n * d <= 2^24 (d == 1: n itself)
-    uint32_t slot;                // bitmap of the box's chunk, or kNoSlot if the box spans several chunks
-    uint32_t pad[2];
+    SpanSat sat;
+    uint32_t leaf;        // leaf index (queue entries name it)
+    uint32_t x0, y0, z0;  // box min corner, sample space
+    uint32_t dx, dy;      // box extent in x and y (rows = dy * extent in z)
+    uint32_t magicDy;     // n / dy == __umulhi(n, magic) for dy > 1, n * dy <= 2^24
+    uint32_t slot;        // bitmap of the box's chunk, or kNoSlot if the box spans several chunks
+    uint32_t noSat;       // kLeafNoPrefilter: the leaf's normal is too noisy for the SAT, every candidate is undecided
+    uint32_t pad[3];
 };
+static_assert(sizeof(BatchEntry) == 84 * 4, "bank-conflict-free stride");
+static_assert(kOccBatch <= 128, "ClassifyShared::maybe keeps the entry in 7 bits");
 
 constexpr uint32_t kNoSlot = 0xffffffffu;
 
+/// Undecided voxels leave the classifiers as the two x runs at the ends of a row's interval, one entry per row:
+/// {leaf, x | y << 16, z | gap << 16, lengthA | lengthB << 16} = voxels x .. x + lengthA - 1 and, `gap` voxels further,
+/// lengthB more.  A block collects its entries in shared memory and appends them to the global list with one atomic.
+/// Whether the bitmap already decides a voxel is asked later, when every `certain` bit of the run is in place and the
+/// probes of millions of entries can be in flight together (occupancyFilterQueueKernel): inside the classifier the same
+/// probes cost a quarter of its run time in exposed latency (profiles/r02_history.md).
+struct RangeBuffer {
+    uint4 slot[kOccRangeCap];
+    uint32_t count;
+    unsigned long long base;
+};
+
+__device__ __forceinline__ void pushRange(RangeBuffer &rb, const VoxelizeArgs &args, uint32_t leaf, uint32_t x, uint32_t y,
+                                          uint32_t z, uint32_t lengthA, uint32_t gap, uint32_t lengthB)
+{
+    const uint4 entry = make_uint4(leaf, x | (y << 16), z | (gap << 16), lengthA | (lengthB << 16));
+    const uint32_t slot = atomicAdd(&rb.count, 1u);
+    if (slot < kOccRangeCap) {
+        rb.slot[slot] = entry;
+    }
+    else {  // buffer full (a dense batch): straight to the list
+        const unsigned long long index = atomicAdd(&args.counters->ranges, 1ull);
+        if (index < args.occ.rangeCapacity) {  // beyond: counted only; the engine grows the list and reruns
+            args.occ.ranges[index] = entry;
+        }
+    }
+}
+
+/// All threads of the block, after a barrier that follows the last pushRange.
+__device__ __forceinline__ void flushRanges(RangeBuffer &rb, const VoxelizeArgs &args)
+{
+    const uint32_t buffered = min(rb.count, kOccRangeCap);
+    if (buffered == 0) {  // block-uniform
+        return;
+    }
+    if (threadIdx.x == 0) {
+        rb.base = atomicAdd(&args.counters->ranges, (unsigned long long) buffered);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < buffered; k += blockDim.x) {
+        const unsigned long long index = rb.base + k;
+        if (index < args.occ.rangeCapacity) {
+            args.occ.ranges[index] = rb.slot[k];
+        }
+    }
+}
+
 struct ClassifyShared {
     BatchEntry entry[kOccBatch];
-    uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' row-segment counts
-    uint32_t maybe[kOccMaybeCap];     // undecided voxels: entry << 15 | segment << 3 | x & 7; top bit: survived the filter
+    uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' row counts
     uint32_t warpSums[kOccThreads / 32];
-    uint32_t maybeCount;
-    unsigned long long queueBase;
+    RangeBuffer ranges;
+    uint8_t owner[kOccOwnerCap];      // batch entry of row i, for batches of at most kOccOwnerCap rows
 };
 
 __device__ __forceinline__ uint32_t magicOf(uint32_t d)
@@ -377,40 +434,49 @@ __device__ __forceinline__ uint32_t divideBy(uint32_t n, uint32_t d, uint32_t ma
     return d > 1u ? __umulhi(n, magic) : n;
 }
 
-/// Bitmap word of voxel (x, y, z) for an entry: the chunk lookup is skipped when the entry's box lies in one chunk.
-__device__ __forceinline__ size_t entryWord(const OccupancyView &occ, const BatchEntry &e, uint32_t x, uint32_t y,
-                                            uint32_t z)
+/// Bitmap word of OUTPUT voxel (ox, oy, oz) for an entry: the chunk lookup is skipped when the entry's box lies in one
+/// chunk.
+__device__ __forceinline__ size_t entryWord(const OccupancyView &occ, uint32_t slot, uint32_t ox, uint32_t oy, uint32_t oz)
 {
-    if (e.slot == kNoSlot) {
-        return bitmapWord(occ, x, y, z);
+    if (slot == kNoSlot) {
+        return bitmapWord(occ, ox, oy, oz);
     }
-    const uint32_t tileLocal = ((x >> 3) & 7u) | (((y >> 3) & 7u) << 3) | (((z >> 3) & 7u) << 6);
-    return (size_t) e.slot * kChunkWords + tileLocal * kTileEdge + (z & 7u);
+    const uint32_t tileLocal = ((ox >> 3) & 7u) | (((oy >> 3) & 7u) << 3) | (((oz >> 3) & 7u) << 6);
+    return (size_t) slot * kChunkWords + tileLocal * kTileEdge + (oz & 7u);
+}
+
+/// Bitmap slot of the box [lo, hi) (sample space) if it lies in one chunk, else kNoSlot.
+__device__ __forceinline__ uint32_t boxSlot(const OccupancyView &occ, const uint32_t lo[3], const uint32_t hi[3])
+{
+    const uint32_t cs = 6u + occ.shift;
+    const bool oneChunk = (lo[0] >> cs) == ((hi[0] - 1) >> cs) && (lo[1] >> cs) == ((hi[1] - 1) >> cs) &&
+                          (lo[2] >> cs) == ((hi[2] - 1) >> cs);
+    return oneChunk ? __ldg(occ.chunkSlot + (lo[0] >> cs) +
+                            occ.chunksPerAxis * ((lo[1] >> cs) + occ.chunksPerAxis * ((lo[2] >> cs) - occ.chunkZ0)))
+                    : kNoSlot;
 }
 
 /// Fills one batch entry for `leaf` restricted to the box [lo, hi) (at most kOccBigVolume voxels).  Returns the number
-/// of row segments (0 = skip).
+/// of rows (0 = skip).
 __device__ __forceinline__ uint32_t stageBatchEntry(BatchEntry &e, const OccupancyView &occ, uint32_t leafIndex,
-                                                    const uint32_t lo[3], const uint32_t hi[3], LeafStage &s)
+                                                    const uint32_t lo[3], const uint32_t hi[3], LeafStage &s,
+                                                    float certainMargin)
 {
-    const bool oneChunk = (lo[0] >> 6) == ((hi[0] - 1) >> 6) && (lo[1] >> 6) == ((hi[1] - 1) >> 6) &&
-                          (lo[2] >> 6) == ((hi[2] - 1) >> 6);
-    e.slot = oneChunk ? __ldg(occ.chunkSlot + (lo[0] >> 6) +
-                              occ.chunksPerAxis * ((lo[1] >> 6) + occ.chunksPerAxis * ((lo[2] >> 6) - occ.chunkZ0)))
-                      : kNoSlot;
+    e.slot = boxSlot(occ, lo, hi);
     const float origin[3] = {(float) lo[0], (float) lo[1], (float) lo[2]};
     buildPrefilter(s, origin);
-    buildPairSat(e.sat, s, origin);
+    PairSat pair;
+    buildPairSat(pair, s, origin, certainMargin);
+    buildSpanSat(e.sat, pair);
     e.leaf = leafIndex;
     e.x0 = lo[0];
     e.y0 = lo[1];
     e.z0 = lo[2];
     e.dx = hi[0] - lo[0];
-    e.segs = ((hi[0] - 1u) >> 3) - (lo[0] >> 3) + 1u;
-    e.segsDy = e.segs * (hi[1] - lo[1]);
-    e.magicSegs = magicOf(e.segs);
-    e.magicSegsDy = magicOf(e.segsDy);
-    return e.segsDy * (hi[2] - lo[2]);
+    e.dy = hi[1] - lo[1];
+    e.magicDy = magicOf(e.dy);
+    e.noSat = (s.flags & kLeafNoPrefilter) != 0 ? 1u : 0u;
+    return e.dy * (hi[2] - lo[2]);
 }
 
 /// Leaf `index`: slots below firstLeaves hold the first leaf of triangle `index`, the others follow in extraLeaves.
@@ -429,155 +495,108 @@ __device__ __forceinline__ void loadLeafVertices(LeafStage &s, const VoxelizeArg
     s.flags = __float_as_uint(c.w);
 }
 
-/// Row (yi, zi, box-relative) and voxel range [xs, xe) (absolute x) of row segment `unit` of an entry.
-__device__ __forceinline__ void segmentOf(const BatchEntry &e, uint32_t unit, uint32_t &yi, uint32_t &zi, uint32_t &xs,
-                                          uint32_t &xe)
+/// ORs the output voxels ox0 .. ox1 of output row (oy, oz) into the bitmap: one RED per tile column on the 32-bit half
+/// word that holds the row (4 rows of one tile layer); nothing waits for the result.  A run of up to nine voxels — every
+/// run of an ordinary leaf — touches at most two columns: two predicated REDs, no loop.
+__device__ __forceinline__ void setRun(const OccupancyView &occ, uint32_t slot, uint32_t ox0, uint32_t ox1, uint32_t oy,
+                                       uint32_t oz)
 {
-    zi = divideBy(unit, e.segsDy, e.magicSegsDy);
-    const uint32_t inLayer = unit - zi * e.segsDy;
-    yi = divideBy(inLayer, e.segs, e.magicSegs);
-    const uint32_t column = (e.x0 >> 3) + (inLayer - yi * e.segs);
-    xs = max(e.x0, column << 3);
-    xe = min(e.x0 + e.dx, (column + 1u) << 3);
-}
-
-/// Voxel named by an entry of ClassifyShared::maybe.
-__device__ __forceinline__ void maybeVoxel(const BatchEntry &e, uint32_t m, uint32_t &x, uint32_t &y, uint32_t &z)
-{
-    uint32_t yi, zi, xs, xe;
-    segmentOf(e, (m >> 3) & 4095u, yi, zi, xs, xe);
-    x = (xs & ~7u) | (m & 7u);
-    y = e.y0 + yi;
-    z = e.z0 + zi;
+    uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
+    const uint32_t rowShift = 8u * (oy & 3u);
+    const uint32_t first = ox0 & 7u, length = ox1 - ox0 + 1u;
+    if (slot != kNoSlot && first + length <= 16u) {
+        // the whole box lies in one chunk: half word of tile column c = rowBase + 16 c
+        uint32_t *column = bits32 + ((size_t) slot * (kChunkWords * 2u) +
+                                     ((((ox0 >> 3) & 7u) | (((oy >> 3) & 7u) << 3) | (((oz >> 3) & 7u) << 6)) * kTileEdge +
+                                      (oz & 7u)) * 2u +
+                                     ((oy & 7u) >> 2));
+        const uint32_t mask = ((1u << length) - 1u) << first;  // 16 bits: this column and the next
+        atomicOr(column, (mask & 0xffu) << rowShift);
+        if ((mask >> 8) != 0) {
+            atomicOr(column + 16, (mask >> 8) << rowShift);
+        }
+        return;
+    }
+    for (uint32_t column = ox0 >> 3; column <= (ox1 >> 3); ++column) {
+        const uint32_t from = max(ox0, column << 3) & 7u, to = min(ox1, (column << 3) + 7u) & 7u;
+        const uint32_t mask = ((2u << to) - 1u) & ~((1u << from) - 1u);
+        const size_t half = entryWord(occ, slot, column << 3, oy, oz) * 2u + ((oy & 7u) >> 2);
+        atomicOr(bits32 + half, mask << rowShift);
+    }
 }
 
 /// The block-wide part shared by the leaf-batch and the box kernels.  sh.entry[0 .. count) are staged and
-/// sh.prefix[0 .. kOccBatch] holds the exclusive scan of their candidate counts (entries >= count contribute 0).
-/// `noSat[p]` (bit p of a per-entry flag kept in entry.sat.planeLimit < 0) marks kLeafNoPrefilter leaves.
+/// sh.prefix[0 .. kOccBatch] holds the exclusive scan of their row counts (entries >= count contribute 0); the caller
+/// has reset sh.ranges.count and synchronised.
 __device__ __forceinline__ void classifyBatch(ClassifyShared &sh, const VoxelizeArgs &args)
 {
     const OccupancyView &occ = args.occ;
-    const unsigned int full = 0xffffffffu;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t shift = occ.shift;
     const uint32_t total = sh.prefix[kOccBatch];
-    uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
 
-    // ---- verdicts: lane = row segment, the flat segment space of the batch shared out warp by warp.  The row tests
-    // (o2v_sat.cuh: yz edge functions, the plane at both ends of the segment) skip most segments of a thin triangle in a
-    // fat box; the others walk their <= 8 voxels with one multiply-add per axis and voxel. ----
-    for (uint32_t base = warp * 32u; base < total; base += kOccThreads) {  // warp-uniform trip count
-        const uint32_t i = base + lane;
-        uint32_t sure = 0, open = 0, p = 0, code = 0, x8 = 0, y = 0, z = 0;  // bit x & 7: certain / undecided
-        if (i < total) {
-#pragma unroll
-            for (uint32_t step = kOccBatch / 2; step > 0; step >>= 1) {  // last entry with prefix[p] <= i
-                p += sh.prefix[p + step] <= i ? step : 0u;
+    // ---- who owns row i: a table for batches of ordinary leaves (two threads fill the rows of one entry), a binary
+    // search over the prefix sums otherwise ----
+    const bool table = total <= kOccOwnerCap;  // block-uniform
+    if (table) {
+        for (uint32_t t = tid; t < 2u * kOccBatch; t += kOccThreads) {
+            const uint32_t p = t >> 1;
+            const uint32_t first = sh.prefix[p], rows = sh.prefix[p + 1] - first, half = (rows + 1u) >> 1;
+            const uint32_t from = (t & 1u) != 0 ? half : 0u, to = (t & 1u) != 0 ? rows : half;
+            for (uint32_t r = from; r < to; ++r) {
+                sh.owner[first + r] = (uint8_t) p;
             }
-            const BatchEntry &e = sh.entry[p];
-            const uint32_t unit = i - sh.prefix[p];
-            code = (p << 15) | (unit << 3);
-            uint32_t yi, zi, xs, xe;
-            segmentOf(e, unit, yi, zi, xs, xe);
-            x8 = xs & ~7u;
-            y = e.y0 + yi;
-            z = e.z0 + zi;
-            // planeLimit < 0 marks a leaf whose normal is too noisy for the SAT (kLeafNoPrefilter): all undecided
-            if (args.prefilter && e.sat.planeLimit >= 0.0f) {
-                RowSat row;
-                buildRowSat(e.sat, (float) yi, (float) zi, row);
-                if (!rowPlaneSpanMisses(e.sat, row, (float) (xs - e.x0), (float) (xe - 1u - e.x0))) {
-                    for (uint32_t x = xs; x < xe; ++x) {
-                        const int verdict = classifyInRow(e.sat, row, (float) (x - e.x0));
-                        sure |= verdict == kSatCertain ? 1u << (x & 7u) : 0u;
-                        open |= verdict == kSatUncertain ? 1u << (x & 7u) : 0u;
-                    }
-                }
-            }
-            else {
-                open = ((1u << (xe - x8)) - 1u) & ~((1u << (xs - x8)) - 1u);
-            }
-        }
-        if (sure != 0) {
-            // one RED per segment on its 32-bit half word (4 rows of one tile layer); nothing waits for the result
-            const size_t half = entryWord(occ, sh.entry[p], x8, y, z) * 2u + ((y & 7u) >> 2);
-            atomicOr(bits32 + half, sure << (8u * (y & 3u)));
-        }
-        if (open != 0) {
-            // undecided voxels are rare (a few per warp round): each lane reserves its own slots
-            uint32_t slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(open));
-            while (open != 0) {
-                const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
-                open &= open - 1u;
-                if (slot < kOccMaybeCap) {
-                    sh.maybe[slot] = code | bit;
-                }
-                else {  // buffer full (dense batch): straight to the queue, unfiltered
-                    const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
-                    if (index < occ.queueCapacity) {
-                        occ.queue[index] = make_uint4(sh.entry[p].leaf, (x8 | bit) | (y << 16), z, 0u);
-                    }
-                }
-                ++slot;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- filter the undecided voxels by what the bitmap shows now (this block's own `certain` bits included) ----
-    const uint32_t buffered = min(sh.maybeCount, kOccMaybeCap);
-    uint32_t count = 0;
-    for (uint32_t k = tid; k < buffered; k += kOccThreads) {
-        const uint32_t m = sh.maybe[k];
-        uint32_t x, y, z;
-        maybeVoxel(sh.entry[m >> 15], m, x, y, z);
-        const size_t word = entryWord(occ, sh.entry[m >> 15], x, y, z);
-        unsigned long long known = __ldcg(occ.bits + word);
-        if (downscale) {
-            known = smear2x2(known | __ldcg(occ.bits + (word ^ 1u)));
-        }
-        if ((known & bitmapBit(x, y)) == 0) {  // a stale read only costs a redundant clip
-            sh.maybe[k] = m | 0x80000000u;
-            ++count;
-        }
-    }
-    uint32_t inclusive = count;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(full, inclusive, o);
-        inclusive += lane >= (uint32_t) o ? up : 0u;
-    }
-    if (lane == 31) {
-        sh.warpSums[warp] = inclusive;
-    }
-    __syncthreads();
-    uint32_t blockTotal = 0, warpBase = 0;
-    for (uint32_t w = 0; w < kOccThreads / 32; ++w) {
-        warpBase += w < warp ? sh.warpSums[w] : 0u;
-        blockTotal += sh.warpSums[w];
-    }
-    if (blockTotal != 0) {  // block-uniform
-        if (tid == 0) {
-            sh.queueBase = atomicAdd(&args.counters->survivors, (unsigned long long) blockTotal);
         }
         __syncthreads();
-        unsigned long long index = sh.queueBase + warpBase + (inclusive - count);
-        for (uint32_t k = tid; k < buffered; k += kOccThreads) {
-            const uint32_t m = sh.maybe[k];
-            if ((m & 0x80000000u) != 0) {
-                uint32_t x, y, z;
-                const BatchEntry &e = sh.entry[(m >> 15) & 0xffffu];
-                maybeVoxel(e, m, x, y, z);
-                if (index < occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
-                    occ.queue[index] = make_uint4(e.leaf, x | (y << 16), z, 0u);
+    }
+
+    // ---- verdicts: lane = row, the flat row space of the batch shared out warp by warp ----
+    for (uint32_t base = warp * 32u; base < total; base += kOccThreads) {  // warp-uniform trip count
+        const uint32_t i = base + lane;
+        if (i < total) {
+            uint32_t p = 0;
+            if (table) {
+                p = sh.owner[i];
+            }
+            else {
+#pragma unroll
+                for (uint32_t step = kOccBatch / 2; step > 0; step >>= 1) {  // last entry with prefix[p] <= i
+                    p += sh.prefix[p + step] <= i ? step : 0u;
                 }
-                ++index;
+            }
+            const BatchEntry &e = sh.entry[p];
+            const uint32_t row = i - sh.prefix[p];
+            const uint32_t zi = divideBy(row, e.dy, e.magicDy);
+            const uint32_t yi = row - zi * e.dy;
+            int i0 = 0, i1 = (int) e.dx - 1, j0 = 0, j1 = -1;
+            if (args.prefilter && e.noSat == 0) {
+                classifySpan(e.sat, (float) yi, (float) zi, (float) (e.dx - 1u), i0, i1, j0, j1);
+            }
+            if (i0 <= i1) {
+                const uint32_t y = e.y0 + yi, z = e.z0 + zi;
+                // undecided voxels: [i0, j0) and (j1, i1] — all of [i0, i1] without a certain run — minus the siblings of
+                // this row's own certain voxels
+                int a1 = i1, b0 = i1 + 1;
+                if (j0 <= j1) {
+                    const uint32_t ox0 = (e.x0 + (uint32_t) j0) >> shift, ox1 = (e.x0 + (uint32_t) j1) >> shift;
+                    setRun(occ, e.slot, ox0, ox1, y >> shift, z >> shift);
+                    a1 = min(j0 - 1, (int) (ox0 << shift) - (int) e.x0 - 1);
+                    b0 = max(j1 + 1, (int) ((ox1 + 1u) << shift) - (int) e.x0);
+                }
+                const int lengthA = max(a1 - i0 + 1, 0), lengthB = max(i1 - b0 + 1, 0);
+                if (lengthA + lengthB != 0) {
+                    pushRange(sh.ranges, args, e.leaf, e.x0 + (uint32_t) i0, y, z, (uint32_t) lengthA,
+                              (uint32_t) (b0 - i0 - lengthA), (uint32_t) lengthB);
+                }
             }
         }
     }
+    __syncthreads();
+    flushRanges(sh.ranges, args);
 }
 
 /// One block = kOccBatch consecutive leaves (big leaves are left to the box kernel).
-__global__ void __launch_bounds__(kOccThreads)
+__global__ void __launch_bounds__(kOccThreads, O2V_OCC_MIN_BLOCKS)
 occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
 {
     __shared__ ClassifyShared sh;
@@ -593,15 +612,12 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
         if ((s.flags & kLeafEmpty) == 0 && leafBoxInSlab(s.v, args.grid, lo, hi)) {
             const unsigned long long v64 = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
             if (v64 <= kOccBigVolume) {
-                volume = stageBatchEntry(sh.entry[tid], args.occ, leafIndex, lo, hi, s);
-                if ((s.flags & kLeafNoPrefilter) != 0) {
-                    sh.entry[tid].sat.planeLimit = -1.0f;
-                }
+                volume = stageBatchEntry(sh.entry[tid], args.occ, leafIndex, lo, hi, s, args.certainMargin);
             }
         }
     }
     if (tid == 0) {
-        sh.maybeCount = 0;
+        sh.ranges.count = 0;
         sh.prefix[0] = 0;
     }
     uint32_t inclusive = volume;
@@ -628,30 +644,21 @@ occupancyClassifyKernel(const VoxelizeArgs args, uint32_t leafTotal)
 }
 
 constexpr int kOccDirectThreads = 128;
-constexpr uint32_t kOccDirectMaybeCap = 1024;
-
-struct DirectShared {
-    uint4 maybe[kOccDirectMaybeCap];  // undecided voxels as queue entries; .w = 1: survived the filter
-    uint32_t warpSums[kOccDirectThreads / 32];
-    uint32_t maybeCount;
-    unsigned long long queueBase;
-};
 
 /// Thread = leaf, for meshes of micro-triangles (on average at most kOccDirectCandidates candidate voxels per leaf:
-/// BASELINE config 5).  Sharing a leaf's few voxels out over a block costs more than testing them: the SAT constants
-/// stay in registers and the thread walks its own rows.  Same verdict functions, same bitmap and queue as
-/// occupancyClassifyKernel; big leaves are left to the box kernel.
+/// BASELINE config 5).  Sharing a leaf's one or two rows out over a block costs more than testing its few voxels: the
+/// per-voxel form of the SAT with its constants in registers, the thread walks its own rows.  Same bitmap and range list
+/// as occupancyClassifyKernel; big leaves are left to the box kernel.
 __global__ void __launch_bounds__(kOccDirectThreads)
 occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
 {
-    __shared__ DirectShared sh;
+    __shared__ RangeBuffer ranges;
     const OccupancyView &occ = args.occ;
-    const unsigned int full = 0xffffffffu;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const bool downscale = args.grid.supersampling == 2;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t shift = occ.shift;
     uint32_t *bits32 = reinterpret_cast<uint32_t *>(occ.bits);
     if (tid == 0) {
-        sh.maybeCount = 0;
+        ranges.count = 0;
     }
     __syncthreads();
 
@@ -662,16 +669,11 @@ occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
         uint32_t lo[3], hi[3];
         if ((s.flags & kLeafEmpty) == 0 && leafBoxInSlab(s.v, args.grid, lo, hi) &&
             (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]) <= kOccBigVolume) {
-            const bool oneChunk = (lo[0] >> 6) == ((hi[0] - 1) >> 6) && (lo[1] >> 6) == ((hi[1] - 1) >> 6) &&
-                                  (lo[2] >> 6) == ((hi[2] - 1) >> 6);
-            BatchEntry where;  // only .slot is used (entryWord)
-            where.slot = oneChunk ? __ldg(occ.chunkSlot + (lo[0] >> 6) +
-                                          occ.chunksPerAxis * ((lo[1] >> 6) + occ.chunksPerAxis * ((lo[2] >> 6) - occ.chunkZ0)))
-                                  : kNoSlot;
+            const uint32_t slot = boxSlot(occ, lo, hi);
             const float origin[3] = {(float) lo[0], (float) lo[1], (float) lo[2]};
             buildPrefilter(s, origin);
             PairSat sat;
-            buildPairSat(sat, s, origin);
+            buildPairSat(sat, s, origin, args.certainMargin);
             // a leaf whose normal is too noisy for the SAT (kLeafNoPrefilter): all undecided
             const bool useSat = args.prefilter && (s.flags & kLeafNoPrefilter) == 0;
             for (uint32_t z = lo[2]; z < hi[2]; ++z) {
@@ -692,26 +694,25 @@ occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
                             }
                         }
                         if (sure != 0) {
-                            const size_t half = entryWord(occ, where, x8, y, z) * 2u + ((y & 7u) >> 2);
-                            atomicOr(bits32 + half, sure << (8u * (y & 3u)));
-                        }
-                        if (open != 0) {
-                            uint32_t slot = atomicAdd(&sh.maybeCount, (uint32_t) __popc(open));
-                            while (open != 0) {
-                                const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
-                                open &= open - 1u;
-                                const uint4 entry = make_uint4(leafIndex, (x8 | bit) | (y << 16), z, 0u);
-                                if (slot < kOccDirectMaybeCap) {
-                                    sh.maybe[slot] = entry;
-                                }
-                                else {  // buffer full: straight to the queue, unfiltered
-                                    const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
-                                    if (index < occ.queueCapacity) {
-                                        occ.queue[index] = entry;
-                                    }
-                                }
-                                ++slot;
+                            // the segment's output voxels: itself, or its 4 parents (bits 2k and 2k + 1 -> bit k)
+                            uint32_t mask = sure;
+                            if (shift != 0) {
+                                mask = (sure | (sure >> 1)) & 0x55u;
+                                mask = (mask | (mask >> 1)) & 0x33u;
+                                mask = ((mask | (mask >> 2)) & 0x0fu) << ((x8 >> 1) & 4u);
+                                // siblings of a certain voxel need no clip
+                                const uint32_t pairs = (sure | (sure >> 1)) & 0x55u;
+                                open &= ~(pairs | (pairs << 1));
                             }
+                            const uint32_t oy = y >> shift;
+                            const size_t half = entryWord(occ, slot, x8 >> shift, oy, z >> shift) * 2u + ((oy & 7u) >> 2);
+                            atomicOr(bits32 + half, mask << (8u * (oy & 3u)));
+                        }
+                        while (open != 0) {  // runs of undecided voxels (one, as a rule)
+                            const uint32_t first = (uint32_t) __ffs((int) open) - 1u;
+                            const uint32_t length = (uint32_t) __ffs((int) ~(open >> first)) - 1u;
+                            pushRange(ranges, args, leafIndex, x8 + first, y, z, length, 0u, 0u);
+                            open &= ~(((1u << length) - 1u) << first);
                         }
                     }
                 }
@@ -719,50 +720,7 @@ occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
         }
     }
     __syncthreads();
-
-    // ---- filter the undecided voxels by what the bitmap shows now, then one reservation in the queue per block ----
-    const uint32_t buffered = min(sh.maybeCount, kOccDirectMaybeCap);
-    if (buffered == 0) {
-        return;
-    }
-    uint32_t count = 0;
-    for (uint32_t k = tid; k < buffered; k += kOccDirectThreads) {
-        const uint4 m = sh.maybe[k];
-        if (!alreadyDecided(occ, downscale, m.y & 0xffffu, m.y >> 16, m.z)) {  // a stale read only costs a redundant clip
-            sh.maybe[k].w = 1u;
-            ++count;
-        }
-    }
-    uint32_t inclusive = count;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(full, inclusive, o);
-        inclusive += lane >= (uint32_t) o ? up : 0u;
-    }
-    if (lane == 31) {
-        sh.warpSums[warp] = inclusive;
-    }
-    __syncthreads();
-    uint32_t blockTotal = 0, warpBase = 0;
-    for (uint32_t w = 0; w < kOccDirectThreads / 32; ++w) {
-        warpBase += w < warp ? sh.warpSums[w] : 0u;
-        blockTotal += sh.warpSums[w];
-    }
-    if (blockTotal != 0) {  // block-uniform
-        if (tid == 0) {
-            sh.queueBase = atomicAdd(&args.counters->survivors, (unsigned long long) blockTotal);
-        }
-        __syncthreads();
-        unsigned long long index = sh.queueBase + warpBase + (inclusive - count);
-        for (uint32_t k = tid; k < buffered; k += kOccDirectThreads) {
-            const uint4 m = sh.maybe[k];
-            if (m.w != 0) {
-                if (index < occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
-                    occ.queue[index] = make_uint4(m.x, m.y, m.z, 0u);
-                }
-                ++index;
-            }
-        }
-    }
+    flushRanges(ranges, args);
 }
 
 /// Persistent blocks over the 16^3 boxes of the big leaves (axis-aligned triangles the reference does not subdivide).
@@ -797,11 +755,8 @@ occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigne
             uint32_t lo3[3] = {leafLo[0] + bx * kOccBoxEdge, leafLo[1] + by * kOccBoxEdge, leafLo[2] + bz * kOccBoxEdge};
             uint32_t hi3[3] = {min(lo3[0] + kOccBoxEdge, leafHi[0]), min(lo3[1] + kOccBoxEdge, leafHi[1]),
                                min(lo3[2] + kOccBoxEdge, leafHi[2])};
-            const uint32_t volume = stageBatchEntry(sh.entry[0], args.occ, row.x, lo3, hi3, s);
-            if ((s.flags & kLeafNoPrefilter) != 0) {
-                sh.entry[0].sat.planeLimit = -1.0f;
-            }
-            sh.maybeCount = 0;
+            const uint32_t volume = stageBatchEntry(sh.entry[0], args.occ, row.x, lo3, hi3, s, args.certainMargin);
+            sh.ranges.count = 0;
             sh.prefix[0] = 0;
             for (uint32_t k = 1; k <= kOccBatch; ++k) {
                 sh.prefix[k] = volume;
@@ -809,6 +764,117 @@ occupancyClassifyBoxesKernel(const VoxelizeArgs args, uint32_t bigCount, unsigne
         }
         __syncthreads();
         classifyBatch(sh, args);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// filter: undecided ranges -> queue of the voxels the bitmap has not decided
+
+/// Appends `count` voxels per lane, {leaf, xy, z} from the lane's arrays, to the clip queue: one atomic for the warp
+/// (all 32 lanes call).
+template <uint32_t N>
+__device__ __forceinline__ void appendSurvivors(const VoxelizeArgs &args, const uint32_t (&leaf)[N],
+                                                const uint32_t (&xy)[N], const uint32_t (&z)[N], uint32_t count)
+{
+    const unsigned int full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t inclusive = count;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(full, inclusive, o);
+        inclusive += lane >= (uint32_t) o ? up : 0u;
+    }
+    const uint32_t warpTotal = __shfl_sync(full, inclusive, 31);
+    if (warpTotal == 0) {
+        return;
+    }
+    unsigned long long index = 0;
+    if (lane == 31) {
+        index = atomicAdd(&args.counters->survivors, (unsigned long long) warpTotal);
+    }
+    index = __shfl_sync(full, index, 31) + (inclusive - count);
+#pragma unroll
+    for (uint32_t k = 0; k < N; ++k) {
+        if (k < count && index + k < args.occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
+            args.occ.queue[index + k] = make_uint4(leaf[k], xy[k], z[k], 0u);
+        }
+    }
+}
+
+/// Thread = kFilterEntries range entries per round.  Runs after every classifier of the run: all `certain` bits are in
+/// place, so a voxel whose output voxel is already set (by another leaf, or by a sibling when downscaling) needs no
+/// clip — about two thirds of the undecided voxels on BASELINE config 4.  The kernel is a gather: what matters is how
+/// many probes are in flight, so a thread loads its entries, then issues the probes of the first kFilterProbe voxels of
+/// all their runs back to back, and the warp reserves queue slots with one atomic per round; the rest of a long run
+/// (slivers: whole rows) follows in a plain loop.
+__global__ void __launch_bounds__(kOccFilterThreads)
+occupancyFilterQueueKernel(const VoxelizeArgs args)
+{
+    const OccupancyView &occ = args.occ;
+    const unsigned int full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long total = args.counters->ranges;
+    total = total < occ.rangeCapacity ? total : occ.rangeCapacity;
+    const unsigned long long perRound = (unsigned long long) gridDim.x * blockDim.x;
+    constexpr uint32_t kSlots = kFilterEntries * 2 * kFilterProbe;
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x - lane;
+         base < total; base += perRound * kFilterEntries) {  // warp-uniform
+        uint4 r[kFilterEntries];
+#pragma unroll
+        for (uint32_t e = 0; e < kFilterEntries; ++e) {
+            const unsigned long long i = base + e * perRound + lane;
+            // entries beyond the end probe the last entry's first voxel (a valid address) and keep nothing
+            r[e] = __ldcs(occ.ranges + (i < total ? i : total - 1));
+            r[e].w = i < total ? r[e].w : 0u;
+        }
+        uint32_t px[kSlots];
+        bool wanted[kSlots], decided[kSlots];
+#pragma unroll
+        for (uint32_t e = 0; e < kFilterEntries; ++e) {
+            const uint32_t x0 = r[e].y & 0xffffu, lengthA = r[e].w & 0xffffu, lengthB = r[e].w >> 16;
+            const uint32_t xB = x0 + lengthA + (r[e].z >> 16);
+#pragma unroll
+            for (uint32_t k = 0; k < kFilterProbe; ++k) {
+                wanted[(e * 2) * kFilterProbe + k] = k < lengthA;
+                wanted[(e * 2 + 1) * kFilterProbe + k] = k < lengthB;
+                px[(e * 2) * kFilterProbe + k] = k < lengthA ? x0 + k : x0;  // (x0 is always inside the grid)
+                px[(e * 2 + 1) * kFilterProbe + k] = k < lengthB ? xB + k : x0;
+            }
+        }
+#pragma unroll
+        for (uint32_t s = 0; s < kSlots; ++s) {  // every probe loads: no branch between them
+            const uint32_t e = s / (2 * kFilterProbe);
+            decided[s] = alreadyDecided(occ, px[s], r[e].y >> 16, r[e].z & 0xffffu);
+        }
+        uint32_t leaf[kSlots], xy[kSlots], z[kSlots], count = 0;
+#pragma unroll
+        for (uint32_t s = 0; s < kSlots; ++s) {
+            const uint32_t e = s / (2 * kFilterProbe);
+            if (wanted[s] && !decided[s]) {
+                leaf[count] = r[e].x;
+                xy[count] = px[s] | (r[e].y & 0xffff0000u);
+                z[count] = r[e].z & 0xffffu;
+                ++count;
+            }
+        }
+        appendSurvivors<kSlots>(args, leaf, xy, z, count);
+        // what is left of long runs
+#pragma unroll
+        for (uint32_t e = 0; e < kFilterEntries; ++e) {
+            const uint32_t x0 = r[e].y & 0xffffu, y = r[e].y >> 16, zz = r[e].z & 0xffffu;
+            const uint32_t lengthA = r[e].w & 0xffffu, lengthB = r[e].w >> 16;
+            const uint32_t xB = x0 + lengthA + (r[e].z >> 16);
+            const uint32_t longest = __reduce_max_sync(full, max(lengthA, lengthB));
+            for (uint32_t k = kFilterProbe; k < longest; ++k) {  // warp-uniform trip count
+                uint32_t l2[2], xy2[2], z2[2], n = 0;
+                if (k < lengthA && !alreadyDecided(occ, x0 + k, y, zz)) {
+                    l2[n] = r[e].x; xy2[n] = (x0 + k) | (y << 16); z2[n] = zz; ++n;
+                }
+                if (k < lengthB && !alreadyDecided(occ, xB + k, y, zz)) {
+                    l2[n] = r[e].x; xy2[n] = (xB + k) | (y << 16); z2[n] = zz; ++n;
+                }
+                appendSurvivors<2>(args, l2, xy2, z2, n);
+            }
+        }
     }
 }
 
@@ -821,7 +887,6 @@ occupancyClipKernel(const VoxelizeArgs args)
 {
     const OccupancyView &occ = args.occ;
     const unsigned int full = 0xffffffffu;
-    const bool downscale = args.grid.supersampling == 2;
     unsigned long long total = args.counters->survivors;
     total = total < occ.queueCapacity ? total : occ.queueCapacity;
     const uint32_t lane = threadIdx.x & 31u;
@@ -862,7 +927,7 @@ occupancyClipKernel(const VoxelizeArgs args)
                 if (e < end) {
                     const uint4 entry = occ.queue[e];
                     const uint32_t x = entry.y & 0xffffu, y = entry.y >> 16, z = entry.z;
-                    if (!alreadyDecided(occ, downscale, x, y, z)) {
+                    if (!alreadyDecided(occ, x, y, z)) {
                         const float4 *src = reinterpret_cast<const float4 *>(leafAt(args, entry.x));
                         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
                         Tri<false> leaf;
@@ -874,8 +939,8 @@ occupancyClipKernel(const VoxelizeArgs args)
                             clipper.done = true;  // voxelization.cpp:451-458 (slivers only)
                         }
                         hasEntry = true;
-                        word = occ.bits + bitmapWord(occ, x, y, z);
-                        bit = bitmapBit(x, y);
+                        word = occ.bits + bitmapWord(occ, x >> occ.shift, y >> occ.shift, z >> occ.shift);
+                        bit = bitmapBit(x >> occ.shift, y >> occ.shift);
                     }
                 }
             }
@@ -924,7 +989,7 @@ struct ExpandShared {
     ExpandTile tile[kOccExpandThreads / 32][32];
 };
 
-/// Two steps per warp and 32 tiles: (1) lane = tile: load the 8 layer words, fold 2x2x2 when downscaling, count;
+/// Two steps per warp and 32 tiles: (1) lane = tile: load the 8 layer words (already in output space), count;
 /// (2) lane = output record: records are numbered across the warp's tiles, record j finds its tile, layer and bit by
 /// rank/select in shared memory — all lanes busy whatever the fill of the tiles, and a warp stores 512 contiguous bytes.
 __global__ void __launch_bounds__(kOccExpandThreads)
@@ -934,8 +999,6 @@ occupancyExpandKernel(const VoxelizeArgs args)
     const OccupancyView &occ = args.occ;
     const unsigned int full = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const bool downscale = args.grid.supersampling == 2;
-    const uint32_t shift = downscale ? 1u : 0u;
     const unsigned long long tiles = (unsigned long long) occ.activeChunks * (kChunkWords / kTileEdge);
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
     unsigned long long overflow = 0;
@@ -958,20 +1021,6 @@ occupancyExpandKernel(const VoxelizeArgs args)
                 m[2 * k + 1] = w.y;
             }
         }
-        if (downscale) {
-            // parent (qx, qy, qz) = OR of its 8 children; kept at bit (2 qx + 16 qy) of word qz
-#pragma unroll
-            for (int q = 0; q < (int) kTileEdge / 2; ++q) {
-                unsigned long long w = m[2 * q] | m[2 * q + 1];
-                w = (w | (w >> 1)) & 0x5555555555555555ull;
-                w = (w | (w >> 8)) & 0x00ff00ff00ff00ffull;
-                m[q] = w;
-            }
-#pragma unroll
-            for (int q = (int) kTileEdge / 2; q < (int) kTileEdge; ++q) {
-                m[q] = 0;
-            }
-        }
         uint32_t count = 0;
         uint16_t wordFirst[kTileEdge + 1];
 #pragma unroll
@@ -992,9 +1041,9 @@ occupancyExpandKernel(const VoxelizeArgs args)
         if (count != 0) {
             const uint32_t chunk = occ.chunkList[t >> 9], tileLocal = (uint32_t) t & 511u;
             const uint32_t C = occ.chunksPerAxis;
-            origin[0] = ((chunk % C) * kChunkEdge + (tileLocal & 7u) * kTileEdge) >> shift;
-            origin[1] = (((chunk / C) % C) * kChunkEdge + ((tileLocal >> 3) & 7u) * kTileEdge) >> shift;
-            origin[2] = ((chunk / (C * C) + occ.chunkZ0) * kChunkEdge + (tileLocal >> 6) * kTileEdge) >> shift;
+            origin[0] = (chunk % C) * kChunkEdge + (tileLocal & 7u) * kTileEdge;
+            origin[1] = ((chunk / C) % C) * kChunkEdge + ((tileLocal >> 3) & 7u) * kTileEdge;
+            origin[2] = (chunk / (C * C) + occ.chunkZ0) * kChunkEdge + (tileLocal >> 6) * kTileEdge;
         }
         __syncwarp();  // the previous round's readers are done
         ExpandTile &mine = sh.tile[warp][lane];
@@ -1034,8 +1083,8 @@ occupancyExpandKernel(const VoxelizeArgs args)
             const uint32_t b = selectBit64(sh.mask[warp][z][tile], r - info.wordFirst[z]);
             if (index + j < args.outCapacity) {
                 VoxelRecord rec;
-                rec.x = (int32_t) (info.origin[0] + ((b & 7u) >> shift));
-                rec.y = (int32_t) (info.origin[1] + ((b >> 3) >> shift));
+                rec.x = (int32_t) (info.origin[0] + (b & 7u));
+                rec.y = (int32_t) (info.origin[1] + (b >> 3));
                 rec.z = (int32_t) (info.origin[2] + z);
                 rec.argb = 0xFFFFFFFFu;  // quantizeArgb(1, 1, 1)
                 __stcs(reinterpret_cast<int4 *>(args.out + index + j), *reinterpret_cast<const int4 *>(&rec));
@@ -1117,6 +1166,13 @@ void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTo
         blocks = blocks < boxTotal ? blocks : boxTotal;
         occupancyClassifyBoxesKernel<<<(unsigned) blocks, kOccThreads, 0, stream>>>(args, bigCount, boxTotal);
     }
+}
+
+void launchOccupancyFilterQueue(const VoxelizeArgs &args, int smCount, cudaStream_t stream)
+{
+    // the length of the range list lives on the device (RunCounters::ranges)
+    occupancyFilterQueueKernel<<<occupancyPersistentBlocks(occupancyFilterQueueKernel, kOccFilterThreads, smCount),
+                                 kOccFilterThreads, 0, stream>>>(args);
 }
 
 void launchOccupancyClip(const VoxelizeArgs &args, int smCount, cudaStream_t stream)

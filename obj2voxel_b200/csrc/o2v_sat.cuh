@@ -124,12 +124,22 @@ struct alignas(16) PairSat {
     float plane[4];        // n . q + d at the voxel centre, q = voxel min corner - origin
     float planeLimit;      // (0.5 + kPrefilterMargin) * |n|_1
     float planeSure;       // (0.5 - kCertainMargin) * |n|_1
-    float lo[3], hi[3];    // origin-relative float AABB of the leaf (box-normal axes of the SAT)
+    float lo[3], hi[3];    // origin-relative float AABB of the leaf (box-normal axes of the SAT), shrunk by the
+                           // `certain` margin: voxel l is inside on axis a iff lo[a] <= l[a] <= hi[a]
     SatEdge edge[9];
 };
 
+/// Shrink of the voxel box for `certain` at sample resolution S: the displacement e of a computed intersection point in
+/// the six sequential clips is <= 3e-4 for S <= 2048 (header), so s = 1/64 - 1/128 - 1e-3 = 0.0068 still exceeds 6 e =
+/// 0.0018 almost fourfold; above that the header's 1/32 stands.  A third fewer `uncertain` voxels (exact clips) on the
+/// resolutions BASELINE.json names.  tests/test_sat_classifier.py fuzzes both.
+O2V_HD float certainMarginFor(uint32_t sampleResolution)
+{
+    return sampleResolution <= 2048u ? 0.015625f : kCertainMargin;
+}
+
 /// Builds the constants from a leaf staged with buildPrefilter(s, origin).
-O2V_HD void buildPairSat(PairSat &out, const LeafStage &s, const float origin[3])
+O2V_HD void buildPairSat(PairSat &out, const LeafStage &s, const float origin[3], float certainMargin = kCertainMargin)
 {
     const float norm1 = fabsf(s.plane[0]) + fabsf(s.plane[1]) + fabsf(s.plane[2]);
 O2V_UNROLL
@@ -137,13 +147,14 @@ O2V_UNROLL
         out.plane[k] = s.plane[k];
     }
     out.planeLimit = s.planeLimit;
-    out.planeSure = (0.5f - kCertainMargin) * norm1;
+    out.planeSure = (0.5f - certainMargin) * norm1;
 O2V_UNROLL
     for (int a = 0; a < 3; ++a) {
-        out.lo[a] = fminf(fminf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
-        out.hi[a] = fmaxf(fmaxf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a];
+        // l + margin <= max  and  l + 1 - margin >= min
+        out.lo[a] = fminf(fminf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a] - 1.0f + certainMargin;
+        out.hi[a] = fmaxf(fmaxf(s.v[a], s.v[3 + a]), s.v[6 + a]) - origin[a] - certainMargin;
     }
-    const float shift = kPrefilterMargin + kCertainMargin;
+    const float shift = kPrefilterMargin + certainMargin;
 O2V_UNROLL
     for (int k = 0; k < 9; ++k) {
         out.edge[k].a = s.edge[k * 3];
@@ -167,8 +178,7 @@ O2V_HD void buildRowSat(const PairSat &s, float ly, float lz, RowSat &r)
 {
     r.planeRow = s.plane[1] * ly + s.plane[2] * lz + s.plane[3];
     r.miss = false;
-    r.sure = (ly + kCertainMargin <= s.hi[1]) && (ly + 1.0f - kCertainMargin >= s.lo[1]) &&
-             (lz + kCertainMargin <= s.hi[2]) && (lz + 1.0f - kCertainMargin >= s.lo[2]);
+    r.sure = ly <= s.hi[1] && ly >= s.lo[1] && lz <= s.hi[2] && lz >= s.lo[2];
 O2V_UNROLL
     for (int i = 0; i < 3; ++i) {
         r.xyBase[i] = s.edge[i].b * ly + s.edge[i].c;
@@ -208,8 +218,7 @@ O2V_HD int classifyInRow(const PairSat &s, const RowSat &r, float lx)
 {
     const float dist = fabsf(s.plane[0] * lx + r.planeRow);
     bool miss = dist > s.planeLimit;
-    bool sure = r.sure && dist <= s.planeSure && (lx + kCertainMargin <= s.hi[0]) &&
-                (lx + 1.0f - kCertainMargin >= s.lo[0]);
+    bool sure = r.sure && dist <= s.planeSure && lx <= s.hi[0] && lx >= s.lo[0];
 O2V_UNROLL
     for (int i = 0; i < 3; ++i) {
         const float xy = s.edge[i].a * lx + r.xyBase[i];
@@ -220,6 +229,133 @@ O2V_UNROLL
         sure = sure && zx >= s.edge[6 + i].k;
     }
     return miss ? kSatMiss : (sure ? kSatCertain : kSatUncertain);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same SAT solved per row instead of evaluated per voxel.  Along a row (fixed ly, lz) each of the seven axes that
+// vary with x is a linear function g * lx + base, so "not a miss" and "certain" are each an interval of lx: the
+// intersection of one half-line per edge function and one band for the plane.  A row costs the same whatever its length,
+// every lane does the same work (no per-lane voxel loops), and the `certain` voxels come out as one run of bits.
+// Against the per-voxel form the interval ends carry the rounding of one multiplication by a reciprocal (relative 2^-22):
+// a voxel can only change verdict if its value lies within ~1e-6 of a threshold, i.e. the effective margins move by
+// ~1e-6 of 1/64 — inside every slack of the header.  tests/test_sat_classifier.py fuzzes this form against the exact clip.
+
+constexpr float kSpanBig = 1.0e30f;       // "no bound from this edge"
+constexpr float kSpanInvLimit = 1.0e18f;  // reciprocal of a coefficient that is (nearly) zero: the function is row-constant
+
+/// An x-varying edge function of a row as bounds on lx: with base = coef * (ly or lz) + c and t = base * inv = -base / g,
+/// not-a-miss <=> t + dLo <= lx <= t + dHi and certain <=> t + dLoSure <= lx <= t + dHiSure; the side the edge does not
+/// bound carries -/+ kSpanBig.  g == 0 is the limit g -> +0: t = -base * kSpanInvLimit puts the bound far below the row
+/// when base passes and far above when it fails.
+struct alignas(16) SpanEdge {
+    float coef, c, inv, dLo;
+    float dHi, dLoSure, dHiSure, pad;
+};
+
+struct alignas(16) SpanSat {
+    float ny, nz, d, pn;                      // plane value = nx * lx + (ny * ly + nz * lz + d); pn = -1 / nx
+    float wMiss, wSure, loSure, hiSure;       // half widths planeLimit / |nx|, planeSure / |nx|; x box normal of `certain`
+    float ySureLo, ySureHi, zSureLo, zSureHi; // rows whose y / z box normals allow `certain`
+    SatEdge yz[3];                            // the yz projection: constant along a row
+    SpanEdge xy[3];                           // base = coef * ly + c
+    SpanEdge zx[3];                           // base = coef * lz + c
+};
+
+/// 1 / x for x in [1e-18, 1e18]; one ulp more or less does not matter to the interval ends (see above).
+O2V_HD float spanReciprocal(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdividef(1.0f, x);
+#else
+    return 1.0f / x;
+#endif
+}
+
+O2V_HD void makeSpanEdge(SpanEdge &e, float g, float coef, float c, float k)
+{
+    const float ag = fabsf(g);
+    const float invAbs = ag > 1.0f / kSpanInvLimit ? spanReciprocal(ag) : kSpanInvLimit;
+    const bool lower = !(g < 0.0f);
+    const float ks = k * invAbs;
+    e.coef = coef;
+    e.c = c;
+    e.inv = lower ? -invAbs : invAbs;
+    e.dLo = lower ? 0.0f : -kSpanBig;
+    e.dHi = lower ? kSpanBig : 0.0f;
+    e.dLoSure = lower ? ks : -kSpanBig;
+    e.dHiSure = lower ? kSpanBig : -ks;
+    e.pad = 0.0f;
+}
+
+O2V_HD void buildSpanSat(SpanSat &out, const PairSat &s)
+{
+    const float anx = fabsf(s.plane[0]);
+    const float invAbs = anx > 1.0f / kSpanInvLimit ? spanReciprocal(anx) : kSpanInvLimit;
+    out.ny = s.plane[1];
+    out.nz = s.plane[2];
+    out.d = s.plane[3];
+    out.pn = s.plane[0] < 0.0f ? invAbs : -invAbs;
+    out.wMiss = s.planeLimit * invAbs;
+    out.wSure = s.planeSure * invAbs;
+    out.loSure = s.lo[0];
+    out.hiSure = s.hi[0];
+    out.ySureLo = s.lo[1];
+    out.ySureHi = s.hi[1];
+    out.zSureLo = s.lo[2];
+    out.zSureHi = s.hi[2];
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        out.yz[i] = s.edge[3 + i];
+        makeSpanEdge(out.xy[i], s.edge[i].a, s.edge[i].b, s.edge[i].c, s.edge[i].k);          // a * lx + b * ly + c
+        makeSpanEdge(out.zx[i], s.edge[6 + i].b, s.edge[6 + i].a, s.edge[6 + i].c, s.edge[6 + i].k);  // a * lz + b * lx + c
+    }
+}
+
+/// The verdicts of row (ly, lz) of a box whose voxels are lx = 0 .. lastX: voxels in [i0, i1] are not a `miss`, those in
+/// [j0, j1] (a sub-range, empty when j0 > j1) are `certain`, the rest of [i0, i1] is `uncertain`.  i0 > i1: the whole
+/// row misses.
+O2V_HD void classifySpan(const SpanSat &s, float ly, float lz, float lastX, int &i0, int &i1, int &j0, int &j1)
+{
+    bool miss = false;
+    bool sure = ly >= s.ySureLo && ly <= s.ySureHi && lz >= s.zSureLo && lz <= s.zSureHi;
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const float value = s.yz[i].a * ly + s.yz[i].b * lz + s.yz[i].c;
+        miss = miss || value < 0.0f;
+        sure = sure && value >= s.yz[i].k;
+    }
+    const float centre = (s.ny * ly + s.nz * lz + s.d) * s.pn;
+    float loM = fmaxf(0.0f, centre - s.wMiss), hiM = fminf(lastX, centre + s.wMiss);
+    float loS = fmaxf(s.loSure, centre - s.wSure), hiS = fminf(s.hiSure, centre + s.wSure);
+O2V_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const float t = (s.xy[i].coef * ly + s.xy[i].c) * s.xy[i].inv;
+        loM = fmaxf(loM, t + s.xy[i].dLo);
+        hiM = fminf(hiM, t + s.xy[i].dHi);
+        loS = fmaxf(loS, t + s.xy[i].dLoSure);
+        hiS = fminf(hiS, t + s.xy[i].dHiSure);
+        const float u = (s.zx[i].coef * lz + s.zx[i].c) * s.zx[i].inv;
+        loM = fmaxf(loM, u + s.zx[i].dLo);
+        hiM = fminf(hiM, u + s.zx[i].dHi);
+        loS = fmaxf(loS, u + s.zx[i].dLoSure);
+        hiS = fminf(hiS, u + s.zx[i].dHiSure);
+    }
+    // into [-1, lastX + 1] before the conversions (the bounds may be +-1e30)
+    loM = fminf(loM, lastX + 1.0f);
+    hiM = fmaxf(hiM, -1.0f);
+    loS = fminf(fmaxf(loS, loM), lastX + 1.0f);
+    hiS = fmaxf(fminf(hiS, hiM), -1.0f);
+#if defined(__CUDA_ARCH__)
+    i0 = __float2int_ru(loM);
+    i1 = miss ? i0 - 1 : __float2int_rd(hiM);
+    j0 = __float2int_ru(loS);
+    j1 = sure ? __float2int_rd(hiS) : j0 - 1;
+#else
+    i0 = (int) ceilf(loM);
+    i1 = miss ? i0 - 1 : (int) floorf(hiM);
+    j0 = (int) ceilf(loS);
+    j1 = sure ? (int) floorf(hiS) : j0 - 1;
+#endif
 }
 
 /// Three-way verdict for the voxel whose min corner is origin + (lx, ly, lz).  Leaves flagged kLeafNoPrefilter must not

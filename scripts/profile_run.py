@@ -30,4 +30,4 @@ for i in range(steps):
     torch.cuda.synchronize()
     print(json.dumps({k: st[k] for k in ("voxels", "leaves", "pairs", "light_tiles", "heavy_tiles", "clip_calls",
                                          "contributions", "candidate_voxels", "survivors", "occupancy_path", "ms_total", "ms_setup",
-                                         "ms_voxelize", "ms_clip", "ms_classify")}), flush=True)
+                                         "ms_voxelize", "ms_clip", "ms_classify", "ms_filter", "ms_expand", "undecided_ranges")}), flush=True)

@@ -21,7 +21,6 @@ def profiled(rep, kernel):
     h = rows[1]
     ia, isamp, iex, ith = (h.index(k) for k in ("Source", "# Samples", "Instructions Executed", "Avg. Threads Executed"))
     data = [r for r in rows[2:] if len(r) > 10 and r[isamp].isdigit()]
-    data = data[:len(data) // 2]  # the page lists the kernel twice
     return [(int(r[isamp]), int(r[iex]), float(r[ith]), r[ia]) for r in data]
 
 
@@ -48,6 +47,8 @@ def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     hint = sys.argv[3] if len(sys.argv) > 3 else "o2v_occupancy"
     prof, lines = profiled(rep, kernel), line_table(kernel, hint)
+    if len(prof) == 2 * len(lines):  # some captures list the kernel twice
+        prof = prof[:len(lines)]
     if len(prof) != len(lines):
         sys.exit("report (%d instructions) and library (%d) are not the same build" % (len(prof), len(lines)))
     total = sum(p[1] for p in prof)

@@ -25,15 +25,22 @@ def shim():
         import obj2voxel_b200
         obj2voxel_b200.build()
     lib = C.CDLL(SHIM)
-    lib.o2vt_classify_fuzz.argtypes = [fp, C.c_size_t, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
+    lib.o2vt_classify_fuzz.argtypes = [fp, C.c_size_t, C.c_ulonglong, C.c_float, C.POINTER(C.c_ulonglong)]
     return lib
 
 
-def run(shim, leaves, max_volume=200_000):
+def certain_margin(grid):
+    """certainMarginFor(S) of o2v_sat.cuh: what the kernels use at sample resolution S."""
+    return 1.0 / 64 if grid <= 2048 else 1.0 / 32
+
+
+def run(shim, leaves, grid=8192, max_volume=200_000):
     leaves = np.ascontiguousarray(leaves, np.float32).reshape(-1, 9)
-    out = (C.c_ulonglong * 8)()
-    shim.o2vt_classify_fuzz(leaves.ctypes.data_as(fp), len(leaves), max_volume, out)
-    keys = ["pairs", "miss", "uncertain", "certain", "hits", "miss_but_hit", "certain_but_no_hit", "skipped"]
+    out = (C.c_ulonglong * 16)()
+    shim.o2vt_classify_fuzz(leaves.ctypes.data_as(fp), len(leaves), max_volume, certain_margin(grid), out)
+    keys = ["pairs", "miss", "uncertain", "certain", "hits", "miss_but_hit", "certain_but_no_hit", "skipped",
+            "span_miss", "span_uncertain", "span_certain", "span_miss_but_hit", "span_certain_but_no_hit",
+            "span_differs"]
     return dict(zip(keys, [int(x) for x in out]))
 
 
@@ -85,34 +92,44 @@ def grid_sized(rng, n, grid):
 
 
 REGIMES = [
-    ("voxel-sized @64", lambda r: blobs(r, 4000, 64, 1.2)),
-    ("voxel-sized @2048", lambda r: blobs(r, 4000, 2048, 1.2)),
-    ("voxel-sized @8192", lambda r: blobs(r, 4000, 8192, 1.2)),
-    ("cfg4-sized @2048", lambda r: blobs(r, 3000, 2048, 2.05)),
-    ("leaf-sized @8192", lambda r: blobs(r, 1500, 8192, 4.0)),
-    ("large @8192", lambda r: blobs(r, 60, 8192, 25.0)),
-    ("needles @2048", lambda r: needles(r, 600, 2048, 60.0, (1e-7, 1e-1))),
-    ("needles @8192", lambda r: needles(r, 600, 8192, 200.0, (1e-6, 1.0))),
-    ("snapped @256", lambda r: snapped(r, 3000, 256, 2.5)),
-    ("snapped @8192", lambda r: snapped(r, 3000, 8192, 2.5)),
-    ("grid-sized @2048", lambda r: grid_sized(r, 60, 2048)),
-    ("grid-sized @8192", lambda r: grid_sized(r, 60, 8192)),
+    ("voxel-sized @64", 64, lambda r: blobs(r, 4000, 64, 1.2)),
+    ("voxel-sized @2048", 2048, lambda r: blobs(r, 4000, 2048, 1.2)),
+    ("voxel-sized @8192", 8192, lambda r: blobs(r, 4000, 8192, 1.2)),
+    ("cfg4-sized @2048", 2048, lambda r: blobs(r, 3000, 2048, 2.05)),
+    ("leaf-sized @2048", 2048, lambda r: blobs(r, 1500, 2048, 4.0)),
+    ("leaf-sized @8192", 8192, lambda r: blobs(r, 1500, 8192, 4.0)),
+    ("large @2048", 2048, lambda r: blobs(r, 60, 2048, 25.0)),
+    ("large @8192", 8192, lambda r: blobs(r, 60, 8192, 25.0)),
+    ("needles @2048", 2048, lambda r: needles(r, 600, 2048, 60.0, (1e-7, 1e-1))),
+    ("needles @8192", 8192, lambda r: needles(r, 600, 8192, 200.0, (1e-6, 1.0))),
+    ("snapped @256", 256, lambda r: snapped(r, 3000, 256, 2.5)),
+    ("snapped @2048", 2048, lambda r: snapped(r, 3000, 2048, 2.5)),
+    ("snapped @8192", 8192, lambda r: snapped(r, 3000, 8192, 2.5)),
+    ("grid-sized @2048", 2048, lambda r: grid_sized(r, 60, 2048)),
+    ("grid-sized @8192", 8192, lambda r: grid_sized(r, 60, 8192)),
 ]
 
 
-@pytest.mark.parametrize("name,make", REGIMES, ids=[r[0] for r in REGIMES])
-def test_verdicts_agree_with_the_reference_semantics(shim, name, make):
+@pytest.mark.parametrize("name,grid,make", REGIMES, ids=[r[0] for r in REGIMES])
+def test_verdicts_agree_with_the_reference_semantics(shim, name, grid, make):
+    """Both forms of the classifier — per voxel (thread-per-leaf kernel, weighted-path prefilter) and per row
+    (classifySpan: the block classifier) — with the `certain` margin the kernels use at that grid size."""
     rng = np.random.default_rng(sum(map(ord, name)))
-    stats = run(shim, make(rng))
+    stats = run(shim, make(rng), grid)
     assert stats["pairs"] > 1000, stats
     assert stats["miss_but_hit"] == 0, (name, stats)
     assert stats["certain_but_no_hit"] == 0, (name, stats)
+    assert stats["span_miss_but_hit"] == 0, (name, stats)
+    assert stats["span_certain_but_no_hit"] == 0, (name, stats)
+    # the two forms differ only by rounding at a threshold: a handful of voxels at most
+    assert stats["span_differs"] <= max(4, stats["pairs"] // 100_000), (name, stats)
     if "needles" not in name:
-        assert stats["certain"] > 0, (name, stats)  # the sweep exercises the verdict it is about
+        assert stats["certain"] > 0 and stats["span_certain"] > 0, (name, stats)  # the sweep exercises the verdicts
 
 
 def test_certain_covers_most_hits_on_the_bench_workload(shim):
     """The occupancy-only path pays an exact clip only for the `uncertain` band: on cfg4-like triangles it must be a small
     fraction of the hits (this is a performance property, pinned loosely)."""
-    stats = run(shim, blobs(np.random.default_rng(3), 5000, 2048, 2.05))
-    assert stats["certain"] > 0.75 * stats["hits"], stats
+    stats = run(shim, blobs(np.random.default_rng(3), 5000, 2048, 2.05), 2048)
+    assert stats["certain"] > 0.8 * stats["hits"], stats
+    assert stats["span_certain"] > 0.8 * stats["hits"], stats
