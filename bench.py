@@ -477,11 +477,15 @@ def run_ours(args, cfg, workload):
     rank_tri = int(stats["slab_triangles"]) if occupancy_path else n_tri
     rank_voxels = int(stats["voxels"])
 
-    # ---- end to end with HOST buffers (H2D + kernels + D2H inside the timed region) ----
-    e2e = run_e2e(args, cfg, leg, engine, rank, world, device, sync_all, voxels, golden)
-
     # ---- BASELINE.json's other named configs, same measurement, each checked against the reference's checksum ----
-    leg_bounds = leg.bounds
+    pinned_verts = pinned_uvs = None
+    if rank == 0:
+        pinned_verts = torch.empty(leg.full_verts.shape, dtype=torch.float32, pin_memory=True)
+        pinned_verts.copy_(leg.full_verts)
+        if leg.full_uvs is not None:
+            pinned_uvs = torch.empty(leg.full_uvs.shape, dtype=torch.float32, pin_memory=True)
+            pinned_uvs.copy_(leg.full_uvs)
+    leg_bounds, tri_bytes_e2e = leg.bounds, leg.tri_bytes
     del leg
     torch.cuda.empty_cache()
     side = {}
@@ -489,6 +493,18 @@ def run_ours(args, cfg, workload):
     for name in ("cfg2", "cfg3", "cfg5"):
         if name != workload and os.environ.get("O2V_BENCH_SIDE", "1") != "0":
             side[name] = side_config(engine, name, rank, world, device, sync_all, golden, side_steps)
+
+    # ---- end to end with HOST buffers: one process, all N devices (rank 0); the other ranks release theirs first ----
+    engine.close()
+    torch.cuda.empty_cache()
+    sync_all()
+    cpu_group = dist.new_group(backend="gloo") if distributed else None
+    e2e = None
+    if rank == 0:
+        e2e = run_e2e(args, cfg, pinned_verts.numpy(), None if pinned_uvs is None else pinned_uvs.numpy(), n_tri,
+                      tri_bytes_e2e, rank, world, voxels, golden, workload)
+    if distributed:
+        dist.barrier(group=cpu_group)  # on the CPU: no kernel of the waiting ranks sits on the devices rank 0 is driving
 
     if rank == 0:
         peak, peak_source = measured_peak()
@@ -537,116 +553,113 @@ def run_ours(args, cfg, workload):
         if baseline is not None:
             line["cpu_baseline"] = baseline
         print(json.dumps(line), flush=True)
-    engine.close()
     if distributed:
-        dist.barrier()
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(args, cfg, leg, engine, rank, world, device, sync_all, voxels, golden):
-    """End to end with HOST buffers.
-    N = 1: the reference-facing C API (obj2voxel instance, bulk input, voxel callback).
-    N > 1: every rank uploads its 1/N share of the host triangle array from pinned memory, the shares are all-gathered
-           over NVLink, each rank voxelizes its Z-slab through the Engine API and downloads its own voxels into pinned
-           host memory."""
-    import torch
-    import torch.distributed as dist
+def run_e2e(args, cfg, host_verts, host_uvs, n_tri, tri_bytes, rank, world, voxels, golden, workload):
+    """End to end with HOST buffers through the reference-facing C API: obj2voxel instance, bulk triangle input (pinned host
+    memory), obj2voxel_voxelize(), voxel callback receiving reference-layout quads.  H2D, kernels, D2H and the host-side
+    expansion of downloaded bitmaps are all inside the timed region.  With N GPUs this is ONE process driving N devices
+    (obj2voxel_b200_set_devices: Z-slabs, triangles exchanged over peer memory) — rank 0 runs it while the other ranks
+    have released their devices.  Also timed at N = 1: the same job from a pageable array and through the reference's
+    one-callback-per-triangle ingestion."""
+    import ctypes as C
 
     import obj2voxel_b200 as o2v
-    from obj2voxel_b200 import meshes, slabs
+    from obj2voxel_b200 import _lib, meshes
 
-    distributed = world > 1
-    verts, uvs, n_tri = leg.full_verts, leg.full_uvs, leg.n_tri
-    pinned_verts = torch.empty(verts.shape, dtype=verts.dtype, pin_memory=True)
-    pinned_verts.copy_(verts)
-    host_verts = pinned_verts.numpy()
-    host_uvs = None
-    pinned_uvs = None
-    if uvs is not None:
-        pinned_uvs = torch.empty(uvs.shape, dtype=uvs.dtype, pin_memory=True)
-        pinned_uvs.copy_(uvs)
-        host_uvs = pinned_uvs.numpy()
-    e2e_times, e2e_voxels = [], 0
+    lib = o2v.load()
+    lib.obj2voxel_set_log_level(_lib.LOG_ERROR)
+    tex_obj = o2v.Texture(meshes.random_texture(256, 256, 3), wrap=o2v.UV_WRAP) if host_uvs is not None else None
+    devices = list(range(world))
     e2e_steps = max(1, min(args.steps, 5))
-    if not distributed:
-        tex_obj = o2v.Texture(meshes.random_texture(256, 256, 3), wrap=o2v.UV_WRAP) if uvs is not None else None
-        lib = o2v.load()
-        lib.obj2voxel_set_log_level(o2v._lib.LOG_ERROR)
-        for step in range(1 + e2e_steps):
-            inst = o2v.Instance()
-            inst.set_input_triangles(host_verts, uvs=host_uvs, texture=tex_obj)
-            received = {"n": 0}
 
-            def on_voxels(_data, _quads, count, received=received):
+    def one_job(verts, mode="bulk", collect=False):
+        inst = o2v.Instance()
+        source = None
+        if mode == "callback":
+            source = _lib.ArraySource(verts.ctypes.data, len(verts), 0)
+            lib.obj2voxel_set_input_callback(inst.handle, C.cast(lib.obj2voxel_b200_array_source_next,
+                                                                 _lib.TRIANGLE_CALLBACK), C.addressof(source))
+        else:
+            inst.set_input_triangles(verts, uvs=host_uvs, texture=tex_obj)
+        received = {"n": 0, "chunks": []}
+        counter = _lib.CountingSink(0, 0)
+        if collect:
+            # untimed verification run: a Python callback that keeps a copy of every batch
+            def on_voxels(_data, quads, count, received=received):
                 received["n"] += count
+                if count:
+                    received["chunks"].append(np.ctypeslib.as_array(quads, shape=(count, 4)).copy())
                 return True
 
-            cb = o2v._lib.VOXEL_CALLBACK(on_voxels)
-            lib.obj2voxel_set_output_callback(inst.handle, cb, None)
-            inst.set_resolution(cfg["resolution"])
-            inst.set_supersampling(cfg["supersampling"])
-            inst.set_color_strategy(cfg["strategy"])
-            if cfg["bounds"] is not None:
-                inst.set_mesh_boundaries(cfg["bounds"])
-            sync_all()
-            t0 = time.perf_counter()
-            err = inst.voxelize()
-            torch.cuda.synchronize(device)
-            dt = time.perf_counter() - t0
-            inst.free()
-            if err != 0:
-                raise RuntimeError("obj2voxel_voxelize failed with error %d" % err)
+            cb = _lib.VOXEL_CALLBACK(on_voxels)
+        else:
+            # timed runs: the C callback a C caller would pass (it counts); a Python callback would add the
+            # interpreter's cost per call to a path whose calls come from the library's own threads
+            cb = C.cast(lib.obj2voxel_b200_counting_sink_write, _lib.VOXEL_CALLBACK)
+        lib.obj2voxel_set_output_callback(inst.handle, cb, C.addressof(counter))
+        inst.set_resolution(cfg["resolution"])
+        inst.set_supersampling(cfg["supersampling"])
+        inst.set_color_strategy(cfg["strategy"])
+        if cfg["bounds"] is not None:
+            inst.set_mesh_boundaries(cfg["bounds"])
+        inst.set_devices(devices)
+        t0 = time.perf_counter()
+        err = inst.voxelize()
+        dt = time.perf_counter() - t0
+        stats = inst.stats()
+        inst.free()
+        if err != 0:
+            raise RuntimeError("obj2voxel_voxelize failed with error %d" % err)
+        if not collect:
+            received["n"] = int(counter.voxels)
+        return dt, received, stats
+
+    def timed(verts, mode="bulk", steps=e2e_steps):
+        times, got = [], 0
+        for step in range(1 + steps):
+            dt, received, _ = one_job(verts, mode)
             if step > 0:
-                e2e_times.append(dt)
-                e2e_voxels = received["n"]
-        e2e_api = ("obj2voxel_b200_set_input_triangles + obj2voxel_voxelize + voxel callback (the job runs in 4 z parts: "
-                   "the download of one under the kernels of the next)")
-    else:
-        params = o2v.make_params(slab=slabs.my_slab(leg.bounds, rank), **leg.kw)
-        per_rank = -(-n_tri // world)
-        lo, hi = min(rank * per_rank, n_tri), min((rank + 1) * per_rank, n_tri)
-        share_v = torch.zeros((per_rank, 9), dtype=torch.float32, device=device)
-        full_v = torch.empty((per_rank * world, 9), dtype=torch.float32, device=device)
-        share_u = full_u = None
-        if uvs is not None:
-            share_u = torch.zeros((per_rank, 6), dtype=torch.float32, device=device)
-            full_u = torch.empty((per_rank * world, 6), dtype=torch.float32, device=device)
-        out_pinned = torch.empty((max(int(engine.result_count() * 1.1) + 1024, 1), 4), dtype=torch.int32,
-                                 pin_memory=True)
-        out_np = out_pinned.numpy().view(np.uint32)
-        stream = torch.cuda.current_stream(device).cuda_stream
-        for step in range(1 + e2e_steps):
-            sync_all()
-            t0 = time.perf_counter()
-            share_v[: hi - lo].copy_(pinned_verts[lo:hi], non_blocking=True)
-            dist.all_gather_into_tensor(full_v, share_v)
-            if uvs is not None:
-                share_u[: hi - lo].copy_(pinned_uvs[lo:hi], non_blocking=True)
-                dist.all_gather_into_tensor(full_u, share_u)
-            got = []
-            if not leg.empty:
-                engine.voxelize_device(full_v[:n_tri], params, uvs=None if uvs is None else full_u[:n_tri],
-                                       textures=leg.textures)
-                got = engine.download(out=out_np, stream=stream)
-            torch.cuda.synchronize(device)
-            dt = time.perf_counter() - t0
-            if step > 0:
-                e2e_times.append(dt)
-                e2e_voxels = len(got)
-        e2e_api = ("pinned host share -> H2D -> all_gather (NVLink) -> Engine.voxelize_device(slab) -> "
-                   "Engine.download to pinned host")
-    e2e_t = torch.tensor([float(np.mean(e2e_times))], dtype=torch.float64, device=device)
-    e2e_counts = [e2e_voxels]
-    if distributed:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_counts = slabs.allreduce_counts(e2e_counts, device)
-    e2e_seconds = float(e2e_t.item())
-    if e2e_counts[0] != voxels:
-        raise RuntimeError("e2e voxel count %d != device-resident count %d" % (e2e_counts[0], voxels))
-    return {"value": n_tri / e2e_seconds / 1e6, "unit": "Mtri/s", "ms_per_step": e2e_seconds * 1e3,
-            "h2d_bytes_per_step": int(n_tri * leg.tri_bytes), "d2h_bytes_per_step": int(16 * voxels),
-            "api": e2e_api}
+                times.append(dt)
+                got = received["n"]
+        if got != voxels:
+            raise RuntimeError("e2e (%s) voxel count %d != device-resident count %d" % (mode, got, voxels))
+        return float(np.mean(times))
+
+    seconds = timed(host_verts)
+    # the records the callback received, once, untimed: same order-independent hash as the reference's output
+    _, received, stats = one_job(host_verts, collect=True)
+    records = np.concatenate(received["chunks"]) if received["chunks"] else np.zeros((0, 4), np.uint32)
+    digest = meshes.record_hash(records)
+    ref = golden.get(workload)
+    hash_ok = bool(len(records) == ref["voxels"] and digest == ref["hash64"]) if ref and "hash64" in ref else None
+    del records, received
+    if hash_ok is False:
+        raise RuntimeError("e2e records differ from the reference's (hash %d)" % digest)
+    bitmap = bool(stats["download_bytes"] < 16 * voxels)
+    out = {"value": n_tri / seconds / 1e6, "unit": "Mtri/s", "ms_per_step": seconds * 1e3,
+           "h2d_bytes_per_step": int(n_tri * tri_bytes),
+           "d2h_bytes_per_step": int(stats["download_bytes"]), "voxel_callback_bytes_per_step": int(16 * voxels),
+           "hash_ok": hash_ok, "devices": world,
+           "api": "obj2voxel_b200_set_input_triangles (pinned host array) + obj2voxel_b200_set_devices(%d) + "
+                  "obj2voxel_voxelize + voxel callback; %s" %
+                  (world, "the result crosses PCIe as occupancy bitmaps (1 bit per output voxel of the touched 64^3 "
+                          "chunks) and host threads write the quads the callback receives" if bitmap else
+                   "records cross PCIe as they are, each device's over its own link")}
+    if world == 1 and host_uvs is None:
+        pageable = np.array(host_verts, copy=True)  # plain numpy memory
+        ms = timed(pageable, steps=min(e2e_steps, 3)) * 1e3
+        out["pageable_input"] = {"ms_per_step": ms, "value": n_tri / (ms * 1e-3) / 1e6, "unit": "Mtri/s",
+                                 "note": "same job from a pageable array: host threads stage it through pinned buffers"}
+        ms = timed(host_verts, mode="callback", steps=1) * 1e3
+        out["callback_input"] = {"ms_per_step": ms, "value": n_tri / (ms * 1e-3) / 1e6, "unit": "Mtri/s",
+                                 "note": "same job through obj2voxel_set_input_callback: one indirect call per triangle "
+                                         "(src/obj2voxel.cpp:585-588), then the same device path"}
+    return out
 
 
 def main():

@@ -93,6 +93,7 @@ typedef struct o2v_b200_stats {
                                  * against the bitmap; `survivors` of them reach the exact clip) */
     float ms_filter;            /* occupancy-only path: duration of that check (occupancyFilterQueueKernel) */
     float ms_expand;            /* occupancy-only path: bitmap -> records (occupancyExpandKernel) */
+    uint64_t download_bytes;    /* obj2voxel_voxelize(): bytes copied device -> host (records, or bitmaps + chunk lists) */
 } o2v_b200_stats;
 
 /* NULL when no CUDA device is usable (no CPU fallback); see o2v_b200_last_error(). */
@@ -134,6 +135,21 @@ int o2v_b200_voxelize_host(o2v_b200_engine *engine, const o2v_b200_params *param
                            const o2v_b200_texture *textures, uint32_t texture_count, uint32_t *out_voxels,
                            uint64_t out_capacity, uint64_t *out_count, o2v_b200_stats *out_stats);
 
+/* Host side of the bitmap download that obj2voxel_voxelize() uses on one GPU (16 bytes per voxel over one PCIe link is
+ * the longest leg of a host-to-host job; an all-white result travels as 1 bit per OUTPUT voxel of every touched 64^3
+ * chunk instead and the host's threads write the Voxel32 quads the voxel callback receives, src/io.cpp:638-653).
+ * bits: `chunks` bitmaps of 4096 64-bit words — word = tile (x | y << 3 | z << 6 in units of 8 voxels) * 8 + layer z,
+ * bit = x + 8 y inside the tile; chunk_ids[c] = cx + chunks_per_axis * (cy + chunks_per_axis * (cz - chunk_z0));
+ * chunk_counts[c] = set bits of bitmap c.  Writes sum(chunk_counts) quads {x, y, z, 0xFFFFFFFF} to out_quads and returns
+ * that number, or UINT64_MAX if a bitmap disagrees with its count.  Pure host code: no device needed. */
+uint64_t o2v_b200_expand_bitmaps(const uint64_t *bits, const uint32_t *chunk_ids, const uint32_t *chunk_counts,
+                                 uint32_t chunks, uint32_t chunks_per_axis, uint32_t chunk_z0, uint32_t *out_quads);
+
+/* The default on one GPU: the positions of an all-white result cross PCIe packed into `bits` = 32 (x | y << 10 | z << 20,
+ * output grids up to 1024^3) or 64 (x | y << 21 | z << 42) bits per voxel and the host's threads write the Voxel32 quads
+ * {x, y, z, 0xFFFFFFFF} the voxel callback receives.  Pure host code: no device needed. */
+void o2v_b200_expand_packed(const void *packed, int32_t bits, uint64_t count, uint32_t *out_quads);
+
 /* How obj2voxel_voxelize() would cut a job into z parts (see obj2voxel_b200_get_stats below): returns the number of parts
  * and writes parts + 1 ascending bounds (at most bounds_capacity) — part k covers sample-space z in
  * [out_bounds[k], out_bounds[k + 1]); inner bounds are multiples of 64 (the reference's chunk rows,
@@ -148,6 +164,31 @@ uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint3
  * copied and must stay valid until obj2voxel_voxelize() returns. */
 void obj2voxel_b200_set_input_triangles(obj2voxel_instance *instance, const float *vertices, const float *uvs,
                                         size_t count, obj2voxel_texture *texture);
+/* A ready-made obj2voxel_triangle_callback (include/obj2voxel.h:177) over a flat array, for callers that want the
+ * reference's one-call-per-triangle ingestion (src/obj2voxel.cpp:585-588) without writing the callback:
+ * obj2voxel_set_input_callback(instance, obj2voxel_b200_array_source_next, &source).  Triangles are MATERIALLESS. */
+typedef struct o2v_b200_array_source {
+    const float *vertices; /* 9 floats per triangle */
+    size_t count;
+    size_t next; /* start at 0 */
+} o2v_b200_array_source;
+bool obj2voxel_b200_array_source_next(void *source, obj2voxel_triangle *out_triangle);
+
+/* A ready-made obj2voxel_voxel_callback (include/obj2voxel.h:188) that only counts what it receives:
+ * obj2voxel_set_output_callback(instance, obj2voxel_b200_counting_sink_write, &sink).  The callback of one job is never
+ * called concurrently (calls come from several host threads, one at a time). */
+typedef struct o2v_b200_counting_sink {
+    uint64_t voxels; /* start at 0 */
+    uint64_t calls;
+} o2v_b200_counting_sink;
+bool obj2voxel_b200_counting_sink_write(void *sink, uint32_t *voxel_data, size_t voxel_count);
+
+/* The CUDA devices obj2voxel_voxelize() spreads this job over, one Z-slab of whole chunk rows each (default: the
+ * environment's O2V_B200_DEVICES = "all" | count | "0,2,5", else O2V_B200_DEVICE, else device 0).  The reference spreads a
+ * job over worker threads that pull 64^3 chunks (src/obj2voxel.cpp:957-996, CLI -j, src/main.cpp:155-158); here a device
+ * owns a slab of chunk rows.  On the occupancy-only path each device uploads 1/N of the triangles and the devices
+ * exchange them by slab over peer memory; the sink receives every device's records, one writer at a time. */
+void obj2voxel_b200_set_devices(obj2voxel_instance *instance, const int32_t *devices, uint32_t count);
 /* Restrict the job to a Z-slab of the sample grid (multiples of 8). */
 void obj2voxel_b200_set_slab(obj2voxel_instance *instance, uint32_t z0, uint32_t z1);
 /* Statistics of the last obj2voxel_voxelize() on this instance.  A big job (>= 2^20 triangles) runs as up to four z parts

@@ -41,6 +41,14 @@ class Texture(C.Structure):
                 ("wrap", C.c_uint32)]
 
 
+class ArraySource(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("count", C.c_size_t), ("next", C.c_size_t)]
+
+
+class CountingSink(C.Structure):
+    _fields_ = [("voxels", C.c_uint64), ("calls", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [("voxels", C.c_uint64), ("leaves", C.c_uint64), ("pairs", C.c_uint64), ("active_tiles", C.c_uint64),
                 ("candidate_voxels", C.c_uint64), ("clip_calls", C.c_uint64), ("contributions", C.c_uint64),
@@ -50,7 +58,8 @@ class Stats(C.Structure):
                 ("light_tiles", C.c_uint64), ("heavy_tiles", C.c_uint64), ("survivors", C.c_uint64),
                 ("ms_clip", C.c_float), ("occupancy_path", C.c_int32),
                 ("ms_classify", C.c_float), ("reserved", C.c_float), ("slab_triangles", C.c_uint64),
-                ("undecided_ranges", C.c_uint64), ("ms_filter", C.c_float), ("ms_expand", C.c_float)]
+                ("undecided_ranges", C.c_uint64), ("ms_filter", C.c_float), ("ms_expand", C.c_float),
+                ("download_bytes", C.c_uint64)]
 
     def as_dict(self):
         d = {name: getattr(self, name) for name, _ in self._fields_ if name != "transform"}
@@ -77,7 +86,7 @@ ADDITIVE_SYMBOLS = [
     "o2v_b200_engine_create", "o2v_b200_engine_destroy", "o2v_b200_last_error", "o2v_b200_sm_count",
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
     "o2v_b200_result_download", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
-    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab",
+    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab", "obj2voxel_b200_set_devices", "o2v_b200_expand_bitmaps", "o2v_b200_expand_packed", "obj2voxel_b200_array_source_next", "obj2voxel_b200_counting_sink_write",
 ]
 
 
@@ -150,6 +159,11 @@ def load():
                                              C.POINTER(Stats)]),
         "obj2voxel_b200_set_input_triangles": (None, [vp, fp, fp, sz, vp]),
         "obj2voxel_b200_set_slab": (None, [vp, u32, u32]),
+        "obj2voxel_b200_set_devices": (None, [vp, C.POINTER(C.c_int32), u32]),
+        "o2v_b200_expand_bitmaps": (C.c_uint64, [vp, vp, vp, u32, u32, u32, vp]),
+        "o2v_b200_expand_packed": (None, [vp, C.c_int32, C.c_uint64, vp]),
+        "obj2voxel_b200_array_source_next": (C.c_bool, [vp, vp]),
+        "obj2voxel_b200_counting_sink_write": (C.c_bool, [vp, vp, sz]),
         "obj2voxel_b200_get_stats": (None, [vp, C.POINTER(Stats)]),
         "o2v_b200_plan_parts": (u32, [u32, u32, u32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), u32]),
     }

@@ -180,6 +180,11 @@ class Instance:
     def set_slab(self, z0, z1):
         self._lib.obj2voxel_b200_set_slab(self.handle, z0, z1)
 
+    def set_devices(self, devices):
+        """obj2voxel_b200_set_devices: the CUDA devices this job is spread over (one Z-slab each)."""
+        arr = (C.c_int32 * max(len(devices), 1))(*[int(d) for d in devices])
+        self._lib.obj2voxel_b200_set_devices(self.handle, arr, len(devices))
+
     # -- run ----------------------------------------------------------------------------------------------------
     def voxelize(self):
         return int(self._lib.obj2voxel_voxelize(self.handle))

@@ -12,6 +12,7 @@
 
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -20,6 +21,7 @@
 
 #include "o2v_engine.h"
 #include "o2v_io.h"
+#include "o2v_job.h"
 
 using namespace o2v;
 
@@ -50,13 +52,22 @@ namespace o2v {
 
 void logMessage(unsigned char level, const std::string &message)
 {
-    std::lock_guard<std::mutex> lock{gLogMutex};
-    if (level > gLogLevel) {
+    obj2voxel_log_callback *callback = nullptr;
+    void *callbackData = nullptr;
+    {
+        std::lock_guard<std::mutex> lock{gLogMutex};
+        if (level > gLogLevel) {
+            return;
+        }
+        callback = gLogCallback;
+        callbackData = gLogCallbackData;
+    }
+    // the callback runs outside the lock: it may call obj2voxel_set_log_level / _get_log_level itself
+    if (callback != nullptr && callback(callbackData, message.c_str(), level)) {
         return;
     }
-    if (gLogCallback != nullptr && gLogCallback(gLogCallbackData, message.c_str(), level)) {
-        return;
-    }
+    static std::mutex printMutex;
+    std::lock_guard<std::mutex> lock{printMutex};
     fprintf(stdout, "[obj2voxel_b200] [%s] %s\n", levelName(level), message.c_str());
     fflush(stdout);
 }
@@ -116,32 +127,6 @@ namespace {
 
 enum class IoKind { MISSING, CALLBACK, FILE, MEMORY, BULK };
 
-struct EngineDeleter {
-    void operator()(Engine *e) const { delete e; }
-};
-
-std::mutex gEngineMutex;
-std::unordered_map<int, std::unique_ptr<Engine, EngineDeleter>> gEngines;
-
-/// One engine per device per process, created on first use (obj2voxel instances are throwaway objects).
-Engine *sharedEngine(std::string *error)
-{
-    int device = 0;
-    if (const char *env = getenv("O2V_B200_DEVICE")) {
-        device = atoi(env);
-    }
-    std::lock_guard<std::mutex> lock{gEngineMutex};
-    auto found = gEngines.find(device);
-    if (found != gEngines.end()) {
-        return found->second.get();
-    }
-    Engine *engine = Engine::create(device, error);
-    if (engine != nullptr) {
-        gEngines[device].reset(engine);
-    }
-    return engine;
-}
-
 void statsToC(const RunStats &in, o2v_b200_stats *out)
 {
     memset(out, 0, sizeof *out);
@@ -172,67 +157,7 @@ void statsToC(const RunStats &in, o2v_b200_stats *out)
     out->undecided_ranges = in.counters.ranges;
     out->ms_filter = in.msFilter;
     out->ms_expand = in.msExpand;
-}
-
-constexpr uint32_t kMaxJobParts = 128;  // a part is at least one 64-voxel chunk row; sample resolution <= 8192
-
-/// How obj2voxel_voxelize() cuts a job into z parts (bounds[0 .. parts], ascending, inner bounds multiples of 64; the
-/// parts tile [z0, z1) clipped to the chunk grid).  requested > 0 forces the number of parts (at most one per chunk row),
-/// otherwise jobs of at least 2^20 triangles run in up to four parts and smaller ones in one.
-uint32_t planJobParts(uint32_t sampleRes, uint32_t slabZ0, uint32_t slabZ1, unsigned long long triangles, int requested,
-                      uint32_t *bounds)
-{
-    const uint32_t gridExtent = (sampleRes + 63u) / 64u * 64u;
-    uint32_t jobZ0 = slabZ0, jobZ1 = slabZ1;
-    if (jobZ0 == 0 && jobZ1 == 0) {
-        jobZ1 = gridExtent;
-    }
-    jobZ1 = std::min(jobZ1, gridExtent);
-    jobZ0 = std::min(jobZ0, jobZ1);
-    const uint32_t row0 = jobZ0 / 64u, row1 = std::max((jobZ1 + 63u) / 64u, row0 + 1u);
-    const uint32_t rows = row1 - row0;
-    uint32_t parts = (triangles >= (1ull << 20) && rows > 1u) ? std::min(4u, rows) : 1u;
-    if (requested > 0) {
-        parts = std::min(std::min((uint32_t) requested, rows), kMaxJobParts);
-    }
-    for (uint32_t k = 0; k <= parts; ++k) {
-        const uint32_t z = (row0 + (uint32_t) ((unsigned long long) rows * k / parts)) * 64u;
-        bounds[k] = std::min(std::max(z, jobZ0), jobZ1);
-    }
-    return parts;
-}
-
-/// Totals of a job that ran as several z parts (every voxel, leaf and clip belongs to exactly one part; a dropped
-/// triangle may be seen by several parts: the largest count is reported).
-void accumulateStats(RunStats &total, const RunStats &part)
-{
-    RunCounters &t = total.counters;
-    const RunCounters &p = part.counters;
-    t.voxels += p.voxels;
-    t.leaves += p.leaves;
-    t.pairs += p.pairs;
-    t.activeTiles += p.activeTiles;
-    t.candidateVoxels += p.candidateVoxels;
-    t.clipCalls += p.clipCalls;
-    t.contributions += p.contributions;
-    t.droppedTriangles = std::max(t.droppedTriangles, p.droppedTriangles);
-    t.depthOverflow = std::max(t.depthOverflow, p.depthOverflow);
-    t.lightTiles += p.lightTiles;
-    t.bigLightTiles += p.bigLightTiles;
-    t.heavyTiles += p.heavyTiles;
-    t.survivors += p.survivors;
-    total.outCapacity = std::max(total.outCapacity, part.outCapacity);
-    total.msTotal += part.msTotal;
-    total.msSetup += part.msSetup;
-    total.msVoxelize += part.msVoxelize;
-    total.msClip += part.msClip;
-    total.msClassify += part.msClassify;
-    total.msExpand += part.msExpand;
-    total.msFilter += part.msFilter;
-    t.ranges += p.ranges;
-    total.kernelLaunches += part.kernelLaunches;
-    total.voxelizeLaunches += part.voxelizeLaunches;
-    total.occupancyPath = total.occupancyPath && part.occupancyPath;
+    out->download_bytes = in.downloadBytes;
 }
 
 EngineParams paramsFromC(const o2v_b200_params &p)
@@ -254,55 +179,6 @@ EngineParams paramsFromC(const o2v_b200_params &p)
     e.slabFiltered = p.slab_filtered != 0;
     return e;
 }
-
-/// Device copies of a host mesh + textures for one run.
-struct UploadedMesh {
-    DeviceBuffer verts, uvs, types, colors, textureIds;
-    std::vector<std::unique_ptr<DeviceBuffer>> texturePixels;
-    std::vector<TextureView> textureViews;
-    MeshView view{};
-
-    bool upload(const o2v_b200_mesh &mesh, const o2v_b200_texture *textures, uint32_t textureCount, cudaStream_t stream,
-                std::string *error)
-    {
-        const size_t n = static_cast<size_t>(mesh.count);
-        auto copy = [&](DeviceBuffer &dst, const void *src, size_t bytes) -> bool {
-            if (src == nullptr || bytes == 0) {
-                return true;
-            }
-            if (!dst.ensure(bytes)) {
-                *error = "device allocation failed (mesh upload)";
-                return false;
-            }
-            if (cudaMemcpyAsync(dst.as<void>(), src, bytes, cudaMemcpyHostToDevice, stream) != cudaSuccess) {
-                *error = std::string("mesh upload failed: ") + cudaGetErrorString(cudaGetLastError());
-                return false;
-            }
-            return true;
-        };
-        if (!copy(verts, mesh.verts, n * 9 * sizeof(float)) || !copy(uvs, mesh.uvs, n * 6 * sizeof(float)) ||
-            !copy(types, mesh.types, n) || !copy(colors, mesh.colors, n * 3 * sizeof(float)) ||
-            !copy(textureIds, mesh.texture_ids, n * sizeof(uint32_t))) {
-            return false;
-        }
-        view.verts = mesh.verts != nullptr ? verts.as<float>() : nullptr;
-        view.uvs = mesh.uvs != nullptr ? uvs.as<float>() : nullptr;
-        view.types = mesh.types != nullptr ? types.as<uint8_t>() : nullptr;
-        view.colors = mesh.colors != nullptr ? colors.as<float>() : nullptr;
-        view.textureIds = mesh.texture_ids != nullptr ? textureIds.as<uint32_t>() : nullptr;
-        view.count = mesh.count;
-        for (uint32_t i = 0; i < textureCount; ++i) {
-            texturePixels.emplace_back(new DeviceBuffer());
-            const size_t bytes = (size_t) textures[i].width * textures[i].height * textures[i].channels;
-            if (!copy(*texturePixels.back(), textures[i].pixels, bytes)) {
-                return false;
-            }
-            textureViews.push_back(TextureView{texturePixels.back()->as<uint8_t>(), textures[i].width,
-                                               textures[i].height, textures[i].channels, textures[i].wrap});
-        }
-        return true;
-    }
-};
 
 }  // namespace
 
@@ -333,6 +209,7 @@ struct obj2voxel_instance {
     bool parallel = false;
     int unitTransform[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     uint32_t slabZ0 = 0, slabZ1 = 0;
+    std::vector<int> devices;  // obj2voxel_b200_set_devices; empty = the process default
 
     // run state
     bool done = false;
@@ -352,6 +229,8 @@ struct obj2voxel_instance {
 namespace {
 
 struct HostMesh {
+    // positions and types for every triangle; uvs / texture ids / colours only from the first triangle that has them
+    // (zero-filled before): a MATERIALLESS stream — any STL, obj2voxel_set_triangle_basic — costs 37 bytes per triangle
     std::vector<float> verts, uvs, colors;
     std::vector<uint8_t> types;
     std::vector<uint32_t> textureIds;
@@ -371,27 +250,41 @@ struct HostMesh {
 
     void push(const obj2voxel_triangle &t)
     {
+        const size_t index = types.size();
         verts.insert(verts.end(), t.v, t.v + 9);
-        uvs.insert(uvs.end(), t.t, t.t + 6);
-        colors.insert(colors.end(), t.color, t.color + 3);
         uint8_t type = t.type;
-        uint32_t id = 0;
         if (type == kTextured) {
             if (t.texture != nullptr && t.texture->loaded) {
-                id = textureIndex(t.texture);
-                anyTextured = true;
+                if (!anyTextured) {
+                    anyTextured = true;
+                    uvs.assign(index * 6, 0.0f);
+                    textureIds.assign(index, 0u);
+                }
             }
             else {
                 type = kMaterialless;
             }
         }
-        anyColored |= type == kUntextured;
+        if (type == kUntextured && !anyColored) {
+            anyColored = true;
+            colors.assign(index * 3, 0.0f);
+        }
+        if (anyTextured) {
+            const bool textured = type == kTextured;
+            static const float zeros[6] = {0, 0, 0, 0, 0, 0};
+            uvs.insert(uvs.end(), textured ? t.t : zeros, (textured ? t.t : zeros) + 6);
+            textureIds.push_back(textured ? textureIndex(t.texture) : 0u);
+        }
+        if (anyColored) {
+            colors.insert(colors.end(), t.color, t.color + 3);
+        }
         types.push_back(type);
-        textureIds.push_back(id);
     }
 };
 
-obj2voxel_error_t runJob(obj2voxel_instance &inst)
+/// openSink: creates inst.sink — called once the input has been read, so that a missing or unreadable input leaves an
+/// existing output file alone (the reference opens its input first as well: src/obj2voxel.cpp:617-625).
+obj2voxel_error_t runJob(obj2voxel_instance &inst, const std::function<obj2voxel_error_t()> &openSink)
 {
     // ---- gather the triangle stream into flat arrays (reference: "Caching triangles", obj2voxel.cpp:583-588) ----
     HostMesh host;
@@ -453,6 +346,9 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
                                             (uint32_t) t->channels, t->wrap});
     }
 
+    if (const obj2voxel_error_t opened = openSink()) {
+        return opened;
+    }
     if (mesh.count == 0) {
         logMessage(OBJ2VOXEL_LOG_LEVEL_WARNING, "Model has no triangles, aborting and writing empty voxel model");
         inst.sink->finalize();
@@ -460,26 +356,9 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     }
     logMessage(OBJ2VOXEL_LOG_LEVEL_INFO, "Cached model with " + withThousands(mesh.count) + " triangles");
 
-    // ---- device run ----
-    std::string error;
-    Engine *engine = sharedEngine(&error);
-    if (engine == nullptr) {
-        logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Cannot voxelize: " + error);
-        return OBJ2VOXEL_ERR_DEVICE;
-    }
-    cudaSetDevice(engine->device());
-    cudaStream_t stream = nullptr;
-    if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) {
-        logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, std::string("cudaStreamCreate failed: ") +
-                                                  cudaGetErrorString(cudaGetLastError()));
-        return OBJ2VOXEL_ERR_DEVICE;
-    }
-    struct StreamGuard {
-        cudaStream_t s;
-        ~StreamGuard() { cudaStreamDestroy(s); }
-    } guard{stream};
-
-    EngineParams params;
+    // ---- device run (o2v_job.cpp): upload, kernels per z part, download under the next part's kernels, sink ----
+    JobOptions options;
+    EngineParams &params = options.params;
     params.resolution = inst.outputResolution;
     params.supersampling = inst.supersampling;
     params.strategy = inst.strategy;
@@ -497,6 +376,10 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     if (const char *env = getenv("O2V_B200_OCCUPANCY_PATH")) {
         params.occupancyPath = atoi(env);
     }
+    if (const char *env = getenv("O2V_B200_PIPELINE_PARTS")) {
+        options.parts = atoi(env);
+    }
+    options.devices = inst.devices;  // empty: O2V_B200_DEVICES / O2V_B200_DEVICE / device 0
 
     if (inst.supersampling > 1) {
         logMessage(OBJ2VOXEL_LOG_LEVEL_INFO, "Chunks will be downscaled from " +
@@ -506,187 +389,26 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst)
     }
 
     RunStats stats;
-    const auto tJob = std::chrono::steady_clock::now();
-    auto msSince = [](std::chrono::steady_clock::time_point t0) {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    };
-    {
-        std::lock_guard<std::mutex> lock{gEngineMutex};  // one job at a time per process-wide engine
-        // the mesh staging buffers are kept per device across jobs (grow-only) like the engine's own buffers
-        static std::unordered_map<int, std::unique_ptr<UploadedMesh>> uploads;
-        std::unique_ptr<UploadedMesh> &uploadSlot = uploads[engine->device()];
-        if (uploadSlot == nullptr) {
-            uploadSlot.reset(new UploadedMesh());
-        }
-        UploadedMesh &uploaded = *uploadSlot;
-        uploaded.texturePixels.clear();
-        uploaded.textureViews.clear();
-        if (!uploaded.upload(mesh, textures.data(), (uint32_t) textures.size(), stream, &error)) {
-            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, error);
-            return OBJ2VOXEL_ERR_DEVICE;
-        }
-        cudaStreamSynchronize(stream);
-        const double msUpload = msSince(tJob);
-        const auto tRun = std::chrono::steady_clock::now();
-
-        // ---- plan: a big job runs as up to four z sub-slabs of whole 64-voxel chunk rows, so that the download of one
-        // part (PCIe, the longest leg of a host-to-host job) runs under the kernels of the next.  Every voxel belongs to
-        // exactly one part: same records, part by part. ----
-        uint32_t partBounds[kMaxJobParts + 1];
-        const char *partsEnv = getenv("O2V_B200_PIPELINE_PARTS");
-        const uint32_t parts = planJobParts(inst.outputResolution * inst.supersampling, inst.slabZ0, inst.slabZ1, mesh.count,
-                                            partsEnv != nullptr ? atoi(partsEnv) : 0, partBounds);
-        auto partBound = [&](uint32_t k) { return partBounds[k]; };
-
-        cudaStream_t copyStream = nullptr;
-        cudaEvent_t copied[2] = {nullptr, nullptr};
-        if (cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&copied[0], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&copied[1], cudaEventDisableTiming) != cudaSuccess) {
-            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, std::string("cudaStreamCreate failed: ") +
-                                                      cudaGetErrorString(cudaGetLastError()));
-            return OBJ2VOXEL_ERR_DEVICE;
-        }
-        struct CopyGuard {
-            cudaStream_t s;
-            cudaEvent_t *e;
-            ~CopyGuard()
-            {
-                cudaStreamSynchronize(s);
-                cudaStreamDestroy(s);
-                cudaEventDestroy(e[0]);
-                cudaEventDestroy(e[1]);
-            }
-        } copyGuard{copyStream, copied};
-
-        const size_t batch = 1u << 21;  // records per sink call (32 MiB)
-        bool sinkOk = true, deviceOk = true;
-        double msKernels = 0;
-        bool firstPart = true;
-
-        // What is still on its way to the sink: a part whose records are being copied into pinned buffer `slot`.
-        struct Pending {
-            bool active = false;
-            int slot = 0;
-            uint32_t *records = nullptr;
-            unsigned long long count = 0;
-        } pending;
-        auto deliver = [&](Pending &p) {  // waits for the copy, then hands the records to the sink batch by batch
-            if (!p.active) {
-                return;
-            }
-            p.active = false;
-            deviceOk = deviceOk && cudaEventSynchronize(copied[p.slot]) == cudaSuccess;
-            for (unsigned long long done = 0; done < p.count && sinkOk && deviceOk; done += batch) {
-                sinkOk = inst.sink->write(p.records + done * 4, (size_t) std::min<unsigned long long>(batch, p.count - done));
-            }
-        };
-        // Fallback for a part whose records do not fit a pinned buffer: two 32 MiB staging buffers, the copy of batch
-        // k+1 under the sink call of batch k (also the whole story of a job that runs as one part).
-        auto streamOut = [&](const unsigned char *deviceRecords, unsigned long long total) {
-            uint32_t *staging[2] = {static_cast<uint32_t *>(engine->pinnedStaging(0, batch * 16)),
-                                    static_cast<uint32_t *>(engine->pinnedStaging(1, batch * 16))};
-            std::vector<uint32_t> pageable;
-            if (staging[0] == nullptr || staging[1] == nullptr) {  // pinned memory exhausted: plain host memory still works
-                pageable.resize(batch * 4 * 2);
-                staging[0] = pageable.data();
-                staging[1] = pageable.data() + batch * 4;
-            }
-            auto startCopy = [&](unsigned long long done, int slot) -> bool {
-                const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
-                return cudaMemcpyAsync(staging[slot], deviceRecords + done * 16, count * 16, cudaMemcpyDeviceToHost,
-                                       copyStream) == cudaSuccess &&
-                       cudaEventRecord(copied[slot], copyStream) == cudaSuccess;
-            };
-            int slot = 0;
-            deviceOk = deviceOk && startCopy(0, 0);
-            for (unsigned long long done = 0; done < total && sinkOk && deviceOk; done += batch, slot ^= 1) {
-                const size_t count = (size_t) std::min<unsigned long long>(batch, total - done);
-                if (done + batch < total) {
-                    deviceOk = startCopy(done + batch, slot ^ 1);
-                }
-                deviceOk = deviceOk && cudaEventSynchronize(copied[slot]) == cudaSuccess;
-                if (deviceOk) {
-                    sinkOk = inst.sink->write(staging[slot], count);
-                }
-            }
-            cudaStreamSynchronize(copyStream);
-        };
-
-        for (uint32_t k = 0; k < parts && sinkOk && deviceOk; ++k) {
-            EngineParams partParams = params;
-            if (parts > 1) {
-                partParams.slabZ0 = partBound(k);
-                partParams.slabZ1 = partBound(k + 1);
-                if (partParams.slabZ0 >= partParams.slabZ1) {
-                    continue;
-                }
-            }
-            RunStats partStats;
-            const int rc = engine->voxelize(uploaded.view, uploaded.textureViews.data(),
-                                            (uint32_t) uploaded.textureViews.size(), partParams, stream, &partStats);
-            if (rc != 0) {
-                logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed on the device: " + engine->lastError());
-                return OBJ2VOXEL_ERR_DEVICE;
-            }
-            msKernels += partStats.msTotal;
-            if (firstPart) {
-                stats = partStats;
-                firstPart = false;
-            }
-            else {
-                accumulateStats(stats, partStats);
-            }
-            const unsigned long long total = engine->voxelCount();
-            const auto *deviceRecords = reinterpret_cast<const unsigned char *>(engine->deviceVoxels());
-            if (parts == 1) {
-                if (total != 0) {
-                    streamOut(deviceRecords, total);
-                }
-                break;
-            }
-            // this part's records start their way to the host before the previous part is handed to the sink, and stay
-            // in their device buffer while the next part writes the other one
-            const int slot = (int) (k & 1u);
-            uint32_t *host = total != 0 && total * 16 <= (1ull << 30)
-                                 ? static_cast<uint32_t *>(engine->pinnedStaging(slot, (size_t) total * 16))
-                                 : nullptr;
-            Pending mine;
-            if (host != nullptr) {
-                deviceOk = deviceOk &&
-                           cudaMemcpyAsync(host, deviceRecords, (size_t) total * 16, cudaMemcpyDeviceToHost, copyStream) ==
-                               cudaSuccess &&
-                           cudaEventRecord(copied[slot], copyStream) == cudaSuccess;
-                mine.active = true;
-                mine.slot = slot;
-                mine.records = host;
-                mine.count = total;
-            }
-            deliver(pending);
-            if (host == nullptr && total != 0) {
-                streamOut(deviceRecords, total);  // too big to pin in one piece (or pinning failed)
-            }
-            pending = mine;
-            engine->swapOutputBuffers();
-        }
-        deliver(pending);
-        cudaStreamSynchronize(copyStream);
-        const double msRun = msSince(tRun);
-        statsToC(stats, &inst.stats);
-        if (!deviceOk) {
-            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR,
-                       std::string("voxel download failed: ") + cudaGetErrorString(cudaGetLastError()));
-            return OBJ2VOXEL_ERR_DEVICE;
-        }
-        if (!sinkOk || !inst.sink->good()) {
-            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed because of IO error");
-            return OBJ2VOXEL_ERR_IO_ERROR_DURING_VOXEL_WRITE;
-        }
-        char timing[160];
-        snprintf(timing, sizeof timing, "timing: upload %.2f ms, %u part(s): kernels %.2f ms, run + download + sink %.2f ms",
-                 msUpload, parts, msKernels, msRun);
-        logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, timing);
+    JobTimings timings;
+    const obj2voxel_error_t rc = runDeviceJob(mesh, textures, options, *inst.sink, &stats, &timings);
+    statsToC(stats, &inst.stats);
+    if (rc != OBJ2VOXEL_ERR_OK) {
+        return rc;
     }
+    if (!inst.sink->good()) {
+        logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Voxelization failed because of IO error");
+        return OBJ2VOXEL_ERR_IO_ERROR_DURING_VOXEL_WRITE;
+    }
+    char timing[512];
+    snprintf(timing, sizeof timing,
+             "timing: %u device(s), upload %.2f ms%s, slab exchange %.2f ms%s, %u part(s) each: kernels %.2f ms, run + "
+             "download%s + sink %.2f ms (device 0: voxelize calls %.2f, waiting for copies %.2f, host expansion %.2f, sink "
+             "%.2f ms)",
+             timings.devices, timings.msUpload, timings.stagedUpload ? " (pageable input staged by host threads)" : "",
+             timings.msExchange, timings.peerExchange ? " (peer stores)" : "", timings.parts, timings.msKernels,
+             timings.bitmapDownload ? " of bitmaps + host expansion" : "", timings.msRun, timings.msVoxelizeCalls,
+             timings.msWaitCopy, timings.msExpandHost, timings.msSink);
+    logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, timing);
 
     logMessage(OBJ2VOXEL_LOG_LEVEL_INFO,
                "Voxelized " + withThousands(mesh.count) + " triangles, writing any buffered voxels ...");
@@ -991,20 +713,23 @@ obj2voxel_error_t obj2voxel_voxelize(obj2voxel_instance *instance)
         return OBJ2VOXEL_ERR_IO_ERROR_ON_OPEN_INPUT_FILE;
     }
 
-    std::string error;
-    if (inst.outputKind == IoKind::CALLBACK) {
-        inst.sink = makeCallbackSink(inst.outputCallback, inst.outputCallbackData);
-    }
-    else {
-        inst.sink = makeFormatSink(inst.outputFormat, inst.outputKind == IoKind::MEMORY ? nullptr : inst.outputFile,
-                                   inst.outputResolution, &error);
-    }
-    if (inst.sink == nullptr) {
-        logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Failed to open output: " + error);
-        return OBJ2VOXEL_ERR_IO_ERROR_ON_OPEN_OUTPUT_FILE;
-    }
+    auto openSink = [&inst]() -> obj2voxel_error_t {
+        std::string error;
+        if (inst.outputKind == IoKind::CALLBACK) {
+            inst.sink = makeCallbackSink(inst.outputCallback, inst.outputCallbackData);
+        }
+        else {
+            inst.sink = makeFormatSink(inst.outputFormat, inst.outputKind == IoKind::MEMORY ? nullptr : inst.outputFile,
+                                       inst.outputResolution, &error);
+        }
+        if (inst.sink == nullptr) {
+            logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Failed to open output: " + error);
+            return OBJ2VOXEL_ERR_IO_ERROR_ON_OPEN_OUTPUT_FILE;
+        }
+        return OBJ2VOXEL_ERR_OK;
+    };
 
-    const obj2voxel_error_t result = runJob(inst);
+    const obj2voxel_error_t result = runJob(inst, openSink);
     if (inst.outputKind != IoKind::MEMORY) {
         inst.sink.reset();  // src/obj2voxel.cpp:631-633: only memory sinks outlive the job
     }
@@ -1049,6 +774,30 @@ uint32_t obj2voxel_get_worker_count(obj2voxel_instance *instance)
 struct o2v_b200_engine {
     Engine *engine;
 };
+
+bool obj2voxel_b200_array_source_next(void *source, obj2voxel_triangle *out_triangle)
+{
+    o2v_b200_array_source *s = static_cast<o2v_b200_array_source *>(source);
+    if (s->next >= s->count) {
+        return false;
+    }
+    obj2voxel_set_triangle_basic(out_triangle, s->vertices + 9 * s->next++);
+    return true;
+}
+
+bool obj2voxel_b200_counting_sink_write(void *sink, uint32_t *, size_t voxel_count)
+{
+    o2v_b200_counting_sink *s = static_cast<o2v_b200_counting_sink *>(sink);
+    s->voxels += voxel_count;
+    ++s->calls;
+    return true;
+}
+
+void obj2voxel_b200_set_devices(obj2voxel_instance *instance, const int32_t *devices, uint32_t count)
+{
+    O2V_REQUIRE(instance != nullptr && (devices != nullptr || count == 0), "instance or devices is NULL");
+    instance->devices.assign(devices, devices + count);
+}
 
 o2v_b200_engine *o2v_b200_engine_create(int device)
 {
@@ -1127,6 +876,19 @@ uint64_t o2v_b200_result_count(const o2v_b200_engine *engine)
     return engine->engine->voxelCount();
 }
 
+uint64_t o2v_b200_expand_bitmaps(const uint64_t *bits, const uint32_t *chunk_ids, const uint32_t *chunk_counts,
+                                 uint32_t chunks, uint32_t chunks_per_axis, uint32_t chunk_z0, uint32_t *out_quads)
+{
+    static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "bitmap words");
+    return expandBitmapsOnHost(reinterpret_cast<const unsigned long long *>(bits), chunk_ids, chunk_counts, chunks,
+                               chunks_per_axis, chunk_z0, out_quads);
+}
+
+void o2v_b200_expand_packed(const void *packed, int32_t bits, uint64_t count, uint32_t *out_quads)
+{
+    expandPackedOnHost(packed, bits, count, out_quads);
+}
+
 uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint32_t slab_z1, uint64_t triangles,
                              int32_t requested_parts, uint32_t *out_bounds, uint32_t bounds_capacity)
 {
@@ -1178,16 +940,53 @@ int o2v_b200_voxelize_host(o2v_b200_engine *engine, const o2v_b200_params *param
                            const o2v_b200_texture *textures, uint32_t texture_count, uint32_t *out_voxels,
                            uint64_t out_capacity, uint64_t *out_count, o2v_b200_stats *out_stats)
 {
+    // plain: synchronous copies, one run, one download (obj2voxel_voxelize() is the pipelined host path)
     cudaSetDevice(engine->engine->device());
-    UploadedMesh uploaded;
-    std::string error;
-    if (!uploaded.upload(*mesh, textures, texture_count, nullptr, &error)) {
-        gLastError = error;
+    struct Buffers {
+        std::vector<void *> all;
+        ~Buffers()
+        {
+            for (void *p : all) {
+                cudaFree(p);
+            }
+        }
+        void *upload(const void *src, size_t bytes)
+        {
+            if (src == nullptr || bytes == 0) {
+                return nullptr;
+            }
+            void *dst = nullptr;
+            if (cudaMalloc(&dst, bytes) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaGetLastError();
+                cudaFree(dst);
+                failed = true;
+                return nullptr;
+            }
+            all.push_back(dst);
+            return dst;
+        }
+        bool failed = false;
+    } buffers;
+    const size_t n = (size_t) mesh->count;
+    MeshView view{};
+    view.verts = static_cast<const float *>(buffers.upload(mesh->verts, n * 9 * sizeof(float)));
+    view.uvs = static_cast<const float *>(buffers.upload(mesh->uvs, n * 6 * sizeof(float)));
+    view.types = static_cast<const uint8_t *>(buffers.upload(mesh->types, n));
+    view.colors = static_cast<const float *>(buffers.upload(mesh->colors, n * 3 * sizeof(float)));
+    view.textureIds = static_cast<const uint32_t *>(buffers.upload(mesh->texture_ids, n * sizeof(uint32_t)));
+    view.count = mesh->count;
+    std::vector<TextureView> views;
+    for (uint32_t i = 0; i < texture_count; ++i) {
+        const size_t bytes = (size_t) textures[i].width * textures[i].height * textures[i].channels;
+        views.push_back(TextureView{static_cast<const uint8_t *>(buffers.upload(textures[i].pixels, bytes)),
+                                    textures[i].width, textures[i].height, textures[i].channels, textures[i].wrap});
+    }
+    if (buffers.failed) {
+        gLastError = "mesh upload failed (device allocation or copy)";
         return kErrCuda;
     }
     RunStats stats;
-    const int rc = engine->engine->voxelize(uploaded.view, uploaded.textureViews.data(), texture_count,
-                                            paramsFromC(*params), nullptr, &stats);
+    const int rc = engine->engine->voxelize(view, views.data(), texture_count, paramsFromC(*params), nullptr, &stats);
     if (out_stats != nullptr) {
         statsToC(stats, out_stats);
     }

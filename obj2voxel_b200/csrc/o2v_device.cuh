@@ -71,10 +71,9 @@ __device__ __forceinline__ bool loadTriangle(const MeshView &mesh, const GridVie
     return setupTriangle<UV>(grid, in, t, area);
 }
 
-/// true if the voxel z range of the model-space triangle `in` provably misses this rank's slab: the decision of
-/// traverseLeaves' root test, taken from the three transformed z coordinates alone (same arithmetic as affineApply).
-/// Triangles with a negative z are kept: the count pass drops and counts them.
-__device__ __forceinline__ bool triangleMissesSlab(const GridView &grid, const float in[9])
+/// floor of the least and the greatest voxel-space z of the model-space triangle `in`: the three transformed z
+/// coordinates alone, with the arithmetic of affineApply (so that the answer is traverseLeaves' root test).
+__device__ __forceinline__ void triangleZRange(const GridView &grid, const float in[9], float &zlo, float &zhi)
 {
     const float *m = grid.xf;
     float z[3];
@@ -82,7 +81,16 @@ __device__ __forceinline__ bool triangleMissesSlab(const GridView &grid, const f
     for (int k = 0; k < 3; ++k) {
         z[k] = xadd(dot3(m[6], m[7], m[8], in[k * 3], in[k * 3 + 1], in[k * 3 + 2]), m[11]);
     }
-    const float zlo = floorf(min3(z[0], z[1], z[2])), zhi = floorf(max3(z[0], z[1], z[2]));
+    zlo = floorf(min3(z[0], z[1], z[2]));
+    zhi = floorf(max3(z[0], z[1], z[2]));
+}
+
+/// true if the voxel z range of the model-space triangle `in` provably misses this rank's slab.
+/// Triangles with a negative z are kept: the count pass drops and counts them.
+__device__ __forceinline__ bool triangleMissesSlab(const GridView &grid, const float in[9])
+{
+    float zlo, zhi;
+    triangleZRange(grid, in, zlo, zhi);
     return zlo >= 0.0f && (toU32(zhi) + 1u <= grid.slabZ0 || toU32(zlo) >= grid.slabZ1);
 }
 

@@ -195,6 +195,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     }
     error_.clear();
     voxelCount_ = 0;
+    bitmapValid_ = false;
+    packedBits_ = 0;
     RunStats local;
     RunStats &st = stats != nullptr ? *stats : local;
     st = RunStats();
@@ -544,6 +546,9 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
             return kOccupancyFallback;  // e.g. a dense 8192^3 job: the caller takes the weighted path
         }
     }
+    if (params.bitmapResult && !chunkCounts_.ensure((size_t) std::max(occ.activeChunks, 1u) * 4)) {
+        return fail(kErrOutOfMemory, "device allocation failed (chunk counts)");
+    }
     if (!tileBits_.ensure(bitmapBytes) ||
         !extraLeaves_.ensure((size_t) std::max<unsigned long long>(extraLeaves, 1) * sizeof(LeafRecord)) ||
         !occQueue_.ensure((size_t) queueCapacity * sizeof(uint4)) ||
@@ -551,14 +556,19 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         !bigLeaves_.ensure((size_t) std::max<unsigned long long>(bigLeaves, 1) * sizeof(uint2))) {
         return fail(kErrOutOfMemory, "device allocation failed (occupancy path buffers)");
     }
-    if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
-        size_t freeBytes = 0, totalBytes = 0;
-        O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
-        const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
-        capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
+    if (params.bitmapResult) {
+        capacity = ~0ull;  // no records are written
     }
-    if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
-        return fail(kErrOutOfMemory, "device allocation failed (voxel output)");
+    else {
+        if (capacity * sizeof(VoxelRecord) > out_.size()) {  // only when the buffer has to grow: bound it by free memory
+            size_t freeBytes = 0, totalBytes = 0;
+            O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
+            const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
+            capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
+        }
+        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+            return fail(kErrOutOfMemory, "device allocation failed (voxel output)");
+        }
     }
     occ.bits = tileBits_.as<unsigned long long>();
     occ.queue = occQueue_.as<uint4>();
@@ -590,6 +600,8 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     args.variant = params.variant < 0 ? 0 : params.variant;
     args.prefilter = params.prefilter;
     args.certainMargin = certainMarginFor(grid.sampleRes);
+    // packed positions: 10 bits per axis while the OUTPUT chunk grid allows it (voxels up to the chunk grid survive)
+    args.packedBits = !params.packedResult || params.bitmapResult ? 0 : ((grid.gridExtent >> occ.shift) <= 1024u ? 32 : 64);
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
@@ -604,7 +616,12 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         O2V_CUDA(cudaEventRecord(evClipStart_, stream));
         launchOccupancyClip(args, smCount_, stream);
         O2V_CUDA(cudaEventRecord(evClipEnd_, stream));
-        launchOccupancyExpand(args, smCount_, stream);
+        if (params.bitmapResult) {
+            launchOccupancyChunkCount(args.occ, chunkCounts_.as<uint32_t>(), dCounters, smCount_, stream);
+        }
+        else {
+            launchOccupancyExpand(args, smCount_, stream);
+        }
         O2V_CUDA(cudaEventRecord(evVoxEnd_, stream));
         const int launched = 4 + (bigLeaves != 0 ? 1 : 0);
         st.voxelizeLaunches += launched;
@@ -662,8 +679,18 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
 
     hostCounters_->clipCalls = hostCounters_->survivors;  // every queued voxel is (at most) one exact clip
     st.counters = *hostCounters_;
-    st.outCapacity = capacity;
+    st.outCapacity = params.bitmapResult ? 0 : capacity;
     voxelCount_ = hostCounters_->voxels;
+    packedBits_ = args.packedBits;
+    if (params.bitmapResult) {
+        bitmapValid_ = true;
+        bitmap_.bits = args.occ.bits;
+        bitmap_.chunkIds = args.occ.chunkList;
+        bitmap_.chunkCounts = chunkCounts_.as<uint32_t>();
+        bitmap_.chunks = args.occ.activeChunks;
+        bitmap_.chunksPerAxis = args.occ.chunksPerAxis;
+        bitmap_.chunkZ0 = args.occ.chunkZ0;
+    }
     cudaEventElapsedTime(&st.msTotal, evStart_, evVoxEnd_);
     cudaEventElapsedTime(&st.msSetup, evStart_, evSetup_);
     cudaEventElapsedTime(&st.msVoxelize, evVoxStart_, evVoxEnd_);
@@ -671,6 +698,91 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     cudaEventElapsedTime(&st.msFilter, evFilterStart_, evClipStart_);
     cudaEventElapsedTime(&st.msClip, evClipStart_, evClipEnd_);
     cudaEventElapsedTime(&st.msExpand, evClipEnd_, evVoxEnd_);
+    return kErrOk;
+}
+
+int Engine::meshBounds(const MeshView &mesh, cudaStream_t stream, float outMin[3], float outMax[3])
+{
+    error_.clear();
+    O2V_CUDA(cudaSetDevice(device_));
+    RunCounters *dCounters = counters_.as<RunCounters>();
+    O2V_CUDA(cudaMemcpyAsync(dCounters, hostCountersInit_, sizeof(RunCounters), cudaMemcpyHostToDevice, stream));
+    launchBounds(mesh, dCounters, stream);
+    launchFinishBounds(dCounters, stream);
+    launchPublishCounters(dCounters, hostCountersDevice_, stream);
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
+    memcpy(outMin, hostCounters_->boundsMin, 3 * sizeof(float));
+    memcpy(outMax, hostCounters_->boundsMax, 3 * sizeof(float));
+    return kErrOk;
+}
+
+float *Engine::receiveRegion(uint32_t source, uint32_t sources, unsigned long long capacity)
+{
+    cudaSetDevice(device_);
+    if (!received_.ensure((size_t) sources * capacity * 9 * sizeof(float))) {
+        return nullptr;
+    }
+    return received_.as<float>() + (size_t) source * capacity * 9;
+}
+
+const float *Engine::packReceived(const unsigned long long *counts, uint32_t sources, unsigned long long capacity,
+                                  cudaStream_t stream, unsigned long long *total)
+{
+    cudaSetDevice(device_);
+    unsigned long long sum = 0;
+    for (uint32_t r = 0; r < sources; ++r) {
+        sum += counts[r];
+    }
+    *total = sum;
+    // a dense copy in a buffer of its own: packing in place would overlap source and destination as soon as a slab
+    // receives more than its even share (boundary triangles go to two slabs)
+    if (!receivedPacked_.ensure((size_t) std::max<unsigned long long>(sum, 1) * 9 * sizeof(float))) {
+        return nullptr;
+    }
+    unsigned long long filled = 0;
+    for (uint32_t r = 0; r < sources; ++r) {
+        if (counts[r] != 0) {
+            cudaMemcpyAsync(receivedPacked_.as<float>() + filled * 9, received_.as<float>() + (size_t) r * capacity * 9,
+                            (size_t) counts[r] * 9 * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+        }
+        filled += counts[r];
+    }
+    return receivedPacked_.as<float>();
+}
+
+int Engine::scatterToSlabs(const MeshView &mesh, const EngineParams &params, SlabScatter scatter, cudaStream_t stream,
+                           unsigned long long *sentCounts)
+{
+    error_.clear();
+    O2V_CUDA(cudaSetDevice(device_));
+    for (uint32_t s = 0; s < scatter.slabs; ++s) {
+        sentCounts[s] = 0;
+    }
+    if (mesh.count == 0) {
+        return kErrOk;
+    }
+    if (!params.boundsKnown) {
+        return fail(kErrBadParams, "scatterToSlabs needs the mesh bounds");
+    }
+    RunStats st;
+    GridView grid;
+    bool emptySlab = false;
+    EngineParams whole = params;
+    whole.slabZ0 = whole.slabZ1 = 0;
+    if (const int rc = setupGrid(mesh, whole, stream, st, grid, &emptySlab)) {
+        return rc;
+    }
+    if (!scatterCounts_.ensure(kMaxSlabs * sizeof(unsigned long long))) {
+        return fail(kErrOutOfMemory, "device allocation failed (scatter counters)");
+    }
+    O2V_CUDA(cudaMemsetAsync(scatterCounts_.as<void>(), 0, kMaxSlabs * sizeof(unsigned long long), stream));
+    scatter.count = scatterCounts_.as<unsigned long long>();
+    launchOccupancySlabScatter(mesh, grid, scatter, smCount_, stream);
+    O2V_CUDA(cudaMemcpyAsync(sentCounts, scatterCounts_.as<void>(), scatter.slabs * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
     return kErrOk;
 }
 

@@ -31,6 +31,22 @@ struct EngineParams {
     int prefilter = 1;
     int occupancyPath = 1;            // 1 = all-MATERIALLESS meshes take the occupancy-only path; 0 = always fold weights
     bool slabFiltered = false;        // the mesh is the output of filterSlab() for this very slab: skip the filter pass
+    bool bitmapResult = false;        // occupancy-only path: stop at the bitmaps (no records on the device); the caller
+                                      // downloads them and expands them on the host (see Engine::bitmapResult)
+    bool packedResult = false;        // occupancy-only path: packed positions instead of 16-byte records (every voxel is
+                                      // white): 4 bytes per voxel while the output grid fits 10 bits per axis, else 8
+                                      // (see Engine::packedBits); a host-to-host job expands them on the host
+};
+
+/// What a run with EngineParams::bitmapResult leaves on the device: `chunks` bitmaps of kChunkWords 64-bit words
+/// (layout: OccupancyView::bits, OUTPUT space), the chunk id of each (cx + C * (cy + C * (cz - chunkZ0))) and its number
+/// of occupied voxels.  Every occupied voxel is white (0xFFFFFFFF).
+struct BitmapResult {
+    const unsigned long long *bits = nullptr;
+    const uint32_t *chunkIds = nullptr;
+    const uint32_t *chunkCounts = nullptr;
+    uint32_t chunks = 0;
+    uint32_t chunksPerAxis = 0, chunkZ0 = 0;
 };
 
 struct RunStats {
@@ -48,6 +64,7 @@ struct RunStats {
     unsigned long long outCapacity = 0;
     bool occupancyPath = false;  // this run took the occupancy-only path
     unsigned long long slabTriangles = 0;  // occupancy-only path: triangles the passes worked on (= kept by the slab filter)
+    unsigned long long downloadBytes = 0;  // host-to-host jobs (o2v_job.cpp): bytes copied device -> host
 };
 
 class DeviceBuffer {
@@ -100,6 +117,35 @@ public:
     /// Copies the result of the last run to host memory (count * 16 bytes) on `stream` and synchronises it.
     int download(void *hostDst, cudaStream_t stream);
 
+    /// 0: deviceVoxels() holds Voxel32 records; 32 / 64: the last run (packedResult, occupancy-only path) left packed
+    /// positions there instead — x | y << 10 | z << 20 as u32, or x | y << 21 | z << 42 as u64 — voxelCount() of them.
+    int packedBits() const { return packedBits_; }
+    /// true if the last run ended with bitmaps instead of records (bitmapResult was asked for and the run took the
+    /// occupancy-only path); voxelCount() is valid either way.
+    bool hasBitmapResult() const { return bitmapValid_; }
+    BitmapResult bitmapResult() const { return bitmap_; }
+    /// Like swapOutputBuffers, for the bitmaps: the result of the last run stays put while the next run writes others.
+    void swapBitmapBuffers()
+    {
+        tileBits_.swap(tileBitsSpare_);
+        chunkList_.swap(chunkListSpare_);
+        chunkCounts_.swap(chunkCountsSpare_);
+    }
+
+    /// Bounds of a device-resident mesh (src/obj2voxel.cpp:180-200 findMeshBounds) — one device's share of a job.
+    int meshBounds(const MeshView &mesh, cudaStream_t stream, float outMin[3], float outMax[3]);
+
+    /// Region `source` (of `sources`) of this device's receive buffer for a multi-device job: room for `capacity`
+    /// triangles per region.  Peers write into it directly (SlabScatter).
+    float *receiveRegion(uint32_t source, uint32_t sources, unsigned long long capacity);
+    /// Copies the first counts[r] triangles of every region into one dense array; returns it (nullptr: out of memory).
+    const float *packReceived(const unsigned long long *counts, uint32_t sources, unsigned long long capacity,
+                              cudaStream_t stream, unsigned long long *total);
+    /// Bins `mesh` (this device's share) by Z-slab and stores every triangle into scatter.dest of the slabs it can reach;
+    /// sentCounts[s] = triangles sent to slab s.  params must carry the mesh bounds.  Synchronises `stream`.
+    int scatterToSlabs(const MeshView &mesh, const EngineParams &params, SlabScatter scatter, cudaStream_t stream,
+                       unsigned long long *sentCounts);
+
     /// The ingest step of a multi-GPU job on the occupancy-only path: copies the triangles of `mesh` whose z range can
     /// reach the slab of `params` into an engine-owned dense array (*kept, valid until the next filterSlab).  A later
     /// voxelize() on that array with EngineParams::slabFiltered never reads the rest of the mesh.  Order is arbitrary.
@@ -129,6 +175,9 @@ private:
     size_t totalMemory_ = 0;
     std::string error_;
     unsigned long long voxelCount_ = 0;
+    bool bitmapValid_ = false;
+    int packedBits_ = 0;
+    BitmapResult bitmap_;
 
     void *staging_[2] = {nullptr, nullptr};  // pinned, for host sinks
     size_t stagingBytes_[2] = {0, 0};
@@ -142,7 +191,8 @@ private:
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;
-    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, occRanges_, bigLeaves_, slabVerts_, slabKept_, extraLeaves_;  // occupancy-only path
+    DeviceBuffer chunkFlag_, chunkSlot_, chunkList_, tileBits_, occQueue_, occRanges_, bigLeaves_, slabVerts_, slabKept_, extraLeaves_;
+    DeviceBuffer tileBitsSpare_, chunkListSpare_, chunkCounts_, chunkCountsSpare_, received_, receivedPacked_, scatterCounts_;  // occupancy-only path
 };
 
 // error codes of Engine::voxelize / the additive C-ABI (include/obj2voxel_b200.h)

@@ -163,6 +163,20 @@ constexpr uint32_t kOccBoxEdge = 16;      // ... in 16^3 boxes
 constexpr uint32_t kOccDirectCandidates = 8;  // see launchOccupancyClassify
 constexpr uint32_t kLeafEmpty = 4u;       // LeafRecord::flags on this path: the triangle of this slot has no leaf in the slab
 
+constexpr uint32_t kMaxSlabs = 16;  // devices one job is spread over
+
+/// Multi-device ingest on the occupancy-only path: a device bins its share of the triangles by Z-slab and writes each
+/// triangle straight into the memory of the device(s) owning the slab(s) it can reach (peer stores over NVLink).
+/// Device s receives what source r sends in region r of its receive buffer (dest[s] points at that region), so no
+/// counter is shared between devices: count[s] lives on the source.
+struct SlabScatter {
+    uint32_t slabs;
+    uint32_t bound[kMaxSlabs + 1];    // slab s owns sample-space z in [bound[s], bound[s + 1])
+    float *dest[kMaxSlabs];           // region of this source in the receive buffer of slab s's device
+    unsigned long long capacity;      // triangles a region holds
+    unsigned long long *count;        // [slabs], on the source device: triangles sent to slab s so far
+};
+
 /// Buffers of the occupancy-only path (o2v_occupancy.cu): meshes whose every triangle is MATERIALLESS voxelize white
 /// whatever the weights are (src/triangle.hpp:186; BLEND of equal colours is exact, MAX keeps a colour), so only the
 /// occupancy has to be decided — an order-independent OR into per-chunk bitmaps.
@@ -204,6 +218,8 @@ struct VoxelizeArgs {
     OccupancyView occ;
     int variant;  // reserved for kernel A/B experiments
     int prefilter;  // 0 disables the conservative SAT prefilter (debug / validation)
+    int packedBits;  // occupancy-only path: 0 = `out` receives Voxel32 records; 32 / 64 = it receives packed positions
+                     // x | y << 10 | z << 20 (u32) / x | y << 21 | z << 42 (u64) of the all-white voxels instead
     float certainMargin;  // occupancy-only path: shrink of the voxel box for `certain` (certainMarginFor(sample resolution))
 };
 
@@ -226,6 +242,11 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
                           LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, int smCount,
                           cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
+void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
+                                cudaStream_t stream);
+/// chunkCounts[slot] = occupied voxels of bitmap `slot`; their sum is added to counters->voxels.
+void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,
+                               cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
                          const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,
                          cudaStream_t stream);

@@ -164,6 +164,109 @@ occupancySlabFilterKernel(MeshView mesh, GridView grid, float *__restrict__ kept
     }
 }
 
+/// Multi-device ingest (SlabScatter): every triangle of this device's share goes to the device(s) whose slab its z
+/// range can reach.  Per batch of kOccSetupThreads triangles the block counts its triangles per slab (ballots), reserves
+/// their places with one LOCAL atomic per slab, and the threads store their 36 bytes to the peer's memory — posted
+/// writes over NVLink, nothing comes back.  A triangle with a negative z goes to slab 0, which drops and counts it.
+__global__ void __launch_bounds__(kOccSetupThreads)
+occupancySlabScatterKernel(MeshView mesh, GridView grid, SlabScatter scatter)
+{
+    __shared__ TriangleBatch<kOccSetupThreads> batch;
+    __shared__ uint32_t warpCount[kOccSetupThreads / 32][kMaxSlabs];
+    __shared__ unsigned long long slabBase[kMaxSlabs];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t below = (1u << lane) - 1u;
+    const uint32_t gridEnd = scatter.bound[scatter.slabs];
+
+    streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
+                                      [&](unsigned long long, const float in[9], bool valid) {
+        uint32_t first = 1, last = 0;  // slabs [first, last] receive the triangle
+        if (valid) {
+            float zlo, zhi;
+            triangleZRange(grid, in, zlo, zhi);
+            if (zlo < 0.0f) {
+                first = last = 0;
+            }
+            else if (toU32(zlo) < gridEnd) {
+                const uint32_t z0 = toU32(zlo), z1 = min(toU32(zhi), gridEnd - 1u);
+                first = last = 0;
+                for (uint32_t s = 1; s < scatter.slabs; ++s) {
+                    first += scatter.bound[s] <= z0 ? 1u : 0u;
+                    last += scatter.bound[s] <= z1 ? 1u : 0u;
+                }
+            }
+        }
+        for (uint32_t s = 0; s < scatter.slabs; ++s) {
+            const unsigned int votes = __ballot_sync(0xffffffffu, first <= s && s <= last);
+            if (lane == 0) {
+                warpCount[warp][s] = (uint32_t) __popc(votes);
+            }
+        }
+        __syncthreads();
+        if (tid < scatter.slabs) {
+            uint32_t total = 0;
+#pragma unroll
+            for (uint32_t w = 0; w < kOccSetupThreads / 32; ++w) {
+                total += warpCount[w][tid];
+            }
+            slabBase[tid] = total != 0 ? atomicAdd(scatter.count + tid, (unsigned long long) total) : 0ull;
+        }
+        __syncthreads();
+        for (uint32_t s = 0; s < scatter.slabs; ++s) {  // block-uniform loop; a triangle sends to one slab as a rule
+            const bool mine = first <= s && s <= last;
+            const unsigned int votes = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                unsigned long long slot = slabBase[s] + __popc(votes & below);
+                for (uint32_t w = 0; w < warp; ++w) {
+                    slot += warpCount[w][s];
+                }
+                if (slot < scatter.capacity) {  // (a region holds the source's whole share: always true)
+                    float *dst = scatter.dest[s] + slot * 9;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) {
+                        dst[k] = in[k];
+                    }
+                }
+            }
+        }
+        __syncthreads();  // warpCount / slabBase are rewritten by the next batch
+    });
+}
+
+/// Block = bitmap: the occupied voxels of each chunk, for a host that expands downloaded bitmaps itself.
+__global__ void __launch_bounds__(256)
+occupancyChunkCountKernel(OccupancyView occ, uint32_t *__restrict__ chunkCounts, RunCounters *counters)
+{
+    __shared__ uint32_t warpSum[8];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t slot = blockIdx.x; slot < occ.activeChunks; slot += gridDim.x) {
+        const ulonglong2 *words = reinterpret_cast<const ulonglong2 *>(occ.bits + (size_t) slot * kChunkWords);
+        uint32_t sum = 0;
+        for (uint32_t k = threadIdx.x; k < kChunkWords / 2; k += 256u) {
+            const ulonglong2 w = words[k];
+            sum += (uint32_t) (__popcll(w.x) + __popcll(w.y));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        }
+        if (lane == 0) {
+            warpSum[warp] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t total = 0;
+            for (int w = 0; w < 8; ++w) {
+                total += warpSum[w];
+            }
+            chunkCounts[slot] = total;
+            if (total != 0) {
+                atomicAdd(&counters->voxels, (unsigned long long) total);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 constexpr uint32_t kOccBlockChunkWords = 2048;  // chunk bits a block collects in shared memory: 65536 chunks (8 KB)
 
 /// The one pass every triangle takes: transform, subdivision DFS, statistics, chunk marks — and the triangle's first leaf
@@ -415,6 +518,43 @@ __device__ __forceinline__ void flushRanges(RangeBuffer &rb, const VoxelizeArgs 
     }
 }
 
+/// The same buffer holding single voxels {leaf, x | y << 16, z, 0} that go to the clip queue as they are: on a mesh of
+/// micro-triangles hardly any undecided voxel is decided by another leaf (BASELINE config 5: 17.2 of 17.7 million
+/// survive), so the check against the bitmap is left to the clip kernel's own.
+__device__ __forceinline__ void pushVoxel(RangeBuffer &rb, const VoxelizeArgs &args, uint32_t leaf, uint32_t x, uint32_t y,
+                                          uint32_t z)
+{
+    const uint4 entry = make_uint4(leaf, x | (y << 16), z, 0u);
+    const uint32_t slot = atomicAdd(&rb.count, 1u);
+    if (slot < kOccRangeCap) {
+        rb.slot[slot] = entry;
+    }
+    else {
+        const unsigned long long index = atomicAdd(&args.counters->survivors, 1ull);
+        if (index < args.occ.queueCapacity) {  // beyond: counted only; the engine grows the queue and reruns
+            args.occ.queue[index] = entry;
+        }
+    }
+}
+
+__device__ __forceinline__ void flushVoxels(RangeBuffer &rb, const VoxelizeArgs &args)
+{
+    const uint32_t buffered = min(rb.count, kOccRangeCap);
+    if (buffered == 0) {  // block-uniform
+        return;
+    }
+    if (threadIdx.x == 0) {
+        rb.base = atomicAdd(&args.counters->survivors, (unsigned long long) buffered);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < buffered; k += blockDim.x) {
+        const unsigned long long index = rb.base + k;
+        if (index < args.occ.queueCapacity) {
+            args.occ.queue[index] = rb.slot[k];
+        }
+    }
+}
+
 struct ClassifyShared {
     BatchEntry entry[kOccBatch];
     uint32_t prefix[kOccBatch + 1];   // exclusive scan of the entries' row counts
@@ -647,8 +787,8 @@ constexpr int kOccDirectThreads = 128;
 
 /// Thread = leaf, for meshes of micro-triangles (on average at most kOccDirectCandidates candidate voxels per leaf:
 /// BASELINE config 5).  Sharing a leaf's one or two rows out over a block costs more than testing its few voxels: the
-/// per-voxel form of the SAT with its constants in registers, the thread walks its own rows.  Same bitmap and range list
-/// as occupancyClassifyKernel; big leaves are left to the box kernel.
+/// per-voxel form of the SAT with its constants in registers, the thread walks its own rows.  Same bitmap as
+/// occupancyClassifyKernel, undecided voxels straight to the clip queue; big leaves are left to the box kernel.
 __global__ void __launch_bounds__(kOccDirectThreads)
 occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
 {
@@ -708,11 +848,10 @@ occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
                             const size_t half = entryWord(occ, slot, x8 >> shift, oy, z >> shift) * 2u + ((oy & 7u) >> 2);
                             atomicOr(bits32 + half, mask << (8u * (oy & 3u)));
                         }
-                        while (open != 0) {  // runs of undecided voxels (one, as a rule)
-                            const uint32_t first = (uint32_t) __ffs((int) open) - 1u;
-                            const uint32_t length = (uint32_t) __ffs((int) ~(open >> first)) - 1u;
-                            pushRange(ranges, args, leafIndex, x8 + first, y, z, length, 0u, 0u);
-                            open &= ~(((1u << length) - 1u) << first);
+                        while (open != 0) {
+                            const uint32_t bit = (uint32_t) __ffs((int) open) - 1u;
+                            open &= open - 1u;
+                            pushVoxel(ranges, args, leafIndex, x8 + bit, y, z);
                         }
                     }
                 }
@@ -720,7 +859,7 @@ occupancyClassifyDirectKernel(const VoxelizeArgs args, uint32_t leafTotal)
         }
     }
     __syncthreads();
-    flushRanges(ranges, args);
+    flushVoxels(ranges, args);
 }
 
 /// Persistent blocks over the 16^3 boxes of the big leaves (axis-aligned triangles the reference does not subdivide).
@@ -1082,12 +1221,22 @@ occupancyExpandKernel(const VoxelizeArgs args)
             }
             const uint32_t b = selectBit64(sh.mask[warp][z][tile], r - info.wordFirst[z]);
             if (index + j < args.outCapacity) {
-                VoxelRecord rec;
-                rec.x = (int32_t) (info.origin[0] + (b & 7u));
-                rec.y = (int32_t) (info.origin[1] + (b >> 3));
-                rec.z = (int32_t) (info.origin[2] + z);
-                rec.argb = 0xFFFFFFFFu;  // quantizeArgb(1, 1, 1)
-                __stcs(reinterpret_cast<int4 *>(args.out + index + j), *reinterpret_cast<const int4 *>(&rec));
+                const uint32_t x = info.origin[0] + (b & 7u), y = info.origin[1] + (b >> 3), zz = info.origin[2] + z;
+                if (args.packedBits == 32) {  // (block-uniform) positions only: a host expands them (o2v_job.cpp)
+                    __stcs(reinterpret_cast<uint32_t *>(args.out) + index + j, x | (y << 10) | (zz << 20));
+                }
+                else if (args.packedBits == 64) {
+                    __stcs(reinterpret_cast<unsigned long long *>(args.out) + index + j,
+                           (unsigned long long) x | ((unsigned long long) y << 21) | ((unsigned long long) zz << 42));
+                }
+                else {
+                    VoxelRecord rec;
+                    rec.x = (int32_t) x;
+                    rec.y = (int32_t) y;
+                    rec.z = (int32_t) zz;
+                    rec.argb = 0xFFFFFFFFu;  // quantizeArgb(1, 1, 1)
+                    __stcs(reinterpret_cast<int4 *>(args.out + index + j), *reinterpret_cast<const int4 *>(&rec));
+                }
             }
             else {
                 ++overflow;
@@ -1135,6 +1284,23 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
     // countFromFilter: mesh.count is only an upper bound (the grid is sized by it; blocks without a batch leave at once)
     occupancyCountKernel<<<setupBlocks(occupancyCountKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
         mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
+}
+
+void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
+                                cudaStream_t stream)
+{
+    occupancySlabScatterKernel<<<setupBlocks(occupancySlabScatterKernel, mesh.count, smCount), kOccSetupThreads, 0,
+                                 stream>>>(mesh, grid, scatter);
+}
+
+void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,
+                               cudaStream_t stream)
+{
+    if (occ.activeChunks == 0) {
+        return;
+    }
+    const unsigned blocks = occ.activeChunks < (unsigned) smCount * 8u ? occ.activeChunks : (unsigned) smCount * 8u;
+    occupancyChunkCountKernel<<<blocks, 256, 0, stream>>>(occ, chunkCounts, counters);
 }
 
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream)

@@ -8,6 +8,7 @@
 #define O2V_POOL_H
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <memory>
@@ -15,7 +16,35 @@
 #include <thread>
 #include <vector>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
 namespace o2v {
+
+inline void spinPause()
+{
+#if defined(__SSE2__)
+    _mm_pause();
+#endif
+}
+
+/// Polls `ready` for up to `microseconds` before the caller falls back to blocking: the loops of a job follow each other
+/// within microseconds, a condition variable wakes a thread in tens of them.
+template <typename Ready>
+inline bool spinUntil(Ready &&ready, int microseconds)
+{
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(microseconds);
+    for (int round = 0;; ++round) {
+        if (ready()) {
+            return true;
+        }
+        if ((round & 63) == 63 && std::chrono::steady_clock::now() >= deadline) {
+            return false;
+        }
+        spinPause();
+    }
+}
 
 /// One index-parallel loop in flight: fn(i) for i in [0, count), indices handed out by an atomic counter.
 class ParallelLoop {
@@ -39,11 +68,11 @@ public:
         }
     }
 
-    /// Helps, then blocks until every index has run.
+    /// Helps, then waits until every index has run (polling first: the stragglers are microseconds away).
     void wait()
     {
         help();
-        if (count_ == 0) {
+        if (count_ == 0 || spinUntil([this] { return done_.load(std::memory_order_acquire) == count_; }, 200)) {
             return;
         }
         std::unique_lock<std::mutex> lock{mutex_};
@@ -89,10 +118,13 @@ public:
     {
         auto loop = std::make_shared<ParallelLoop>(count, std::move(fn));
         if (count != 0) {
-            std::lock_guard<std::mutex> lock{mutex_};
-            loops_.push_back(loop);
+            {
+                std::lock_guard<std::mutex> lock{mutex_};
+                loops_.push_back(loop);
+                epoch_.fetch_add(1, std::memory_order_release);
+            }
+            wake_.notify_all();
         }
-        wake_.notify_all();
         return loop;
     }
 
@@ -100,24 +132,33 @@ public:
     void parallelFor(size_t count, std::function<void(size_t)> fn) { start(count, std::move(fn))->wait(); }
 
 private:
+    /// The first loop that still has indices to hand out, or null.
+    std::shared_ptr<ParallelLoop> take()
+    {
+        std::lock_guard<std::mutex> lock{mutex_};
+        while (!loops_.empty() && loops_.front()->exhausted()) {
+            loops_.erase(loops_.begin());
+        }
+        return loops_.empty() ? nullptr : loops_.front();
+    }
+
     void run()
     {
         for (;;) {
-            std::shared_ptr<ParallelLoop> loop;
-            {
-                std::unique_lock<std::mutex> lock{mutex_};
-                wake_.wait(lock, [this] {
-                    while (!loops_.empty() && loops_.front()->exhausted()) {
-                        loops_.erase(loops_.begin());
-                    }
-                    return stopping_ || !loops_.empty();
-                });
-                if (stopping_) {
-                    return;
-                }
-                loop = loops_.front();
+            const unsigned long long seen = epoch_.load(std::memory_order_acquire);
+            if (std::shared_ptr<ParallelLoop> loop = take()) {
+                loop->help();
+                continue;
             }
-            loop->help();
+            // nothing to do: poll for the next loop for a while (a job issues them back to back), then sleep
+            if (spinUntil([&] { return epoch_.load(std::memory_order_acquire) != seen; }, 300)) {
+                continue;
+            }
+            std::unique_lock<std::mutex> lock{mutex_};
+            wake_.wait(lock, [&] { return stopping_ || epoch_.load(std::memory_order_acquire) != seen; });
+            if (stopping_) {
+                return;
+            }
         }
     }
 
@@ -125,6 +166,7 @@ private:
     std::mutex mutex_;
     std::condition_variable wake_;
     std::vector<std::shared_ptr<ParallelLoop>> loops_;
+    std::atomic<unsigned long long> epoch_{0};  // bumped by every start()
     bool stopping_ = false;
 };
 

@@ -235,3 +235,102 @@ def test_job_part_plan_tiles_the_slab_in_whole_chunk_rows():
         assert 1 <= n <= 128 and b[0] == lo and b[-1] == hi
         assert all(b[k] < b[k + 1] for k in range(n)), (res, z0, z1, b)
         assert all(x % 64 == 0 for x in b[1:-1])
+
+
+def test_missing_input_file_leaves_the_output_file_alone(tmp_path):
+    """The reference opens its input before its output (src/obj2voxel.cpp:617-625): an unreadable input must not
+    truncate an existing output file."""
+    o2v.load().obj2voxel_set_log_level(_lib.LOG_SILENT)
+    out = tmp_path / "model.vl32"
+    out.write_bytes(b"precious")
+    inst = o2v.Instance()
+    inst.set_input_file(str(tmp_path / "missing.stl"))
+    inst.set_output_file(str(out))
+    inst.set_resolution(8)
+    assert inst.voxelize() == _lib.ERR_IO_OPEN_INPUT
+    inst.free()
+    assert out.read_bytes() == b"precious"
+    o2v.load().obj2voxel_set_log_level(_lib.LOG_INFO)
+
+
+def test_log_callback_may_call_back_into_the_log_api():
+    """The log callback runs outside the library's log lock (a callback that reads or sets the log level must not
+    deadlock)."""
+    lib = o2v.load()
+    seen = []
+
+    def on_log(_data, msg, level):
+        seen.append(lib.obj2voxel_get_log_level())
+        return True
+
+    cb = _lib.LOG_CALLBACK(on_log)
+    lib.obj2voxel_set_log_callback(cb, None)
+    inst = o2v.Instance()
+    inst.set_output_callback()
+    inst.set_resolution(4)
+    done = []
+    t = threading.Thread(target=lambda: done.append(inst.voxelize()))
+    t.start()
+    t.join(timeout=20)
+    assert not t.is_alive(), "log callback deadlocked"
+    assert done == [o2v.ERR_NO_INPUT] and seen
+    lib.obj2voxel_set_log_callback(None, None)
+    inst.free()
+
+
+def test_job_devices_setter():
+    """obj2voxel_b200_set_devices only records the choice (no device needed)."""
+    inst = o2v.Instance()
+    inst.set_devices([0, 1, 2])
+    inst.set_devices([])
+    inst.free()
+
+
+def test_host_bitmap_expansion_matches_numpy():
+    """o2v_b200_expand_bitmaps: the host side of the single-GPU bitmap download (64^3 chunks of 8^3 tiles, one 64-bit word
+    per tile layer).  Random chunks against a numpy restatement of the layout; a wrong count is reported."""
+    lib = o2v.load()
+    rng = np.random.default_rng(5)
+    chunks, per_axis, z0 = 7, 5, 2
+    occupied = rng.random((chunks, 64, 64, 64)) < 0.03  # [chunk][z][y][x]
+    occupied[3] = False  # an empty chunk
+    ids = rng.choice(per_axis * per_axis * 3, size=chunks, replace=False).astype(np.uint32)
+    bits = np.zeros((chunks, 4096), dtype=np.uint64)
+    want = []
+    for c in range(chunks):
+        cz, cy, cx = (int(ids[c]) // (per_axis * per_axis) + z0, (int(ids[c]) // per_axis) % per_axis, int(ids[c]) % per_axis)
+        z, y, x = np.nonzero(occupied[c])
+        tile = (x >> 3) | ((y >> 3) << 3) | ((z >> 3) << 6)
+        np.bitwise_or.at(bits[c], tile * 8 + (z & 7), np.uint64(1) << ((x & 7) + 8 * (y & 7)).astype(np.uint64))
+        want.append(np.stack([x + 64 * cx, y + 64 * cy, z + 64 * cz, np.full_like(x, 0xFFFFFFFF)], axis=1))
+    want = o2v.sort_voxels(np.concatenate(want).astype(np.uint32))
+    counts = occupied.reshape(chunks, -1).sum(axis=1).astype(np.uint32)
+    out = np.zeros((int(counts.sum()), 4), dtype=np.uint32)
+
+    def ptr(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    n = lib.o2v_b200_expand_bitmaps(ptr(bits), ptr(ids), ptr(counts), chunks, per_axis, z0, ptr(out))
+    assert n == len(want)
+    assert np.array_equal(o2v.sort_voxels(out), want)
+    counts[1] += 1  # the device's count and the bitmap must agree
+    big = np.zeros((int(counts.sum()), 4), dtype=np.uint32)
+    assert lib.o2v_b200_expand_bitmaps(ptr(bits), ptr(ids), ptr(counts), chunks, per_axis, z0, ptr(big)) == 2 ** 64 - 1
+
+
+@pytest.mark.parametrize("bits,count", [(32, 1), (32, 70_003), (64, 5), (64, 40_001)])
+def test_host_expansion_of_packed_positions(bits, count):
+    """o2v_b200_expand_packed: the host side of the default single-GPU download (positions packed into 4 or 8 bytes per
+    voxel, quads written by the host's threads); odd counts exercise the vector loop's tail."""
+    lib = o2v.load()
+    rng = np.random.default_rng(bits + count)
+    limit = 1024 if bits == 32 else 8192
+    xyz = rng.integers(0, limit, size=(count, 3), dtype=np.uint64)
+    if bits == 32:
+        packed = (xyz[:, 0] | (xyz[:, 1] << np.uint64(10)) | (xyz[:, 2] << np.uint64(20))).astype(np.uint32)
+    else:
+        packed = xyz[:, 0] | (xyz[:, 1] << np.uint64(21)) | (xyz[:, 2] << np.uint64(42))
+    out = np.zeros((count, 4), dtype=np.uint32)
+    lib.o2v_b200_expand_packed(packed.ctypes.data_as(C.c_void_p), bits, count, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out[:, :3], xyz.astype(np.uint32))
+    assert (out[:, 3] == 0xFFFFFFFF).all()
