@@ -42,6 +42,10 @@ typedef struct o2v_b200_params {
     int32_t variant;            /* kernel A/B switch, -1 = default (occupancy-only path: 1 / 2 force the block-per-batch /
                                  * thread-per-leaf classifier; both give the same records) */
     int32_t prefilter;          /* 1 = conservative SAT prefilter on (default); 0 = off (validation only) */
+    int32_t float_records;      /* parity / debug: 1 = also keep every voxel's float (weight, r, g, b) as the fold left it,
+                                 * before the ARGB8 truncation — what obj2voxel::Voxelizer::voxels() holds in the
+                                 * reference (src/voxelization.hpp:55-108); forces the weighted pipeline; read them with
+                                 * o2v_b200_result_floats_device() */
     int32_t slab_filtered;      /* 1 = mesh is the output of o2v_b200_filter_slab() for this very slab: the step skips
                                  * its own filter pass (multi-GPU ingest distributes triangles by z range once) */
     int32_t occupancy_path;     /* 1 (default) = meshes whose every triangle is MATERIALLESS (output colour is white
@@ -113,6 +117,9 @@ int o2v_b200_voxelize_device(o2v_b200_engine *engine, const o2v_b200_params *par
 const void *o2v_b200_result_device(const o2v_b200_engine *engine);
 uint64_t o2v_b200_result_count(const o2v_b200_engine *engine);
 int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda_stream);
+/* `count` x 4 floats (weight, r, g, b), index-aligned with o2v_b200_result_device(); NULL unless the last run had
+ * float_records = 1. */
+const float *o2v_b200_result_floats_device(const o2v_b200_engine *engine);
 
 /* Multi-GPU ingest on the occupancy-only path (all-MATERIALLESS meshes): copies the triangles of the DEVICE mesh whose z
  * range can reach the slab [slab_z0, slab_z1) of `params` into an engine-owned dense device array (*out_kept: 9 floats
@@ -191,7 +198,7 @@ bool obj2voxel_b200_counting_sink_write(void *sink, uint32_t *voxel_data, size_t
 void obj2voxel_b200_set_devices(obj2voxel_instance *instance, const int32_t *devices, uint32_t count);
 /* Restrict the job to a Z-slab of the sample grid (multiples of 8). */
 void obj2voxel_b200_set_slab(obj2voxel_instance *instance, uint32_t z0, uint32_t z1);
-/* Statistics of the last obj2voxel_voxelize() on this instance.  A big job (>= 2^20 triangles) runs as up to four z parts
+/* Statistics of the last obj2voxel_voxelize() on this instance.  A big job runs as z parts (one per 2^20 triangles, at most four)
  * so that the download of one part overlaps the kernels of the next (O2V_B200_PIPELINE_PARTS overrides the number): the
  * counts and the device times are then sums over the parts (dropped_triangles: the largest of the parts), and the sink /
  * voxel callback receives the parts one after the other. */

@@ -28,7 +28,7 @@ class Params(C.Structure):
     _fields_ = [("resolution", C.c_uint32), ("supersampling", C.c_uint32), ("strategy", C.c_uint32),
                 ("bounds_known", C.c_uint32), ("bounds", C.c_float * 6), ("unit_transform", C.c_int32 * 9),
                 ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("variant", C.c_int32), ("prefilter", C.c_int32),
-                ("slab_filtered", C.c_int32), ("occupancy_path", C.c_int32)]
+                ("float_records", C.c_int32), ("slab_filtered", C.c_int32), ("occupancy_path", C.c_int32)]
 
 
 class Mesh(C.Structure):
@@ -66,6 +66,17 @@ class Stats(C.Structure):
         d["transform"] = list(self.transform)
         return d
 
+    def __getitem__(self, name):  # stats["voxels"]: the struct itself serves as the mapping (no dict per run)
+        if name == "transform":
+            return list(self.transform)
+        try:
+            return getattr(self, name)
+        except AttributeError:
+            raise KeyError(name)
+
+    def keys(self):
+        return [name for name, _ in self._fields_]
+
 
 # every symbol include/obj2voxel.h declares (35) ...
 REFERENCE_SYMBOLS = [
@@ -85,7 +96,7 @@ REFERENCE_SYMBOLS = [
 ADDITIVE_SYMBOLS = [
     "o2v_b200_engine_create", "o2v_b200_engine_destroy", "o2v_b200_last_error", "o2v_b200_sm_count",
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
-    "o2v_b200_result_download", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
+    "o2v_b200_result_download", "o2v_b200_result_floats_device", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
     "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab", "obj2voxel_b200_set_devices", "o2v_b200_expand_bitmaps", "o2v_b200_expand_packed", "obj2voxel_b200_array_source_next", "obj2voxel_b200_counting_sink_write",
 ]
 
@@ -151,6 +162,7 @@ def load():
         "o2v_b200_result_device": (vp, [vp]),
         "o2v_b200_result_count": (C.c_uint64, [vp]),
         "o2v_b200_result_download": (C.c_int, [vp, vp, vp]),
+        "o2v_b200_result_floats_device": (vp, [vp]),
         "o2v_b200_result_hash": (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
         "o2v_b200_filter_slab": (C.c_int, [vp, C.POINTER(Params), C.POINTER(Mesh), vp, C.POINTER(vp),
                                            C.POINTER(C.c_uint64)]),

@@ -213,7 +213,7 @@ def sort_voxels(voxels):
 
 
 def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None, unit=None, slab=None, variant=-1,
-                prefilter=1, occupancy_path=1, slab_filtered=0):
+                prefilter=1, occupancy_path=1, slab_filtered=0, float_records=0):
     p = Params()
     _lib.load().o2v_b200_default_params(C.byref(p))
     p.resolution = resolution
@@ -230,6 +230,7 @@ def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None,
     p.prefilter = prefilter
     p.occupancy_path = occupancy_path
     p.slab_filtered = slab_filtered
+    p.float_records = float_records
     return p
 
 
@@ -247,6 +248,7 @@ class Engine:
         if not self.handle:
             raise DeviceError(self._lib.o2v_b200_last_error().decode())
         self.last_stats = None
+        self._marshalled = None
 
     @property
     def sm_count(self):
@@ -270,13 +272,22 @@ class Engine:
             assert t.is_cuda and t.is_contiguous() and t.dtype == dtype, "expected a contiguous CUDA tensor"
             return t.data_ptr()
 
-        mesh = Mesh(ptr(verts, torch.float32), ptr(uvs, torch.float32), ptr(types, torch.uint8),
-                    ptr(colors, torch.float32), ptr(texture_ids, torch.int32), verts.numel() // 9)
-        tex_array = (_lib.Texture * max(len(textures), 1))()
-        for i, (pixels, wrap) in enumerate(textures):
-            assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.is_contiguous()
-            h, w, ch = pixels.shape
-            tex_array[i] = _lib.Texture(pixels.data_ptr(), w, h, ch, wrap)
+        # the marshalled arguments of the last call are kept: a caller that steps the same tensors again (a benchmark, a
+        # simulation loop) pays the ctypes call and nothing else
+        key = (verts.data_ptr(), verts.numel(), None if uvs is None else uvs.data_ptr(),
+               None if types is None else types.data_ptr(), None if colors is None else colors.data_ptr(),
+               None if texture_ids is None else texture_ids.data_ptr(),
+               tuple((p.data_ptr(), tuple(p.shape), w) for p, w in textures))
+        if self._marshalled is None or self._marshalled[0] != key:
+            mesh = Mesh(ptr(verts, torch.float32), ptr(uvs, torch.float32), ptr(types, torch.uint8),
+                        ptr(colors, torch.float32), ptr(texture_ids, torch.int32), verts.numel() // 9)
+            tex_array = (_lib.Texture * max(len(textures), 1))()
+            for i, (pixels, wrap) in enumerate(textures):
+                assert pixels.is_cuda and pixels.dtype == torch.uint8 and pixels.is_contiguous()
+                h, w, ch = pixels.shape
+                tex_array[i] = _lib.Texture(pixels.data_ptr(), w, h, ch, wrap)
+            self._marshalled = (key, mesh, tex_array)
+        _, mesh, tex_array = self._marshalled
         if stream is None:
             stream = torch.cuda.current_stream(verts.device).cuda_stream
         stats = Stats()
@@ -285,8 +296,8 @@ class Engine:
         if rc != 0:
             raise DeviceError("o2v_b200_voxelize_device failed (%d): %s" %
                               (rc, self._lib.o2v_b200_last_error().decode()))
-        self.last_stats = stats.as_dict()
-        return self.last_stats
+        self.last_stats = stats  # indexable like a dict (stats["voxels"]); .as_dict() for a real one
+        return stats
 
     def result_count(self):
         return int(self._lib.o2v_b200_result_count(self.handle))
@@ -306,6 +317,23 @@ class Engine:
         view.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<i4",
                                          "data": (int(self._lib.o2v_b200_result_device(self.handle)), False),
                                          "version": 2}
+        return torch.as_tensor(view, device="cuda:%d" % self.device)
+
+    def result_floats_tensor(self):
+        """Zero-copy torch view (n, 4) float32 (weight, r, g, b) per record of a run with float_records=1, index-aligned
+        with result_tensor(); None otherwise."""
+        import torch
+
+        ptr = self._lib.o2v_b200_result_floats_device(self.handle)
+        n = self.result_count()
+        if not ptr or n == 0:
+            return None
+
+        class _View:
+            pass
+
+        view = _View()
+        view.__cuda_array_interface__ = {"shape": (n, 4), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
         return torch.as_tensor(view, device="cuda:%d" % self.device)
 
     def filter_slab(self, verts, params, stream=None):

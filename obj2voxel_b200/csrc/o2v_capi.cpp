@@ -177,6 +177,7 @@ EngineParams paramsFromC(const o2v_b200_params &p)
     e.prefilter = p.prefilter;
     e.occupancyPath = p.occupancy_path;
     e.slabFiltered = p.slab_filtered != 0;
+    e.floatRecords = p.float_records != 0;
     return e;
 }
 
@@ -869,6 +870,11 @@ int o2v_b200_voxelize_device(o2v_b200_engine *engine, const o2v_b200_params *par
 const void *o2v_b200_result_device(const o2v_b200_engine *engine)
 {
     return engine->engine->deviceVoxels();
+}
+
+const float *o2v_b200_result_floats_device(const o2v_b200_engine *engine)
+{
+    return engine->engine->floatRecords();
 }
 
 uint64_t o2v_b200_result_count(const o2v_b200_engine *engine)

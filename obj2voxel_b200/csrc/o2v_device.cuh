@@ -226,6 +226,16 @@ __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridVi
     });
 }
 
+/// Debug / parity record: the voxel's float WeightedColor (weight, r, g, b) as the fold left it, before the ARGB8
+/// truncation — what obj2voxel::Voxelizer::voxels() holds in the reference (src/voxelization.hpp:55-108).
+__device__ __forceinline__ void storeFloatRecord(const VoxelizeArgs &args, unsigned long long index, float w, float r,
+                                                 float g, float b)
+{
+    if (args.floatOut != nullptr) {
+        args.floatOut[index] = make_float4(w, r, g, b);
+    }
+}
+
 struct VoxelAccumulator {
     // per-triangle uv buffer entry (voxelization.cpp:426-472) and the voxel itself (voxelization.cpp:513-526)
     WeightedUv partial;

@@ -186,7 +186,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
 {
     // Every triangle MATERIALLESS (no per-triangle types, no usable texture): the output is white wherever a voxel is
     // occupied, whatever the weights — the occupancy-only path decides just that (o2v_occupancy.cu).
-    bool occupancy = params.occupancyPath != 0 && meshIn.types == nullptr &&
+    bool occupancy = params.occupancyPath != 0 && !params.floatRecords && meshIn.types == nullptr &&
                      !(meshIn.uvs != nullptr && textureCount != 0);
     MeshView mesh = meshIn;
     if (occupancy) {
@@ -197,6 +197,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     voxelCount_ = 0;
     bitmapValid_ = false;
     packedBits_ = 0;
+    floatValid_ = false;
     RunStats local;
     RunStats &st = stats != nullptr ? *stats : local;
     st = RunStats();
@@ -306,7 +307,8 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         const unsigned long long affordable = (freeBytes + out_.size()) / sizeof(VoxelRecord) * 9 / 10;
         capacity = std::min(capacity, std::max<unsigned long long>(affordable, 1));
     }
-    if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+    if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord)) ||
+        (params.floatRecords && !floatOut_.ensure((size_t) capacity * sizeof(float4)))) {
         return fail(kErrOutOfMemory, "device allocation failed (voxel output)");
     }
     if (textureCount != 0) {
@@ -342,6 +344,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     args.textures = textureCount != 0 ? textures_.as<TextureView>() : nullptr;
     args.textureCount = textureCount;
     args.out = out_.as<VoxelRecord>();
+    args.floatOut = params.floatRecords ? floatOut_.as<float4>() : nullptr;
     args.outCapacity = capacity;
     args.counters = dCounters;
     args.lightTiles = lightTiles_.as<LightTile>();
@@ -421,10 +424,12 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
         }
         // the exact count is now known: grow once and redo the tile pass (setup results are still valid)
         capacity = hostCounters_->voxels;
-        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord))) {
+        if (!out_.ensure((size_t) capacity * sizeof(VoxelRecord)) ||
+            (params.floatRecords && !floatOut_.ensure((size_t) capacity * sizeof(float4)))) {
             return fail(kErrOutOfMemory, "device allocation failed (voxel output, exact size)");
         }
         args.out = out_.as<VoxelRecord>();
+        args.floatOut = params.floatRecords ? floatOut_.as<float4>() : nullptr;
         args.outCapacity = capacity;
         RunCounters reset = *hostCounters_;
         reset.voxels = 0;
@@ -442,6 +447,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     }
 
     hostCounters_->clipCalls += hostCounters_->survivors;  // every sparse-path survivor is one exact clip
+    floatValid_ = params.floatRecords;
     st.counters = *hostCounters_;
     st.outCapacity = capacity;
     voxelCount_ = hostCounters_->voxels;

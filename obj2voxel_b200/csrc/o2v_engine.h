@@ -33,6 +33,8 @@ struct EngineParams {
     bool slabFiltered = false;        // the mesh is the output of filterSlab() for this very slab: skip the filter pass
     bool bitmapResult = false;        // occupancy-only path: stop at the bitmaps (no records on the device); the caller
                                       // downloads them and expands them on the host (see Engine::bitmapResult)
+    bool floatRecords = false;        // parity / debug: also keep every voxel's float (weight, r, g, b) as the fold left it,
+                                      // before the ARGB8 truncation (forces the weighted pipeline; see floatRecords())
     bool packedResult = false;        // occupancy-only path: packed positions instead of 16-byte records (every voxel is
                                       // white): 4 bytes per voxel while the output grid fits 10 bits per axis, else 8
                                       // (see Engine::packedBits); a host-to-host job expands them on the host
@@ -107,6 +109,9 @@ public:
                  cudaStream_t stream, RunStats *stats);
 
     const VoxelRecord *deviceVoxels() const { return out_.as<VoxelRecord>(); }
+    /// float4 (weight, r, g, b) per record of the last run, index-aligned with deviceVoxels(); null unless the run had
+    /// EngineParams::floatRecords.
+    const float *floatRecords() const { return floatValid_ ? floatOut_.as<float>() : nullptr; }
     unsigned long long voxelCount() const { return voxelCount_; }
     const std::string &lastError() const { return error_; }
 
@@ -177,6 +182,7 @@ private:
     unsigned long long voxelCount_ = 0;
     bool bitmapValid_ = false;
     int packedBits_ = 0;
+    bool floatValid_ = false;
     BitmapResult bitmap_;
 
     void *staging_[2] = {nullptr, nullptr};  // pinned, for host sinks
@@ -187,7 +193,7 @@ private:
     cudaEvent_t evStart_ = nullptr, evSetup_ = nullptr, evVoxStart_ = nullptr, evVoxEnd_ = nullptr;
     cudaEvent_t evClipStart_ = nullptr, evClipEnd_ = nullptr, evClassifyStart_ = nullptr, evFilterStart_ = nullptr;
 
-    DeviceBuffer hash_, counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
+    DeviceBuffer hash_, floatOut_, counters_, leafCount_, leafOffset_, tileCount_, tileStart_, tileFill_, tileCand_, activeTiles_, lightTiles_, bigLightTiles_,
         scratch_;
     DeviceBuffer leaves_, leafUvs_, tileList_, out_, outSpare_, textures_;
     DeviceBuffer allTiles_, longTiles_, pairTile_, pairSurvivors_, pairOffset_, pairMask_, pairBox_, entries_, contribUvs_;

@@ -163,7 +163,9 @@ public:
         if (format_ == FileFormat::PLY) {
             writeText("ply\r\n");
             writeText("format binary_big_endian 1.0\r\n");
-            writeText("comment voxel list written by obj2voxel_b200; body is byte-identical to the VL32 format\r\n");
+            // the reference's own comment line, so that the 299-byte header is byte-identical to what voxelio writes
+            // (voxelio/src/format/ply.cpp:24): a reader keyed to the fixed header length of obj2voxel's PLY files keeps working
+            writeText("comment generated by voxel-io: a C++ library by Jan \"Eisenwave\" Schultke\r\n");
             writeText("element vertex ");
             countOffset_ = stream_.position();
             writeText("....;....;....;....;....;...\r\n");  // patched with the count + a trailing comment on finalize

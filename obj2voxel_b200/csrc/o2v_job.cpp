@@ -730,7 +730,9 @@ uint32_t planJobParts(uint32_t sampleRes, uint32_t slabZ0, uint32_t slabZ1, unsi
     jobZ0 = std::min(jobZ0, jobZ1);
     const uint32_t row0 = jobZ0 / 64u, row1 = std::max((jobZ1 + 63u) / 64u, row0 + 1u);
     const uint32_t rows = row1 - row0;
-    uint32_t parts = (triangles >= (1ull << 20) && rows > 1u) ? std::min(4u, rows) : 1u;
+    // one part per 2^20 triangles, at most four: the download of a part (and the host threads' work on it) runs under the
+    // kernels of the next, but every part pays a filter pass over the slab's triangles and two host round trips
+    uint32_t parts = std::min<uint32_t>({4u, rows, (uint32_t) std::max<unsigned long long>(triangles >> 20, 1ull)});
     if (requested > 0) {
         parts = std::min(std::min((uint32_t) requested, rows), kMaxJobParts);
     }

@@ -642,6 +642,7 @@ voxelizeTilesKernel(const VoxelizeArgs args)
                 rec.z = oz;
                 rec.argb = quantizeArgb(result.r, result.g, result.b);
                 *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
             }
             else {
                 atomicAdd(&args.counters->outputOverflow, 1ull);

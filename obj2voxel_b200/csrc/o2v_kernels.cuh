@@ -208,6 +208,7 @@ struct VoxelizeArgs {
     const TextureView *textures;
     uint32_t textureCount;
     VoxelRecord *out;
+    float4 *floatOut;  // null, or per record the float (weight, r, g, b) before quantisation (weighted pipeline only)
     unsigned long long outCapacity;
     RunCounters *counters;
     const LightTile *lightTiles;     // <= kWarpFoldMax candidates

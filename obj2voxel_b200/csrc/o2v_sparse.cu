@@ -403,6 +403,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                     rec.z = oz;
                     rec.argb = quantizeArgb(result.r, result.g, result.b);
                     *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
                 }
                 else {
                     atomicAdd(&args.counters->outputOverflow, 1ull);
@@ -548,6 +549,7 @@ sparseTinyFoldKernel(const VoxelizeArgs args)
                 rec.z = oz;
                 rec.argb = quantizeArgb(result.r, result.g, result.b);
                 *reinterpret_cast<int4 *>(args.out + outIndex) = *reinterpret_cast<const int4 *>(&rec);
+                storeFloatRecord(args, outIndex, result.w, result.r, result.g, result.b);
             }
             else {
                 atomicAdd(&args.counters->outputOverflow, 1ull);
@@ -730,6 +732,7 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
                 rec.z = oz;
                 rec.argb = quantizeArgb(result.r, result.g, result.b);
                 *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
             }
             else {
                 atomicAdd(&args.counters->outputOverflow, 1ull);

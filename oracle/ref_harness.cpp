@@ -18,6 +18,10 @@
 #include <cstdlib>
 #include <thread>
 
+#include "voxelio/format/qef.hpp"
+#include "voxelio/format/vl32.hpp"
+#include "voxelio/format/vox.hpp"
+
 namespace {
 
 struct ArrayInput {
@@ -269,6 +273,100 @@ long long o2vref_run_internal(const float *verts, const float *uvs, const uint8_
     *outXyz = xyzBuffer;
     *outWrgb = wrgbBuffer;
     return static_cast<long long>(count);
+}
+
+/// Reads a voxel file written by anyone with the reference's own voxelio reader for `type` ("qef", "vox", "vl32"):
+/// *outVoxels receives a malloc'ed array of 4*n u32 (x, y, z, argb) in file order.  Returns n, or -1 if the file cannot
+/// be opened, -2 if the type has no reader, -3 if the reader reports an error.
+long long o2vref_read_voxel_file(const char *path, const char *type, uint32_t **outVoxels)
+{
+    std::optional<voxelio::FileInputStream> stream = voxelio::FileInputStream::open(path);
+    if (not stream.has_value()) {
+        return -1;
+    }
+    std::unique_ptr<voxelio::AbstractReader> reader;
+    const std::string t = type;
+    if (t == "qef") {
+        reader.reset(new voxelio::qef::Reader{*stream});
+    }
+    else if (t == "vox") {
+        reader.reset(new voxelio::vox::Reader{*stream});
+    }
+    else if (t == "vl32") {
+        reader.reset(new voxelio::vl32::Reader{*stream});
+    }
+    else {
+        return -2;
+    }
+    std::vector<uint32_t> voxels;
+    std::vector<voxelio::Voxel64> buffer(8192);
+    for (;;) {
+        const voxelio::ReadResult result = reader->read(buffer.data(), buffer.size());
+        if (result.isBad()) {
+            return -3;
+        }
+        for (uint64_t i = 0; i < result.voxelsRead; ++i) {
+            const voxelio::Voxel64 &v = buffer[i];
+            voxels.insert(voxels.end(), {static_cast<uint32_t>(v.pos[0]), static_cast<uint32_t>(v.pos[1]),
+                                         static_cast<uint32_t>(v.pos[2]), v.argb});
+        }
+        if (result.isEnd()) {
+            break;
+        }
+    }
+    const size_t n = voxels.size() / 4;
+    auto *out = static_cast<uint32_t *>(std::malloc(std::max<size_t>(1, n * 4) * sizeof(uint32_t)));
+    std::memcpy(out, voxels.data(), n * 4 * sizeof(uint32_t));
+    *outVoxels = out;
+    return static_cast<long long>(n);
+}
+
+/// Runs the reference from an input FILE (its own OBJ / STL readers: tinyobjloader, src/io.cpp) to either a voxel
+/// callback (outputPath == nullptr: *outVoxels receives 4*n u32) or an output FILE written by voxelio's writers.
+/// Returns the voxel count (callback) or 0 (file), or -(error code).
+long long o2vref_run_file(const char *inputPath, const char *outputPath, uint32_t resolution, uint32_t supersampling,
+                          int strategy, int workers, uint32_t **outVoxels)
+{
+    obj2voxel_set_log_level(OBJ2VOXEL_LOG_LEVEL_ERROR);
+    CollectOutput collected;
+    obj2voxel_instance *instance = obj2voxel_alloc();
+    obj2voxel_set_input_file(instance, inputPath, nullptr);
+    if (outputPath != nullptr) {
+        obj2voxel_set_output_file(instance, outputPath, nullptr);
+    }
+    else {
+        obj2voxel_set_output_callback(instance, &collectOutputCallback, &collected);
+    }
+    obj2voxel_set_resolution(instance, resolution);
+    obj2voxel_set_supersampling(instance, supersampling);
+    obj2voxel_set_color_strategy(instance, static_cast<obj2voxel_enum_t>(strategy));
+    obj2voxel_set_parallel(instance, workers > 0);
+    std::vector<std::thread> threads;
+    for (int i = 0; i < workers; ++i) {
+        threads.emplace_back(&obj2voxel_run_worker, instance);
+    }
+    if (workers > 0) {
+        while (obj2voxel_get_worker_count(instance) != static_cast<uint32_t>(workers)) {
+            std::this_thread::yield();
+        }
+    }
+    const obj2voxel_error_t error = obj2voxel_voxelize(instance);
+    obj2voxel_stop_workers(instance);
+    for (std::thread &t : threads) {
+        t.join();
+    }
+    obj2voxel_free(instance);
+    if (error != OBJ2VOXEL_ERR_OK) {
+        return -static_cast<long long>(error);
+    }
+    if (outputPath != nullptr) {
+        return 0;
+    }
+    const size_t n = collected.voxels.size() / 4;
+    auto *buffer = static_cast<uint32_t *>(std::malloc(std::max<size_t>(1, n * 4) * sizeof(uint32_t)));
+    std::memcpy(buffer, collected.voxels.data(), n * 4 * sizeof(uint32_t));
+    *outVoxels = buffer;
+    return static_cast<long long>(n);
 }
 
 void o2vref_free(void *pointer)

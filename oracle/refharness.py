@@ -36,6 +36,11 @@ def _load(patched_downscale=False):
     lib.o2vref_run_internal.argtypes = [fp, fp, u8p, fp, C.c_size_t, u8p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
                                         C.c_uint32, C.c_uint32, C.c_int, fp, ip, C.c_int,
                                         C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(fp), fp]
+    lib.o2vref_read_voxel_file.restype = C.c_longlong
+    lib.o2vref_read_voxel_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.POINTER(C.c_uint32))]
+    lib.o2vref_run_file.restype = C.c_longlong
+    lib.o2vref_run_file.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                    C.POINTER(C.POINTER(C.c_uint32))]
     lib.o2vref_free.argtypes = [C.c_void_p]
     lib.o2vref_hardware_threads.restype = C.c_uint
     _LIBS[key] = lib
@@ -109,6 +114,34 @@ def run_internal(verts, resolution, uvs=None, types=None, colors=None, texture=N
     lib.o2vref_free(wrgb)
     order = np.lexsort((x[:, 2], x[:, 1], x[:, 0]))
     return dict(xyz=x[order], wrgb=w[order], transform=transform)
+
+
+def read_voxel_file(path, type_):
+    """Reads a voxel file with the reference's own voxelio reader ("qef", "vox", "vl32"); (n, 4) u32 sorted by (x,y,z)."""
+    lib = _load()
+    out = C.POINTER(C.c_uint32)()
+    n = lib.o2vref_read_voxel_file(str(path).encode(), type_.encode(), C.byref(out))
+    if n < 0:
+        raise RuntimeError("voxelio reader failed for %s (%d)" % (path, n))
+    voxels = np.ctypeslib.as_array(out, shape=(max(n, 1), 4))[:n].copy()
+    lib.o2vref_free(out)
+    return sort_voxels(voxels)
+
+
+def run_file(input_path, resolution, output_path=None, supersampling=1, strategy=0, workers=0):
+    """The reference from an input file (its own OBJ / STL readers) to sorted voxels, or to an output file written by its
+    own writers (then returns None)."""
+    lib = _load()
+    out = C.POINTER(C.c_uint32)()
+    n = lib.o2vref_run_file(str(input_path).encode(), None if output_path is None else str(output_path).encode(),
+                            resolution, supersampling, strategy, workers, C.byref(out))
+    if n < 0:
+        raise RuntimeError("reference returned error code %d" % (-n))
+    if output_path is not None:
+        return None
+    voxels = np.ctypeslib.as_array(out, shape=(max(n, 1), 4))[:n].copy()
+    lib.o2vref_free(out)
+    return sort_voxels(voxels)
 
 
 def sort_voxels(voxels):

@@ -25,6 +25,24 @@ slab = tuple(int(x) for x in os.environ["O2V_SLAB"].split(",")) if "O2V_SLAB" in
 params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
                          bounds=cfg["bounds"], variant=int(os.environ.get("O2V_VARIANT", "-1")), slab=slab,
                          occupancy_path=int(os.environ.get("O2V_OCC", "1")), prefilter=int(os.environ.get("O2V_PREFILTER", "1")))
+if slab is not None and os.environ.get("O2V_PREFILTERED", "0") == "1" and uvs is None:
+    # what a rank of a multi-GPU run does: the slab's triangles were distributed once at ingest
+    verts = eng.filter_slab(verts, params)
+    params = o2v.make_params(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
+                             bounds=cfg["bounds"], slab=slab, slab_filtered=1)
+    print("slab triangles:", verts.shape[0], flush=True)
+if os.environ.get("O2V_TIMED", "0") != "0":
+    for i in range(3):
+        eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = int(os.environ["O2V_TIMED"])
+    e0.record()
+    for i in range(reps):
+        eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
+    e1.record()
+    torch.cuda.synchronize()
+    print("ms per step over %d steps: %.4f" % (reps, e0.elapsed_time(e1) / reps), flush=True)
 for i in range(steps):
     st = eng.voxelize_device(verts, params, uvs=uvs, textures=textures)
     torch.cuda.synchronize()

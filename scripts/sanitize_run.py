@@ -25,5 +25,29 @@ v, st = eng.voxelize_host(meshes.random_triangles(3000, 0.03), o2v.make_params(r
 print(len(v), st["occupancy_path"], st["survivors"], flush=True)
 v, st = eng.voxelize_host(meshes.random_triangles(3000, 0.03), o2v.make_params(resolution=64, supersampling=2, slab=(40, 104), bounds=meshes.UNIT_BOUNDS))
 print(len(v), st["occupancy_path"], st["survivors"], flush=True)
+# float records (weighted fold with the debug output), record hash, slab ingest
+v, st = eng.voxelize_host(meshes.random_triangles(1500, 0.03), o2v.make_params(resolution=64, strategy=1, float_records=1, bounds=meshes.UNIT_BOUNDS))
+print(len(v), st["occupancy_path"], flush=True)
+import torch
+tv = torch.from_numpy(meshes.random_triangles(4000, 0.02, seed=6)).cuda()
+p = o2v.make_params(resolution=128, slab=(64, 128), bounds=meshes.UNIT_BOUNDS)
+kept = eng.filter_slab(tv, p)
+st = eng.voxelize_device(kept, o2v.make_params(resolution=128, slab=(64, 128), slab_filtered=1, bounds=meshes.UNIT_BOUNDS))
+print(kept.shape[0], st["voxels"], hex(eng.result_hash()), flush=True)
 eng.close()
+# the host-to-host job: parts, packed positions / bitmaps / records over PCIe, staged pageable upload
+import os
+big = meshes.random_triangles(250_000, 0.004, seed=8)
+for mode, parts in (("packed", "3"), ("bitmap", "2"), ("records", "3")):
+    os.environ["O2V_B200_DOWNLOAD"] = mode
+    os.environ["O2V_B200_PIPELINE_PARTS"] = parts
+    inst = o2v.Instance()
+    inst.set_input_triangles(big)
+    inst.set_output_callback()
+    inst.set_resolution(200)
+    inst.set_supersampling(2 if mode == "packed" else 1)
+    inst.set_mesh_boundaries(meshes.UNIT_BOUNDS)
+    err = inst.voxelize()
+    print(mode, err, len(inst.collected()), flush=True)
+    inst.free()
 print("sanitize run done")

@@ -209,8 +209,10 @@ def test_job_part_plan_tiles_the_slab_in_whole_chunk_rows():
     """How obj2voxel_voxelize() cuts a big job into z parts (download of one part under the kernels of the next): the
     parts must tile the job's z range exactly, without empty parts, with inner bounds on the reference's 64-voxel chunk
     rows (src/obj2voxel.cpp:245-252) — every voxel then belongs to exactly one part."""
-    # default rule: small jobs in one part, big ones in up to four
+    # default rule: one part per 2^20 triangles, at most four
     assert plan_parts(2048, 0, 0, 1000, 0) == (1, [0, 2048])
+    assert plan_parts(2048, 0, 0, 1_300_000, 0) == (1, [0, 2048])
+    assert plan_parts(2048, 0, 0, 2_500_000, 0) == (2, [0, 1024, 2048])
     assert plan_parts(2048, 0, 0, 10_000_000, 0) == (4, [0, 512, 1024, 1536, 2048])
     assert plan_parts(100, 0, 0, 10_000_000, 0) == (2, [0, 64, 128])        # 2 chunk rows: at most one part per row
     assert plan_parts(64, 0, 0, 10_000_000, 0) == (1, [0, 64])

@@ -254,3 +254,98 @@ def test_obj_with_materials(tmp_path):
     want = oracle.voxelize(verts, 32, types=types, colors=colors, strategy=0)["voxels"]
     assert r["err"] == o2v.ERR_OK and np.array_equal(r["voxels"], want)
     assert {0xFFFF0000, 0xFF00FF00, 0xFFFFFFFF} <= set(np.unique(r["voxels"][:, 3]).tolist())
+
+
+# ---- against the reference's own readers, writers and a real model -------------------------------------------------
+
+def reference_harness():
+    from oracle import refharness
+
+    if not refharness.available():
+        pytest.skip("oracle/_ref (the compiled reference) is not on this machine")
+    return refharness
+
+
+def test_cornell_box_obj_matches_the_reference(tmp_path):
+    """Real-mesh parity of the OBJ(+MTL) reader: tinyobjloader's cornell_box.obj — quads, several objects,
+    `usemtl` per object, comments and blank lines with trailing spaces — at resolution 64 gives the unmodified
+    reference's 25 574 voxels (17 639 white / 3 970 red / 3 965 green; fixture made by tests/golden/make_golden_models.py
+    from oracle/_ref with its tinyobjloader-based reader)."""
+    from conftest import GOLDEN_DIR
+
+    g = np.load(os.path.join(GOLDEN_DIR, "models", "cornell_box_r64.npz"))
+    (tmp_path / "cornell_box.obj").write_bytes(g["obj"].tobytes())
+    (tmp_path / "cornell_box.mtl").write_bytes(g["mtl"].tobytes())
+    r = run_file_job(str(tmp_path / "cornell_box.obj"), int(g["resolution"]))
+    assert r["err"] == o2v.ERR_OK
+    colours, counts = np.unique(r["voxels"][:, 3], return_counts=True)
+    assert dict(zip(colours.tolist(), counts.tolist())) == {0xFFFFFFFF: 17639, 0xFFFF0000: 3970, 0xFF00FF00: 3965}
+    assert np.array_equal(r["voxels"], g["voxels"])
+
+
+def test_output_files_read_back_with_the_references_readers(tmp_path):
+    """QEF, VOX and VL32 files written by this library, parsed by voxelio's own readers (oracle/_ref), give the voxels
+    the callback sink receives; the PLY header is the reference's fixed 299 bytes (voxelio/src/format/ply.cpp:18-35,
+    63-77)."""
+    ref = reference_harness()
+    (tmp_path / "m.mtl").write_text("newmtl red\nKd 1 0 0\nnewmtl teal\nKd 0 0.5 0.5\n")
+    obj = tmp_path / "m.obj"
+    obj.write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0 0 1\nv 1 0 1\n"
+                   "usemtl red\nf 1 2 3 4\nusemtl teal\nf 1 2 6 5\n")
+    res = 96
+    want = run_file_job(str(obj), res)["voxels"]
+    for ext in ("qef", "vox", "vl32"):
+        path = str(tmp_path / ("m." + ext))
+        assert run_file_job(str(obj), res, out=path)["err"] == o2v.ERR_OK
+        got = ref.read_voxel_file(path, ext)
+        assert np.array_equal(got, want), ext
+    ply = str(tmp_path / "m.ply")
+    assert run_file_job(str(obj), res, out=ply)["err"] == o2v.ERR_OK
+    count = ("%d\r\ncomment " % len(want)).encode()
+    placeholder = b"....;....;....;....;....;...\r\n"
+    expected = (b"ply\r\nformat binary_big_endian 1.0\r\n"
+                b"comment generated by voxel-io: a C++ library by Jan \"Eisenwave\" Schultke\r\n"
+                b"element vertex " + count + placeholder[len(count):] +
+                b"property int x\r\nproperty int y\r\nproperty int z\r\n"
+                b"property uchar alpha\r\nproperty uchar red\r\nproperty uchar green\r\nproperty uchar blue\r\n"
+                b"end_header\r\n")
+    data = open(ply, "rb").read()
+    assert len(expected) == 299 and data[:299] == expected  # (ply.cpp:18 says 300; what it writes is 299)
+    assert len(data) == 299 + 16 * len(want)
+
+
+def test_output_files_equal_the_references_own_files(tmp_path):
+    """The same OBJ through the reference (oracle/_ref, its tinyobjloader reader and voxelio writers) and through this
+    library: VL32, PLY and XYZRGB files hold the same records (the order of a voxel list is free), QEF and VOX read back
+    to the same voxels.  (OBJ, not STL: the reference's STL stream mis-indexes its vertex array)"""
+    ref = reference_harness()
+    tris = meshes.lumpy_sphere(14, 15)
+    stl = str(tmp_path / "s.obj")
+    with open(stl, "w") as f:
+        for t in tris:
+            for k in range(3):
+                f.write("v %r %r %r\n" % tuple(float(x) for x in t[3 * k:3 * k + 3]))
+        for i in range(len(tris)):
+            f.write("f %d %d %d\n" % (3 * i + 1, 3 * i + 2, 3 * i + 3))
+
+    def body(path, skip):
+        raw = open(path, "rb").read()[skip:]
+        return o2v.sort_voxels(np.frombuffer(raw, dtype=">u4").reshape(-1, 4).astype(np.uint32))
+
+    for ext, skip in (("vl32", 0), ("ply", 299)):
+        ours, theirs = str(tmp_path / ("ours." + ext)), str(tmp_path / ("theirs." + ext))
+        assert run_file_job(stl, 48, out=ours)["err"] == o2v.ERR_OK
+        ref.run_file(stl, 48, output_path=theirs)
+        assert os.path.getsize(ours) == os.path.getsize(theirs)
+        assert np.array_equal(body(ours, skip), body(theirs, skip)), ext
+        if ext == "ply":
+            assert open(ours, "rb").read()[:299] == open(theirs, "rb").read()[:299]
+    ours, theirs = str(tmp_path / "ours.xyzrgb"), str(tmp_path / "theirs.xyzrgb")
+    assert run_file_job(stl, 48, out=ours)["err"] == o2v.ERR_OK
+    ref.run_file(stl, 48, output_path=theirs)
+    assert sorted(open(ours).read().splitlines()) == sorted(open(theirs).read().splitlines())
+    for ext in ("qef", "vox"):
+        ours, theirs = str(tmp_path / ("ours." + ext)), str(tmp_path / ("theirs." + ext))
+        assert run_file_job(stl, 48, out=ours)["err"] == o2v.ERR_OK
+        ref.run_file(stl, 48, output_path=theirs)
+        assert np.array_equal(ref.read_voxel_file(ours, ext), ref.read_voxel_file(theirs, ext)), ext
