@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libobj2voxel_b200.so")
+# O2V_B200_LIB: another build of the same library (kernel A/B experiments, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("O2V_B200_LIB") or os.path.join(_HERE, "libobj2voxel_b200.so")
 _LIB = None
 
 # include/obj2voxel.h enum constants
