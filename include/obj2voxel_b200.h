@@ -152,7 +152,14 @@ int o2v_b200_voxelize_host(o2v_b200_engine *engine, const o2v_b200_params *param
 uint64_t o2v_b200_expand_bitmaps(const uint64_t *bits, const uint32_t *chunk_ids, const uint32_t *chunk_counts,
                                  uint32_t chunks, uint32_t chunks_per_axis, uint32_t chunk_z0, uint32_t *out_quads);
 
-/* The default on one GPU: the positions of an all-white result cross PCIe packed into `bits` = 32 (x | y << 10 | z << 20,
+/* The chunk scan behind the bitmap download as obj2voxel_voxelize() runs it (a host thread per chunk, quads handed on in
+ * batches of at most buffer_quads >= 64 from a buffer that stays in the thread's cache; VPCOMPRESSB where the CPU has
+ * AVX-512 VBMI2): writes the quads of one chunk bitmap (4096 words, chunk at output origin (cx, cy, cz)) to out_quads (at
+ * most out_capacity) and returns their number.  Pure host code. */
+uint64_t o2v_b200_scan_chunk_bitmap(const uint64_t *words, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t buffer_quads,
+                                    uint32_t *out_quads, uint64_t out_capacity);
+
+/* The positions of an all-white result cross PCIe packed into `bits` = 32 (x | y << 10 | z << 20,
  * output grids up to 1024^3) or 64 (x | y << 21 | z << 42) bits per voxel and the host's threads write the Voxel32 quads
  * {x, y, z, 0xFFFFFFFF} the voxel callback receives.  Pure host code: no device needed. */
 void o2v_b200_expand_packed(const void *packed, int32_t bits, uint64_t count, uint32_t *out_quads);

@@ -98,7 +98,7 @@ ADDITIVE_SYMBOLS = [
     "o2v_b200_engine_create", "o2v_b200_engine_destroy", "o2v_b200_last_error", "o2v_b200_sm_count",
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
     "o2v_b200_result_download", "o2v_b200_result_floats_device", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
-    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab", "obj2voxel_b200_set_devices", "o2v_b200_expand_bitmaps", "o2v_b200_expand_packed", "obj2voxel_b200_array_source_next", "obj2voxel_b200_counting_sink_write",
+    "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab", "obj2voxel_b200_set_devices", "o2v_b200_expand_bitmaps", "o2v_b200_expand_packed", "o2v_b200_scan_chunk_bitmap", "obj2voxel_b200_array_source_next", "obj2voxel_b200_counting_sink_write",
 ]
 
 
@@ -175,6 +175,7 @@ def load():
         "obj2voxel_b200_set_devices": (None, [vp, C.POINTER(C.c_int32), u32]),
         "o2v_b200_expand_bitmaps": (C.c_uint64, [vp, vp, vp, u32, u32, u32, vp]),
         "o2v_b200_expand_packed": (None, [vp, C.c_int32, C.c_uint64, vp]),
+        "o2v_b200_scan_chunk_bitmap": (C.c_uint64, [vp, u32, u32, u32, u32, vp, C.c_uint64]),
         "obj2voxel_b200_array_source_next": (C.c_bool, [vp, vp]),
         "obj2voxel_b200_counting_sink_write": (C.c_bool, [vp, vp, sz]),
         "obj2voxel_b200_get_stats": (None, [vp, C.POINTER(Stats)]),

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -888,6 +889,24 @@ uint64_t o2v_b200_expand_bitmaps(const uint64_t *bits, const uint32_t *chunk_ids
     static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "bitmap words");
     return expandBitmapsOnHost(reinterpret_cast<const unsigned long long *>(bits), chunk_ids, chunk_counts, chunks,
                                chunks_per_axis, chunk_z0, out_quads);
+}
+
+uint64_t o2v_b200_scan_chunk_bitmap(const uint64_t *words, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t buffer_quads,
+                                    uint32_t *out_quads, uint64_t out_capacity)
+{
+    std::vector<uint32_t> buffer((size_t) std::max(buffer_quads, 64u) * 4 + 16);
+    uint64_t written = 0;
+    const unsigned long long n = scanChunkBitmap(
+        reinterpret_cast<const unsigned long long *>(words), cx, cy, cz, buffer.data(), std::max(buffer_quads, 64u),
+        [&](uint32_t *quads, size_t count) {
+            if (written + count > out_capacity) {
+                return false;
+            }
+            memcpy(out_quads + written * 4, quads, count * 16);
+            written += count;
+            return true;
+        });
+    return n == ~0ull ? UINT64_MAX : written;
 }
 
 void o2v_b200_expand_packed(const void *packed, int32_t bits, uint64_t count, uint32_t *out_quads)

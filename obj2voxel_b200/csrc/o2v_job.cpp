@@ -263,6 +263,43 @@ struct SharedSink {
         });
     }
 
+    /// Occupancy bitmaps -> quads -> sink, the same way: a host thread takes a chunk, scans its 4096 words into its own
+    /// cache-resident buffer (scanChunkBitmap: VPCOMPRESSB on CPUs that have it) and hands the buffer to the sink whenever
+    /// it is full.  Returns the number of voxels delivered.
+    unsigned long long writeBitmaps(const unsigned long long *bits, const uint32_t *chunkIds, uint32_t chunks,
+                                    uint32_t chunksPerAxis, uint32_t chunkZ0)
+    {
+        constexpr uint32_t kBatch = 1u << 16;
+        std::atomic<unsigned long long> delivered{0};
+        hostPool().parallelFor(chunks, [&](size_t c) {
+            if (failed) {
+                return;
+            }
+            thread_local uint32_t *mine = nullptr;
+            if (mine == nullptr) {
+                mine = static_cast<uint32_t *>(aligned_alloc(4096, (size_t) kBatch * 16));
+                if (mine == nullptr) {
+                    failed = true;
+                    return;
+                }
+            }
+            const uint32_t chunk = chunkIds[c], C = chunksPerAxis;
+            const unsigned long long n = scanChunkBitmap(
+                bits + c * kChunkWords, (chunk % C) * kChunkEdge, ((chunk / C) % C) * kChunkEdge,
+                (chunk / (C * C) + chunkZ0) * kChunkEdge, mine, kBatch, [&](uint32_t *quads, size_t count) {
+                    std::lock_guard<std::mutex> lock{mutex};
+                    return !failed && sink.write(quads, count);
+                });
+            if (n == ~0ull) {
+                failed = true;
+            }
+            else {
+                delivered += n;
+            }
+        });
+        return delivered;
+    }
+
     void write(uint32_t *quads, unsigned long long count)
     {
         const size_t batch = 1u << 21;  // records per sink call (32 MiB)
@@ -391,25 +428,32 @@ bool SlabRun::run()
             msSink += msSince(t0);
             return;
         }
-        uint32_t *records = state->recordBuffer(p.slot, (size_t) p.count * 16);
-        if (records == nullptr) {
-            failWith("host allocation failed (voxel records)");
-            return;
-        }
         const size_t bitsBytes = (size_t) p.chunks * kChunkWords * 8;
         const uint32_t *ids = reinterpret_cast<const uint32_t *>(p.host + bitsBytes);
-        const uint32_t *counts = ids + p.chunks;
-        const unsigned long long written =
-            expandBitmapsOnHost(reinterpret_cast<const unsigned long long *>(p.host), ids, counts, p.chunks,
-                                p.geometry.chunksPerAxis, p.geometry.chunkZ0, records);
-        msExpandHost += msSince(t0);
-        if (written != p.count) {
-            failWith("bitmap expansion produced a different voxel count than the device");
-            return;
+        unsigned long long written = 0;
+        if (!wholePartExpansion()) {
+            written = sink->writeBitmaps(reinterpret_cast<const unsigned long long *>(p.host), ids, p.chunks,
+                                         p.geometry.chunksPerAxis, p.geometry.chunkZ0);
+            msExpandHost += msSince(t0);
         }
-        t0 = std::chrono::steady_clock::now();
-        sink->write(records, p.count);
-        msSink += msSince(t0);
+        else {
+            uint32_t *records = state->recordBuffer(p.slot, (size_t) p.count * 16);
+            if (records == nullptr) {
+                failWith("host allocation failed (voxel records)");
+                return;
+            }
+            written = expandBitmapsOnHost(reinterpret_cast<const unsigned long long *>(p.host), ids, ids + p.chunks,
+                                          p.chunks, p.geometry.chunksPerAxis, p.geometry.chunkZ0, records);
+            msExpandHost += msSince(t0);
+            if (written == p.count) {
+                t0 = std::chrono::steady_clock::now();
+                sink->write(records, p.count);
+                msSink += msSince(t0);
+            }
+        }
+        if (written != p.count && !sink->failed) {
+            failWith("bitmap expansion produced a different voxel count than the device");
+        }
     };
     struct Delivery {
         std::mutex mutex;
@@ -983,9 +1027,11 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
                                                  : download;
     }
     if (download == DownloadMode::AUTO) {
-        // Positions packed into 4 (or 8) bytes per voxel cross PCIe and the host's threads write the quads batch by batch
-        // into a buffer that stays in their caches: 16 bytes per voxel through a copy engine cost a link 4 times the
-        // traffic and the host's memory a write per voxel that nobody needs (measured: profiles/r02_history.md).
+        // An all-white result crosses PCIe as positions packed into 4 (or 8) bytes per voxel, and the host's threads write
+        // the quads batch by batch into buffers that stay in their caches.  Measured against it (profiles/r02_history.md):
+        // 16-byte records through the copy engine (4 times the traffic), and the occupancy bitmaps themselves (a third
+        // less traffic again, but scanning bits costs the host 4 times what unpacking positions does — with VPCOMPRESSB
+        // as without).
         download = DownloadMode::PACKED;
     }
     const bool wantBitmap = download == DownloadMode::BITMAP && occupancy;

@@ -9,6 +9,7 @@
 #ifndef O2V_JOB_H
 #define O2V_JOB_H
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -55,6 +56,13 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
 unsigned long long expandBitmapsOnHost(const unsigned long long *bits, const uint32_t *chunkIds,
                                        const uint32_t *chunkCounts, uint32_t chunks, uint32_t chunksPerAxis,
                                        uint32_t chunkZ0, uint32_t *records);
+
+/// One chunk's bitmap (kChunkWords words, chunk at OUTPUT origin (cx, cy, cz)) into quads, through `buffer` (room for
+/// bufferQuads >= 64 quads): flush(buffer, n) is called whenever the buffer is full and once at the end.  Returns the
+/// number of quads, ~0 if flush failed.  Uses VPCOMPRESSB where the CPU has AVX-512 VBMI2 (hostHasFastBitScan).
+unsigned long long scanChunkBitmap(const unsigned long long *words, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t *buffer,
+                                   uint32_t bufferQuads, const std::function<bool(uint32_t *, size_t)> &flush);
+bool hostHasFastBitScan();
 
 /// Expands `count` packed positions (Engine::packedBits: 32 = x | y << 10 | z << 20, 64 = x | y << 21 | z << 42) into
 /// Voxel32 quads {x, y, z, 0xFFFFFFFF} on the host threads.

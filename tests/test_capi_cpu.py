@@ -336,3 +336,36 @@ def test_host_expansion_of_packed_positions(bits, count):
     lib.o2v_b200_expand_packed(packed.ctypes.data_as(C.c_void_p), bits, count, out.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out[:, :3], xyz.astype(np.uint32))
     assert (out[:, 3] == 0xFFFFFFFF).all()
+
+
+def test_portable_bitmap_scan_in_a_fresh_process():
+    """The scan is chosen once per process: run the same test with the portable form forced."""
+    import sys
+
+    env = dict(os.environ, O2V_B200_PORTABLE_SCAN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-k",
+                        "test_fast_and_portable_bitmap_scans_agree"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_fast_and_portable_bitmap_scans_agree():
+    """The bitmap download's host side has a VPCOMPRESSB form (AVX-512 VBMI2) and a portable one; through the C ABI the
+    chunk scan must give the quads of the numpy restatement whichever the CPU selects — dense words (more than 16 bits
+    set: several rounds), full words, and buffers that fill up in the middle of a chunk included."""
+    lib = o2v.load()
+    rng = np.random.default_rng(11)
+    occupied = rng.random((64, 64, 64)) < 0.05  # [z][y][x]
+    occupied[8:16, 0:8, 0:8] = True             # a full tile: every word all ones
+    occupied[40, 17, :] |= rng.random(64) < 0.7
+    z, y, x = np.nonzero(occupied)
+    bits = np.zeros(4096, dtype=np.uint64)
+    tile = (x >> 3) | ((y >> 3) << 3) | ((z >> 3) << 6)
+    np.bitwise_or.at(bits, tile * 8 + (z & 7), np.uint64(1) << ((x & 7) + 8 * (y & 7)).astype(np.uint64))
+    want = o2v.sort_voxels(np.stack([x + 128, y + 64, z + 192, np.full_like(x, 0xFFFFFFFF)], axis=1).astype(np.uint32))
+    for buffer_quads in (64, 1000, 1 << 16):
+        out = np.zeros((len(want) + 8, 4), dtype=np.uint32)
+        n = lib.o2v_b200_scan_chunk_bitmap(bits.ctypes.data_as(C.c_void_p), 128, 64, 192, buffer_quads,
+                                           out.ctypes.data_as(C.c_void_p), len(out))
+        assert n == len(want), (buffer_quads, n)
+        assert np.array_equal(o2v.sort_voxels(out[:n]), want)
+        assert not out[n:].any()  # nothing written past the count
