@@ -292,6 +292,15 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst, const std::function<obj2voxel
     HostMesh host;
     o2v_b200_mesh mesh{};
     std::vector<o2v_b200_texture> textures;
+    struct LoadedTextures {  // what an OBJ's material library made the reader load: freed when the job is over
+        std::vector<obj2voxel_texture *> all;
+        ~LoadedTextures()
+        {
+            for (obj2voxel_texture *t : all) {
+                obj2voxel_texture_free(t);
+            }
+        }
+    } loaded;
 
     if (inst.inputKind == IoKind::BULK) {
         mesh.verts = inst.bulkVerts;
@@ -325,7 +334,7 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst, const std::function<obj2voxel
                 t.texture = texture;
                 host.push(t);
             };
-            if (!readTriangleFile(inst.inputFile, inst.inputFormat, inst.defaultTexture, appender, &error)) {
+            if (!readTriangleFile(inst.inputFile, inst.inputFormat, inst.defaultTexture, appender, &loaded.all, &error)) {
                 logMessage(OBJ2VOXEL_LOG_LEVEL_ERROR, "Failed to open input: " + error);
                 return OBJ2VOXEL_ERR_IO_ERROR_ON_OPEN_INPUT_FILE;
             }
@@ -411,6 +420,13 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst, const std::function<obj2voxel
              timings.bitmapDownload ? " of bitmaps + host expansion" : "", timings.msRun, timings.msVoxelizeCalls,
              timings.msWaitCopy, timings.msExpandHost, timings.msSink);
     logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, timing);
+    if (timings.devices > 1) {
+        std::string bounds = "slab bounds (sample-space z, balanced by triangles per chunk row):";
+        for (uint32_t z : timings.slabBounds) {
+            bounds += " " + std::to_string(z);
+        }
+        logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, bounds);
+    }
 
     logMessage(OBJ2VOXEL_LOG_LEVEL_INFO,
                "Voxelized " + withThousands(mesh.count) + " triangles, writing any buffered voxels ...");

@@ -723,6 +723,40 @@ int Engine::meshBounds(const MeshView &mesh, cudaStream_t stream, float outMin[3
     return kErrOk;
 }
 
+int Engine::zRowHistogram(const MeshView &mesh, const EngineParams &params, uint32_t unit, uint32_t rows,
+                          cudaStream_t stream, unsigned long long *outHistogram)
+{
+    error_.clear();
+    O2V_CUDA(cudaSetDevice(device_));
+    for (uint32_t r = 0; r < rows; ++r) {
+        outHistogram[r] = 0;
+    }
+    if (mesh.count == 0 || rows == 0) {
+        return kErrOk;
+    }
+    if (!params.boundsKnown || rows > 128 || unit == 0) {
+        return fail(kErrBadParams, "zRowHistogram needs the mesh bounds and at most 128 rows");
+    }
+    RunStats st;
+    GridView grid;
+    bool emptySlab = false;
+    EngineParams whole = params;
+    whole.slabZ0 = whole.slabZ1 = 0;
+    if (const int rc = setupGrid(mesh, whole, stream, st, grid, &emptySlab)) {
+        return rc;
+    }
+    if (!scatterCounts_.ensure(128 * sizeof(unsigned long long))) {
+        return fail(kErrOutOfMemory, "device allocation failed (z histogram)");
+    }
+    O2V_CUDA(cudaMemsetAsync(scatterCounts_.as<void>(), 0, 128 * sizeof(unsigned long long), stream));
+    launchOccupancyZHistogram(mesh, grid, unit, rows, scatterCounts_.as<unsigned long long>(), smCount_, stream);
+    O2V_CUDA(cudaMemcpyAsync(outHistogram, scatterCounts_.as<void>(), rows * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, stream));
+    O2V_CUDA(cudaStreamSynchronize(stream));
+    O2V_CUDA(cudaGetLastError());
+    return kErrOk;
+}
+
 float *Engine::receiveRegion(uint32_t source, uint32_t sources, unsigned long long capacity)
 {
     cudaSetDevice(device_);
@@ -779,7 +813,7 @@ int Engine::scatterToSlabs(const MeshView &mesh, const EngineParams &params, Sla
     if (const int rc = setupGrid(mesh, whole, stream, st, grid, &emptySlab)) {
         return rc;
     }
-    if (!scatterCounts_.ensure(kMaxSlabs * sizeof(unsigned long long))) {
+    if (!scatterCounts_.ensure(128 * sizeof(unsigned long long))) {
         return fail(kErrOutOfMemory, "device allocation failed (scatter counters)");
     }
     O2V_CUDA(cudaMemsetAsync(scatterCounts_.as<void>(), 0, kMaxSlabs * sizeof(unsigned long long), stream));

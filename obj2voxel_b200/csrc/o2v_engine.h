@@ -140,6 +140,11 @@ public:
     /// Bounds of a device-resident mesh (src/obj2voxel.cpp:180-200 findMeshBounds) — one device's share of a job.
     int meshBounds(const MeshView &mesh, cudaStream_t stream, float outMin[3], float outMax[3]);
 
+    /// Triangles of `mesh` per row of `unit` sample-space z layers (rows <= 128 rows from z = 0): the work estimate a job
+    /// over several devices balances its Z-slabs by.  params must carry the mesh bounds.  Synchronises `stream`.
+    int zRowHistogram(const MeshView &mesh, const EngineParams &params, uint32_t unit, uint32_t rows, cudaStream_t stream,
+                      unsigned long long *outHistogram);
+
     /// Region `source` (of `sources`) of this device's receive buffer for a multi-device job: room for `capacity`
     /// triangles per region.  Peers write into it directly (SlabScatter).
     float *receiveRegion(uint32_t source, uint32_t sources, unsigned long long capacity);

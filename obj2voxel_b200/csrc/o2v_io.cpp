@@ -611,7 +611,7 @@ struct ObjMaterial {
     float kd[3] = {1, 1, 1};
     bool hasKd = false;
     std::string mapKd;
-    std::shared_ptr<void> texture;  // obj2voxel_texture owned here (allocated through the C API)
+    obj2voxel_texture *texture = nullptr;  // allocated through the C API; the job that called the reader frees it
 };
 
 std::string directoryOf(const std::string &path)
@@ -624,7 +624,7 @@ std::string directoryOf(const std::string &path)
 /// Material mapping follows src/io.cpp:194-312: no material -> MATERIALLESS (or the default texture when the face has
 /// uvs), material with a diffuse texture -> TEXTURED, otherwise UNTEXTURED with the diffuse colour.
 bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const TriangleAppender &append,
-             std::string *error)
+             std::vector<obj2voxel_texture *> *loadedTextures, std::string *error)
 {
     FILE *f = fopen(path, "r");
     if (f == nullptr) {
@@ -642,8 +642,9 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
             logMessage(OBJ2VOXEL_LOG_LEVEL_WARNING, "Failed to open material library \"" + dir + name + "\"");
             return;
         }
-        char line[1024];
-        while (fgets(line, sizeof line, m) != nullptr) {
+        char *line = nullptr;  // getline: lines of any length
+        size_t lineCapacity = 0;
+        while (getline(&line, &lineCapacity, m) >= 0) {
             char key[64];
             if (sscanf(line, "%63s", key) != 1) {
                 continue;
@@ -667,20 +668,18 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
                 }
             }
         }
+        free(line);
         fclose(m);
         for (ObjMaterial &mat : materials) {
-            if (mat.mapKd.empty() || mat.texture) {
+            if (mat.mapKd.empty() || mat.texture != nullptr) {
                 continue;
             }
             std::string file = dir + mat.mapKd;
             std::replace(file.begin(), file.end(), '\\', '/');
             obj2voxel_texture *tex = obj2voxel_texture_alloc();
             if (obj2voxel_texture_load_from_file(tex, file.c_str(), "png")) {
-                mat.texture = std::shared_ptr<void>(tex, [](void *p) {
-                    // textures must outlive the job (the engine uploads them before the stream ends); keep them alive
-                    // for the process lifetime like a caller-owned texture would be
-                    (void) p;
-                });
+                mat.texture = tex;  // lives until the job has uploaded it: handed to the caller, who frees it
+                loadedTextures->push_back(tex);
                 logMessage(OBJ2VOXEL_LOG_LEVEL_INFO, "Loaded texture \"" + file + "\"");
             }
             else {
@@ -691,8 +690,10 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
         }
     };
 
-    char line[4096];
-    while (fgets(line, sizeof line, f) != nullptr) {
+    char *line = nullptr;  // getline: an n-gon's `f` line may be longer than any fixed buffer
+    size_t lineCapacity = 0;
+    std::vector<int> vi, ti;
+    while (getline(&line, &lineCapacity, f) >= 0) {
         if (line[0] == 'v' && line[1] == ' ') {
             float x, y, z;
             if (sscanf(line + 2, "%f %f %f", &x, &y, &z) == 3) {
@@ -706,10 +707,10 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
             }
         }
         else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
-            int vi[64], ti[64];
-            int n = 0;
+            vi.clear();
+            ti.clear();
             const char *p = line + 1;
-            while (n < 64) {
+            for (;;) {
                 while (*p == ' ' || *p == '\t') {
                     ++p;
                 }
@@ -735,10 +736,10 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
                     }
                 }
                 const int vcount = (int) (positions.size() / 3), tcount = (int) (texcoords.size() / 2);
-                vi[n] = v > 0 ? v - 1 : vcount + v;
-                ti[n] = t > 0 ? t - 1 : (t < 0 ? tcount + t : -1);
-                ++n;
+                vi.push_back(v > 0 ? v - 1 : vcount + v);
+                ti.push_back(t > 0 ? t - 1 : (t < 0 ? tcount + t : -1));
             }
+            const int n = (int) vi.size();
             for (int k = 1; k + 1 < n; ++k) {
                 const int idx[3] = {0, k, k + 1};
                 float v[9], uv[6] = {0, 0, 0, 0, 0, 0};
@@ -772,8 +773,8 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
                 }
                 else {
                     const ObjMaterial &mat = materials[(size_t) current];
-                    if (mat.texture && hasUv) {
-                        append(v, uv, 3, nullptr, static_cast<const obj2voxel_texture *>(mat.texture.get()));
+                    if (mat.texture != nullptr && hasUv) {
+                        append(v, uv, 3, nullptr, mat.texture);
                     }
                     else {
                         append(v, nullptr, 2, mat.kd, nullptr);
@@ -799,6 +800,7 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
             }
         }
     }
+    free(line);
     fclose(f);
     return true;
 }
@@ -806,13 +808,13 @@ bool readObj(const char *path, const obj2voxel_texture *defaultTexture, const Tr
 }  // namespace
 
 bool readTriangleFile(const char *path, FileFormat format, const obj2voxel_texture *defaultTexture,
-                      const TriangleAppender &append, std::string *error)
+                      const TriangleAppender &append, std::vector<obj2voxel_texture *> *loadedTextures, std::string *error)
 {
     if (format == FileFormat::STL) {
         return readStl(path, append, error);
     }
     if (format == FileFormat::OBJ) {
-        return readObj(path, defaultTexture, append, error);
+        return readObj(path, defaultTexture, append, loadedTextures, error);
     }
     *error = "unsupported triangle file type";
     return false;

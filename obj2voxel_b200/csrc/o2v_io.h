@@ -43,9 +43,11 @@ std::unique_ptr<VoxelSink> makeFormatSink(FileFormat format, const char *path, u
 using TriangleAppender = std::function<void(const float v[9], const float uv[6], uint8_t type, const float color[3],
                                             const obj2voxel_texture *texture)>;
 
-/// Streams every triangle of an STL / OBJ file into `append`.
+/// Streams every triangle of an STL / OBJ file into `append`.  Textures an OBJ's material library names are loaded
+/// through the C API and appended to *loadedTextures: the triangles point at them, the caller frees them
+/// (obj2voxel_texture_free) once the job has uploaded them.
 bool readTriangleFile(const char *path, FileFormat format, const obj2voxel_texture *defaultTexture,
-                      const TriangleAppender &append, std::string *error);
+                      const TriangleAppender &append, std::vector<obj2voxel_texture *> *loadedTextures, std::string *error);
 
 bool readWholeFile(const char *path, std::vector<uint8_t> *out);
 

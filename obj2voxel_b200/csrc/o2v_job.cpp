@@ -700,6 +700,32 @@ void planDeviceSlabs(uint32_t sampleRes, uint32_t supersampling, uint32_t jobZ0,
     bounds[devices] = jobZ1;
 }
 
+/// Slab bounds that give every device about the same number of (triangle, row) pairs: `histogram` = triangles per row
+/// of `unit` sample layers from z = 0; the job covers [jobZ0, jobZ1) (as planDeviceSlabs left bounds[0] and
+/// bounds[devices]).  Inner bounds stay multiples of `unit`; a device may end up with an empty slab (it sits the job out).
+void balanceDeviceSlabs(const std::vector<unsigned long long> &histogram, uint32_t unit, uint32_t devices, uint32_t *bounds)
+{
+    const uint32_t jobZ0 = bounds[0], jobZ1 = bounds[devices];
+    const uint32_t row0 = jobZ0 / unit, row1 = std::min<uint32_t>((jobZ1 + unit - 1) / unit, (uint32_t) histogram.size());
+    unsigned long long total = 0;
+    for (uint32_t r = row0; r < row1; ++r) {
+        total += histogram[r];
+    }
+    if (total == 0 || row1 <= row0) {
+        return;  // nothing to go by: the equal rows stand
+    }
+    unsigned long long running = 0;
+    uint32_t row = row0;
+    for (uint32_t d = 1; d < devices; ++d) {
+        const unsigned long long target = total * d / devices;
+        while (row < row1 && running + histogram[row] / 2 < target) {  // the row goes to the side its middle falls on
+            running += histogram[row];
+            ++row;
+        }
+        bounds[d] = std::min(std::max(row * unit, jobZ0), jobZ1);
+    }
+}
+
 }  // namespace
 
 Engine *sharedEngine(int device, std::string *error)
@@ -1048,6 +1074,11 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
     std::string firstError;
     std::vector<float> shareMin((size_t) D * 3, 0.0f), shareMax((size_t) D * 3, 0.0f);
     std::vector<unsigned long long> sent((size_t) D * D, 0);  // [source][slab]
+    const uint32_t slabUnit = 64u * options.params.supersampling;  // a slab bound: a whole row of output chunks
+    const uint32_t histogramRows = std::min<uint32_t>(((S + 63u) / 64u * 64u + slabUnit - 1) / slabUnit, 128u);
+    std::vector<unsigned long long> rowHistogram((size_t) D * 128, 0);  // [device][row]
+    std::vector<uint32_t> slabs(activeBounds);  // the plan every device thread ends up with (equal rows, then balanced)
+    static const bool balanceEnabled = getenv("O2V_B200_BALANCE") == nullptr || atoi(getenv("O2V_B200_BALANCE")) != 0;
     std::atomic<bool> staged{false}, usedBitmap{false};
     double msUpload = 0, msExchange = 0, msKernels = 0;
     uint32_t partsUsed = 0;
@@ -1115,11 +1146,32 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
                     params.bounds[3 + a] = hi;
                 }
             }
+            // ---- slabs of equal work: triangles per chunk row, summed over the shares ----
+            std::vector<uint32_t> mine(activeBounds);
+            if (balanceEnabled) {
+                if (ok && !failed && engine->zRowHistogram(view, params, slabUnit, histogramRows, stream,
+                                                           &rowHistogram[(size_t) d * 128]) != 0) {
+                    fail("z histogram failed: " + engine->lastError());
+                }
+                barrier.arriveAndWait();
+                std::vector<unsigned long long> total(histogramRows, 0);
+                for (uint32_t r = 0; r < D; ++r) {
+                    for (uint32_t row = 0; row < histogramRows; ++row) {
+                        total[row] += rowHistogram[(size_t) r * 128 + row];
+                    }
+                }
+                balanceDeviceSlabs(total, slabUnit, D, mine.data());  // (every thread computes the same bounds)
+                params.slabZ0 = mine[d];
+                params.slabZ1 = mine[d + 1];
+                if (d == 0) {
+                    slabs = mine;
+                }
+            }
             const unsigned long long capacity = (unsigned long long) ((n + D - 1) / D);
             SlabScatter scatter{};
             scatter.slabs = D;
             for (uint32_t s = 0; s <= D; ++s) {
-                scatter.bound[s] = activeBounds[s];
+                scatter.bound[s] = mine[s];
             }
             scatter.capacity = capacity;
             if (ok && !failed && engine->receiveRegion(0, D, capacity) == nullptr) {  // this device's own buffer
@@ -1166,7 +1218,8 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
         run.wantPacked = wantPacked;
         run.stream = stream;
         run.sink = &sink;
-        if (ok && !failed) {
+        const bool emptySlab = D > 1 && params.slabZ0 >= params.slabZ1;  // (never hand (0, 0) on: it means "the whole grid")
+        if (ok && !failed && !emptySlab) {
             if (!run.run()) {
                 fail(run.error);
             }
@@ -1222,6 +1275,7 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
         }
     }
 
+    timings.slabBounds = slabs;
     timings.msUpload = msUpload;
     timings.msExchange = msExchange;
     timings.msKernels = msKernels;

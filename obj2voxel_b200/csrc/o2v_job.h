@@ -31,6 +31,7 @@ struct JobOptions {
 struct JobTimings {
     double msUpload = 0, msExchange = 0, msRun = 0, msKernels = 0;
     double msWaitCopy = 0, msExpandHost = 0, msSink = 0, msVoxelizeCalls = 0;  // device 0's host side, summed over its parts
+    std::vector<uint32_t> slabBounds;  // devices + 1 sample-space z bounds of the devices' slabs
     uint32_t parts = 0, devices = 0;
     bool bitmapDownload = false, peerExchange = false, stagedUpload = false;
 };

@@ -245,6 +245,9 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
                                 cudaStream_t stream);
+/// histogram[r] += triangles whose z range reaches row r (rows of `unit` sample-space layers, rows <= 128).
+void launchOccupancyZHistogram(const MeshView &mesh, const GridView &grid, uint32_t unit, uint32_t rows,
+                               unsigned long long *histogram, int smCount, cudaStream_t stream);
 /// chunkCounts[slot] = occupied voxels of bitmap `slot`; their sum is added to counters->voxels.
 void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,
                                cudaStream_t stream);

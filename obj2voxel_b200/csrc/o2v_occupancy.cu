@@ -233,6 +233,40 @@ occupancySlabScatterKernel(MeshView mesh, GridView grid, SlabScatter scatter)
     });
 }
 
+/// Triangles per row of `unit` sample-space z layers (rows [0, rows) of the grid): what a job over several devices
+/// balances its slabs by.  A triangle counts in every row its z range reaches.
+__global__ void __launch_bounds__(kOccSetupThreads)
+occupancyZHistogramKernel(MeshView mesh, GridView grid, uint32_t unit, uint32_t rows, unsigned long long *histogram)
+{
+    __shared__ TriangleBatch<kOccSetupThreads> batch;
+    __shared__ uint32_t local[128];
+    for (uint32_t r = threadIdx.x; r < 128u; r += kOccSetupThreads) {
+        local[r] = 0;
+    }
+    // (streamTriangles starts with a barrier)
+    streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
+                                      [&](unsigned long long, const float in[9], bool valid) {
+        if (!valid) {
+            return;
+        }
+        float zlo, zhi;
+        triangleZRange(grid, in, zlo, zhi);
+        if (zlo < 0.0f || toU32(zlo) >= rows * unit) {
+            return;  // dropped as a whole, or beyond the grid
+        }
+        const uint32_t r0 = toU32(zlo) / unit, r1 = min(toU32(zhi) / unit, rows - 1u);
+        for (uint32_t r = r0; r <= r1; ++r) {
+            atomicAdd(&local[r], 1u);
+        }
+    });
+    __syncthreads();
+    for (uint32_t r = threadIdx.x; r < rows; r += kOccSetupThreads) {
+        if (local[r] != 0) {
+            atomicAdd(histogram + r, (unsigned long long) local[r]);
+        }
+    }
+}
+
 /// Block = bitmap: the occupied voxels of each chunk, for a host that expands downloaded bitmaps itself.
 __global__ void __launch_bounds__(256)
 occupancyChunkCountKernel(OccupancyView occ, uint32_t *__restrict__ chunkCounts, RunCounters *counters)
@@ -1291,6 +1325,13 @@ void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, cons
 {
     occupancySlabScatterKernel<<<setupBlocks(occupancySlabScatterKernel, mesh.count, smCount), kOccSetupThreads, 0,
                                  stream>>>(mesh, grid, scatter);
+}
+
+void launchOccupancyZHistogram(const MeshView &mesh, const GridView &grid, uint32_t unit, uint32_t rows,
+                               unsigned long long *histogram, int smCount, cudaStream_t stream)
+{
+    occupancyZHistogramKernel<<<setupBlocks(occupancyZHistogramKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
+        mesh, grid, unit, rows, histogram);
 }
 
 void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,

@@ -349,3 +349,26 @@ def test_output_files_equal_the_references_own_files(tmp_path):
         assert run_file_job(stl, 48, out=ours)["err"] == o2v.ERR_OK
         ref.run_file(stl, 48, output_path=theirs)
         assert np.array_equal(ref.read_voxel_file(ours, ext), ref.read_voxel_file(theirs, ext)), ext
+
+
+def test_obj_face_longer_than_any_line_buffer(tmp_path):
+    """A 600-gon on one `f` line (about 8 KB, above the 4 KB a fixed line buffer used to hold) with long-hand indices:
+    every vertex is read and the polygon is fan-triangulated."""
+    n = 600
+    angle = np.linspace(0.0, 2.0 * np.pi, n, endpoint=False)
+    ring = np.stack([0.5 + 0.45 * np.cos(angle), 0.5 + 0.45 * np.sin(angle), np.full(n, 0.25)], axis=1).astype(np.float32)
+    obj = tmp_path / "ngon.obj"
+    with open(obj, "w") as f:
+        f.write("v 0 0 0\nv 1 1 1\n")  # bounds
+        for p in ring:
+            f.write("v %r %r %r\n" % tuple(float(x) for x in p))
+        f.write("f " + " ".join("%d//%d" % (k + 3, k + 3) for k in range(n)) + "\n")
+        f.write("f 1 2 2\n")  # a degenerate face keeps the bounds vertices referenced
+    assert os.path.getsize(obj) > 8000
+    r = run_file_job(str(obj), 64)
+    tris = np.array([np.concatenate([ring[0], ring[k], ring[k + 1]]) for k in range(1, n - 1)], dtype=np.float32)
+    assert r["err"] == o2v.ERR_OK
+    # the mesh bounds come from every triangle, the degenerate one included
+    full = np.concatenate([tris, np.array([[0, 0, 0, 1, 1, 1, 1, 1, 1]], dtype=np.float32)])
+    want = oracle.voxelize(full, 64)["voxels"]
+    assert np.array_equal(r["voxels"], want)

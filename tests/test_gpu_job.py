@@ -104,7 +104,7 @@ def test_pageable_input_is_staged_by_host_threads(monkeypatch):
     assert np.array_equal(pageable, o2v.sort_voxels(dev))
 
 
-@pytest.mark.parametrize("case", ["white", "white_autobounds", "white_ss2", "textured_blend"])
+@pytest.mark.parametrize("case", ["white", "white_autobounds", "white_ss2", "white_skewed", "textured_blend"])
 def test_two_devices_deliver_the_oracles_records(case):
     """Two GPUs of one process: Z-slabs of whole chunk rows, each device uploads half of the triangles and stores every
     triangle into the memory of the device(s) whose slab it can reach (all-white meshes), or takes the whole mesh
@@ -116,6 +116,12 @@ def test_two_devices_deliver_the_oracles_records(case):
     res = 256
     if case == "white_autobounds":
         kw, okw = {}, {}
+    elif case == "white_skewed":
+        # nine tenths of the triangles below z = 0.2: the slabs are balanced by triangles per chunk row, not split in
+        # the middle (and the union is still the oracle's result)
+        low = meshes.random_triangles(18_000, 0.03, seed=47)
+        low[:, 2::3] *= np.float32(0.2)
+        verts = np.concatenate([low, meshes.random_triangles(2_000, 0.03, seed=48)])
     elif case == "white_ss2":
         res = 128
         kw.update(supersampling=2)
