@@ -29,9 +29,14 @@ constexpr int kTinyFoldThreads = 128;
 // ---------------------------------------------------------------------------------------------------------------------
 // stages 1 + 2: thread per (leaf, tile) pair
 
+/// ceil(65536 / d) for d = 1 .. 8: n / d == (n * kReciprocal16[d]) >> 16 for n < 64 (box positions of a masked pair).
+__constant__ uint32_t kReciprocal16[9] = {0u, 65536u, 32768u, 21846u, 16384u, 13108u, 10923u, 9363u, 8192u};
+
 /// Pass 1 (WRITE = false) evaluates the SAT for every candidate voxel of the pair, counts the survivors and, when the pair
 /// has at most 64 candidates (always, for triangles up to 4 voxels across), keeps them as a bit mask; pass 2 (WRITE = true)
 /// runs after the scan and only expands the mask into survivor entries (pairs with more candidates redo the SAT).
+/// Both walk the box as ONE loop (position index, coordinates carried along): the lanes of a warp hold boxes of different
+/// shapes, and nested z / y / x loops make the warp pay for the union of the shapes (measured: 8.7 of 32 lanes active).
 template <bool WRITE>
 __global__ void __launch_bounds__(kPairThreads)
 sparseSurvivorsKernel(const VoxelizeArgs args)
@@ -61,36 +66,49 @@ sparseSurvivorsKernel(const VoxelizeArgs args)
             }
             const uint32_t x0 = box & 15u, y0 = (box >> 4) & 15u, z0 = (box >> 8) & 15u;
             const uint32_t x1 = (box >> 12) & 15u, y1 = (box >> 16) & 15u, z1 = (box >> 20) & 15u;
-            const bool small = (x1 - x0) * (y1 - y0) * (z1 - z0) <= 64u;
-            uint32_t offset = WRITE ? sp.pairOffset[pair] : 0u;
-            uint32_t bit = 0;
-            for (uint32_t z = z0; z < z1; ++z) {
-                for (uint32_t y = y0; y < y1; ++y) {
-                    for (uint32_t x = x0; x < x1; ++x, ++bit) {
-                        bool pass;
-                        if (WRITE && masked) {
-                            pass = ((mask >> bit) & 1ull) != 0;
+            const uint32_t dx = x1 - x0, dy = y1 - y0;
+            const uint32_t total = dx * dy * (z1 - z0);
+            if (WRITE && masked) {
+                uint32_t offset = sp.pairOffset[pair];
+                const uint32_t rx = kReciprocal16[dx], ry = kReciprocal16[dy];
+                while (mask != 0) {
+                    const uint32_t bit = (uint32_t) __ffsll((long long) mask) - 1u;
+                    mask &= mask - 1ull;
+                    const uint32_t row = (bit * rx) >> 16, z = (row * ry) >> 16;
+                    const uint32_t x = x0 + bit - row * dx, y = y0 + row - z * dy;
+                    sp.entries[offset] = make_uint4(pair, x | (y << 3) | ((z0 + z) << 6), 0u, 0u);
+                    ++offset;
+                }
+            }
+            else {
+                const bool small = total <= 64u;
+                uint32_t offset = WRITE ? sp.pairOffset[pair] : 0u;
+                uint32_t x = x0, y = y0, z = z0;
+                for (uint32_t bit = 0; bit < total; ++bit) {
+                    const bool pass = !args.prefilter || prefilterPass(s, (float) x, (float) y, (float) z);
+                    if (pass) {
+                        if (WRITE) {
+                            sp.entries[offset] = make_uint4(pair, x | (y << 3) | (z << 6), 0u, 0u);
+                            ++offset;
                         }
-                        else {
-                            pass = !args.prefilter || prefilterPass(s, (float) x, (float) y, (float) z);
+                        else if (small) {
+                            mask |= 1ull << bit;
                         }
-                        if (pass) {
-                            if (WRITE) {
-                                sp.entries[offset] = make_uint4(pair, x | (y << 3) | (z << 6), 0u, 0u);
-                                ++offset;
-                            }
-                            else if (small) {
-                                mask |= 1ull << bit;
-                            }
-                            ++count;
+                        ++count;
+                    }
+                    if (++x == x1) {
+                        x = x0;
+                        if (++y == y1) {
+                            y = y0;
+                            ++z;
                         }
                     }
                 }
-            }
-            if (!WRITE) {
-                sp.pairBox[pair] = (box & 0x00ffffffu) | (small ? 0x80000000u : 0u);
-                if (small) {
-                    sp.pairMask[pair] = mask;
+                if (!WRITE) {
+                    sp.pairBox[pair] = (box & 0x00ffffffu) | (small ? 0x80000000u : 0u);
+                    if (small) {
+                        sp.pairMask[pair] = mask;
+                    }
                 }
             }
         }
@@ -126,7 +144,7 @@ sparseClipKernel(const VoxelizeArgs args)
     __shared__ uint8_t caseTable[64];
     fillClipCaseTable(caseTable);
     __syncthreads();
-    const int refillThreshold = args.variant > 0 ? args.variant : (int) kRefillThreshold;
+    const int refillThreshold = (int) kRefillThreshold;
     WarpClipper<UV> clipper;
     ClipStack<UV> stack;
     clipper.idle();
@@ -288,8 +306,33 @@ sparseFoldKernel(const VoxelizeArgs args)
             }
             sh.sortKey[lane] = key;
         }
+        else if (kept <= 96) {
+            // rank sort: a lane counts, for each of its (at most three) keys, the keys below it — one broadcast read per
+            // key of the tile, no exchange steps (a padded bitonic network of 64 / 128 keys costs twice the instructions
+            // and a warp barrier per stage); keys are unique (slot in the low bits), so the ranks are a permutation
+            const uint32_t k0 = lane < kept ? sh.sortKey[lane] : 0xffffffffu;
+            const uint32_t k1 = lane + 32 < kept ? sh.sortKey[lane + 32] : 0xffffffffu;
+            const uint32_t k2 = lane + 64 < kept ? sh.sortKey[lane + 64] : 0xffffffffu;
+            uint32_t r0 = 0, r1 = 0, r2 = 0;
+            for (uint32_t j = 0; j < kept; ++j) {
+                const uint32_t key = sh.sortKey[j];
+                r0 += key < k0 ? 1u : 0u;
+                r1 += key < k1 ? 1u : 0u;
+                r2 += key < k2 ? 1u : 0u;
+            }
+            __syncwarp();
+            if (lane < kept) {
+                sh.sortKey[r0] = k0;
+            }
+            if (lane + 32 < kept) {
+                sh.sortKey[r1] = k1;
+            }
+            if (lane + 64 < kept) {
+                sh.sortKey[r2] = k2;
+            }
+        }
         else {
-            uint32_t padded = 64u;
+            uint32_t padded = 128u;
             while (padded < kept) {
                 padded <<= 1;
             }

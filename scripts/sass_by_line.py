@@ -1,7 +1,7 @@
 """Joins the per-instruction counters of an `ncu --set full --import-source on` report (SASS page) with the line table of
 the same build (`nvdisasm -g`) and prints, per source line of a kernel, the share of executed warp instructions, the
 average number of active lanes and the share of stall samples.  Runs here (no GPU):
-  python scripts/sass_by_line.py <report.ncu-rep> <kernel name substring> [<cubin name substring, default o2v_occupancy>]
+  python scripts/sass_by_line.py <report.ncu-rep> <kernel name substring> [<cubin name substring, default o2v_occupancy> [<mangled name substring>]]
 The report and the library must come from the same build (same instruction count, checked)."""
 import collections
 import csv
@@ -46,7 +46,8 @@ def line_table(kernel, cubin_hint):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     hint = sys.argv[3] if len(sys.argv) > 3 else "o2v_occupancy"
-    prof, lines = profiled(rep, kernel), line_table(kernel, hint)
+    mangled = sys.argv[4] if len(sys.argv) > 4 else kernel  # e.g. sparseFoldKernelILb1 for the <true> instance
+    prof, lines = profiled(rep, kernel), line_table(mangled, hint)
     if len(prof) == 2 * len(lines):  # some captures list the kernel twice
         prof = prof[:len(lines)]
     if len(prof) != len(lines):
@@ -63,7 +64,7 @@ def main():
     print("Source: %s (SASS page) joined with `nvdisasm -g` of the same build; %.3f G warp instructions, %d stall "
           "samples.\n" % (os.path.basename(rep), total / 1e9, samples))
     print("| file:line | % of executed instructions | active lanes | % of stall samples | source |\n|---|---|---|---|---|")
-    for (f, ln), e in ex.most_common(30):
+    for (f, ln), e in ex.most_common(int(os.environ.get("O2V_LINES", "30"))):
         if f not in source:
             path = os.path.join(ROOT, "obj2voxel_b200", "csrc", f)
             source[f] = open(path).read().splitlines() if os.path.exists(path) else []
