@@ -217,12 +217,13 @@ sparseClipKernel(const VoxelizeArgs args)
 // ---------------------------------------------------------------------------------------------------------------------
 // stage 4: warp per tile -> ordered fold + output
 
-/// Per-warp scratch, carved out of dynamic shared memory: tri | sortKey | cW [| cU | cV], kWarpFoldMax entries each.
+/// Per-warp scratch, carved out of dynamic shared memory: tri | sortKey | cW [| cU | cV], kWarpFoldMax entries each, then
+/// the positions of the first contribution of every output voxel (16 bits each).
 /// Sort key = (voxel key << 18) | (list slot << 9) | contribution slot — 9 bits each.
 template <bool UV>
 struct FoldWarpLayout {
     static constexpr uint32_t kArrays = UV ? 5u : 3u;
-    static constexpr size_t kBytesPerWarp = (size_t) kArrays * kWarpFoldMax * 4u;
+    static constexpr size_t kBytesPerWarp = (size_t) kArrays * kWarpFoldMax * 4u + (size_t) kWarpFoldMax * 2u;
 };
 
 template <bool UV>
@@ -233,6 +234,7 @@ sparseFoldKernel(const VoxelizeArgs args)
     struct {
         uint32_t *tri, *sortKey;
         float *cW, *cU, *cV;
+        uint16_t *heads;
     } sh;
     {
         uint32_t *warpBase = reinterpret_cast<uint32_t *>(foldSmem + (threadIdx.x >> 5) * FoldWarpLayout<UV>::kBytesPerWarp);
@@ -241,6 +243,7 @@ sparseFoldKernel(const VoxelizeArgs args)
         sh.cW = reinterpret_cast<float *>(warpBase + 2 * kWarpFoldMax);
         sh.cU = UV ? sh.cW + kWarpFoldMax : sh.cW;
         sh.cV = UV ? sh.cW + 2 * kWarpFoldMax : sh.cW;
+        sh.heads = reinterpret_cast<uint16_t *>(warpBase + FoldWarpLayout<UV>::kArrays * kWarpFoldMax);
     }
     const SparseView &sp = args.sparse;
     const uint32_t lane = threadIdx.x & 31u;
@@ -369,24 +372,27 @@ sparseFoldKernel(const VoxelizeArgs args)
         }
         __syncwarp();
 
-        // ---- one lane per output voxel replays the fold in order; one atomic per tile reserves the output range ----
+        // ---- one lane per output voxel replays the fold in order; one atomic per tile reserves the output range.  The
+        // first contributions of the voxels are listed first, so that every lane of the fold loop has a voxel ----
         uint32_t runs = 0;
         for (uint32_t base = 0; base < kept; base += 32) {
             const uint32_t p = base + lane;
             const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
-            runs += __popc(__ballot_sync(full, start));
+            const uint32_t ballot = __ballot_sync(full, start);
+            if (start) {
+                sh.heads[runs + __popc(ballot & below)] = (uint16_t) p;
+            }
+            runs += __popc(ballot);
         }
         unsigned long long outBase = 0;
         if (lane == 0) {
             outBase = atomicAdd(&args.counters->voxels, (unsigned long long) runs);
         }
         outBase = __shfl_sync(full, outBase, 0);
-        uint32_t emitted = 0;
-        for (uint32_t base = 0; base < kept; base += 32) {
-            const uint32_t p = base + lane;
-            const bool start = p < kept && (p == 0 || (sh.sortKey[p] >> groupShift) != (sh.sortKey[p - 1] >> groupShift));
-            const uint32_t ballot = __ballot_sync(full, start);
-            if (start) {
+        __syncwarp();
+        for (uint32_t h = lane; h < runs; h += 32) {
+            const uint32_t p = sh.heads[h];
+            {
                 const uint32_t group = sh.sortKey[p] >> groupShift;
                 uint32_t currentVoxel = (sh.sortKey[p] >> 18) & 511u;
                 VoxelAccumulator child;
@@ -438,7 +444,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                     oy = (int32_t) (origin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
                     oz = (int32_t) (origin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
                 }
-                const unsigned long long index = outBase + emitted + __popc(ballot & below);
+                const unsigned long long index = outBase + h;
                 if (index < args.outCapacity) {
                     VoxelRecord rec;
                     rec.x = ox;
@@ -446,13 +452,12 @@ sparseFoldKernel(const VoxelizeArgs args)
                     rec.z = oz;
                     rec.argb = quantizeArgb(result.r, result.g, result.b);
                     *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
-                storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
+                    storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
                 }
                 else {
                     atomicAdd(&args.counters->outputOverflow, 1ull);
                 }
             }
-            emitted += __popc(ballot);
         }
         __syncwarp();
     }
@@ -466,138 +471,200 @@ sparseFoldKernel(const VoxelizeArgs args)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// stage 4, tiny tiles: thread per tile.  With ~10 contributions per tile a whole warp per tile leaves most lanes idle; here
-// every lane sorts and folds its own tile (insertion sort of <= kTinyFoldMax keys), and the warp reserves its output range
-// with one atomic.
+// stage 4, tiny tiles (<= kTinyFoldMax survivors, ~10 on BASELINE-sized triangles): a warp folds 32 tiles at a time.
+// A warp per tile leaves most lanes idle, and a thread per tile (round 1) ran at 6.8 of 32 lanes: the tiles of a warp
+// hold 1 .. 24 survivors and every lane ran its own load / insertion sort / fold loops.  Here the unit of work changes
+// from stage to stage so that the lanes stay level: the survivors of the 32 tiles are loaded as one flat list (lane =
+// entry), sorted inside their tile by rank (lane = entry: count the keys of the same tile that are smaller), and folded
+// per output voxel (lane = voxel: ~2 contributions each); the warp reserves its output range with one atomic.
+
+constexpr int kTinyWarps = kTinyFoldThreads / 32;
+constexpr uint32_t kTinyBatchEntries = 32u * kTinyFoldMax;
+static_assert(kTinyFoldMax <= 32u, "the entry of a tile takes 5 bits of the sort key");
 
 template <bool UV>
 __global__ void __launch_bounds__(kTinyFoldThreads)
 sparseTinyFoldKernel(const VoxelizeArgs args)
 {
+    // key = (tile of the batch << 15) | (voxel key, 512 = no contribution << 5) | entry of the tile: ascending keys list a
+    // tile's contributions by voxel (children of one parent adjacent, ascending Morton order) and, per voxel, in list order
+    // (the entries of a tile lie in list order: the entry index orders like the list slot)
+    __shared__ uint32_t keysShared[kTinyWarps][kTinyBatchEntries];
+    __shared__ uint32_t sortedShared[kTinyWarps][kTinyBatchEntries];
+    __shared__ uint32_t baseShared[kTinyWarps][33];
+    __shared__ uint32_t beginShared[kTinyWarps][32];
+    __shared__ uint32_t originShared[kTinyWarps][32][3];
     const SparseView &sp = args.sparse;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t full = 0xffffffffu;
+    const uint32_t below = (1u << lane) - 1u;
     const bool blend = args.grid.strategy == kBlend;
     const bool downscale = args.grid.supersampling == 2;
-    const uint32_t groupShift = downscale ? 21u : 18u;
-    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t groupShift = downscale ? 8u : 5u;  // group = parent voxel when downscaling, else the voxel
+    uint32_t *keys = keysShared[warp], *sorted = sortedShared[warp], *base = baseShared[warp];
+    const uint32_t warpsTotal = gridDim.x * kTinyWarps;
+    const uint32_t batches = (args.lightCount + 31u) / 32u;
     unsigned long long contributions = 0;
 
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < args.lightCount; base += stride) {
-        const uint32_t t = base + lane;
-        uint32_t key[kTinyFoldMax];
-        uint32_t n = 0, begin = 0, listStart = 0;
-        uint32_t origin[3] = {0, 0, 0};
+    for (uint32_t batch = blockIdx.x * kTinyWarps + warp; batch < batches; batch += warpsTotal) {
+        // ---- lane = tile: where its survivors are ----
+        const uint32_t t = batch * 32u + lane;
+        uint32_t count = 0;
         if (t < args.lightCount) {
             const LightTile d = args.lightTiles[t];
-            begin = sp.pairOffset[d.listStart];
-            const uint32_t count = sp.pairOffset[d.listStart + d.leafCount] - begin;
-            if (count != 0 && count <= kTinyFoldMax) {
-                listStart = d.listStart;
-                tileOriginOf(args.grid, d.tile, origin);
-                for (uint32_t e = 0; e < count; ++e) {
-                    const uint4 entry = sp.entries[begin + e];
-                    if (__uint_as_float(entry.z) != 0.0f) {
-                        const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
-                        // insertion sort by (voxel key, list slot); e identifies the contribution
-                        const uint32_t k = (voxelKey(x, y, z) << 18) | ((entry.x - listStart) << 9) | e;
-                        uint32_t i = n;
-                        while (i > 0 && key[i - 1] > k) {
-                            key[i] = key[i - 1];
-                            --i;
-                        }
-                        key[i] = k;
-                        ++n;
-                    }
-                }
-            }
+            const uint32_t begin = sp.pairOffset[d.listStart];
+            count = sp.pairOffset[d.listStart + d.leafCount] - begin;
+            count = count <= kTinyFoldMax ? count : 0u;  // the others: sparseFoldKernel
+            uint32_t origin[3];
+            tileOriginOf(args.grid, d.tile, origin);
+            beginShared[warp][lane] = begin;
+            originShared[warp][lane][0] = origin[0];
+            originShared[warp][lane][1] = origin[1];
+            originShared[warp][lane][2] = origin[2];
         }
-        uint32_t runs = 0;
-        for (uint32_t p = 0; p < n; ++p) {
-            runs += (p == 0 || (key[p] >> groupShift) != (key[p - 1] >> groupShift)) ? 1u : 0u;
-        }
-        // warp-aggregated output reservation
-        uint32_t inclusive = runs;
+        uint32_t inclusive = count;
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t up = __shfl_up_sync(full, inclusive, o);
             inclusive += lane >= (uint32_t) o ? up : 0u;
         }
-        const uint32_t warpRuns = __shfl_sync(full, inclusive, 31);
-        unsigned long long outIndex = 0;
-        if (lane == 31 && warpRuns != 0) {
-            outIndex = atomicAdd(&args.counters->voxels, (unsigned long long) warpRuns);
+        const uint32_t total = __shfl_sync(full, inclusive, 31);
+        if (total == 0) {
+            continue;  // warp-uniform
         }
-        outIndex = __shfl_sync(full, outIndex, 31) + (inclusive - runs);
+        base[lane] = inclusive - count;
+        if (lane == 31) {
+            base[32] = total;
+        }
+        __syncwarp(full);
 
-        uint32_t p = 0;
-        while (p < n) {
-            const uint32_t group = key[p] >> groupShift;
-            uint32_t currentVoxel = (key[p] >> 18) & 511u;
-            VoxelAccumulator child;
-            resetAccumulator(child);
-            WeightedColor parent;
-            parent.w = parent.r = parent.g = parent.b = 0.0f;
-            bool hasParent = false;
-            for (; p < n && (key[p] >> groupShift) == group; ++p) {
-                const uint32_t vk = (key[p] >> 18) & 511u, listSlot = (key[p] >> 9) & 511u, e = key[p] & 511u;
-                if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
-                    flushPartial(child, args);
-                    contributions += child.contributions;
-                    if (!hasParent) {
-                        hasParent = true;
-                        parent = child.voxel;
+        // ---- lane = entry: load, build the key ----
+        for (uint32_t i = lane; i < total; i += 32) {
+            uint32_t tileOfBatch = 0;
+            for (uint32_t step = 16; step > 0; step >>= 1) {
+                tileOfBatch += base[tileOfBatch + step] <= i ? step : 0u;  // base[32] = total > i: never read past it
+            }
+            const uint32_t e = i - base[tileOfBatch];
+            const uint4 entry = sp.entries[beginShared[warp][tileOfBatch] + e];
+            const uint32_t x = entry.y & 7u, y = (entry.y >> 3) & 7u, z = (entry.y >> 6) & 7u;
+            const uint32_t vk = __uint_as_float(entry.z) != 0.0f ? voxelKey(x, y, z) : 512u;
+            keys[i] = (tileOfBatch << 15) | (vk << 5) | e;
+        }
+        __syncwarp(full);
+
+        // ---- lane = entry: rank inside the tile ----
+        for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t key = keys[i];
+            const uint32_t b = base[key >> 15], n = base[(key >> 15) + 1] - b;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) {
+                rank += keys[b + j] < key ? 1u : 0u;
+            }
+            sorted[b + rank] = key;
+        }
+        __syncwarp(full);
+
+        // ---- the first contribution of every output voxel, as a dense list (the keys are no longer needed) ----
+        uint32_t runs = 0;
+        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+            const uint32_t p = p0 + lane;
+            const uint32_t key = p < total ? sorted[p] : 0xffffffffu;
+            const bool start = p < total && ((key >> 5) & 1023u) < 512u &&
+                               (p == 0 || (sorted[p - 1] >> groupShift) != (key >> groupShift));
+            const uint32_t ballot = __ballot_sync(full, start);
+            if (start) {
+                keys[runs + __popc(ballot & below)] = p;
+            }
+            runs += __popc(ballot);
+        }
+        unsigned long long outBase = 0;
+        if (lane == 0 && runs != 0) {
+            outBase = atomicAdd(&args.counters->voxels, (unsigned long long) runs);
+        }
+        outBase = __shfl_sync(full, outBase, 0);
+        __syncwarp(full);
+
+        // ---- lane = output voxel: replay the fold in order ----
+        for (uint32_t h = lane; h < runs; h += 32) {
+            const uint32_t p = keys[h];
+            const uint32_t first = sorted[p];
+            {
+                const uint32_t group = first >> groupShift;
+                const uint32_t tileOfBatch = first >> 15;
+                const uint32_t begin = beginShared[warp][tileOfBatch];
+                const uint32_t tileEnd = base[tileOfBatch + 1];
+                uint32_t currentVoxel = (first >> 5) & 511u;
+                VoxelAccumulator child;
+                resetAccumulator(child);
+                WeightedColor parent;
+                parent.w = parent.r = parent.g = parent.b = 0.0f;
+                bool hasParent = false;
+                for (uint32_t q = p; q < tileEnd; ++q) {
+                    const uint32_t key = sorted[q];
+                    if ((key >> groupShift) != group) {
+                        break;
                     }
-                    else {
+                    const uint32_t vk = (key >> 5) & 511u, e = key & 31u;
+                    if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
+                        flushPartial(child, args);
+                        contributions += child.contributions;
+                        if (!hasParent) {
+                            hasParent = true;
+                            parent = child.voxel;
+                        }
+                        else {
+                            combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        }
+                        resetAccumulator(child);
+                        currentVoxel = vk;
+                    }
+                    const uint2 clipped = reinterpret_cast<const uint2 *>(sp.entries + begin + e)[1];  // {weight, triangle}
+                    const uint32_t tri = clipped.y;
+                    if (child.hasPartial && child.partialTri != tri) {
+                        flushPartial(child, args);  // the previous triangle's uv-buffer entry is complete
+                    }
+                    float u = 0.0f, v = 0.0f;
+                    if (UV) {
+                        const float2 uv = sp.uvs[begin + e];
+                        u = uv.x;
+                        v = uv.y;
+                    }
+                    addContribution(child, tri, __uint_as_float(clipped.x), u, v);
+                }
+                flushPartial(child, args);
+                contributions += child.contributions;
+                WeightedColor result = child.voxel;
+                const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
+                const uint32_t originX = originShared[warp][tileOfBatch][0], originY = originShared[warp][tileOfBatch][1],
+                               originZ = originShared[warp][tileOfBatch][2];
+                int32_t ox, oy, oz;
+                if (downscale) {
+                    if (hasParent) {
                         combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
+                        result = parent;
                     }
-                    resetAccumulator(child);
-                    currentVoxel = vk;
+                    ox = (int32_t) (originX / 2 + (pk & 3u));
+                    oy = (int32_t) (originY / 2 + ((pk >> 2) & 3u));
+                    oz = (int32_t) (originZ / 2 + ((pk >> 4) & 3u));
                 }
-                const uint2 clipped = reinterpret_cast<const uint2 *>(sp.entries + begin + e)[1];  // {weight, triangle}
-                const uint32_t tri = clipped.y;
-                if (child.hasPartial && child.partialTri != tri) {
-                    flushPartial(child, args);
+                else {
+                    ox = (int32_t) (originX + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
+                    oy = (int32_t) (originY + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
+                    oz = (int32_t) (originZ + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
                 }
-                float u = 0.0f, v = 0.0f;
-                if (UV) {
-                    const float2 uv = sp.uvs[begin + e];
-                    u = uv.x;
-                    v = uv.y;
+                const unsigned long long index = outBase + h;
+                if (index < args.outCapacity) {
+                    VoxelRecord rec;
+                    rec.x = ox;
+                    rec.y = oy;
+                    rec.z = oz;
+                    rec.argb = quantizeArgb(result.r, result.g, result.b);
+                    *reinterpret_cast<int4 *>(args.out + index) = *reinterpret_cast<const int4 *>(&rec);
+                    storeFloatRecord(args, index, result.w, result.r, result.g, result.b);
                 }
-                addContribution(child, tri, __uint_as_float(clipped.x), u, v);
-            }
-            flushPartial(child, args);
-            contributions += child.contributions;
-            WeightedColor result = child.voxel;
-            const uint32_t pk = currentVoxel >> 3, ck = currentVoxel & 7u;
-            int32_t ox, oy, oz;
-            if (downscale) {
-                if (hasParent) {
-                    combineColorInto(parent, child.voxel.w, child.voxel.r, child.voxel.g, child.voxel.b, blend);
-                    result = parent;
+                else {
+                    atomicAdd(&args.counters->outputOverflow, 1ull);
                 }
-                ox = (int32_t) (origin[0] / 2 + (pk & 3u));
-                oy = (int32_t) (origin[1] / 2 + ((pk >> 2) & 3u));
-                oz = (int32_t) (origin[2] / 2 + ((pk >> 4) & 3u));
             }
-            else {
-                ox = (int32_t) (origin[0] + (((pk & 3u) << 1) | ((ck >> 2) & 1u)));
-                oy = (int32_t) (origin[1] + ((((pk >> 2) & 3u) << 1) | ((ck >> 1) & 1u)));
-                oz = (int32_t) (origin[2] + ((((pk >> 4) & 3u) << 1) | (ck & 1u)));
-            }
-            if (outIndex < args.outCapacity) {
-                VoxelRecord rec;
-                rec.x = ox;
-                rec.y = oy;
-                rec.z = oz;
-                rec.argb = quantizeArgb(result.r, result.g, result.b);
-                *reinterpret_cast<int4 *>(args.out + outIndex) = *reinterpret_cast<const int4 *>(&rec);
-                storeFloatRecord(args, outIndex, result.w, result.r, result.g, result.b);
-            }
-            else {
-                atomicAdd(&args.counters->outputOverflow, 1ull);
-            }
-            ++outIndex;
         }
         __syncwarp(full);
     }
