@@ -304,14 +304,15 @@ class Leg:
             self.textures = [(torch.from_numpy(meshes.random_texture(256, 256, 3)).to(device), o2v.UV_WRAP)]
         S = cfg["resolution"] * cfg["supersampling"]
         self.bounds = slabs.equal_slabs(S, world)
-        z0, z1 = slabs.my_slab(self.bounds, rank)
-        self.empty = world > 1 and z0 == z1  # more ranks than rows: this rank owns nothing (and must not pass (0, 0))
+        slab = slabs.my_slab(self.bounds, rank)
+        self.empty = world > 1 and slab is None  # more ranks than rows: this rank owns nothing and skips the steps
+        z0, z1 = slab if slab is not None else (0, 0)
         kw = dict(resolution=cfg["resolution"], supersampling=cfg["supersampling"], strategy=cfg["strategy"],
                   bounds=cfg["bounds"])
         self.kw = kw
         self.full_verts, self.full_uvs = verts, uvs
         self.verts, self.uvs = verts, uvs
-        self.params = o2v.make_params(slab=(z0, z1) if world > 1 else None, **kw)
+        self.params = o2v.make_params(slab=(z0, z1) if world > 1 and not self.empty else None, **kw)
         self.distributed_once = False
         if world > 1 and uvs is None and not self.empty and cfg["bounds"] is not None:
             # z-binned distribution: this rank keeps what can reach its slab (o2v_b200_filter_slab)

@@ -203,7 +203,8 @@ bool obj2voxel_b200_counting_sink_write(void *sink, uint32_t *voxel_data, size_t
  * owns a slab of chunk rows.  On the occupancy-only path each device uploads 1/N of the triangles and the devices
  * exchange them by slab over peer memory; the sink receives every device's records, one writer at a time. */
 void obj2voxel_b200_set_devices(obj2voxel_instance *instance, const int32_t *devices, uint32_t count);
-/* Restrict the job to a Z-slab of the sample grid (multiples of 8). */
+/* Restrict the job to a Z-slab [z0, z1) of the sample grid (multiples of 8).  (0, 0) restores the whole grid, any other
+ * z0 == z1 is an empty slab (no voxels): a rank that owns no rows skips the job instead of passing (0, 0). */
 void obj2voxel_b200_set_slab(obj2voxel_instance *instance, uint32_t z0, uint32_t z1);
 /* Statistics of the last obj2voxel_voxelize() on this instance.  A big job runs as z parts (one per 2^20 triangles, at most four)
  * so that the download of one part overlaps the kernels of the next (O2V_B200_PIPELINE_PARTS overrides the number): the

@@ -225,6 +225,9 @@ def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None,
     if unit is not None:
         p.unit_transform = (C.c_int32 * 9)(*[int(u) for u in unit])
     if slab is not None:
+        if int(slab[0]) >= int(slab[1]):
+            # (0, 0) is the engine's "whole grid"; an empty slab must be skipped by its rank, never passed down
+            raise ValueError("empty slab %r: skip the rank instead (slabs.my_slab returns None for it)" % (slab,))
         p.slab_z0, p.slab_z1 = int(slab[0]), int(slab[1])
     p.variant = variant
     p.prefilter = prefilter

@@ -162,6 +162,12 @@ int Engine::setupGrid(const MeshView &mesh, const EngineParams &params, cudaStre
     grid.sampleRes = S;
     grid.gridExtent = (S + 63u) / 64u * 64u;
     grid.tilesPerAxis = grid.gridExtent / kTileEdge;
+    grid.tileShift = 32;
+    for (uint32_t shift = 0; shift < 32; ++shift) {
+        if (grid.tilesPerAxis == (1u << shift)) {
+            grid.tileShift = shift;
+        }
+    }
     const uint32_t gridZ = (S + 63u) / 64u * 64u;
     uint32_t z0 = params.slabZ0, z1 = params.slabZ1;
     if (z0 == 0 && z1 == 0) {

@@ -35,6 +35,7 @@ struct GridView {
     float xf[12];           // mesh -> voxel affine (3x3 row-major, translation)
     uint32_t sampleRes;     // S = resolution * supersampling
     uint32_t tilesPerAxis;  // tiles per axis of the chunk grid: ceil(S / 64) * 8
+    uint32_t tileShift;     // log2(tilesPerAxis) when that is a power of two (tile id -> origin by shifts), else 32
     uint32_t gridExtent;    // ceil(S / 64) * 64: the reference voxelizes whole 64^3 chunks (src/obj2voxel.cpp:245-252,580-581)
     uint32_t slabZ0, slabZ1;        // owned voxel z range [z0, z1), multiples of 8
     uint32_t slabTileZ0, slabTileZCount;

@@ -53,7 +53,10 @@ def z_row_histogram(verts_z_min, verts_z_max, transform_row, sample_resolution, 
 
 
 def my_slab(bounds, rank):
-    return int(bounds[rank]), int(bounds[rank + 1])
+    """(z0, z1) of the rank's slab, or None when the rank owns nothing (more ranks than rows: equal_slabs(8, 2) ==
+    [0, 0, 8]).  Such a rank skips the job: a (0, 0) pair means "whole grid" to the engine."""
+    z0, z1 = int(bounds[rank]), int(bounds[rank + 1])
+    return (z0, z1) if z1 > z0 else None
 
 
 def broadcast_mesh(tensors, src=0):

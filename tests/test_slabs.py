@@ -20,6 +20,16 @@ def test_equal_slabs_cover_the_grid_once(res, world):
         assert all(x % 64 == 0 for x in b)  # whole reference chunk rows
 
 
+def test_a_rank_without_rows_gets_no_slab():
+    """More ranks than rows: the surplus rank must skip the job — (0, 0) would mean 'whole grid' to the engine."""
+    b = slabs.equal_slabs(8, 2)
+    assert b == [0, 0, 8]
+    assert slabs.my_slab(b, 0) is None and slabs.my_slab(b, 1) == (0, 8)
+    import obj2voxel_b200 as o2v
+    with pytest.raises(ValueError):
+        o2v.make_params(resolution=8, slab=(0, 0))
+
+
 def test_balanced_slabs_follow_the_histogram():
     hist = np.zeros(16)
     hist[:4] = 100.0  # all the work is in the first quarter of the grid
