@@ -195,9 +195,39 @@ __device__ __forceinline__ void streamTriangles(const float *verts, unsigned lon
     }
 }
 
-/// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
+/// visit(leaf, lo, hi) with the leaf's voxel AABB clamped to the chunk grid and this rank's slab, if anything is left.
 template <bool UV, typename Visit>
-__device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit)
+__device__ __forceinline__ void visitClamped(const Tri<UV> &leaf, const GridView &grid, Visit &&visit)
+{
+    uint32_t lo[3], hi[3];
+    triVoxelBounds(leaf.v, lo, hi);
+    // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
+    hi[0] = min(hi[0], grid.gridExtent);
+    hi[1] = min(hi[1], grid.gridExtent);
+    lo[2] = max(lo[2], grid.slabZ0);
+    hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
+    if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
+        return;
+    }
+    visit(leaf, lo, hi);
+}
+
+// Huge triangles.  The subdivision of a triangle is walked by the thread that owns the triangle; a non-aligned triangle
+// that spans thousands of voxels has 10^4 .. 10^5 leaves (a low-poly model at a high resolution), and one thread walking
+// them takes tens of milliseconds while the rest of the device is done in one.  From kHugeRootVolume on the owner sets
+// the triangle aside (traverseLeaves, `huge`) and the warp walks it together afterwards (walkHugeTriangles):
+// 4^kHugeSplitDepth = 64 subtrees, two per lane, in forEachLeaf's order.
+#ifndef O2V_HUGE_ROOT_VOLUME
+#define O2V_HUGE_ROOT_VOLUME (1ull << 21)  // voxels of the root AABB (128^3): >= ~10^3 leaves; A/B builds raise it to "never"
+#endif
+constexpr unsigned long long kHugeRootVolume = O2V_HUGE_ROOT_VOLUME;
+constexpr int kHugeSplitDepth = 3;
+
+/// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
+/// With `huge` given, a huge triangle is not walked: *huge = true and the caller hands it to walkHugeTriangles.
+template <bool UV, typename Visit>
+__device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit,
+                                               bool *huge = nullptr)
 {
     uint32_t rlo[3], rhi[3];
     triVoxelBounds(root.v, rlo, rhi);
@@ -217,19 +247,77 @@ __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridVi
         }
         return true;
     }
-    return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) {
-        uint32_t lo[3], hi[3];
-        triVoxelBounds(leaf.v, lo, hi);
-        // voxels beyond the chunk grid belong to chunks the reference never dispatches (obj2voxel.cpp:503-505)
-        hi[0] = min(hi[0], grid.gridExtent);
-        hi[1] = min(hi[1], grid.gridExtent);
-        lo[2] = max(lo[2], grid.slabZ0);
-        hi[2] = min(hi[2], min(grid.slabZ1, grid.gridExtent));
-        if (lo[0] >= hi[0] || lo[1] >= hi[1] || lo[2] >= hi[2]) {
-            return;
+    if (huge != nullptr &&
+        (unsigned long long) (rhi[0] - rlo[0]) * (rhi[1] - rlo[1]) * (rhi[2] - rlo[2]) >= kHugeRootVolume &&
+        !triRoughlyAxisAligned(root.v)) {
+        *huge = true;
+        return true;
+    }
+    return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) { visitClamped<UV>(leaf, grid, visit); });
+}
+
+/// The triangles the lanes of `waiting` set aside, one after the other, walked by all 32 lanes (all lanes call this with
+/// the same `waiting`; `index` = the lane's own triangle): every lane loads and transforms the owner's triangle again — the
+/// same arithmetic, so the same root in every lane, and the kernels do not have to keep their root alive for this rare
+/// path — and takes two of the 64 subtrees.  visit(ownerIndex, ownerArea, leaf, lo, hi, seq) for every leaf, seq = the
+/// leaf's position among the visited leaves of its triangle in the reference's order (when SEQ; else 0).  ownLeaves /
+/// depthOk are set for the lanes of `waiting`: the number of visited leaves of their triangle, and whether it stayed
+/// within kMaxSubdivisionDepth.
+template <bool UV, bool SEQ, typename Visit>
+__device__ __forceinline__ void walkHugeTriangles(unsigned int waiting, unsigned long long index, const MeshView &mesh,
+                                                  const GridView &grid, uint32_t &ownLeaves, bool &depthOk, Visit &&visit)
+{
+    const unsigned int full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    while (waiting != 0) {
+        const int src = __ffs(waiting) - 1;
+        waiting &= waiting - 1u;
+        const unsigned long long ownerIndex = __shfl_sync(full, index, src);
+        Tri<UV> shared;
+        float ownerArea = 0.0f;
+        loadTriangle<UV>(mesh, grid, ownerIndex, shared, ownerArea);
+        uint32_t firstAt = 0, secondAt = 0;
+        if (SEQ) {
+            // the leaves of the subtrees before this lane's: count first (the same walk without the visit)
+            uint32_t first = 0, second = 0;
+            forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane, [&](const Tri<UV> &leaf) {
+                visitClamped<UV>(leaf, grid, [&](const Tri<UV> &, const uint32_t *, const uint32_t *) { ++first; });
+            });
+            forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane + 32u, [&](const Tri<UV> &leaf) {
+                visitClamped<UV>(leaf, grid, [&](const Tri<UV> &, const uint32_t *, const uint32_t *) { ++second; });
+            });
+            uint32_t scanFirst = first, scanSecond = second;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t a = __shfl_up_sync(full, scanFirst, o), b = __shfl_up_sync(full, scanSecond, o);
+                scanFirst += lane >= (uint32_t) o ? a : 0u;
+                scanSecond += lane >= (uint32_t) o ? b : 0u;
+            }
+            firstAt = scanFirst - first;
+            secondAt = __shfl_sync(full, scanFirst, 31) + scanSecond - second;
         }
-        visit(leaf, lo, hi);
-    });
+        uint32_t visited = 0;
+        bool ok = forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane, [&](const Tri<UV> &leaf) {
+            visitClamped<UV>(leaf, grid, [&](const Tri<UV> &l, const uint32_t *lo, const uint32_t *hi) {
+                visit(ownerIndex, ownerArea, l, lo, hi, firstAt + visited);
+                ++visited;
+            });
+        });
+        const uint32_t visitedFirst = visited;
+        ok &= forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane + 32u, [&](const Tri<UV> &leaf) {
+            visitClamped<UV>(leaf, grid, [&](const Tri<UV> &l, const uint32_t *lo, const uint32_t *hi) {
+                visit(ownerIndex, ownerArea, l, lo, hi, secondAt + (visited - visitedFirst));
+                ++visited;
+            });
+        });
+        for (int o = 16; o > 0; o >>= 1) {
+            visited += __shfl_xor_sync(full, visited, o);
+        }
+        const bool allOk = __all_sync(full, ok);
+        if ((int) lane == src) {
+            ownLeaves = visited;
+            depthOk = allOk;
+        }
+    }
 }
 
 /// Debug / parity record: the voxel's float WeightedColor (weight, r, g, b) as the fold left it, before the ARGB8

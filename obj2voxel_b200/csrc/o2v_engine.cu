@@ -190,6 +190,16 @@ int Engine::setupGrid(const MeshView &mesh, const EngineParams &params, cudaStre
 int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
                      const EngineParams &params, cudaStream_t stream, RunStats *stats)
 {
+    int rc = voxelizeOnce(meshIn, textures, textureCount, params, stream, stats);
+    if (rc == kRetryHugeWalk) {
+        rc = voxelizeOnce(meshIn, textures, textureCount, params, stream, stats);
+    }
+    return rc;
+}
+
+int Engine::voxelizeOnce(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
+                         const EngineParams &params, cudaStream_t stream, RunStats *stats)
+{
     // Every triangle MATERIALLESS (no per-triangle types, no usable texture): the output is white wherever a voxel is
     // occupied, whatever the weights — the occupancy-only path decides just that (o2v_occupancy.cu).
     bool occupancy = params.occupancyPath != 0 && !params.floatRecords && meshIn.types == nullptr &&
@@ -271,7 +281,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     O2V_CUDA(cudaMemsetAsync(tileCand_.as<void>(), 0, (size_t) tileTotal * 4, stream));
 
     launchCountLeaves(mesh, grid, leafCount_.as<uint32_t>(), tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(),
-                      dCounters, stream);
+                      dCounters, walkHuge_, stream);
     launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                         &dCounters->leaves, stream);
     launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
@@ -285,6 +295,11 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
+    if (hostCounters_->hugeTriangles != 0 && !walkHuge_) {
+        walkHuge_ = true;  // their leaves are not counted yet: once more, with the warp walking them
+        return kRetryHugeWalk;
+    }
+    walkHuge_ = hostCounters_->hugeTriangles != 0;
     const unsigned long long leafTotal = hostCounters_->leaves;
     const unsigned long long pairTotal = hostCounters_->pairs;
     const unsigned long long activeTotal = hostCounters_->activeTiles;
@@ -327,7 +342,7 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
 
     launchEmitLeaves(mesh, grid, leafOffset_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileFill_.as<uint32_t>(),
                      leaves_.as<LeafRecord>(), hasUv ? leafUvs_.as<LeafUv>() : nullptr, tileList_.as<uint32_t>(),
-                     pairTile_.as<uint32_t>(), dCounters, stream);
+                     pairTile_.as<uint32_t>(), dCounters, walkHuge_, stream);
     TileWork work;
     work.allTiles = allTiles_.as<uint32_t>();
     work.allCount = (uint32_t) activeTotal;
@@ -507,7 +522,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
 
     // the one pass over the triangles: statistics, chunk marks, and the first leaf of triangle i into leaf slot i
     launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, partOfGrid,
-                         smCount_, stream);
+                         walkHuge_, smCount_, stream);
     launchOccupancyAssignChunks(occ, dCounters, stream);
     st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
@@ -515,6 +530,11 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
+    if (hostCounters_->hugeTriangles != 0 && !walkHuge_) {
+        walkHuge_ = true;  // their leaves are not counted yet: once more, with the warp walking them
+        return kRetryHugeWalk;
+    }
+    walkHuge_ = hostCounters_->hugeTriangles != 0;
     if (partOfGrid) {
         mesh.count = hostCounters_->slabTriangles;
     }
@@ -596,7 +616,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                             &dCounters->scanTotal, stream);
         launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), extraLeaves_.as<LeafRecord>(), dCounters,
-                            smCount_, stream);
+                            walkHuge_, smCount_, stream);
         st.kernelLaunches += 4;
     }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));

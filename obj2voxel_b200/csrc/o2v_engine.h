@@ -179,6 +179,12 @@ private:
     int voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid, cudaStream_t stream,
                           RunStats &st);
     static constexpr int kOccupancyFallback = 1;
+    /// The count pass met triangles that only the warp-wide subdivision walk handles in reasonable time (o2v_device.cuh,
+    /// walkHugeTriangles): the run starts over with those kernels.  Sticky until a run meets none.
+    static constexpr int kRetryHugeWalk = 2;
+    bool walkHuge_ = false;
+    int voxelizeOnce(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
+                     cudaStream_t stream, RunStats *stats);
 
     int device_ = 0;
     int smCount_ = 0;

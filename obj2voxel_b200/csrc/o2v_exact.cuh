@@ -245,20 +245,17 @@ O2V_HD bool triIsLeaf(const float *v)
 /// leaf; otherwise depth-first with children visited 3, 2, 1, centre (LIFO stack, centre replaces the top).
 /// fn(const Tri<UV>&) is called per leaf.  Returns false if kMaxSubdivisionDepth was exceeded (leaf emitted as is).
 template <bool UV, typename LeafFn>
-O2V_HD bool forEachLeaf(const Tri<UV> &root, LeafFn &&fn)
+O2V_HD bool forEachLeafBelow(const Tri<UV> &start, int startLevel, LeafFn &&fn)
 {
-    if (triRoughlyAxisAligned(root.v)) {
-        fn(root);
-        return true;
-    }
+    // `start` sits `startLevel` splits below its input triangle (0: it is the triangle): the depth limit counts from there
     Tri<UV> parents[kMaxSubdivisionDepth];
     uint8_t next[kMaxSubdivisionDepth];
     int level = 0;
     bool ok = true;
-    Tri<UV> node = root;
+    Tri<UV> node = start;
     for (;;) {
         while (!triIsLeaf(node.v)) {
-            if (level == kMaxSubdivisionDepth) {
+            if (level + startLevel >= kMaxSubdivisionDepth) {
                 ok = false;
                 break;
             }
@@ -285,6 +282,39 @@ O2V_HD bool forEachLeaf(const Tri<UV> &root, LeafFn &&fn)
         }
     }
     return ok;
+}
+
+template <bool UV, typename LeafFn>
+O2V_HD bool forEachLeaf(const Tri<UV> &root, LeafFn &&fn)
+{
+    if (triRoughlyAxisAligned(root.v)) {
+        fn(root);
+        return true;
+    }
+    return forEachLeafBelow<UV>(root, 0, fn);
+}
+
+/// The leaves of one of the 4^depth subtrees `depth` splits below a (non-aligned) triangle, subtrees numbered in the
+/// order forEachLeaf reaches them (two bits per level, most significant first; position p = child 3 - p): walking the
+/// subtrees 0, 1, 2, ... one after the other visits the leaves in forEachLeaf's order.  A node that is a leaf above the
+/// split depth belongs to the first subtree below it.
+template <bool UV, typename LeafFn>
+O2V_HD bool forEachLeafOfSubtree(const Tri<UV> &root, int depth, uint32_t subtree, LeafFn &&fn)
+{
+    Tri<UV> node = root;
+    for (int level = 0; level < depth; ++level) {
+        const int below = 2 * (depth - 1 - level);  // bits of the levels under this one
+        if (triIsLeaf(node.v)) {
+            if ((subtree & ((1u << (below + 2)) - 1u)) == 0) {
+                fn(node);
+            }
+            return true;
+        }
+        Tri<UV> child;
+        triChild<UV>(node, 3 - (int) ((subtree >> below) & 3u), child);
+        node = child;
+    }
+    return forEachLeafBelow<UV>(node, depth, fn);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -77,94 +77,182 @@ __device__ __forceinline__ uint32_t localTileId(const GridView &grid, uint32_t t
     return ((tz - grid.slabTileZ0) * grid.tilesPerAxis + ty) * grid.tilesPerAxis + tx;
 }
 
+/// What the count pass does with one leaf: the tiles its (clamped) box reaches get one more leaf and its candidates.
+__device__ __forceinline__ void countLeafTiles(const GridView &grid, const uint32_t *lo, const uint32_t *hi,
+                                               uint32_t *__restrict__ tileCount, uint32_t *__restrict__ tileCandidates,
+                                               unsigned long long &candidates)
+{
+    candidates += (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
+        const uint32_t dz = min(hi[2], (tz + 1) * kTileEdge) - max(lo[2], tz * kTileEdge);
+        for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
+            const uint32_t dy = min(hi[1], (ty + 1) * kTileEdge) - max(lo[1], ty * kTileEdge);
+            for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
+                const uint32_t dx = min(hi[0], (tx + 1) * kTileEdge) - max(lo[0], tx * kTileEdge);
+                const uint32_t tile = localTileId(grid, tx, ty, tz);
+                atomicAdd(&tileCount[tile], 1u);
+                atomicAdd(&tileCandidates[tile], dx * dy * dz);
+            }
+        }
+    }
+}
+
+struct HugeCount {
+    unsigned long long candidates;
+    uint32_t ownLeaves;
+    bool depthOk;
+};
+
+/// The huge triangles of a warp (rare): kept out of line so that their registers are not the count kernel's.
 template <bool UV>
-__global__ void __launch_bounds__(kSetupThreads)
+__device__ __noinline__ HugeCount countHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
+                                                  const GridView &grid, uint32_t *tileCount, uint32_t *tileCandidates)
+{
+    HugeCount r{0ull, 0u, true};
+    walkHugeTriangles<UV, false>(waiting, index, mesh, grid, r.ownLeaves, r.depthOk,
+                                 [&](unsigned long long, float, const Tri<UV> &, const uint32_t *lo, const uint32_t *hi,
+                                     uint32_t) { countLeafTiles(grid, lo, hi, tileCount, tileCandidates, r.candidates); });
+    return r;
+}
+
+/// HUGE = false (what every run starts with): a huge triangle is only counted (RunCounters::hugeTriangles) and the engine
+/// runs the pass again with HUGE = true, where the warp walks it together — two instantiations, so that the ordinary
+/// one keeps the registers and the code it had before huge triangles were a concern.
+template <bool UV, bool HUGE>
+__global__ void __launch_bounds__(kSetupThreads, UV ? 8 : 9)
 countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount, uint32_t *__restrict__ tileCount,
                   uint32_t *__restrict__ tileCandidates, RunCounters *counters)
 {
-    unsigned long long candidates = 0, dropped = 0, overflow = 0;
+    unsigned long long candidates = 0, dropped = 0, overflow = 0, hugeSeen = 0;
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
-         i += stride) {
+    const uint32_t lane = threadIdx.x & 31u;
+    // the lanes of a warp leave the loop together: a huge triangle is walked by all of them (walkHugeTriangles)
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < mesh.count;
+         base += stride) {
+        const unsigned long long i = base + lane;
+        const bool valid = i < mesh.count;
         Tri<UV> root;
-        float area;
+        float area = 0.0f;
         uint32_t leaves = 0;
-        if (loadTriangle<UV>(mesh, grid, i, root, area)) {
-            const bool ok = traverseLeaves<UV>(root, grid, [&](const Tri<UV> &, const uint32_t *lo, const uint32_t *hi) {
+        bool huge = false, ok = true;
+        const bool active = valid && loadTriangle<UV>(mesh, grid, i, root, area);
+        if (active) {
+            ok = traverseLeaves<UV>(root, grid, [&](const Tri<UV> &, const uint32_t *lo, const uint32_t *hi) {
                 ++leaves;
-                candidates += (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-                for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
-                    const uint32_t dz = min(hi[2], (tz + 1) * kTileEdge) - max(lo[2], tz * kTileEdge);
-                    for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
-                        const uint32_t dy = min(hi[1], (ty + 1) * kTileEdge) - max(lo[1], ty * kTileEdge);
-                        for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
-                            const uint32_t dx = min(hi[0], (tx + 1) * kTileEdge) - max(lo[0], tx * kTileEdge);
-                            const uint32_t tile = localTileId(grid, tx, ty, tz);
-                            atomicAdd(&tileCount[tile], 1u);
-                            atomicAdd(&tileCandidates[tile], dx * dy * dz);
-                        }
-                    }
+                countLeafTiles(grid, lo, hi, tileCount, tileCandidates, candidates);
+            }, &huge);
+        }
+        hugeSeen += huge ? 1 : 0;
+        if (HUGE) {
+            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
+            if (waiting != 0) {
+                const HugeCount r = countHugeLeaves<UV>(waiting, i, mesh, grid, tileCount, tileCandidates);
+                candidates += r.candidates;
+                if (huge) {
+                    leaves = r.ownLeaves;
+                    ok = r.depthOk;
                 }
-            });
+            }
+        }
+        if (valid) {
             overflow += ok ? 0 : 1;
+            dropped += active ? 0 : 1;
+            leafCount[i] = leaves;
         }
-        else {
-            ++dropped;
-        }
-        leafCount[i] = leaves;
     }
     warpTally(&counters->candidateVoxels, candidates);
     warpTally(&counters->droppedTriangles, dropped);
     warpTally(&counters->depthOverflow, overflow);
+    warpTally(&counters->hugeTriangles, hugeSeen);
+}
+
+struct EmitTargets {
+    const uint32_t *leafOffset, *tileStart;
+    uint32_t *tileFill;
+    LeafRecord *leaves;
+    LeafUv *leafUvs;
+    uint32_t *tileList, *pairTile;
+};
+
+/// What the emit pass does with one leaf: record `index`, and an entry in the list of every tile its box reaches.
+template <bool UV>
+__device__ __forceinline__ void emitLeaf(const GridView &grid, const EmitTargets &out, uint32_t index, uint32_t tri,
+                                         float area, const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi)
+{
+    LeafRecord rec;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        rec.v[k] = leaf.v[k];
+    }
+    rec.tri = tri;
+    rec.area = area;
+    rec.flags = leafFlagsOf(leaf.v);
+    out.leaves[index] = rec;
+    if (UV) {
+        LeafUv uv;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            uv.t[k] = leaf.t[k];
+        }
+        uv.pad[0] = uv.pad[1] = 0.0f;
+        out.leafUvs[index] = uv;
+    }
+    for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
+        for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
+            for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
+                const uint32_t tile = localTileId(grid, tx, ty, tz);
+                const uint32_t slot = atomicAdd(&out.tileFill[tile], 1u);
+                out.tileList[out.tileStart[tile] + slot] = index;
+                out.pairTile[out.tileStart[tile] + slot] = tile;
+            }
+        }
+    }
 }
 
 template <bool UV>
-__global__ void __launch_bounds__(kSetupThreads)
+__device__ __noinline__ void emitHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
+                                            const GridView &grid, const EmitTargets &out)
+{
+    uint32_t ownLeaves = 0;
+    bool depthOk = true;
+    // a leaf's index = its triangle's offset + its position in the triangle's (reference-order) leaf sequence
+    walkHugeTriangles<UV, true>(waiting, index, mesh, grid, ownLeaves, depthOk,
+                                [&](unsigned long long owner, float ownerArea, const Tri<UV> &leaf, const uint32_t *lo,
+                                    const uint32_t *hi, uint32_t seq) {
+                                    emitLeaf<UV>(grid, out, out.leafOffset[owner] + seq, static_cast<uint32_t>(owner),
+                                                 ownerArea, leaf, lo, hi);
+                                });
+}
+
+template <bool UV, bool HUGE>
+__global__ void __launch_bounds__(kSetupThreads, HUGE ? 10 : 0)
 emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leafOffset,
                  const uint32_t *__restrict__ tileStart, uint32_t *__restrict__ tileFill,
                  LeafRecord *__restrict__ leaves, LeafUv *__restrict__ leafUvs, uint32_t *__restrict__ tileList,
                  uint32_t *__restrict__ pairTile)
 {
+    const EmitTargets out{leafOffset, tileStart, tileFill, leaves, leafUvs, tileList, pairTile};
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
-         i += stride) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < mesh.count;
+         base += stride) {
+        const unsigned long long i = base + lane;
         Tri<UV> root;
-        float area;
-        if (!loadTriangle<UV>(mesh, grid, i, root, area)) {
-            continue;
+        float area = 0.0f;
+        bool huge = false;
+        if (i < mesh.count && loadTriangle<UV>(mesh, grid, i, root, area)) {
+            uint32_t index = leafOffset[i];
+            traverseLeaves<UV>(root, grid, [&](const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi) {
+                emitLeaf<UV>(grid, out, index, static_cast<uint32_t>(i), area, leaf, lo, hi);
+                ++index;
+            }, &huge);
         }
-        uint32_t index = leafOffset[i];
-        traverseLeaves<UV>(root, grid, [&](const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi) {
-            LeafRecord rec;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                rec.v[k] = leaf.v[k];
+        if (HUGE) {
+            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
+            if (waiting != 0) {
+                emitHugeLeaves<UV>(waiting, i, mesh, grid, out);
             }
-            rec.tri = static_cast<uint32_t>(i);
-            rec.area = area;
-            rec.flags = leafFlagsOf(leaf.v);
-            leaves[index] = rec;
-            if (UV) {
-                LeafUv uv;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    uv.t[k] = leaf.t[k];
-                }
-                uv.pad[0] = uv.pad[1] = 0.0f;
-                leafUvs[index] = uv;
-            }
-            for (uint32_t tz = lo[2] / kTileEdge; tz <= (hi[2] - 1) / kTileEdge; ++tz) {
-                for (uint32_t ty = lo[1] / kTileEdge; ty <= (hi[1] - 1) / kTileEdge; ++ty) {
-                    for (uint32_t tx = lo[0] / kTileEdge; tx <= (hi[0] - 1) / kTileEdge; ++tx) {
-                        const uint32_t tile = localTileId(grid, tx, ty, tz);
-                        const uint32_t slot = atomicAdd(&tileFill[tile], 1u);
-                        tileList[tileStart[tile] + slot] = index;
-                        pairTile[tileStart[tile] + slot] = tile;
-                    }
-                }
-            }
-            ++index;
-        });
+        }
     }
 }
 
@@ -744,16 +832,17 @@ void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
 }
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream)
+                       uint32_t *tileCandidates, RunCounters *counters, bool walkHuge, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
+    auto launch = [&](auto kernel) {
+        kernel<<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates, counters);
+    };
     if (mesh.uvs != nullptr) {
-        countLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
-                                                                       counters);
+        walkHuge ? launch(countLeavesKernel<true, true>) : launch(countLeavesKernel<true, false>);
     }
     else {
-        countLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
-                                                                        counters);
+        walkHuge ? launch(countLeavesKernel<false, true>) : launch(countLeavesKernel<false, false>);
     }
 }
 
@@ -792,16 +881,18 @@ void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCan
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
-                      RunCounters *, cudaStream_t stream)
+                      RunCounters *, bool walkHuge, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
+    auto launch = [&](auto kernel) {
+        kernel<<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves, leafUvs, tileList,
+                                                     pairTile);
+    };
     if (mesh.uvs != nullptr) {
-        emitLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves,
-                                                                      leafUvs, tileList, pairTile);
+        walkHuge ? launch(emitLeavesKernel<true, true>) : launch(emitLeavesKernel<true, false>);
     }
     else {
-        emitLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill,
-                                                                       leaves, leafUvs, tileList, pairTile);
+        walkHuge ? launch(emitLeavesKernel<false, true>) : launch(emitLeavesKernel<false, false>);
     }
 }
 

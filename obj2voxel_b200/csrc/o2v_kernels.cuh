@@ -76,6 +76,7 @@ struct RunCounters {
     unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
     unsigned long long clipCalls;       // exact clips executed (prefilter survivors)
     unsigned long long depthOverflow;   // triangles that hit kMaxSubdivisionDepth
+    unsigned long long hugeTriangles;   // triangles set aside for the warp-wide subdivision walk (o2v_device.cuh)
     unsigned long long droppedTriangles;  // zero-area / non-finite input triangles
     unsigned long long outputOverflow;  // voxels that did not fit the output buffer
     float boundsMin[3];
@@ -124,7 +125,7 @@ void launchRecordHash(const VoxelRecord *records, unsigned long long count, unsi
                       cudaStream_t stream);
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       uint32_t *tileCandidates, RunCounters *counters, cudaStream_t stream);
+                       uint32_t *tileCandidates, RunCounters *counters, bool walkHuge, cudaStream_t stream);
 
 /// Exclusive scan of n u32 values; total (u64) is written to *total.  scratch must hold scanScratchElems(n) u32.
 size_t scanScratchElems(size_t n);
@@ -139,7 +140,7 @@ void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCan
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
-                      RunCounters *counters, cudaStream_t stream);
+                      RunCounters *counters, bool walkHuge, cudaStream_t stream);
 
 void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream);
 
@@ -241,7 +242,7 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
                                int smCount, cudaStream_t stream);
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, int smCount,
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, bool walkHuge, int smCount,
                           cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
@@ -253,7 +254,7 @@ void launchOccupancyZHistogram(const MeshView &mesh, const GridView &grid, uint3
 void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,
                                cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, bool walkHuge, int smCount,
                          cudaStream_t stream);
 /// microLeaves: the mesh averages at most kOccDirectCandidates candidate voxels per leaf — classified thread = leaf
 /// (occupancyClassifyDirectKernel) instead of block = 64 leaves.

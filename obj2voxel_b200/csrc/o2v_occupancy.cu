@@ -303,10 +303,94 @@ occupancyChunkCountKernel(OccupancyView occ, uint32_t *__restrict__ chunkCounts,
 
 constexpr uint32_t kOccBlockChunkWords = 2048;  // chunk bits a block collects in shared memory: 65536 chunks (8 KB)
 
+struct OccCountTally {
+    unsigned long long candidates, bigLeaves, bigBoxes;
+};
+
+/// What the count pass does with one leaf: statistics and the marks of the chunks its box reaches.  `chunkBits` = the
+/// block's marks in shared memory (when the slab's chunk flags fit there), else the marks go to occ.chunkFlag.
+__device__ __forceinline__ void occCountLeaf(const OccupancyView &occ, uint32_t *chunkBits, const uint32_t *lo,
+                                             const uint32_t *hi, OccCountTally &tally)
+{
+    const unsigned long long volume = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    tally.candidates += volume;
+    if (volume > kOccBigVolume) {
+        ++tally.bigLeaves;
+        tally.bigBoxes += boxCountOf(lo, hi);
+    }
+    const uint32_t cs = 6u + occ.shift;  // a chunk is 64^3 OUTPUT voxels
+    auto mark = [&](uint32_t cx, uint32_t cy, uint32_t cz) {
+        const uint32_t chunk = cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0));
+        const uint32_t bit = 1u << (chunk & 31u);
+        if (chunkBits != nullptr) {
+            if ((chunkBits[chunk >> 5] & bit) == 0) {
+                atomicOr(&chunkBits[chunk >> 5], bit);
+            }
+        }
+        else if ((__ldcg(occ.chunkFlag + (chunk >> 5)) & bit) == 0) {  // look before the atomic
+            atomicOr(occ.chunkFlag + (chunk >> 5), bit);
+        }
+    };
+    const uint32_t cx0 = lo[0] >> cs, cy0 = lo[1] >> cs, cz0 = lo[2] >> cs;
+    const uint32_t cx1 = (hi[0] - 1) >> cs, cy1 = (hi[1] - 1) >> cs, cz1 = (hi[2] - 1) >> cs;
+    mark(cx0, cy0, cz0);
+    if (cx0 != cx1 || cy0 != cy1 || cz0 != cz1) {  // rare: the box straddles a chunk boundary
+        for (uint32_t cz = cz0; cz <= cz1; ++cz) {
+            for (uint32_t cy = cy0; cy <= cy1; ++cy) {
+                for (uint32_t cx = cx0; cx <= cx1; ++cx) {
+                    mark(cx, cy, cz);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void storeLeafRecord(LeafRecord *slot, const float *v, uint32_t tri, float area)
+{
+    LeafRecord rec;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        rec.v[k] = v[k];
+    }
+    rec.tri = tri;
+    rec.area = area;
+    rec.flags = leafFlagsOf(v);
+    *slot = rec;
+}
+
+struct OccHugeCount {
+    OccCountTally tally;
+    uint32_t ownLeaves;
+    bool depthOk;
+};
+
+/// The huge triangles of a warp (rare): kept out of line so that their registers are not the count kernel's.
+__device__ __noinline__ OccHugeCount occCountHugeLeaves(unsigned int waiting, unsigned long long index,
+                                                        const MeshView &mesh, const GridView &grid,
+                                                        const OccupancyView &occ, uint32_t *chunkBits,
+                                                        LeafRecord *firstLeaves)
+{
+    OccHugeCount r{{0ull, 0ull, 0ull}, 0u, true};
+    walkHugeTriangles<false, true>(waiting, index, mesh, grid, r.ownLeaves, r.depthOk,
+                                   [&](unsigned long long owner, float ownerArea, const Tri<false> &leaf,
+                                       const uint32_t *lo, const uint32_t *hi, uint32_t seq) {
+                                       if (seq == 0) {
+                                           storeLeafRecord(firstLeaves + owner, leaf.v, static_cast<uint32_t>(owner),
+                                                           ownerArea);
+                                       }
+                                       occCountLeaf(occ, chunkBits, lo, hi, r.tally);
+                                   });
+    return r;
+}
+
 /// The one pass every triangle takes: transform, subdivision DFS, statistics, chunk marks — and the triangle's first leaf
 /// goes straight into leaf slot i, so that a mesh whose triangles are all leaves themselves (anything fine relative to
 /// the grid) needs no second pass.  extraCount[i] = the triangle's leaves beyond the first.
-__global__ void __launch_bounds__(kOccSetupThreads)
+/// HUGE = false (what every run starts with): a huge triangle is only counted (RunCounters::hugeTriangles) and the engine
+/// runs the pass again with HUGE = true, where the warp walks it together (walkHugeTriangles) — two instantiations, so
+/// that the ordinary one keeps the registers and the code it had before huge triangles were a concern.
+template <bool HUGE>
+__global__ void __launch_bounds__(kOccSetupThreads, 9)
 occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ extraCount,
                      LeafRecord *__restrict__ firstLeaves, RunCounters *counters, bool countFromFilter)
 {
@@ -326,70 +410,47 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
             chunkBits[w] = 0;
         }
     }
+    uint32_t *const marks = collect ? chunkBits : nullptr;
     // (streamTriangles starts with a barrier)
-    unsigned long long candidates = 0, dropped = 0, overflow = 0, bigLeaves = 0, bigBoxes = 0, leafTally = 0,
-                       extraTally = 0;
+    OccCountTally tally{0ull, 0ull, 0ull};
+    unsigned long long dropped = 0, overflow = 0, leafTally = 0, extraTally = 0, hugeSeen = 0;
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
                                       [&](unsigned long long i, const float in[9], bool valid) {
+        // every thread of the block comes here, with or without a triangle: a huge triangle is walked by its whole warp
+        Tri<false> root;
+        float area = 0.0f;
+        uint32_t leaves = 0;
+        bool huge = false, ok = true;
+        const bool active = valid && setupTriangle<false>(grid, in, root, area);
+        if (active) {
+            ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
+                if (leaves == 0) {
+                    // tri = position in the array this pass reads (unused on this path)
+                    storeLeafRecord(firstLeaves + i, leaf.v, static_cast<uint32_t>(i), area);
+                }
+                ++leaves;
+                occCountLeaf(occ, marks, lo, hi, tally);
+            }, &huge);
+        }
+        hugeSeen += huge ? 1 : 0;
+        if (HUGE) {
+            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
+            if (waiting != 0) {
+                const OccHugeCount r = occCountHugeLeaves(waiting, i, mesh, grid, occ, marks, firstLeaves);
+                tally.candidates += r.tally.candidates;
+                tally.bigLeaves += r.tally.bigLeaves;
+                tally.bigBoxes += r.tally.bigBoxes;
+                if (huge) {
+                    leaves = r.ownLeaves;
+                    ok = r.depthOk;
+                }
+            }
+        }
         if (!valid) {
             return;
         }
-        Tri<false> root;
-        float area;
-        uint32_t leaves = 0;
-        if (setupTriangle<false>(grid, in, root, area)) {
-            const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo,
-                                                                   const uint32_t *hi) {
-                if (leaves == 0) {
-                    LeafRecord rec;
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        rec.v[k] = leaf.v[k];
-                    }
-                    rec.tri = static_cast<uint32_t>(i);  // position in the array this pass reads (unused on this path)
-                    rec.area = area;
-                    rec.flags = leafFlagsOf(leaf.v);
-                    firstLeaves[i] = rec;
-                }
-                ++leaves;
-                const unsigned long long volume =
-                    (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-                candidates += volume;
-                if (volume > kOccBigVolume) {
-                    ++bigLeaves;
-                    bigBoxes += boxCountOf(lo, hi);
-                }
-                const uint32_t cs = 6u + occ.shift;  // a chunk is 64^3 OUTPUT voxels
-                auto mark = [&](uint32_t cx, uint32_t cy, uint32_t cz) {
-                    const uint32_t chunk = cx + occ.chunksPerAxis * (cy + occ.chunksPerAxis * (cz - occ.chunkZ0));
-                    const uint32_t bit = 1u << (chunk & 31u);
-                    if (collect) {
-                        if ((chunkBits[chunk >> 5] & bit) == 0) {
-                            atomicOr(&chunkBits[chunk >> 5], bit);
-                        }
-                    }
-                    else if ((__ldcg(occ.chunkFlag + (chunk >> 5)) & bit) == 0) {  // look before the atomic
-                        atomicOr(occ.chunkFlag + (chunk >> 5), bit);
-                    }
-                };
-                const uint32_t cx0 = lo[0] >> cs, cy0 = lo[1] >> cs, cz0 = lo[2] >> cs;
-                const uint32_t cx1 = (hi[0] - 1) >> cs, cy1 = (hi[1] - 1) >> cs, cz1 = (hi[2] - 1) >> cs;
-                mark(cx0, cy0, cz0);
-                if (cx0 != cx1 || cy0 != cy1 || cz0 != cz1) {  // rare: the box straddles a chunk boundary
-                    for (uint32_t cz = cz0; cz <= cz1; ++cz) {
-                        for (uint32_t cy = cy0; cy <= cy1; ++cy) {
-                            for (uint32_t cx = cx0; cx <= cx1; ++cx) {
-                                mark(cx, cy, cz);
-                            }
-                        }
-                    }
-                }
-            });
-            overflow += ok ? 0 : 1;
-        }
-        else {
-            ++dropped;
-        }
+        overflow += ok ? 0 : 1;
+        dropped += active ? 0 : 1;
         if (leaves == 0) {  // only the flags of an empty slot are ever read
             reinterpret_cast<float4 *>(firstLeaves + i)[2] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kLeafEmpty));
         }
@@ -400,19 +461,20 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
     if (collect) {
         __syncthreads();
         for (uint32_t w = threadIdx.x; w < chunkWords; w += kOccSetupThreads) {
-            const uint32_t marks = chunkBits[w];
-            if (marks != 0 && (marks & ~__ldcg(occ.chunkFlag + w)) != 0) {
-                atomicOr(occ.chunkFlag + w, marks);
+            const uint32_t bits = chunkBits[w];
+            if (bits != 0 && (bits & ~__ldcg(occ.chunkFlag + w)) != 0) {
+                atomicOr(occ.chunkFlag + w, bits);
             }
         }
     }
     warpTally(&counters->leaves, leafTally);
     warpTally(&counters->extraLeaves, extraTally);
-    warpTally(&counters->candidateVoxels, candidates);
+    warpTally(&counters->candidateVoxels, tally.candidates);
     warpTally(&counters->droppedTriangles, dropped);
     warpTally(&counters->depthOverflow, overflow);
-    warpTally(&counters->bigLeaves, bigLeaves);
-    warpTally(&counters->bigBoxes, bigBoxes);
+    warpTally(&counters->bigLeaves, tally.bigLeaves);
+    warpTally(&counters->bigBoxes, tally.bigBoxes);
+    warpTally(&counters->hugeTriangles, hugeSeen);
 }
 
 __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *counters)
@@ -436,10 +498,50 @@ __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *coun
     }
 }
 
+/// What the second pass does with leaf number `seq` of triangle `tri`: leaves beyond the first are written to
+/// extraLeaves, and a leaf with more than kOccBigVolume candidates — first leaves included — enters the big-leaf table.
+__device__ __forceinline__ void occEmitLeaf(const OccupancyView &occ, const uint32_t *extraOffset, LeafRecord *extraLeaves,
+                                            RunCounters *counters, uint32_t tri, float area, uint32_t seq,
+                                            const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi)
+{
+    uint32_t index = tri;
+    if (seq != 0) {
+        const uint32_t extraAt = extraOffset[tri] + (seq - 1u);
+        index = occ.firstLeaves + extraAt;
+        storeLeafRecord(extraLeaves + extraAt, leaf.v, tri, area);
+    }
+    const unsigned long long volume = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    if (volume > kOccBigVolume) {
+        // one atomic hands out the table row (high 24 bits) and the first box number (low 40 bits) together, so
+        // the rows are sorted by first box: the box kernel finds its leaf by binary search
+        const uint32_t boxes = boxCountOf(lo, hi);
+        const unsigned long long ticket = atomicAdd(&counters->bigTicket, (1ull << 40) | boxes);
+        const uint32_t row = (uint32_t) (ticket >> 40);
+        if (row < occ.bigCapacity) {
+            occ.bigLeaves[row] = make_uint2(index, (uint32_t) (ticket & ((1ull << 40) - 1ull)));
+        }
+    }
+}
+
+__device__ __noinline__ void occEmitHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
+                                               const GridView &grid, const OccupancyView &occ,
+                                               const uint32_t *extraOffset, LeafRecord *extraLeaves, RunCounters *counters)
+{
+    uint32_t ownLeaves = 0;
+    bool depthOk = true;
+    walkHugeTriangles<false, true>(waiting, index, mesh, grid, ownLeaves, depthOk,
+                                   [&](unsigned long long owner, float ownerArea, const Tri<false> &leaf,
+                                       const uint32_t *lo, const uint32_t *hi, uint32_t seq) {
+                                       occEmitLeaf(occ, extraOffset, extraLeaves, counters, static_cast<uint32_t>(owner),
+                                                   ownerArea, seq, leaf, lo, hi);
+                                   });
+}
+
 /// Second pass, only for meshes that need it (some triangle subdivides, or some leaf is big): writes the leaves beyond
 /// the first of each triangle to extraLeaves[extraOffset[i] ...] (leaf index firstLeaves + that) and enters the leaves
 /// with more than kOccBigVolume candidates — first leaves included — into the big-leaf table.
-__global__ void __launch_bounds__(kOccSetupThreads)
+template <bool HUGE>
+__global__ void __launch_bounds__(kOccSetupThreads, HUGE ? 10 : 0)
 occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ extraOffset,
                     LeafRecord *__restrict__ extraLeaves, RunCounters *counters)
 {
@@ -447,38 +549,21 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
                                       [&](unsigned long long i, const float in[9], bool valid) {
         Tri<false> root;
-        float area;
-        if (!valid || !setupTriangle<false>(grid, in, root, area)) {
-            return;
+        float area = 0.0f;
+        bool huge = false;
+        if (valid && setupTriangle<false>(grid, in, root, area)) {
+            uint32_t seen = 0;
+            traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
+                occEmitLeaf(occ, extraOffset, extraLeaves, counters, static_cast<uint32_t>(i), area, seen, leaf, lo, hi);
+                ++seen;
+            }, &huge);
         }
-        uint32_t seen = 0;
-        const uint32_t extraAt = extraOffset[i];
-        traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
-            const uint32_t index = seen == 0 ? static_cast<uint32_t>(i) : occ.firstLeaves + extraAt + (seen - 1u);
-            if (seen != 0) {
-                LeafRecord rec;
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    rec.v[k] = leaf.v[k];
-                }
-                rec.tri = static_cast<uint32_t>(i);
-                rec.area = area;
-                rec.flags = leafFlagsOf(leaf.v);
-                extraLeaves[extraAt + (seen - 1u)] = rec;
+        if (HUGE) {
+            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
+            if (waiting != 0) {
+                occEmitHugeLeaves(waiting, i, mesh, grid, occ, extraOffset, extraLeaves, counters);
             }
-            const unsigned long long volume = (unsigned long long) (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
-            if (volume > kOccBigVolume) {
-                // one atomic hands out the table row (high 24 bits) and the first box number (low 40 bits) together, so
-                // the rows are sorted by first box: the box kernel finds its leaf by binary search
-                const uint32_t boxes = boxCountOf(lo, hi);
-                const unsigned long long ticket = atomicAdd(&counters->bigTicket, (1ull << 40) | boxes);
-                const uint32_t row = (uint32_t) (ticket >> 40);
-                if (row < occ.bigCapacity) {
-                    occ.bigLeaves[row] = make_uint2(index, (uint32_t) (ticket & ((1ull << 40) - 1ull)));
-                }
-            }
-            ++seen;
-        });
+        }
     });
 }
 
@@ -1312,12 +1397,18 @@ void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float
 }
 
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, int smCount,
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, bool walkHuge, int smCount,
                           cudaStream_t stream)
 {
     // countFromFilter: mesh.count is only an upper bound (the grid is sized by it; blocks without a batch leave at once)
-    occupancyCountKernel<<<setupBlocks(occupancyCountKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
-        mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
+    if (walkHuge) {
+        occupancyCountKernel<true><<<setupBlocks(occupancyCountKernel<true>, mesh.count, smCount), kOccSetupThreads, 0,
+                                     stream>>>(mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
+    }
+    else {
+        occupancyCountKernel<false><<<setupBlocks(occupancyCountKernel<false>, mesh.count, smCount), kOccSetupThreads, 0,
+                                      stream>>>(mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
+    }
 }
 
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
@@ -1350,11 +1441,17 @@ void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters
 }
 
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, int smCount,
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, bool walkHuge, int smCount,
                          cudaStream_t stream)
 {
-    occupancyEmitKernel<<<setupBlocks(occupancyEmitKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
-        mesh, grid, occ, leafOffset, leaves, counters);
+    if (walkHuge) {
+        occupancyEmitKernel<true><<<setupBlocks(occupancyEmitKernel<true>, mesh.count, smCount), kOccSetupThreads, 0,
+                                    stream>>>(mesh, grid, occ, leafOffset, leaves, counters);
+    }
+    else {
+        occupancyEmitKernel<false><<<setupBlocks(occupancyEmitKernel<false>, mesh.count, smCount), kOccSetupThreads, 0,
+                                     stream>>>(mesh, grid, occ, leafOffset, leaves, counters);
+    }
 }
 
 void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,

@@ -14,7 +14,7 @@ while [ $# -ge 2 ]; do
             -Xcompiler -fPIC,-ffp-contract=off -I../../include -I. $flags -c $f.cu -o $dir/$f.o &
     done
     wait
-    for f in o2v_host_math o2v_capi o2v_io o2v_job; do
+    for f in o2v_host_math o2v_capi o2v_io o2v_job o2v_bitscan; do
         g++ -std=c++17 -O2 -fPIC -ffp-contract=off -I../../include -I. -I/usr/local/cuda/include -c $f.cpp -o $dir/$f.o &
     done
     wait

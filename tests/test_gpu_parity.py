@@ -240,6 +240,38 @@ def test_large_triangles_deep_subdivision(engine):
     parity(engine, meshes.random_triangles(40, 0.45, seed=17), 512, strategy=1)
 
 
+def test_huge_triangles_are_walked_by_the_warp_in_reference_order(engine):
+    """Triangles whose voxel AABB passes 2^21 voxels are set aside by their thread and subdivided by the whole warp
+    (64 subtrees, walkHugeTriangles): textured + BLEND makes every voxel depend on the order of the leaves, the small
+    triangles around them keep the other lanes busy with the ordinary walk, supersampling adds the downscale."""
+    big = meshes.random_triangles(6, 0.45, seed=29)
+    small = meshes.random_triangles(3000, 0.01, seed=30)
+    rng = np.random.default_rng(31)
+    order = rng.permutation(len(big) + len(small))
+    v = np.concatenate([big, small])[order]
+    uv = meshes.random_uvs(len(v), seed=32)
+    tex = dict(pixels=meshes.random_texture(64, 64, 3, seed=33), wrap=o2v.UV_WRAP)
+    box = [-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]
+    stats = parity(engine, v, 384, uvs=uv, texture=tex, strategy=1, bounds=box)
+    assert stats["leaves"] > len(v) + 1000, stats["leaves"]  # the big ones really subdivide
+    parity(engine, v, 160, uvs=uv, texture=tex, strategy=0, supersampling=2, bounds=box)
+    parity(engine, v, 384, strategy=0, bounds=box)  # all-white: both pipelines
+
+
+def test_huge_triangle_in_a_slab(engine):
+    v = np.concatenate([meshes.random_triangles(3, 0.45, seed=41), meshes.random_triangles(500, 0.02, seed=42)])
+    box = [-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]
+    want = oracle.voxelize(v, 256, strategy=0, bounds=box)["voxels"]
+    parts = []
+    for slab in ((0, 64), (64, 192), (192, 256)):
+        for occupancy in (0, 1):
+            got, _ = engine.voxelize_host(v, o2v.make_params(resolution=256, strategy=0, bounds=box, slab=slab,
+                                                             occupancy_path=occupancy))
+            got = o2v.sort_voxels(got)
+            expect = want[(want[:, 2] >= slab[0]) & (want[:, 2] < slab[1])]
+            assert np.array_equal(got, expect), (slab, occupancy)
+
+
 def test_many_triangles_in_one_tile_long_lists(engine):
     """20 k triangles crowded into a few tiles: exercises the large-list sort and > 32-leaf batches."""
     v = meshes.random_triangles(20000, 0.02, seed=23) * np.float32(0.1)
