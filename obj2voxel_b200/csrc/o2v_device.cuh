@@ -214,17 +214,22 @@ __device__ __forceinline__ void visitClamped(const Tri<UV> &leaf, const GridView
 
 // Huge triangles.  The subdivision of a triangle is walked by the thread that owns the triangle; a non-aligned triangle
 // that spans thousands of voxels has 10^4 .. 10^5 leaves (a low-poly model at a high resolution), and one thread walking
-// them takes tens of milliseconds while the rest of the device is done in one.  From kHugeRootVolume on the owner sets
-// the triangle aside (traverseLeaves, `huge`) and the warp walks it together afterwards (walkHugeTriangles):
-// 4^kHugeSplitDepth = 64 subtrees, two per lane, in forEachLeaf's order.
+// them takes tens of milliseconds while the rest of the device is done in one.  From kHugeRootVolume on the owner only
+// lists the triangle (traverseLeaves: `huge`; listHugeTriangle), and separate kernels spread the listed triangles over
+// the device as (triangle, subtree) items: the 4^kHugeSplitDepth = 256 subtrees four splits below the root, numbered in
+// forEachLeaf's order (forEachLeafOfSubtree, o2v_exact.cuh).  A count-only walk of every item and a scan per triangle
+// give each subtree its place in the triangle's leaf sequence, so that the leaves keep the reference's order wherever
+// it matters.
 #ifndef O2V_HUGE_ROOT_VOLUME
 #define O2V_HUGE_ROOT_VOLUME (1ull << 21)  // voxels of the root AABB (128^3): >= ~10^3 leaves; A/B builds raise it to "never"
 #endif
 constexpr unsigned long long kHugeRootVolume = O2V_HUGE_ROOT_VOLUME;
-constexpr int kHugeSplitDepth = 3;
+constexpr int kHugeSplitDepth = 4;
+constexpr uint32_t kHugeSubtrees = 1u << (2 * kHugeSplitDepth);
+static_assert(kHugeSubtrees == kHugeSubtreesPerTriangle, "the engine sizes HugeWork::subtree by it");
 
 /// Calls visit(leaf, lo, hi) for every leaf whose voxel AABB intersects this rank's slab, in the reference's order.
-/// With `huge` given, a huge triangle is not walked: *huge = true and the caller hands it to walkHugeTriangles.
+/// With `huge` given, a huge triangle is not walked: *huge = true and the caller lists it (listHugeTriangle).
 template <bool UV, typename Visit>
 __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridView &grid, Visit &&visit,
                                                bool *huge = nullptr)
@@ -256,68 +261,44 @@ __device__ __forceinline__ bool traverseLeaves(const Tri<UV> &root, const GridVi
     return forEachLeaf<UV>(root, [&](const Tri<UV> &leaf) { visitClamped<UV>(leaf, grid, visit); });
 }
 
-/// The triangles the lanes of `waiting` set aside, one after the other, walked by all 32 lanes (all lanes call this with
-/// the same `waiting`; `index` = the lane's own triangle): every lane loads and transforms the owner's triangle again — the
-/// same arithmetic, so the same root in every lane, and the kernels do not have to keep their root alive for this rare
-/// path — and takes two of the 64 subtrees.  visit(ownerIndex, ownerArea, leaf, lo, hi, seq) for every leaf, seq = the
-/// leaf's position among the visited leaves of its triangle in the reference's order (when SEQ; else 0).  ownLeaves /
-/// depthOk are set for the lanes of `waiting`: the number of visited leaves of their triangle, and whether it stayed
-/// within kMaxSubdivisionDepth.
-template <bool UV, bool SEQ, typename Visit>
-__device__ __forceinline__ void walkHugeTriangles(unsigned int waiting, unsigned long long index, const MeshView &mesh,
-                                                  const GridView &grid, uint32_t &ownLeaves, bool &depthOk, Visit &&visit)
+__device__ __forceinline__ void listHugeTriangle(const HugeWork &work, RunCounters *counters, unsigned long long index)
 {
-    const unsigned int full = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
-    while (waiting != 0) {
-        const int src = __ffs(waiting) - 1;
-        waiting &= waiting - 1u;
-        const unsigned long long ownerIndex = __shfl_sync(full, index, src);
-        Tri<UV> shared;
-        float ownerArea = 0.0f;
-        loadTriangle<UV>(mesh, grid, ownerIndex, shared, ownerArea);
-        uint32_t firstAt = 0, secondAt = 0;
-        if (SEQ) {
-            // the leaves of the subtrees before this lane's: count first (the same walk without the visit)
-            uint32_t first = 0, second = 0;
-            forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane, [&](const Tri<UV> &leaf) {
-                visitClamped<UV>(leaf, grid, [&](const Tri<UV> &, const uint32_t *, const uint32_t *) { ++first; });
-            });
-            forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane + 32u, [&](const Tri<UV> &leaf) {
-                visitClamped<UV>(leaf, grid, [&](const Tri<UV> &, const uint32_t *, const uint32_t *) { ++second; });
-            });
-            uint32_t scanFirst = first, scanSecond = second;
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t a = __shfl_up_sync(full, scanFirst, o), b = __shfl_up_sync(full, scanSecond, o);
-                scanFirst += lane >= (uint32_t) o ? a : 0u;
-                scanSecond += lane >= (uint32_t) o ? b : 0u;
-            }
-            firstAt = scanFirst - first;
-            secondAt = __shfl_sync(full, scanFirst, 31) + scanSecond - second;
-        }
-        uint32_t visited = 0;
-        bool ok = forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane, [&](const Tri<UV> &leaf) {
-            visitClamped<UV>(leaf, grid, [&](const Tri<UV> &l, const uint32_t *lo, const uint32_t *hi) {
-                visit(ownerIndex, ownerArea, l, lo, hi, firstAt + visited);
-                ++visited;
-            });
-        });
-        const uint32_t visitedFirst = visited;
-        ok &= forEachLeafOfSubtree<UV>(shared, kHugeSplitDepth, lane + 32u, [&](const Tri<UV> &leaf) {
-            visitClamped<UV>(leaf, grid, [&](const Tri<UV> &l, const uint32_t *lo, const uint32_t *hi) {
-                visit(ownerIndex, ownerArea, l, lo, hi, secondAt + (visited - visitedFirst));
-                ++visited;
-            });
-        });
-        for (int o = 16; o > 0; o >>= 1) {
-            visited += __shfl_xor_sync(full, visited, o);
-        }
-        const bool allOk = __all_sync(full, ok);
-        if ((int) lane == src) {
-            ownLeaves = visited;
-            depthOk = allOk;
-        }
+    const unsigned long long slot = atomicAdd(&counters->hugeTriangles, 1ull);
+    if (slot < work.capacity) {
+        work.list[slot] = static_cast<uint32_t>(index);
     }
+}
+
+/// visit(tri, area, leaf, lo, hi, seq) for every leaf of every listed (triangle, subtree) item, the items spread over the
+/// grid (a thread walks whole subtrees).  seq = the leaf's position in its triangle's leaf sequence when the subtree
+/// offsets are in place (hugeScanKernel), else its position in the subtree.  Returns the walks that hit
+/// kMaxSubdivisionDepth.
+template <bool UV, typename Visit>
+__device__ __forceinline__ unsigned long long forEachHugeLeaf(const MeshView &mesh, const GridView &grid,
+                                                              const HugeWork &work, const RunCounters *counters,
+                                                              bool offsetsInPlace, Visit &&visit)
+{
+    const unsigned long long seen = counters->hugeTriangles;
+    const unsigned long long items = (seen < work.capacity ? seen : work.capacity) * kHugeSubtrees;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    unsigned long long overflow = 0;
+    for (unsigned long long item = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; item < items;
+         item += stride) {
+        const uint32_t tri = work.list[item / kHugeSubtrees];
+        Tri<UV> root;
+        float area = 0.0f;
+        loadTriangle<UV>(mesh, grid, tri, root, area);
+        uint32_t seq = offsetsInPlace ? work.subtree[item] : 0u;
+        const bool ok = forEachLeafOfSubtree<UV>(root, kHugeSplitDepth, (uint32_t) (item % kHugeSubtrees),
+                                                 [&](const Tri<UV> &leaf) {
+            visitClamped<UV>(leaf, grid, [&](const Tri<UV> &l, const uint32_t *lo, const uint32_t *hi) {
+                visit(tri, area, l, lo, hi, seq);
+                ++seq;
+            });
+        });
+        overflow += ok ? 0 : 1;
+    }
+    return overflow;
 }
 
 /// Debug / parity record: the voxel's float WeightedColor (weight, r, g, b) as the fold left it, before the ARGB8

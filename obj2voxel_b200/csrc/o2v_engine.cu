@@ -190,11 +190,25 @@ int Engine::setupGrid(const MeshView &mesh, const EngineParams &params, cudaStre
 int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
                      const EngineParams &params, cudaStream_t stream, RunStats *stats)
 {
-    int rc = voxelizeOnce(meshIn, textures, textureCount, params, stream, stats);
-    if (rc == kRetryHugeWalk) {
+    int rc = kRetryHugeWalk;
+    for (int attempt = 0; attempt < 3 && rc == kRetryHugeWalk; ++attempt) {
         rc = voxelizeOnce(meshIn, textures, textureCount, params, stream, stats);
     }
-    return rc;
+    return rc == kRetryHugeWalk ? fail(kErrTooLarge, "the number of huge triangles keeps changing between attempts") : rc;
+}
+
+bool Engine::hugeWork(HugeWork &work)
+{
+    work = HugeWork{nullptr, nullptr, 0};
+    if (!walkHuge_) {
+        return true;
+    }
+    if (hugeExpected_ >= (1ull << 24) || !hugeList_.ensure((size_t) hugeExpected_ * 4) ||
+        !hugeSubtree_.ensure((size_t) hugeExpected_ * kHugeSubtreesPerTriangle * 4)) {
+        return false;
+    }
+    work = HugeWork{hugeList_.as<uint32_t>(), hugeSubtree_.as<uint32_t>(), (uint32_t) hugeExpected_};
+    return true;
 }
 
 int Engine::voxelizeOnce(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount,
@@ -280,8 +294,18 @@ int Engine::voxelizeOnce(const MeshView &meshIn, const TextureView *textures, ui
     O2V_CUDA(cudaMemsetAsync(tileFill_.as<void>(), 0, (size_t) tileTotal * 4, stream));
     O2V_CUDA(cudaMemsetAsync(tileCand_.as<void>(), 0, (size_t) tileTotal * 4, stream));
 
+    HugeWork huge;
+    if (!hugeWork(huge)) {
+        return fail(kErrOutOfMemory, "device allocation failed (huge triangles)");
+    }
     launchCountLeaves(mesh, grid, leafCount_.as<uint32_t>(), tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(),
-                      dCounters, walkHuge_, stream);
+                      dCounters, huge, stream);
+    if (huge.capacity != 0) {
+        launchHugeSubtreeScan(mesh, grid, huge, dCounters, leafCount_.as<uint32_t>(), false, hugeExpected_, stream);
+        launchHugeCountTiles(mesh, grid, huge, tileCount_.as<uint32_t>(), tileCand_.as<uint32_t>(), dCounters,
+                             hugeExpected_, stream);
+        st.kernelLaunches += 3;
+    }
     launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                         &dCounters->leaves, stream);
     launchExclusiveScan(tileCount_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileTotal, scratch_.as<uint32_t>(),
@@ -295,11 +319,13 @@ int Engine::voxelizeOnce(const MeshView &meshIn, const TextureView *textures, ui
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
-    if (hostCounters_->hugeTriangles != 0 && !walkHuge_) {
-        walkHuge_ = true;  // their leaves are not counted yet: once more, with the warp walking them
+    if (hostCounters_->hugeTriangles > huge.capacity) {
+        walkHuge_ = true;  // their leaves are not counted yet: once more, with room to list them
+        hugeExpected_ = hostCounters_->hugeTriangles;
         return kRetryHugeWalk;
     }
     walkHuge_ = hostCounters_->hugeTriangles != 0;
+    hugeExpected_ = hostCounters_->hugeTriangles;
     const unsigned long long leafTotal = hostCounters_->leaves;
     const unsigned long long pairTotal = hostCounters_->pairs;
     const unsigned long long activeTotal = hostCounters_->activeTiles;
@@ -342,7 +368,7 @@ int Engine::voxelizeOnce(const MeshView &meshIn, const TextureView *textures, ui
 
     launchEmitLeaves(mesh, grid, leafOffset_.as<uint32_t>(), tileStart_.as<uint32_t>(), tileFill_.as<uint32_t>(),
                      leaves_.as<LeafRecord>(), hasUv ? leafUvs_.as<LeafUv>() : nullptr, tileList_.as<uint32_t>(),
-                     pairTile_.as<uint32_t>(), dCounters, walkHuge_, stream);
+                     pairTile_.as<uint32_t>(), dCounters, huge, hugeExpected_, stream);
     TileWork work;
     work.allTiles = allTiles_.as<uint32_t>();
     work.allCount = (uint32_t) activeTotal;
@@ -521,8 +547,13 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     O2V_CUDA(cudaMemsetAsync(occ.chunkFlag, 0, ((size_t) occ.chunkTotal + 31) / 32 * 4, stream));
 
     // the one pass over the triangles: statistics, chunk marks, and the first leaf of triangle i into leaf slot i
+    HugeWork huge;
+    if (!hugeWork(huge)) {
+        return fail(kErrOutOfMemory, "device allocation failed (huge triangles)");
+    }
     launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, partOfGrid,
-                         walkHuge_, smCount_, stream);
+                         huge, hugeExpected_, smCount_, stream);
+    st.kernelLaunches += huge.capacity != 0 ? 3 : 0;
     launchOccupancyAssignChunks(occ, dCounters, stream);
     st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
@@ -530,11 +561,13 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     O2V_CUDA(cudaStreamSynchronize(stream));
     O2V_CUDA(cudaGetLastError());
 
-    if (hostCounters_->hugeTriangles != 0 && !walkHuge_) {
-        walkHuge_ = true;  // their leaves are not counted yet: once more, with the warp walking them
+    if (hostCounters_->hugeTriangles > huge.capacity) {
+        walkHuge_ = true;  // their leaves are not counted yet: once more, with room to list them
+        hugeExpected_ = hostCounters_->hugeTriangles;
         return kRetryHugeWalk;
     }
     walkHuge_ = hostCounters_->hugeTriangles != 0;
+    hugeExpected_ = hostCounters_->hugeTriangles;
     if (partOfGrid) {
         mesh.count = hostCounters_->slabTriangles;
     }
@@ -616,7 +649,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         launchExclusiveScan(leafCount_.as<uint32_t>(), leafOffset_.as<uint32_t>(), n, scratch_.as<uint32_t>(),
                             &dCounters->scanTotal, stream);
         launchOccupancyEmit(mesh, grid, occ, leafOffset_.as<uint32_t>(), extraLeaves_.as<LeafRecord>(), dCounters,
-                            walkHuge_, smCount_, stream);
+                            huge, hugeExpected_, smCount_, stream);
         st.kernelLaunches += 4;
     }
     O2V_CUDA(cudaEventRecord(evSetup_, stream));

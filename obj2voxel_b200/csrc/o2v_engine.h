@@ -179,10 +179,14 @@ private:
     int voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid, cudaStream_t stream,
                           RunStats &st);
     static constexpr int kOccupancyFallback = 1;
-    /// The count pass met triangles that only the warp-wide subdivision walk handles in reasonable time (o2v_device.cuh,
-    /// walkHugeTriangles): the run starts over with those kernels.  Sticky until a run meets none.
+    /// The count pass met huge triangles (o2v_device.cuh) without room to list them all: the run starts over with the list
+    /// sized for them.  Sticky until a run meets none.
     static constexpr int kRetryHugeWalk = 2;
     bool walkHuge_ = false;
+    unsigned long long hugeExpected_ = 0;
+    DeviceBuffer hugeList_, hugeSubtree_;
+    /// The list of this attempt (capacity 0 while no run has met a huge triangle).
+    bool hugeWork(HugeWork &work);
     int voxelizeOnce(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
                      cudaStream_t stream, RunStats *stats);
 

@@ -11,6 +11,8 @@
 //   * candidate voxels are culled by a conservative triangle/box SAT (FMA allowed, margin kPrefilterMargin); survivors run
 //     the bit-exact six-plane clip of o2v_exact.cuh.
 #include "o2v_kernels.cuh"
+#include <algorithm>
+
 #include "o2v_device.cuh"
 
 #include <stdio.h>
@@ -97,73 +99,121 @@ __device__ __forceinline__ void countLeafTiles(const GridView &grid, const uint3
     }
 }
 
-struct HugeCount {
-    unsigned long long candidates;
-    uint32_t ownLeaves;
-    bool depthOk;
-};
-
-/// The huge triangles of a warp (rare): kept out of line so that their registers are not the count kernel's.
+/// A huge triangle is only listed here (`work`; its leaf count stays 0): hugeSubtreeCountKernel .. hugeCountTilesKernel
+/// do for it what this kernel does for the others, spread over the device.
 template <bool UV>
-__device__ __noinline__ HugeCount countHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
-                                                  const GridView &grid, uint32_t *tileCount, uint32_t *tileCandidates)
-{
-    HugeCount r{0ull, 0u, true};
-    walkHugeTriangles<UV, false>(waiting, index, mesh, grid, r.ownLeaves, r.depthOk,
-                                 [&](unsigned long long, float, const Tri<UV> &, const uint32_t *lo, const uint32_t *hi,
-                                     uint32_t) { countLeafTiles(grid, lo, hi, tileCount, tileCandidates, r.candidates); });
-    return r;
-}
-
-/// HUGE = false (what every run starts with): a huge triangle is only counted (RunCounters::hugeTriangles) and the engine
-/// runs the pass again with HUGE = true, where the warp walks it together — two instantiations, so that the ordinary
-/// one keeps the registers and the code it had before huge triangles were a concern.
-template <bool UV, bool HUGE>
-__global__ void __launch_bounds__(kSetupThreads, UV ? 8 : 9)
+__global__ void __launch_bounds__(kSetupThreads)
 countLeavesKernel(MeshView mesh, GridView grid, uint32_t *__restrict__ leafCount, uint32_t *__restrict__ tileCount,
-                  uint32_t *__restrict__ tileCandidates, RunCounters *counters)
+                  uint32_t *__restrict__ tileCandidates, RunCounters *counters, HugeWork work)
 {
-    unsigned long long candidates = 0, dropped = 0, overflow = 0, hugeSeen = 0;
+    unsigned long long candidates = 0, dropped = 0, overflow = 0;
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    // the lanes of a warp leave the loop together: a huge triangle is walked by all of them (walkHugeTriangles)
-    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < mesh.count;
-         base += stride) {
-        const unsigned long long i = base + lane;
-        const bool valid = i < mesh.count;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
         Tri<UV> root;
-        float area = 0.0f;
+        float area;
         uint32_t leaves = 0;
-        bool huge = false, ok = true;
-        const bool active = valid && loadTriangle<UV>(mesh, grid, i, root, area);
-        if (active) {
-            ok = traverseLeaves<UV>(root, grid, [&](const Tri<UV> &, const uint32_t *lo, const uint32_t *hi) {
+        if (loadTriangle<UV>(mesh, grid, i, root, area)) {
+            bool huge = false;
+            const bool ok = traverseLeaves<UV>(root, grid, [&](const Tri<UV> &, const uint32_t *lo, const uint32_t *hi) {
                 ++leaves;
                 countLeafTiles(grid, lo, hi, tileCount, tileCandidates, candidates);
             }, &huge);
-        }
-        hugeSeen += huge ? 1 : 0;
-        if (HUGE) {
-            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
-            if (waiting != 0) {
-                const HugeCount r = countHugeLeaves<UV>(waiting, i, mesh, grid, tileCount, tileCandidates);
-                candidates += r.candidates;
-                if (huge) {
-                    leaves = r.ownLeaves;
-                    ok = r.depthOk;
-                }
+            overflow += ok ? 0 : 1;
+            if (huge) {
+                listHugeTriangle(work, counters, i);
             }
         }
-        if (valid) {
-            overflow += ok ? 0 : 1;
-            dropped += active ? 0 : 1;
-            leafCount[i] = leaves;
+        else {
+            ++dropped;
         }
+        leafCount[i] = leaves;
     }
     warpTally(&counters->candidateVoxels, candidates);
     warpTally(&counters->droppedTriangles, dropped);
     warpTally(&counters->depthOverflow, overflow);
-    warpTally(&counters->hugeTriangles, hugeSeen);
+}
+
+// ---- the huge triangles of a run: (triangle, subtree) items over the whole device ----
+
+constexpr int kHugeThreads = 32;  // a thread walks whole subtrees, latency-bound: many small blocks over all SMs
+
+/// subtree[item] = the leaves of the item's subtree that the passes visit (geometry only: no texture coordinates).
+__global__ void __launch_bounds__(kHugeThreads)
+hugeSubtreeCountKernel(MeshView mesh, GridView grid, HugeWork work, const RunCounters *counters)
+{
+    const unsigned long long seen = counters->hugeTriangles;
+    const unsigned long long items = (seen < work.capacity ? seen : work.capacity) * kHugeSubtrees;
+    const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
+    for (unsigned long long item = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; item < items;
+         item += stride) {
+        Tri<false> root;
+        float area = 0.0f;
+        loadTriangle<false>(mesh, grid, work.list[item / kHugeSubtrees], root, area);
+        uint32_t leaves = 0;
+        forEachLeafOfSubtree<false>(root, kHugeSplitDepth, (uint32_t) (item % kHugeSubtrees), [&](const Tri<false> &leaf) {
+            visitClamped<false>(leaf, grid, [&](const Tri<false> &, const uint32_t *, const uint32_t *) { ++leaves; });
+        });
+        work.subtree[item] = leaves;
+    }
+}
+
+/// Block = listed triangle: subtree[] becomes its exclusive scan (the place of every subtree in the triangle's leaf
+/// sequence) and the triangle's leaf count goes where the count pass would have put it — leafCount[tri] on the weighted
+/// pipeline; on the occupancy pipeline extraCount[tri] = leaves beyond the first, and the leaf tallies.
+__global__ void __launch_bounds__(kHugeSubtrees)
+hugeScanKernel(HugeWork work, RunCounters *counters, uint32_t *__restrict__ perTriangle, bool occupancy)
+{
+    __shared__ uint32_t warpSums[kHugeSubtrees / 32];
+    const unsigned long long seen = counters->hugeTriangles;
+    const uint32_t listed = (uint32_t) (seen < work.capacity ? seen : work.capacity);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t h = blockIdx.x; h < listed; h += gridDim.x) {
+        uint32_t *mine = work.subtree + (size_t) h * kHugeSubtrees + threadIdx.x;
+        const uint32_t value = *mine;
+        uint32_t inclusive = value;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, inclusive, o);
+            inclusive += lane >= (uint32_t) o ? up : 0u;
+        }
+        if (lane == 31) {
+            warpSums[warp] = inclusive;
+        }
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (uint32_t w = 0; w < kHugeSubtrees / 32; ++w) {
+            before += w < warp ? warpSums[w] : 0u;
+            total += warpSums[w];
+        }
+        *mine = before + inclusive - value;
+        if (threadIdx.x == 0) {
+            const uint32_t tri = work.list[h];
+            if (occupancy) {
+                const uint32_t extra = total > 1u ? total - 1u : 0u;
+                perTriangle[tri] = extra;
+                atomicAdd(&counters->leaves, (unsigned long long) total);
+                atomicAdd(&counters->extraLeaves, (unsigned long long) extra);
+            }
+            else {
+                perTriangle[tri] = total;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kHugeThreads)
+hugeCountTilesKernel(MeshView mesh, GridView grid, HugeWork work, uint32_t *__restrict__ tileCount,
+                     uint32_t *__restrict__ tileCandidates, RunCounters *counters)
+{
+    unsigned long long candidates = 0;
+    const unsigned long long overflow = forEachHugeLeaf<false>(
+        mesh, grid, work, counters, false,
+        [&](uint32_t, float, const Tri<false> &, const uint32_t *lo, const uint32_t *hi, uint32_t) {
+            countLeafTiles(grid, lo, hi, tileCount, tileCandidates, candidates);
+        });
+    warpTally(&counters->candidateVoxels, candidates);
+    warpTally(&counters->depthOverflow, overflow);
 }
 
 struct EmitTargets {
@@ -209,23 +259,9 @@ __device__ __forceinline__ void emitLeaf(const GridView &grid, const EmitTargets
     }
 }
 
+/// Huge triangles are skipped here (their leaves: hugeEmitLeavesKernel).
 template <bool UV>
-__device__ __noinline__ void emitHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
-                                            const GridView &grid, const EmitTargets &out)
-{
-    uint32_t ownLeaves = 0;
-    bool depthOk = true;
-    // a leaf's index = its triangle's offset + its position in the triangle's (reference-order) leaf sequence
-    walkHugeTriangles<UV, true>(waiting, index, mesh, grid, ownLeaves, depthOk,
-                                [&](unsigned long long owner, float ownerArea, const Tri<UV> &leaf, const uint32_t *lo,
-                                    const uint32_t *hi, uint32_t seq) {
-                                    emitLeaf<UV>(grid, out, out.leafOffset[owner] + seq, static_cast<uint32_t>(owner),
-                                                 ownerArea, leaf, lo, hi);
-                                });
-}
-
-template <bool UV, bool HUGE>
-__global__ void __launch_bounds__(kSetupThreads, HUGE ? 10 : 0)
+__global__ void __launch_bounds__(kSetupThreads)
 emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leafOffset,
                  const uint32_t *__restrict__ tileStart, uint32_t *__restrict__ tileFill,
                  LeafRecord *__restrict__ leaves, LeafUv *__restrict__ leafUvs, uint32_t *__restrict__ tileList,
@@ -233,27 +269,30 @@ emitLeavesKernel(MeshView mesh, GridView grid, const uint32_t *__restrict__ leaf
 {
     const EmitTargets out{leafOffset, tileStart, tileFill, leaves, leafUvs, tileList, pairTile};
     const unsigned long long stride = (unsigned long long) gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    for (unsigned long long base = (unsigned long long) blockIdx.x * blockDim.x + (threadIdx.x - lane); base < mesh.count;
-         base += stride) {
-        const unsigned long long i = base + lane;
+    for (unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; i < mesh.count;
+         i += stride) {
         Tri<UV> root;
-        float area = 0.0f;
+        float area;
+        if (!loadTriangle<UV>(mesh, grid, i, root, area)) {
+            continue;
+        }
+        uint32_t index = leafOffset[i];
         bool huge = false;
-        if (i < mesh.count && loadTriangle<UV>(mesh, grid, i, root, area)) {
-            uint32_t index = leafOffset[i];
-            traverseLeaves<UV>(root, grid, [&](const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi) {
-                emitLeaf<UV>(grid, out, index, static_cast<uint32_t>(i), area, leaf, lo, hi);
-                ++index;
-            }, &huge);
-        }
-        if (HUGE) {
-            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
-            if (waiting != 0) {
-                emitHugeLeaves<UV>(waiting, i, mesh, grid, out);
-            }
-        }
+        traverseLeaves<UV>(root, grid, [&](const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi) {
+            emitLeaf<UV>(grid, out, index, static_cast<uint32_t>(i), area, leaf, lo, hi);
+            ++index;
+        }, &huge);
     }
+}
+
+/// A leaf's index = its triangle's offset + its position in the triangle's (reference-order) leaf sequence.
+template <bool UV>
+__global__ void __launch_bounds__(kHugeThreads)
+hugeEmitLeavesKernel(MeshView mesh, GridView grid, HugeWork work, EmitTargets out, const RunCounters *counters)
+{
+    forEachHugeLeaf<UV>(mesh, grid, work, counters, true,
+                        [&](uint32_t tri, float area, const Tri<UV> &leaf, const uint32_t *lo, const uint32_t *hi,
+                            uint32_t seq) { emitLeaf<UV>(grid, out, out.leafOffset[tri] + seq, tri, area, leaf, lo, hi); });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -832,18 +871,38 @@ void launchFinishBounds(RunCounters *counters, cudaStream_t stream)
 }
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       uint32_t *tileCandidates, RunCounters *counters, bool walkHuge, cudaStream_t stream)
+                       uint32_t *tileCandidates, RunCounters *counters, const HugeWork &work, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
-    auto launch = [&](auto kernel) {
-        kernel<<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates, counters);
-    };
     if (mesh.uvs != nullptr) {
-        walkHuge ? launch(countLeavesKernel<true, true>) : launch(countLeavesKernel<true, false>);
+        countLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
+                                                                       counters, work);
     }
     else {
-        walkHuge ? launch(countLeavesKernel<false, true>) : launch(countLeavesKernel<false, false>);
+        countLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafCount, tileCount, tileCandidates,
+                                                                        counters, work);
     }
+}
+
+static int hugeBlocks(unsigned long long expected)
+{
+    const unsigned long long blocks = (expected * kHugeSubtrees + kHugeThreads - 1) / kHugeThreads;
+    return (int) std::min<unsigned long long>(std::max<unsigned long long>(blocks, 1), 148ull * 32);
+}
+
+void launchHugeSubtreeScan(const MeshView &mesh, const GridView &grid, const HugeWork &work, RunCounters *counters,
+                           uint32_t *perTriangle, bool occupancy, unsigned long long expected, cudaStream_t stream)
+{
+    hugeSubtreeCountKernel<<<hugeBlocks(expected), kHugeThreads, 0, stream>>>(mesh, grid, work, counters);
+    const int blocks = (int) std::min<unsigned long long>(std::max<unsigned long long>(expected, 1), 148ull * 8);
+    hugeScanKernel<<<blocks, kHugeSubtrees, 0, stream>>>(work, counters, perTriangle, occupancy);
+}
+
+void launchHugeCountTiles(const MeshView &mesh, const GridView &grid, const HugeWork &work, uint32_t *tileCount,
+                          uint32_t *tileCandidates, RunCounters *counters, unsigned long long expected, cudaStream_t stream)
+{
+    hugeCountTilesKernel<<<hugeBlocks(expected), kHugeThreads, 0, stream>>>(mesh, grid, work, tileCount, tileCandidates,
+                                                                            counters);
 }
 
 size_t scanScratchElems(size_t n)
@@ -881,18 +940,25 @@ void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCan
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
-                      RunCounters *, bool walkHuge, cudaStream_t stream)
+                      RunCounters *counters, const HugeWork &work, unsigned long long hugeExpected, cudaStream_t stream)
 {
     const int blocks = gridFor(mesh.count, kSetupThreads, 148 * 64);
-    auto launch = [&](auto kernel) {
-        kernel<<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves, leafUvs, tileList,
-                                                     pairTile);
-    };
+    const EmitTargets out{leafOffset, tileStart, tileFill, leaves, leafUvs, tileList, pairTile};
     if (mesh.uvs != nullptr) {
-        walkHuge ? launch(emitLeavesKernel<true, true>) : launch(emitLeavesKernel<true, false>);
+        emitLeavesKernel<true><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill, leaves,
+                                                                      leafUvs, tileList, pairTile);
+        if (work.capacity != 0) {
+            hugeEmitLeavesKernel<true><<<hugeBlocks(hugeExpected), kHugeThreads, 0, stream>>>(mesh, grid, work, out,
+                                                                                              counters);
+        }
     }
     else {
-        walkHuge ? launch(emitLeavesKernel<false, true>) : launch(emitLeavesKernel<false, false>);
+        emitLeavesKernel<false><<<blocks, kSetupThreads, 0, stream>>>(mesh, grid, leafOffset, tileStart, tileFill,
+                                                                       leaves, leafUvs, tileList, pairTile);
+        if (work.capacity != 0) {
+            hugeEmitLeavesKernel<false><<<hugeBlocks(hugeExpected), kHugeThreads, 0, stream>>>(mesh, grid, work, out,
+                                                                                               counters);
+        }
     }
 }
 

@@ -76,7 +76,7 @@ struct RunCounters {
     unsigned long long contributions;   // (triangle, voxel) merges: N_contrib of SURVEY §8
     unsigned long long clipCalls;       // exact clips executed (prefilter survivors)
     unsigned long long depthOverflow;   // triangles that hit kMaxSubdivisionDepth
-    unsigned long long hugeTriangles;   // triangles set aside for the warp-wide subdivision walk (o2v_device.cuh)
+    unsigned long long hugeTriangles;   // triangles listed for the device-wide subdivision walk (o2v_device.cuh)
     unsigned long long droppedTriangles;  // zero-area / non-finite input triangles
     unsigned long long outputOverflow;  // voxels that did not fit the output buffer
     float boundsMin[3];
@@ -93,6 +93,15 @@ struct RunCounters {
     unsigned long long extraLeaves;     // leaves beyond the first of their triangle (the emit pass writes those)
     unsigned long long scanTotal;       // total of the exclusive scan over the per-triangle extra-leaf counts
     unsigned long long ranges;          // rows with voxels the SAT left undecided = entries of OccupancyView::ranges
+};
+
+/// Where the count pass lists the huge triangles of a run (o2v_device.cuh) and what the huge passes keep per
+/// (triangle, subtree) item.
+constexpr uint32_t kHugeSubtreesPerTriangle = 256;  // = kHugeSubtrees (o2v_device.cuh)
+struct HugeWork {
+    uint32_t *list;     // triangle indices, in the order the count pass met them (any)
+    uint32_t *subtree;  // [capacity * 256]: leaves of the subtree; after hugeScanKernel: leaves of the subtrees before it
+    uint32_t capacity;  // triangles the two arrays hold
 };
 
 /// Descriptor of a light tile: everything the warp needs in one 16-byte load.
@@ -125,7 +134,14 @@ void launchRecordHash(const VoxelRecord *records, unsigned long long count, unsi
                       cudaStream_t stream);
 
 void launchCountLeaves(const MeshView &mesh, const GridView &grid, uint32_t *leafCount, uint32_t *tileCount,
-                       uint32_t *tileCandidates, RunCounters *counters, bool walkHuge, cudaStream_t stream);
+                       uint32_t *tileCandidates, RunCounters *counters, const HugeWork &work, cudaStream_t stream);
+/// The listed huge triangles (o2v_device.cuh): leaves per (triangle, subtree) item, then per triangle the scan of its
+/// subtrees and its leaf count into perTriangle[tri] (occupancy: leaves beyond the first, and the leaf tallies).
+/// `expected` sizes the grids (the number of huge triangles the previous attempt of the run met).
+void launchHugeSubtreeScan(const MeshView &mesh, const GridView &grid, const HugeWork &work, RunCounters *counters,
+                           uint32_t *perTriangle, bool occupancy, unsigned long long expected, cudaStream_t stream);
+void launchHugeCountTiles(const MeshView &mesh, const GridView &grid, const HugeWork &work, uint32_t *tileCount,
+                          uint32_t *tileCandidates, RunCounters *counters, unsigned long long expected, cudaStream_t stream);
 
 /// Exclusive scan of n u32 values; total (u64) is written to *total.  scratch must hold scanScratchElems(n) u32.
 size_t scanScratchElems(size_t n);
@@ -140,7 +156,7 @@ void launchCompactActiveTiles(const uint32_t *tileCount, const uint32_t *tileCan
 
 void launchEmitLeaves(const MeshView &mesh, const GridView &grid, const uint32_t *leafOffset, const uint32_t *tileStart,
                       uint32_t *tileFill, LeafRecord *leaves, LeafUv *leafUvs, uint32_t *tileList, uint32_t *pairTile,
-                      RunCounters *counters, bool walkHuge, cudaStream_t stream);
+                      RunCounters *counters, const HugeWork &work, unsigned long long hugeExpected, cudaStream_t stream);
 
 void launchSortTileLists(const TileWork &work, uint32_t *tileList, cudaStream_t stream);
 
@@ -242,8 +258,8 @@ void launchSparseFold(const VoxelizeArgs &args, int smCount, cudaStream_t stream
 void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float *kept, RunCounters *counters,
                                int smCount, cudaStream_t stream);
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, bool walkHuge, int smCount,
-                          cudaStream_t stream);
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, const HugeWork &work,
+                          unsigned long long hugeExpected, int smCount, cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
                                 cudaStream_t stream);
@@ -254,8 +270,8 @@ void launchOccupancyZHistogram(const MeshView &mesh, const GridView &grid, uint3
 void launchOccupancyChunkCount(const OccupancyView &occ, uint32_t *chunkCounts, RunCounters *counters, int smCount,
                                cudaStream_t stream);
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, bool walkHuge, int smCount,
-                         cudaStream_t stream);
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, const HugeWork &work,
+                         unsigned long long hugeExpected, int smCount, cudaStream_t stream);
 /// microLeaves: the mesh averages at most kOccDirectCandidates candidate voxels per leaf — classified thread = leaf
 /// (occupancyClassifyDirectKernel) instead of block = 64 leaves.
 void launchOccupancyClassify(const VoxelizeArgs &args, unsigned long long leafTotal, bool microLeaves, uint32_t bigCount,

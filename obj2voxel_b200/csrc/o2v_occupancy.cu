@@ -28,6 +28,8 @@
 // Exactness: `miss` and `certain` are proofs about the reference's result (o2v_sat.cuh header; fuzzed by
 // tests/test_sat_classifier.py), everything else runs the reference arithmetic.  prefilter = 0 sends every candidate
 // through the exact clip (validation).
+#include <algorithm>
+
 #include "o2v_device.cuh"
 
 namespace o2v {
@@ -358,41 +360,14 @@ __device__ __forceinline__ void storeLeafRecord(LeafRecord *slot, const float *v
     *slot = rec;
 }
 
-struct OccHugeCount {
-    OccCountTally tally;
-    uint32_t ownLeaves;
-    bool depthOk;
-};
-
-/// The huge triangles of a warp (rare): kept out of line so that their registers are not the count kernel's.
-__device__ __noinline__ OccHugeCount occCountHugeLeaves(unsigned int waiting, unsigned long long index,
-                                                        const MeshView &mesh, const GridView &grid,
-                                                        const OccupancyView &occ, uint32_t *chunkBits,
-                                                        LeafRecord *firstLeaves)
-{
-    OccHugeCount r{{0ull, 0ull, 0ull}, 0u, true};
-    walkHugeTriangles<false, true>(waiting, index, mesh, grid, r.ownLeaves, r.depthOk,
-                                   [&](unsigned long long owner, float ownerArea, const Tri<false> &leaf,
-                                       const uint32_t *lo, const uint32_t *hi, uint32_t seq) {
-                                       if (seq == 0) {
-                                           storeLeafRecord(firstLeaves + owner, leaf.v, static_cast<uint32_t>(owner),
-                                                           ownerArea);
-                                       }
-                                       occCountLeaf(occ, chunkBits, lo, hi, r.tally);
-                                   });
-    return r;
-}
-
 /// The one pass every triangle takes: transform, subdivision DFS, statistics, chunk marks — and the triangle's first leaf
 /// goes straight into leaf slot i, so that a mesh whose triangles are all leaves themselves (anything fine relative to
 /// the grid) needs no second pass.  extraCount[i] = the triangle's leaves beyond the first.
-/// HUGE = false (what every run starts with): a huge triangle is only counted (RunCounters::hugeTriangles) and the engine
-/// runs the pass again with HUGE = true, where the warp walks it together (walkHugeTriangles) — two instantiations, so
-/// that the ordinary one keeps the registers and the code it had before huge triangles were a concern.
-template <bool HUGE>
-__global__ void __launch_bounds__(kOccSetupThreads, 9)
+/// A huge triangle is only listed here (`work`, o2v_device.cuh; its slot stays empty): occHugeCountKernel does for it
+/// what this kernel does for the others, spread over the device.
+__global__ void __launch_bounds__(kOccSetupThreads, 9)  // 56 registers, as before huge triangles were listed here
 occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *__restrict__ extraCount,
-                     LeafRecord *__restrict__ firstLeaves, RunCounters *counters, bool countFromFilter)
+                     LeafRecord *__restrict__ firstLeaves, RunCounters *counters, bool countFromFilter, HugeWork work)
 {
     if (countFromFilter) {
         // the array is what the slab filter kept: its length is still on the device (no host round trip in between)
@@ -413,17 +388,19 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
     uint32_t *const marks = collect ? chunkBits : nullptr;
     // (streamTriangles starts with a barrier)
     OccCountTally tally{0ull, 0ull, 0ull};
-    unsigned long long dropped = 0, overflow = 0, leafTally = 0, extraTally = 0, hugeSeen = 0;
+    unsigned long long dropped = 0, overflow = 0, leafTally = 0, extraTally = 0;
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
                                       [&](unsigned long long i, const float in[9], bool valid) {
-        // every thread of the block comes here, with or without a triangle: a huge triangle is walked by its whole warp
+        if (!valid) {
+            return;
+        }
         Tri<false> root;
-        float area = 0.0f;
+        float area;
         uint32_t leaves = 0;
-        bool huge = false, ok = true;
-        const bool active = valid && setupTriangle<false>(grid, in, root, area);
-        if (active) {
-            ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
+        if (setupTriangle<false>(grid, in, root, area)) {
+            bool huge = false;
+            const bool ok = traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo,
+                                                                   const uint32_t *hi) {
                 if (leaves == 0) {
                     // tri = position in the array this pass reads (unused on this path)
                     storeLeafRecord(firstLeaves + i, leaf.v, static_cast<uint32_t>(i), area);
@@ -431,26 +408,14 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
                 ++leaves;
                 occCountLeaf(occ, marks, lo, hi, tally);
             }, &huge);
-        }
-        hugeSeen += huge ? 1 : 0;
-        if (HUGE) {
-            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
-            if (waiting != 0) {
-                const OccHugeCount r = occCountHugeLeaves(waiting, i, mesh, grid, occ, marks, firstLeaves);
-                tally.candidates += r.tally.candidates;
-                tally.bigLeaves += r.tally.bigLeaves;
-                tally.bigBoxes += r.tally.bigBoxes;
-                if (huge) {
-                    leaves = r.ownLeaves;
-                    ok = r.depthOk;
-                }
+            overflow += ok ? 0 : 1;
+            if (huge) {
+                listHugeTriangle(work, counters, i);
             }
         }
-        if (!valid) {
-            return;
+        else {
+            ++dropped;
         }
-        overflow += ok ? 0 : 1;
-        dropped += active ? 0 : 1;
         if (leaves == 0) {  // only the flags of an empty slot are ever read
             reinterpret_cast<float4 *>(firstLeaves + i)[2] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(kLeafEmpty));
         }
@@ -474,7 +439,29 @@ occupancyCountKernel(MeshView mesh, GridView grid, OccupancyView occ, uint32_t *
     warpTally(&counters->depthOverflow, overflow);
     warpTally(&counters->bigLeaves, tally.bigLeaves);
     warpTally(&counters->bigBoxes, tally.bigBoxes);
-    warpTally(&counters->hugeTriangles, hugeSeen);
+}
+
+constexpr int kOccHugeThreads = 32;  // a thread walks whole subtrees, latency-bound: many small blocks over all SMs
+
+/// The count pass for the listed huge triangles, after hugeSubtreeCountKernel / hugeScanKernel (o2v_kernels.cu) placed
+/// the subtrees: leaf 0 of a triangle goes into its slot, every leaf marks its chunks and enters the statistics.
+__global__ void __launch_bounds__(kOccHugeThreads)
+occHugeCountKernel(MeshView mesh, GridView grid, OccupancyView occ, HugeWork work, LeafRecord *__restrict__ firstLeaves,
+                   RunCounters *counters)
+{
+    OccCountTally tally{0ull, 0ull, 0ull};
+    const unsigned long long overflow = forEachHugeLeaf<false>(
+        mesh, grid, work, counters, true,
+        [&](uint32_t tri, float area, const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi, uint32_t seq) {
+            if (seq == 0) {
+                storeLeafRecord(firstLeaves + tri, leaf.v, tri, area);
+            }
+            occCountLeaf(occ, nullptr, lo, hi, tally);
+        });
+    warpTally(&counters->candidateVoxels, tally.candidates);
+    warpTally(&counters->bigLeaves, tally.bigLeaves);
+    warpTally(&counters->bigBoxes, tally.bigBoxes);
+    warpTally(&counters->depthOverflow, overflow);
 }
 
 __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *counters)
@@ -523,25 +510,10 @@ __device__ __forceinline__ void occEmitLeaf(const OccupancyView &occ, const uint
     }
 }
 
-__device__ __noinline__ void occEmitHugeLeaves(unsigned int waiting, unsigned long long index, const MeshView &mesh,
-                                               const GridView &grid, const OccupancyView &occ,
-                                               const uint32_t *extraOffset, LeafRecord *extraLeaves, RunCounters *counters)
-{
-    uint32_t ownLeaves = 0;
-    bool depthOk = true;
-    walkHugeTriangles<false, true>(waiting, index, mesh, grid, ownLeaves, depthOk,
-                                   [&](unsigned long long owner, float ownerArea, const Tri<false> &leaf,
-                                       const uint32_t *lo, const uint32_t *hi, uint32_t seq) {
-                                       occEmitLeaf(occ, extraOffset, extraLeaves, counters, static_cast<uint32_t>(owner),
-                                                   ownerArea, seq, leaf, lo, hi);
-                                   });
-}
-
 /// Second pass, only for meshes that need it (some triangle subdivides, or some leaf is big): writes the leaves beyond
 /// the first of each triangle to extraLeaves[extraOffset[i] ...] (leaf index firstLeaves + that) and enters the leaves
 /// with more than kOccBigVolume candidates — first leaves included — into the big-leaf table.
-template <bool HUGE>
-__global__ void __launch_bounds__(kOccSetupThreads, HUGE ? 10 : 0)
+__global__ void __launch_bounds__(kOccSetupThreads)
 occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint32_t *__restrict__ extraOffset,
                     LeafRecord *__restrict__ extraLeaves, RunCounters *counters)
 {
@@ -549,22 +521,28 @@ occupancyEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, const uint3
     streamTriangles<kOccSetupThreads>(mesh.verts, mesh.count, batch,
                                       [&](unsigned long long i, const float in[9], bool valid) {
         Tri<false> root;
-        float area = 0.0f;
-        bool huge = false;
-        if (valid && setupTriangle<false>(grid, in, root, area)) {
-            uint32_t seen = 0;
-            traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
-                occEmitLeaf(occ, extraOffset, extraLeaves, counters, static_cast<uint32_t>(i), area, seen, leaf, lo, hi);
-                ++seen;
-            }, &huge);
+        float area;
+        if (!valid || !setupTriangle<false>(grid, in, root, area)) {
+            return;
         }
-        if (HUGE) {
-            const unsigned int waiting = __ballot_sync(0xffffffffu, huge);
-            if (waiting != 0) {
-                occEmitHugeLeaves(waiting, i, mesh, grid, occ, extraOffset, extraLeaves, counters);
-            }
-        }
+        uint32_t seen = 0;
+        bool huge = false;  // listed: occHugeEmitKernel
+        traverseLeaves<false>(root, grid, [&](const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi) {
+            occEmitLeaf(occ, extraOffset, extraLeaves, counters, static_cast<uint32_t>(i), area, seen, leaf, lo, hi);
+            ++seen;
+        }, &huge);
     });
+}
+
+__global__ void __launch_bounds__(kOccHugeThreads)
+occHugeEmitKernel(MeshView mesh, GridView grid, OccupancyView occ, HugeWork work, const uint32_t *__restrict__ extraOffset,
+                  LeafRecord *__restrict__ extraLeaves, RunCounters *counters)
+{
+    forEachHugeLeaf<false>(mesh, grid, work, counters, true,
+                           [&](uint32_t tri, float area, const Tri<false> &leaf, const uint32_t *lo, const uint32_t *hi,
+                               uint32_t seq) {
+                               occEmitLeaf(occ, extraOffset, extraLeaves, counters, tri, area, seq, leaf, lo, hi);
+                           });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1396,18 +1374,23 @@ void launchOccupancySlabFilter(const MeshView &mesh, const GridView &grid, float
                                 stream>>>(mesh, grid, kept, counters);
 }
 
+static int occHugeBlocks(unsigned long long expected)
+{
+    const unsigned long long blocks = (expected * kHugeSubtrees + kOccHugeThreads - 1) / kOccHugeThreads;
+    return (int) std::min<unsigned long long>(std::max<unsigned long long>(blocks, 1), 148ull * 32);
+}
+
 void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const OccupancyView &occ, uint32_t *extraCount,
-                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, bool walkHuge, int smCount,
-                          cudaStream_t stream)
+                          LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, const HugeWork &work,
+                          unsigned long long hugeExpected, int smCount, cudaStream_t stream)
 {
     // countFromFilter: mesh.count is only an upper bound (the grid is sized by it; blocks without a batch leave at once)
-    if (walkHuge) {
-        occupancyCountKernel<true><<<setupBlocks(occupancyCountKernel<true>, mesh.count, smCount), kOccSetupThreads, 0,
-                                     stream>>>(mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
-    }
-    else {
-        occupancyCountKernel<false><<<setupBlocks(occupancyCountKernel<false>, mesh.count, smCount), kOccSetupThreads, 0,
-                                      stream>>>(mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter);
+    occupancyCountKernel<<<setupBlocks(occupancyCountKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
+        mesh, grid, occ, extraCount, firstLeaves, counters, countFromFilter, work);
+    if (work.capacity != 0) {
+        launchHugeSubtreeScan(mesh, grid, work, counters, extraCount, true, hugeExpected, stream);
+        occHugeCountKernel<<<occHugeBlocks(hugeExpected), kOccHugeThreads, 0, stream>>>(mesh, grid, occ, work, firstLeaves,
+                                                                                        counters);
     }
 }
 
@@ -1441,16 +1424,14 @@ void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters
 }
 
 void launchOccupancyEmit(const MeshView &mesh, const GridView &grid, const OccupancyView &occ,
-                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, bool walkHuge, int smCount,
-                         cudaStream_t stream)
+                         const uint32_t *leafOffset, LeafRecord *leaves, RunCounters *counters, const HugeWork &work,
+                         unsigned long long hugeExpected, int smCount, cudaStream_t stream)
 {
-    if (walkHuge) {
-        occupancyEmitKernel<true><<<setupBlocks(occupancyEmitKernel<true>, mesh.count, smCount), kOccSetupThreads, 0,
-                                    stream>>>(mesh, grid, occ, leafOffset, leaves, counters);
-    }
-    else {
-        occupancyEmitKernel<false><<<setupBlocks(occupancyEmitKernel<false>, mesh.count, smCount), kOccSetupThreads, 0,
-                                     stream>>>(mesh, grid, occ, leafOffset, leaves, counters);
+    occupancyEmitKernel<<<setupBlocks(occupancyEmitKernel, mesh.count, smCount), kOccSetupThreads, 0, stream>>>(
+        mesh, grid, occ, leafOffset, leaves, counters);
+    if (work.capacity != 0) {
+        occHugeEmitKernel<<<occHugeBlocks(hugeExpected), kOccHugeThreads, 0, stream>>>(mesh, grid, occ, work, leafOffset,
+                                                                                       leaves, counters);
     }
 }
 

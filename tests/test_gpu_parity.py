@@ -240,10 +240,10 @@ def test_large_triangles_deep_subdivision(engine):
     parity(engine, meshes.random_triangles(40, 0.45, seed=17), 512, strategy=1)
 
 
-def test_huge_triangles_are_walked_by_the_warp_in_reference_order(engine):
-    """Triangles whose voxel AABB passes 2^21 voxels are set aside by their thread and subdivided by the whole warp
-    (64 subtrees, walkHugeTriangles): textured + BLEND makes every voxel depend on the order of the leaves, the small
-    triangles around them keep the other lanes busy with the ordinary walk, supersampling adds the downscale."""
+def test_huge_triangles_are_walked_in_reference_order(engine):
+    """Triangles whose voxel AABB passes 2^21 voxels are only listed by the count pass and subdivided as 256 (triangle,
+    subtree) items spread over the device (o2v_device.cuh, forEachHugeLeaf): textured + BLEND makes every voxel depend on
+    the order of the leaves, the small triangles around them take the ordinary walk, supersampling adds the downscale."""
     big = meshes.random_triangles(6, 0.45, seed=29)
     small = meshes.random_triangles(3000, 0.01, seed=30)
     rng = np.random.default_rng(31)
