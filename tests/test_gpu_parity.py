@@ -258,6 +258,21 @@ def test_huge_triangles_are_walked_in_reference_order(engine):
     parity(engine, v, 384, strategy=0, bounds=box)  # all-white: both pipelines
 
 
+def test_huge_triangle_list_grows_and_shrinks_between_runs(engine):
+    """The list of huge triangles is sized by what the previous attempt met: runs with none, a few, many and none again on
+    one engine (every change of the count is a run that starts over once)."""
+    box = [-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]
+    for n_big, seed in ((0, 51), (3, 52), (40, 53), (0, 54), (5, 55)):
+        parts = [meshes.random_triangles(300, 0.02, seed=seed)]
+        if n_big:
+            parts.append(meshes.random_triangles(n_big, 0.45, seed=seed + 100))
+        v = np.concatenate(parts)
+        want = oracle.voxelize(v, 256, strategy=0, bounds=box)["voxels"]
+        for occupancy in (1, 0):
+            got, _ = engine.voxelize_host(v, o2v.make_params(resolution=256, strategy=0, bounds=box, occupancy_path=occupancy))
+            assert np.array_equal(o2v.sort_voxels(got), want), (n_big, occupancy)
+
+
 def test_huge_triangle_in_a_slab(engine):
     v = np.concatenate([meshes.random_triangles(3, 0.45, seed=41), meshes.random_triangles(500, 0.02, seed=42)])
     box = [-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]
