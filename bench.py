@@ -641,15 +641,15 @@ def run_e2e(args, cfg, host_verts, host_uvs, n_tri, tri_bytes, rank, world, voxe
     del records, received
     if hash_ok is False:
         raise RuntimeError("e2e records differ from the reference's (hash %d)" % digest)
-    bitmap = bool(stats["download_bytes"] < 16 * voxels)
+    packed = bool(stats["download_bytes"] < 16 * voxels)
     out = {"value": n_tri / seconds / 1e6, "unit": "Mtri/s", "ms_per_step": seconds * 1e3,
            "h2d_bytes_per_step": int(n_tri * tri_bytes),
            "d2h_bytes_per_step": int(stats["download_bytes"]), "voxel_callback_bytes_per_step": int(16 * voxels),
            "hash_ok": hash_ok, "devices": world,
            "api": "obj2voxel_b200_set_input_triangles (pinned host array) + obj2voxel_b200_set_devices(%d) + "
                   "obj2voxel_voxelize + voxel callback; %s" %
-                  (world, "the result crosses PCIe as occupancy bitmaps (1 bit per output voxel of the touched 64^3 "
-                          "chunks) and host threads write the quads the callback receives" if bitmap else
+                  (world, "the result crosses PCIe as packed positions (%d bytes per voxel) and host threads write the "
+                          "quads the callback receives" % round(stats["download_bytes"] / max(voxels, 1)) if packed else
                    "records cross PCIe as they are, each device's over its own link")}
     if world == 1 and host_uvs is None:
         pageable = np.array(host_verts, copy=True)  # plain numpy memory

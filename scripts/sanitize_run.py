@@ -15,6 +15,12 @@ cases = [
     (meshes.random_triangles(2000, 0.03), dict(resolution=128, strategy=1, bounds=meshes.UNIT_BOUNDS),
      dict(uvs=meshes.random_uvs(2000) * 3 - 1, textures=[(meshes.random_texture(32, 16, 3), 1)])),
     (meshes.random_triangles(5000, 0.002, seed=4), dict(resolution=128, bounds=meshes.UNIT_BOUNDS), {}),  # micro-triangles: thread-per-leaf classifier
+    # huge triangles: listed, then walked as (triangle, subtree) items by the huge* kernels (first run: the retry)
+    (np.concatenate([meshes.random_triangles(3, 0.45, seed=61), meshes.random_triangles(500, 0.02, seed=62)]),
+     dict(resolution=400, strategy=1, bounds=[-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]), {}),
+    (np.concatenate([meshes.random_triangles(2, 0.45, seed=63), meshes.random_triangles(300, 0.02, seed=64)]),
+     dict(resolution=384, strategy=1, bounds=[-0.01, -0.01, -0.01, 1.01, 1.01, 1.01]),
+     dict(uvs=meshes.random_uvs(302, seed=65), textures=[(meshes.random_texture(32, 16, 3), 1)])),
 ]
 for verts, kw, extra in cases:
     for occ in (1, 0):  # all-white meshes: occupancy-only pipeline, then the weighted one; textured: weighted twice
