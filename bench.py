@@ -649,7 +649,10 @@ def run_e2e(args, cfg, host_verts, host_uvs, n_tri, tri_bytes, rank, world, voxe
            "api": "obj2voxel_b200_set_input_triangles (pinned host array) + obj2voxel_b200_set_devices(%d) + "
                   "obj2voxel_voxelize + voxel callback; %s" %
                   (world, "the result crosses PCIe as packed positions (%d bytes per voxel) and host threads write the "
-                          "quads the callback receives" % round(stats["download_bytes"] / max(voxels, 1)) if packed else
+                          "quads the callback receives%s" % (round(stats["download_bytes"] / max(voxels, 1)),
+                                                            "; on one device the triangle array goes up in pieces and "
+                                                            "every piece is voxelized while the next one uploads"
+                                                            if world == 1 else "") if packed else
                    "records cross PCIe as they are, each device's over its own link")}
     if world == 1 and host_uvs is None:
         pageable = np.array(host_verts, copy=True)  # plain numpy memory

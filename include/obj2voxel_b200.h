@@ -51,6 +51,12 @@ typedef struct o2v_b200_params {
     int32_t occupancy_path;     /* 1 (default) = meshes whose every triangle is MATERIALLESS (output colour is white
                                  * whatever the weights, reference src/triangle.hpp:186) take the occupancy-only path;
                                  * 0 = always fold weights and colours (validation / measurement) */
+    int32_t accumulate;         /* occupancy-only path, a mesh voxelized piece by piece (what obj2voxel_voxelize() does while
+                                 * the triangles are still crossing PCIe): 0 = an ordinary run; 1 = the first piece, 2 = a
+                                 * later piece of the same grid / slab on the same engine.  A piece's result is the voxels
+                                 * no earlier piece has produced, so the pieces' results are disjoint and their union is
+                                 * the whole mesh's (the output is an OR).  A piece runs once: o2v_b200_voxelize_host needs
+                                 * room for all of its records on the first call (a repeated call finds them delivered). */
 } o2v_b200_params;
 
 typedef struct o2v_b200_mesh {

@@ -29,7 +29,8 @@ class Params(C.Structure):
     _fields_ = [("resolution", C.c_uint32), ("supersampling", C.c_uint32), ("strategy", C.c_uint32),
                 ("bounds_known", C.c_uint32), ("bounds", C.c_float * 6), ("unit_transform", C.c_int32 * 9),
                 ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32), ("variant", C.c_int32), ("prefilter", C.c_int32),
-                ("float_records", C.c_int32), ("slab_filtered", C.c_int32), ("occupancy_path", C.c_int32)]
+                ("float_records", C.c_int32), ("slab_filtered", C.c_int32), ("occupancy_path", C.c_int32),
+                ("accumulate", C.c_int32)]
 
 
 class Mesh(C.Structure):

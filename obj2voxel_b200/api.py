@@ -213,7 +213,7 @@ def sort_voxels(voxels):
 
 
 def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None, unit=None, slab=None, variant=-1,
-                prefilter=1, occupancy_path=1, slab_filtered=0, float_records=0):
+                prefilter=1, occupancy_path=1, slab_filtered=0, float_records=0, accumulate=0):
     p = Params()
     _lib.load().o2v_b200_default_params(C.byref(p))
     p.resolution = resolution
@@ -234,6 +234,7 @@ def make_params(resolution, supersampling=1, strategy=MAX_STRATEGY, bounds=None,
     p.occupancy_path = occupancy_path
     p.slab_filtered = slab_filtered
     p.float_records = float_records
+    p.accumulate = accumulate
     return p
 
 

@@ -179,6 +179,7 @@ EngineParams paramsFromC(const o2v_b200_params &p)
     e.occupancyPath = p.occupancy_path;
     e.slabFiltered = p.slab_filtered != 0;
     e.floatRecords = p.float_records != 0;
+    e.accumulate = p.accumulate;
     return e;
 }
 
@@ -415,7 +416,10 @@ obj2voxel_error_t runJob(obj2voxel_instance &inst, const std::function<obj2voxel
              "timing: %u device(s), upload %.2f ms%s, slab exchange %.2f ms%s, %u part(s) each: kernels %.2f ms, run + "
              "download%s + sink %.2f ms (device 0: voxelize calls %.2f, waiting for copies %.2f, host expansion %.2f, sink "
              "%.2f ms)",
-             timings.devices, timings.msUpload, timings.stagedUpload ? " (pageable input staged by host threads)" : "",
+             timings.devices, timings.msUpload,
+             timings.streamedUpload ? " (the upload runs under the parts: a part = a piece of the triangle array, voxelized as it arrives)"
+             : timings.stagedUpload ? " (pageable input staged by host threads)"
+                                    : "",
              timings.msExchange, timings.peerExchange ? " (peer stores)" : "", timings.parts, timings.msKernels,
              timings.bitmapDownload ? " of bitmaps + host expansion" : "", timings.msRun, timings.msVoxelizeCalls,
              timings.msWaitCopy, timings.msExpandHost, timings.msSink);

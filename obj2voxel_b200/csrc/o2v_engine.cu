@@ -197,6 +197,22 @@ int Engine::voxelize(const MeshView &meshIn, const TextureView *textures, uint32
     return rc == kRetryHugeWalk ? fail(kErrTooLarge, "the number of huge triangles keeps changing between attempts") : rc;
 }
 
+size_t Engine::accumulateBytes(const EngineParams &params)
+{
+    const unsigned long long S = (unsigned long long) params.resolution * params.supersampling;
+    if (S == 0 || S > 8192ull) {
+        return 0;
+    }
+    const uint32_t shift = params.supersampling == 2 ? 1u : 0u;
+    const uint32_t gridExtent = (uint32_t) ((S + 63u) / 64u * 64u);
+    const uint32_t z0 = params.slabZ0, z1 = (params.slabZ0 == 0 && params.slabZ1 == 0) ? gridExtent
+                                                                                          : std::min(params.slabZ1, gridExtent);
+    const unsigned long long perAxis = ((gridExtent >> shift) + kChunkEdge - 1) / kChunkEdge;
+    const unsigned long long rows = ((z1 >> shift) + kChunkEdge - 1) / kChunkEdge - (z0 >> shift) / kChunkEdge;
+    const unsigned long long bytes = perAxis * perAxis * rows * kChunkWords * 8ull;
+    return bytes <= (2ull << 30) ? (size_t) (2 * bytes) : 0;
+}
+
 bool Engine::hugeWork(HugeWork &work)
 {
     work = HugeWork{nullptr, nullptr, 0};
@@ -554,7 +570,12 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     launchOccupancyCount(mesh, grid, occ, leafCount_.as<uint32_t>(), leaves_.as<LeafRecord>(), dCounters, partOfGrid,
                          huge, hugeExpected_, smCount_, stream);
     st.kernelLaunches += huge.capacity != 0 ? 3 : 0;
-    launchOccupancyAssignChunks(occ, dCounters, stream);
+    if (params.accumulate == 0) {
+        launchOccupancyAssignChunks(occ, dCounters, stream);
+    }
+    else if (params.accumulate == 1) {
+        launchOccupancyAllChunks(occ, stream);  // (later pieces of the job find the two tables as this one leaves them)
+    }
     st.kernelLaunches += 2;
     launchPublishCounters(dCounters, hostCountersDevice_, stream);
     ++st.kernelLaunches;
@@ -578,11 +599,22 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     const unsigned long long leafTotal = hostCounters_->leaves == 0 ? 0 : n + extraLeaves;  // leaf slots
     const unsigned long long candidateBound = hostCounters_->candidateVoxels;
     const unsigned long long bigLeaves = hostCounters_->bigLeaves, bigBoxes = hostCounters_->bigBoxes;
-    occ.activeChunks = (uint32_t) hostCounters_->activeTiles;
+    occ.activeChunks = params.accumulate != 0 ? occ.chunkTotal : (uint32_t) hostCounters_->activeTiles;
     if (leafTotal >= (1ull << 32) || bigBoxes >= (1ull << 32) || bigLeaves >= (1ull << 24)) {
         return fail(kErrTooLarge, "more than 2^32-1 leaves or boxes in this slab");
     }
     st.occupancyPath = true;
+    const size_t accumulateBitmapBytes = params.accumulate != 0 ? (size_t) occ.chunkTotal * kChunkWords * 8 : 0;
+    if (params.accumulate != 0) {
+        // the job checked Engine::accumulateBytes: both bitmap sets exist for all of its pieces, cleared by the first
+        if (!tileBits_.ensure(accumulateBitmapBytes) || !emittedBits_.ensure(accumulateBitmapBytes)) {
+            return fail(kErrOutOfMemory, "device allocation failed (bitmaps of a job in pieces)");
+        }
+        if (params.accumulate == 1) {
+            O2V_CUDA(cudaMemsetAsync(tileBits_.as<void>(), 0, accumulateBitmapBytes, stream));
+            O2V_CUDA(cudaMemsetAsync(emittedBits_.as<void>(), 0, accumulateBitmapBytes, stream));
+        }
+    }
     if (leafTotal == 0) {
         st.counters = *hostCounters_;
         return kErrOk;
@@ -600,11 +632,11 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
     unsigned long long rangeCapacity = queueCapacity;  // one entry per row with undecided voxels
     const size_t bitmapBytes = (size_t) occ.activeChunks * kChunkWords * 8;
     if (const char *env = getenv("O2V_B200_OCCUPANCY_MAX_BYTES")) {  // test hook for the fallback below
-        if (bitmapBytes > strtoull(env, nullptr, 10)) {
+        if (bitmapBytes > strtoull(env, nullptr, 10) && params.accumulate == 0) {
             return kOccupancyFallback;
         }
     }
-    if (bitmapBytes > tileBits_.size()) {
+    if (bitmapBytes > tileBits_.size()) {  // (never with accumulate: the bitmaps exist already)
         size_t freeBytes = 0, totalBytes = 0;
         O2V_CUDA(cudaMemGetInfo(&freeBytes, &totalBytes));
         if (bitmapBytes > (freeBytes + tileBits_.size()) / 2) {
@@ -636,6 +668,7 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         }
     }
     occ.bits = tileBits_.as<unsigned long long>();
+    occ.emitted = params.accumulate != 0 ? emittedBits_.as<unsigned long long>() : nullptr;
     occ.queue = occQueue_.as<uint4>();
     occ.queueCapacity = queueCapacity;
     occ.ranges = occRanges_.as<uint4>();
@@ -670,7 +703,9 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         O2V_CUDA(cudaEventRecord(evVoxStart_, stream));
-        O2V_CUDA(cudaMemsetAsync(occ.bits, 0, bitmapBytes, stream));
+        if (params.accumulate == 0) {
+            O2V_CUDA(cudaMemsetAsync(occ.bits, 0, bitmapBytes, stream));
+        }
         O2V_CUDA(cudaEventRecord(evClassifyStart_, stream));
         // variant 1 / 2 force the block-per-batch / the thread-per-leaf classifier (tests: both must agree)
         const bool microLeaves = args.variant == 2 ||
@@ -742,6 +777,11 @@ int Engine::voxelizeOccupancy(const MeshView &meshIn, const EngineParams &params
         }
     }
 
+    if (params.accumulate != 0) {
+        // what this piece delivered is what every later piece leaves out (the expand kernel read `emitted`, nobody else
+        // does: the copy follows it on the stream)
+        O2V_CUDA(cudaMemcpyAsync(emittedBits_.as<void>(), occ.bits, accumulateBitmapBytes, cudaMemcpyDeviceToDevice, stream));
+    }
     hostCounters_->clipCalls = hostCounters_->survivors;  // every queued voxel is (at most) one exact clip
     st.counters = *hostCounters_;
     st.outCapacity = params.bitmapResult ? 0 : capacity;

@@ -38,6 +38,9 @@ struct EngineParams {
     bool packedResult = false;        // occupancy-only path: packed positions instead of 16-byte records (every voxel is
                                       // white): 4 bytes per voxel while the output grid fits 10 bits per axis, else 8
                                       // (see Engine::packedBits); a host-to-host job expands them on the host
+    int accumulate = 0;               // occupancy-only path, a job whose triangles arrive in pieces: 1 = first piece (every
+                                      // chunk of the slab gets a bitmap, cleared), 2 = a later piece (the bitmaps stay);
+                                      // a piece's result = the voxels no earlier piece has set (Engine::accumulateBytes)
 };
 
 /// What a run with EngineParams::bitmapResult leaves on the device: `chunks` bitmaps of kChunkWords 64-bit words
@@ -105,6 +108,8 @@ public:
 
     /// Voxelizes a device-resident mesh.  textures: HOST array of TextureView whose pixel pointers are DEVICE pointers.
     /// Result stays on the device (deviceVoxels / voxelCount) until the next call.  Returns 0 or a negative error.
+    /// Bytes of the two bitmap sets a job with EngineParams::accumulate keeps for this grid / slab (0: grid too large).
+    static size_t accumulateBytes(const EngineParams &params);
     int voxelize(const MeshView &meshIn, const TextureView *textures, uint32_t textureCount, const EngineParams &params,
                  cudaStream_t stream, RunStats *stats);
 
@@ -178,6 +183,7 @@ private:
                   bool *emptySlab);
     int voxelizeOccupancy(const MeshView &mesh, const EngineParams &params, const GridView &grid, cudaStream_t stream,
                           RunStats &st);
+    DeviceBuffer emittedBits_;
     static constexpr int kOccupancyFallback = 1;
     /// The count pass met huge triangles (o2v_device.cuh) without room to list them all: the run starts over with the list
     /// sized for them.  Sticky until a run meets none.

@@ -159,6 +159,12 @@ struct UploadedMesh {
 /// What a device keeps between jobs besides its engine.
 struct DeviceState {
     UploadedMesh upload;
+    // a mesh that goes up in pieces (runDeviceJob): the stream and the events are made once — creating and destroying
+    // them per job, and asking for the free memory, showed up as occasional 40 ms jobs
+    cudaStream_t uploadStream = nullptr;
+    std::vector<cudaEvent_t> pieceEvents;
+    size_t approvedBytes = 0;  // largest bitmaps + mesh footprint the free-memory check has passed
+
     uint32_t *records[2] = {nullptr, nullptr};  // host buffers the bitmaps are expanded into (plain memory: CPUs write it)
     size_t recordBytes[2] = {0, 0};
 
@@ -325,6 +331,11 @@ struct SlabRun {
     bool wantBitmap = false, wantPacked = false;
     cudaStream_t stream = nullptr;
     SharedSink *sink = nullptr;
+    // A mesh that is still crossing PCIe (occupancy-only path): the parts are pieces of the triangle array instead of z
+    // ranges — piece k = triangles [pieceFirst[k], pieceFirst[k + 1]), on the device once pieceReady[k] has happened —
+    // and every piece delivers the voxels no earlier piece has (EngineParams::accumulate).
+    std::vector<size_t> pieceFirst;
+    std::vector<cudaEvent_t> pieceReady;
     // results
     RunStats stats;
     bool any = false;
@@ -376,8 +387,10 @@ bool SlabRun::run()
     } guard{copyStream, copied};
 
     uint32_t partBounds[kMaxJobParts + 1];
-    parts = planJobParts(params.resolution * params.supersampling, params.slabZ0, params.slabZ1, mesh.count,
-                         requestedParts, partBounds);
+    const bool pieces = !pieceFirst.empty();
+    parts = pieces ? (uint32_t) pieceFirst.size() - 1
+                   : planJobParts(params.resolution * params.supersampling, params.slabZ0, params.slabZ1, mesh.count,
+                                  requestedParts, partBounds);
     const size_t batch = 1u << 21;
 
     // What is on its way to the sink: a part whose download sits in pinned buffer `slot` — records as they are, or
@@ -545,13 +558,25 @@ bool SlabRun::run()
     uint32_t launched = 0;  // parts handed to the delivery thread so far (slot = launched & 1)
     for (uint32_t k = 0; k < parts && !sink->failed && !deviceFailed; ++k) {
         EngineParams partParams = params;
-        partParams.slabZ0 = partBounds[k];
-        partParams.slabZ1 = partBounds[k + 1];
-        if (partParams.slabZ0 >= partParams.slabZ1) {
-            continue;
+        MeshView partMesh = mesh;
+        if (pieces) {
+            partMesh.verts = mesh.verts + pieceFirst[k] * 9;
+            partMesh.count = pieceFirst[k + 1] - pieceFirst[k];
+            partParams.accumulate = k == 0 ? 1 : 2;
+            if (cudaStreamWaitEvent(stream, pieceReady[k], 0) != cudaSuccess) {
+                failWith(std::string("waiting for the upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+                break;
+            }
         }
-        if (parts > 1) {
-            partParams.slabFiltered = false;  // a part filters its own triangles out of the slab's
+        else {
+            partParams.slabZ0 = partBounds[k];
+            partParams.slabZ1 = partBounds[k + 1];
+            if (partParams.slabZ0 >= partParams.slabZ1) {
+                continue;
+            }
+            if (parts > 1) {
+                partParams.slabFiltered = false;  // a part filters its own triangles out of the slab's
+            }
         }
         partParams.bitmapResult = wantBitmap;
         partParams.packedResult = wantPacked;
@@ -562,7 +587,7 @@ bool SlabRun::run()
         }
         RunStats partStats;
         const auto tCall = std::chrono::steady_clock::now();
-        const int rc = engine->voxelize(mesh, textures, textureCount, partParams, stream, &partStats);
+        const int rc = engine->voxelize(partMesh, textures, textureCount, partParams, stream, &partStats);
         msVoxelizeCalls += msSince(tCall);
         if (rc != 0) {
             failWith("Voxelization failed on the device: " + engine->lastError());
@@ -1079,7 +1104,7 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
     std::vector<unsigned long long> rowHistogram((size_t) D * 128, 0);  // [device][row]
     std::vector<uint32_t> slabs(activeBounds);  // the plan every device thread ends up with (equal rows, then balanced)
     static const bool balanceEnabled = getenv("O2V_B200_BALANCE") == nullptr || atoi(getenv("O2V_B200_BALANCE")) != 0;
-    std::atomic<bool> staged{false}, usedBitmap{false};
+    std::atomic<bool> staged{false}, usedBitmap{false}, streamedUpload{false};
     double msUpload = 0, msExchange = 0, msKernels = 0;
     uint32_t partsUsed = 0;
 
@@ -1107,10 +1132,80 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
         const size_t first = exchange ? n * d / D : 0, last = exchange ? n * (d + 1) / D : n;
         std::string error;
         bool wasStaged = false;
-        if (ok && !failed && !state.upload.upload(active[d], mesh, first, last - first, textures, stream, &wasStaged, &error)) {
+        // One device, an all-white mesh with known bounds in pinned memory: the array goes up in pieces and every piece is
+        // voxelized while the next one crosses PCIe (the result is an OR: a piece delivers what no earlier piece has).
+        std::vector<size_t> pieceFirst;
+        std::vector<cudaEvent_t> pieceReady;
+        cudaStream_t uploadStream = nullptr;
+        const char *streamEnv = getenv("O2V_B200_STREAM_UPLOAD");  // (read per job: tests compare both ways)
+        const bool streamEnabled = streamEnv == nullptr || atoi(streamEnv) != 0;
+        const char *streamMinEnv = getenv("O2V_B200_STREAM_MIN");  // triangles from which it pays (tests lower it)
+        const size_t streamMin = streamMinEnv != nullptr ? (size_t) strtoull(streamMinEnv, nullptr, 10) : (size_t) 2 << 20;
+        bool streamed = false;
+        if (ok && !failed && D == 1 && occupancy && wantPacked && streamEnabled && options.params.boundsKnown &&
+            mesh.verts != nullptr && n >= streamMin && isPinnedHost(mesh.verts)) {
+            const size_t bitmapBytes = Engine::accumulateBytes(options.params);
+            // one piece per 1.5 M triangles, two to eight (cfg4, 10 M triangles: 4 pieces 10.1 ms, 6: 9.2, 8: 9.4, 12: 10.5
+            // — every piece pays two host round trips and an expand pass over all bitmaps)
+            const uint32_t pieces = options.parts > 0
+                                        ? std::min((uint32_t) options.parts, kMaxJobParts)
+                                        : (uint32_t) std::min<size_t>(std::max<size_t>(n / 1500000, 2), 8);
+            bool fits = bitmapBytes != 0 && pieces > 1;
+            if (fits && bitmapBytes + n * 36 > state.approvedBytes) {
+                size_t freeBytes = 0, totalBytes = 0;
+                fits = cudaMemGetInfo(&freeBytes, &totalBytes) == cudaSuccess && bitmapBytes + n * 36 < freeBytes / 2;
+                if (fits) {
+                    state.approvedBytes = bitmapBytes + n * 36;
+                }
+            }
+            if (fits && state.uploadStream == nullptr &&
+                cudaStreamCreateWithFlags(&state.uploadStream, cudaStreamNonBlocking) != cudaSuccess) {
+                state.uploadStream = nullptr;
+                fits = false;
+            }
+            while (fits && state.pieceEvents.size() < pieces) {
+                cudaEvent_t made = nullptr;
+                fits = cudaEventCreateWithFlags(&made, cudaEventDisableTiming) == cudaSuccess;
+                if (fits) {
+                    state.pieceEvents.push_back(made);
+                }
+            }
+            uploadStream = state.uploadStream;
+            if (fits && state.upload.verts.ensure(n * 9 * sizeof(float))) {
+                streamed = true;
+                state.upload.view = MeshView{};
+                state.upload.view.verts = state.upload.verts.as<float>();
+                state.upload.view.count = n;
+                state.upload.textureViews.clear();
+                for (uint32_t k = 0; k <= pieces; ++k) {
+                    pieceFirst.push_back(n * k / pieces);
+                }
+                for (uint32_t k = 0; k < pieces && streamed; ++k) {
+                    const size_t offset = pieceFirst[k] * 9, floats = (pieceFirst[k + 1] - pieceFirst[k]) * 9;
+                    if (cudaMemcpyAsync(state.upload.verts.as<float>() + offset, mesh.verts + offset, floats * sizeof(float),
+                                        cudaMemcpyHostToDevice, uploadStream) != cudaSuccess ||
+                        cudaEventRecord(state.pieceEvents[k], uploadStream) != cudaSuccess) {
+                        fail(std::string("mesh upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+                        streamed = false;
+                    }
+                    pieceReady.push_back(state.pieceEvents[k]);
+                }
+            }
+        }
+        if (!streamed && D == 1 && occupancy && n >= streamMin) {
+            char why[256];
+            snprintf(why, sizeof why,
+                     "upload first, then the parts (streaming needs: packed download %d, enabled %d, known bounds %d, pinned "
+                     "input %d, bitmaps of the whole grid %zu bytes, more than one piece)",
+                     (int) wantPacked, (int) streamEnabled, (int) options.params.boundsKnown,
+                     (int) (mesh.verts != nullptr && isPinnedHost(mesh.verts)), Engine::accumulateBytes(options.params));
+            logMessage(OBJ2VOXEL_LOG_LEVEL_DEBUG, why);
+        }
+        if (!streamed && ok && !failed &&
+            !state.upload.upload(active[d], mesh, first, last - first, textures, stream, &wasStaged, &error)) {
             fail(error);
         }
-        if (ok) {
+        if (ok && !streamed) {
             cudaStreamSynchronize(stream);
         }
         if (wasStaged) {
@@ -1218,6 +1313,12 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
         run.wantPacked = wantPacked;
         run.stream = stream;
         run.sink = &sink;
+        if (streamed) {
+            run.pieceFirst = pieceFirst;
+            run.pieceReady = pieceReady;
+            run.textureCount = 0;
+            streamedUpload = true;
+        }
         const bool emptySlab = D > 1 && params.slabZ0 >= params.slabZ1;  // (never hand (0, 0) on: it means "the whole grid")
         if (ok && !failed && !emptySlab) {
             if (!run.run()) {
@@ -1245,6 +1346,9 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
             if (run.usedBitmap) {
                 usedBitmap = true;
             }
+        }
+        if (streamed) {
+            cudaStreamSynchronize(uploadStream);  // (the stream and the events stay with the device state)
         }
         if (stream != nullptr) {
             cudaStreamSynchronize(stream);
@@ -1283,6 +1387,7 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
     timings.parts = partsUsed;
     timings.bitmapDownload = usedBitmap;
     timings.stagedUpload = staged;
+    timings.streamedUpload = streamedUpload;
     if (statsOut != nullptr) {
         *statsOut = total;
     }

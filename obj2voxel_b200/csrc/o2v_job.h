@@ -34,6 +34,7 @@ struct JobTimings {
     std::vector<uint32_t> slabBounds;  // devices + 1 sample-space z bounds of the devices' slabs
     uint32_t parts = 0, devices = 0;
     bool bitmapDownload = false, peerExchange = false, stagedUpload = false;
+    bool streamedUpload = false;  // the mesh was voxelized piece by piece while it crossed PCIe (msUpload is not separate)
 };
 
 /// Process-wide engine of `device`, created on first use; nullptr + *error without a usable CUDA device.

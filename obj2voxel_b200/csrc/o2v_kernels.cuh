@@ -207,6 +207,8 @@ struct OccupancyView {
     uint32_t activeChunks;           // bitmaps in use (host copy of the device count)
     unsigned long long *bits;        // kChunkWords per bitmap: word = tile (x | y << 3 | z << 6) * 8 + layer z,
                                      // bit (x + 8 y) = OUTPUT voxel (x, y, z) of that tile is occupied
+    const unsigned long long *emitted;  // null, or the bits earlier pieces of the job have delivered (EngineParams::
+                                     // accumulate): the expand kernel leaves those voxels out
     uint4 *ranges;                   // per row with undecided voxels: {leaf, x | y << 16, z | gap << 16, lenA | lenB << 16}
     unsigned long long rangeCapacity;
     uint4 *queue;                    // {leaf, x | y << 16, z, -} of the voxels neither the SAT nor the bitmap decided
@@ -261,6 +263,8 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
                           LeafRecord *firstLeaves, RunCounters *counters, bool countFromFilter, const HugeWork &work,
                           unsigned long long hugeExpected, int smCount, cudaStream_t stream);
 void launchOccupancyAssignChunks(const OccupancyView &occ, RunCounters *counters, cudaStream_t stream);
+/// Every chunk of the slab gets a bitmap: slot = chunk (jobs that accumulate pieces, EngineParams::accumulate).
+void launchOccupancyAllChunks(const OccupancyView &occ, cudaStream_t stream);
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,
                                 cudaStream_t stream);
 /// histogram[r] += triangles whose z range reaches row r (rows of `unit` sample-space layers, rows <= 128).

@@ -485,6 +485,15 @@ __global__ void occupancyAssignChunksKernel(OccupancyView occ, RunCounters *coun
     }
 }
 
+__global__ void occupancyAllChunksKernel(OccupancyView occ)
+{
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk < occ.chunkTotal) {
+        occ.chunkSlot[chunk] = chunk;
+        occ.chunkList[chunk] = chunk;
+    }
+}
+
 /// What the second pass does with leaf number `seq` of triangle `tri`: leaves beyond the first are written to
 /// extraLeaves, and a leaf with more than kOccBigVolume candidates — first leaves included — enters the big-leaf table.
 __device__ __forceinline__ void occEmitLeaf(const OccupancyView &occ, const uint32_t *extraOffset, LeafRecord *extraLeaves,
@@ -1250,11 +1259,22 @@ occupancyExpandKernel(const VoxelizeArgs args)
         uint32_t origin[3] = {0, 0, 0};
         if (t < tiles) {
             const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(occ.bits + t * kTileEdge);
+            if (occ.emitted == nullptr) {
 #pragma unroll
-            for (int k = 0; k < (int) kTileEdge / 2; ++k) {
-                const ulonglong2 w = __ldcs(src + k);  // read once
-                m[2 * k] = w.x;
-                m[2 * k + 1] = w.y;
+                for (int k = 0; k < (int) kTileEdge / 2; ++k) {
+                    const ulonglong2 w = __ldcs(src + k);  // read once
+                    m[2 * k] = w.x;
+                    m[2 * k + 1] = w.y;
+                }
+            }
+            else {  // a piece of a job that accumulates: only what no earlier piece has delivered (block-uniform)
+                const ulonglong2 *old = reinterpret_cast<const ulonglong2 *>(occ.emitted + t * kTileEdge);
+#pragma unroll
+                for (int k = 0; k < (int) kTileEdge / 2; ++k) {
+                    const ulonglong2 w = __ldcg(src + k), e = __ldcg(old + k);
+                    m[2 * k] = w.x & ~e.x;
+                    m[2 * k + 1] = w.y & ~e.y;
+                }
             }
         }
         uint32_t count = 0;
@@ -1392,6 +1412,11 @@ void launchOccupancyCount(const MeshView &mesh, const GridView &grid, const Occu
         occHugeCountKernel<<<occHugeBlocks(hugeExpected), kOccHugeThreads, 0, stream>>>(mesh, grid, occ, work, firstLeaves,
                                                                                         counters);
     }
+}
+
+void launchOccupancyAllChunks(const OccupancyView &occ, cudaStream_t stream)
+{
+    occupancyAllChunksKernel<<<(occ.chunkTotal + 255) / 256, 256, 0, stream>>>(occ);
 }
 
 void launchOccupancySlabScatter(const MeshView &mesh, const GridView &grid, const SlabScatter &scatter, int smCount,

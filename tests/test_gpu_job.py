@@ -104,6 +104,46 @@ def test_pageable_input_is_staged_by_host_threads(monkeypatch):
     assert np.array_equal(pageable, o2v.sort_voxels(dev))
 
 
+@pytest.mark.parametrize("supersampling", [1, 2])
+@pytest.mark.parametrize("pieces", [2, 4])
+def test_a_pinned_mesh_is_voxelized_piece_by_piece_while_it_uploads(monkeypatch, pieces, supersampling):
+    """One GPU, an all-white mesh with known bounds in pinned memory: the triangle array goes up in pieces and every piece
+    is voxelized while the next one crosses PCIe; a piece delivers the voxels no earlier piece has (o2v_b200_params::
+    accumulate).  Same records as the job with the upload first (O2V_B200_STREAM_UPLOAD=0), and the oracle's."""
+    import torch
+
+    verts = meshes.random_triangles(40_000, 0.02, seed=47)
+    pinned = torch.from_numpy(verts).pin_memory().numpy()
+    res = 192 // supersampling
+    monkeypatch.setenv("O2V_B200_PIPELINE_PARTS", str(pieces))
+    monkeypatch.setenv("O2V_B200_STREAM_MIN", "1000")
+    monkeypatch.setenv("O2V_B200_STREAM_UPLOAD", "0")
+    first, stats = run_bulk(pinned, res, bounds=meshes.UNIT_BOUNDS, supersampling=supersampling)
+    monkeypatch.setenv("O2V_B200_STREAM_UPLOAD", "1")
+    lib = o2v.load()
+    lines = []
+    def on_log(data, message, level):
+        lines.append(message.decode())
+        return True
+
+    callback = _lib.LOG_CALLBACK(on_log)
+    lib.obj2voxel_set_log_callback(callback, None)
+    lib.obj2voxel_set_log_level(_lib.LOG_DEBUG)
+    try:
+        streamed, streamed_stats = run_bulk(pinned, res, bounds=meshes.UNIT_BOUNDS, supersampling=supersampling)
+    finally:
+        lib.obj2voxel_set_log_callback(None, None)
+        lib.obj2voxel_set_log_level(_lib.LOG_INFO)
+    assert any("the upload runs under the parts" in line for line in lines), lines[-3:]
+    assert np.array_equal(streamed, first) and len(streamed) == streamed_stats["voxels"]
+    want = oracle.voxelize(verts, res, bounds=meshes.UNIT_BOUNDS, supersampling=supersampling)["voxels"]
+    assert np.array_equal(streamed, want)
+    # an ordinary job afterwards starts from clean bitmaps
+    again, _ = run_bulk(verts[:5000], res, bounds=meshes.UNIT_BOUNDS, supersampling=supersampling)
+    assert np.array_equal(again, oracle.voxelize(verts[:5000], res, bounds=meshes.UNIT_BOUNDS,
+                                                 supersampling=supersampling)["voxels"])
+
+
 @pytest.mark.parametrize("case", ["white", "white_autobounds", "white_ss2", "white_skewed", "textured_blend"])
 def test_two_devices_deliver_the_oracles_records(case):
     """Two GPUs of one process: Z-slabs of whole chunk rows, each device uploads half of the triangles and stores every

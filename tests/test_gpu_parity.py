@@ -258,6 +258,27 @@ def test_huge_triangles_are_walked_in_reference_order(engine):
     parity(engine, v, 384, strategy=0, bounds=box)  # all-white: both pipelines
 
 
+@pytest.mark.parametrize("supersampling", [1, 2])
+def test_pieces_of_a_mesh_accumulate_to_the_whole(engine, supersampling):
+    """o2v_b200_params::accumulate: the mesh in three pieces on one engine — every piece returns the voxels no earlier piece
+    has produced, the pieces' results are disjoint, their union is the whole mesh's result."""
+    v = meshes.random_triangles(30000, 0.02, seed=71)
+    res = 256 // supersampling
+    kw = dict(resolution=res, supersampling=supersampling, strategy=0, bounds=meshes.UNIT_BOUNDS)
+    want = oracle.voxelize(v, res, supersampling=supersampling, strategy=0, bounds=meshes.UNIT_BOUNDS)["voxels"]
+    got = []
+    for k, piece in enumerate(np.array_split(v, 3)):
+        # (room for every record at once: a second call for the same piece would find all of its voxels delivered)
+        records, stats = engine.voxelize_host(np.ascontiguousarray(piece), o2v.make_params(accumulate=1 if k == 0 else 2, **kw),
+                                              capacity=1 << 21)
+        assert stats["occupancy_path"] == 1
+        got.append(records)
+    assert sum(len(g) for g in got) == len(want) and len(got[1]) < len(got[0])
+    assert np.array_equal(o2v.sort_voxels(np.concatenate(got)), want)
+    whole, _ = engine.voxelize_host(v, o2v.make_params(**kw))  # an ordinary run afterwards
+    assert np.array_equal(o2v.sort_voxels(whole), want)
+
+
 def test_huge_triangle_list_grows_and_shrinks_between_runs(engine):
     """The list of huge triangles is sized by what the previous attempt met: runs with none, a few, many and none again on
     one engine (every change of the count is a run that starts over once)."""
