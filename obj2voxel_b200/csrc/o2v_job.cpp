@@ -1142,7 +1142,8 @@ obj2voxel_error_t runDeviceJob(const o2v_b200_mesh &mesh, const std::vector<o2v_
         const char *streamMinEnv = getenv("O2V_B200_STREAM_MIN");  // triangles from which it pays (tests lower it)
         const size_t streamMin = streamMinEnv != nullptr ? (size_t) strtoull(streamMinEnv, nullptr, 10) : (size_t) 2 << 20;
         bool streamed = false;
-        if (ok && !failed && D == 1 && occupancy && wantPacked && streamEnabled && options.params.boundsKnown &&
+        const bool wholeGrid = options.params.slabZ0 == 0 && options.params.slabZ1 == 0;  // (a slab job filters per part)
+        if (ok && !failed && D == 1 && occupancy && wantPacked && streamEnabled && options.params.boundsKnown && wholeGrid &&
             mesh.verts != nullptr && n >= streamMin && isPinnedHost(mesh.verts)) {
             const size_t bitmapBytes = Engine::accumulateBytes(options.params);
             // one piece per 1.5 M triangles, two to eight (cfg4, 10 M triangles: 4 pieces 10.1 ms, 6: 9.2, 8: 9.4, 12: 10.5
