@@ -405,7 +405,7 @@ sparseFoldKernel(const VoxelizeArgs args)
                     if ((key >> groupShift) != group) {
                         break;
                     }
-                    const uint32_t vk = (key >> 18) & 511u, listSlot = (key >> 9) & 511u, slot = key & 511u;
+                    const uint32_t vk = (key >> 18) & 511u, slot = key & 511u;  // (bits 9 .. 17: the list slot, only a sort key)
                     if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
                         flushPartial(child, args);
                         contributions += child.contributions;
@@ -787,8 +787,7 @@ sparseBlockFoldKernel(const VoxelizeArgs args)
                 if ((key >> groupShift) != group) {
                     break;
                 }
-                const uint32_t vk = (uint32_t) (key >> 40) & 511u, listSlot = (uint32_t) (key >> 20) & 0xfffffu,
-                               e = (uint32_t) key & 0xfffffu;
+                const uint32_t vk = (uint32_t) (key >> 40) & 511u, e = (uint32_t) key & 0xfffffu;  // (bits 20 .. 39: list slot)
                 if (vk != currentVoxel) {  // next child of the same parent (downscale only), ascending Morton order
                     flushPartial(child, args);
                     contributions += child.contributions;
