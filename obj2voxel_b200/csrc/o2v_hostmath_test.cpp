@@ -45,6 +45,26 @@ size_t o2vt_subdivide(const float tri15[15], float *outLeaves, size_t cap)
     return count;
 }
 
+/// The leaves of forEachLeaf, produced the way the huge-triangle kernels produce them: subtree after subtree
+/// (forEachLeafOfSubtree, 4^depth subtrees).  Must equal o2vt_subdivide for a triangle that is not axis-aligned.
+size_t o2vt_subdivide_by_subtrees(const float tri15[15], int depth, float *outLeaves, size_t cap)
+{
+    Tri<true> t;
+    memcpy(t.v, tri15, sizeof t.v);
+    memcpy(t.t, tri15 + 9, sizeof t.t);
+    size_t count = 0;
+    for (uint32_t subtree = 0; subtree < (1u << (2 * depth)); ++subtree) {
+        forEachLeafOfSubtree<true>(t, depth, subtree, [&](const Tri<true> &leaf) {
+            if (count < cap) {
+                memcpy(outLeaves + count * 15, leaf.v, sizeof leaf.v);
+                memcpy(outLeaves + count * 15 + 9, leaf.t, sizeof leaf.t);
+            }
+            ++count;
+        });
+    }
+    return count;
+}
+
 float o2vt_area(const float v[9])
 {
     return triArea(v);

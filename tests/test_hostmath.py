@@ -24,6 +24,8 @@ def shim():
     lib.o2vt_clip_voxel.argtypes = [fp, C.POINTER(C.c_uint32), C.c_float, C.c_int, fp]
     lib.o2vt_subdivide.restype = C.c_size_t
     lib.o2vt_subdivide.argtypes = [fp, fp, C.c_size_t]
+    lib.o2vt_subdivide_by_subtrees.restype = C.c_size_t
+    lib.o2vt_subdivide_by_subtrees.argtypes = [fp, C.c_int, fp, C.c_size_t]
     lib.o2vt_area.restype = C.c_float
     lib.o2vt_area.argtypes = [fp]
     lib.o2vt_transform.argtypes = [fp, fp, fp]
@@ -83,6 +85,29 @@ def test_subdivision_order_and_values(shim):
         n = shim.o2vt_subdivide(tri.ctypes.data_as(fp), got.ctypes.data_as(fp), len(got))
         assert n == len(want)
         assert np.array_equal(got[:n].view(np.uint32), want.view(np.uint32))
+
+
+def test_subtree_walk_visits_the_leaves_in_the_reference_order(shim):
+    """Huge triangles are subdivided as 4^depth independent subtrees (o2v_exact.cuh, forEachLeafOfSubtree): walking the
+    subtrees one after the other must give the oracle's leaves in the oracle's order — including triangles so small that
+    they (or their children) are leaves above the split depth."""
+    rng = np.random.default_rng(12)
+    checked = 0
+    for it in range(60):
+        scale = [0.5, 3.0, 12.0, 40.0, 90.0][it % 5]
+        tri = np.zeros(15, np.float32)
+        tri[:9] = (rng.random(3)[None, :] * 50 + 60 + (rng.random((3, 3)) * 2 - 1) * scale).reshape(9)
+        tri[9:] = rng.random(6)
+        if shim.o2vt_aligned(tri.ctypes.data_as(fp)):
+            continue  # (an aligned triangle is its own leaf and never takes this path)
+        want = oracle.subdivide(tri)
+        for depth in (1, 3, 4):
+            got = np.zeros((max(len(want), 1), 15), np.float32)
+            n = shim.o2vt_subdivide_by_subtrees(tri.ctypes.data_as(fp), depth, got.ctypes.data_as(fp), len(got))
+            assert n == len(want), (it, depth, n, len(want))
+            assert np.array_equal(got[:n].view(np.uint32), want.view(np.uint32)), (it, depth)
+        checked += 1
+    assert checked > 40
 
 
 def test_transform_and_area(shim):
