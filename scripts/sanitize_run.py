@@ -40,6 +40,12 @@ p = o2v.make_params(resolution=128, slab=(64, 128), bounds=meshes.UNIT_BOUNDS)
 kept = eng.filter_slab(tv, p)
 st = eng.voxelize_device(kept, o2v.make_params(resolution=128, slab=(64, 128), slab_filtered=1, bounds=meshes.UNIT_BOUNDS))
 print(kept.shape[0], st["voxels"], hex(eng.result_hash()), flush=True)
+# a mesh in pieces (o2v_b200_params::accumulate): every chunk has a bitmap that stays, expand masks with the delivered bits
+pieces = np.array_split(meshes.random_triangles(6000, 0.02, seed=9), 3)
+for k, piece in enumerate(pieces):
+    v, st = eng.voxelize_host(np.ascontiguousarray(piece), o2v.make_params(resolution=64, supersampling=2, accumulate=1 if k == 0 else 2,
+                                                                          bounds=meshes.UNIT_BOUNDS), capacity=1 << 20)
+    print("piece", k, len(v), flush=True)
 eng.close()
 # the host-to-host job: parts, packed positions / bitmaps / records over PCIe, staged pageable upload
 import os
