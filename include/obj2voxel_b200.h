@@ -178,6 +178,14 @@ void o2v_b200_expand_packed(const void *packed, int32_t bits, uint64_t count, ui
 uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint32_t slab_z1, uint64_t triangles,
                              int32_t requested_parts, uint32_t *out_bounds, uint32_t bounds_capacity);
 
+/* How obj2voxel_voxelize() cuts a job into Z-slabs for `devices` devices (at most 16): devices + 1 ascending sample-space
+ * bounds, inner ones multiples of 64 * supersampling (a row of output chunks has one owner).  row_histogram = NULL: as
+ * many chunk rows each as the count allows; else row_histogram[r] = triangles whose z range reaches row r (rows of
+ * 64 * supersampling sample layers from z = 0) and the bounds are cut so that every device gets about the same number —
+ * what the job runner does with the histogram its devices take of their shares.  Pure host arithmetic: no device needed. */
+void o2v_b200_plan_slabs(uint32_t sample_resolution, uint32_t supersampling, uint32_t slab_z0, uint32_t slab_z1,
+                         uint32_t devices, const uint64_t *row_histogram, uint32_t rows, uint32_t *out_bounds);
+
 /* ---- additive setters on the reference-compatible instance ------------------------------------------------------- */
 
 /* Bulk input: count triangles as 9 floats each (+ 6 uv floats each and a texture when textured).  The arrays are not

@@ -100,6 +100,7 @@ ADDITIVE_SYMBOLS = [
     "o2v_b200_default_params", "o2v_b200_voxelize_device", "o2v_b200_result_device", "o2v_b200_result_count",
     "o2v_b200_result_download", "o2v_b200_result_floats_device", "o2v_b200_voxelize_host", "obj2voxel_b200_set_input_triangles",
     "obj2voxel_b200_set_slab", "obj2voxel_b200_get_stats", "o2v_b200_plan_parts", "o2v_b200_result_hash", "o2v_b200_filter_slab", "obj2voxel_b200_set_devices", "o2v_b200_expand_bitmaps", "o2v_b200_expand_packed", "o2v_b200_scan_chunk_bitmap", "obj2voxel_b200_array_source_next", "obj2voxel_b200_counting_sink_write",
+    "o2v_b200_plan_slabs",
 ]
 
 
@@ -181,6 +182,7 @@ def load():
         "obj2voxel_b200_counting_sink_write": (C.c_bool, [vp, vp, sz]),
         "obj2voxel_b200_get_stats": (None, [vp, C.POINTER(Stats)]),
         "o2v_b200_plan_parts": (u32, [u32, u32, u32, C.c_uint64, C.c_int32, C.POINTER(C.c_uint32), u32]),
+        "o2v_b200_plan_slabs": (None, [u32, u32, u32, u32, u32, C.POINTER(C.c_uint64), u32, C.POINTER(C.c_uint32)]),
     }
     for name, (restype, argtypes) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

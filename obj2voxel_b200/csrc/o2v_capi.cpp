@@ -945,6 +945,17 @@ uint32_t o2v_b200_plan_parts(uint32_t sample_resolution, uint32_t slab_z0, uint3
     return parts;
 }
 
+void o2v_b200_plan_slabs(uint32_t sample_resolution, uint32_t supersampling, uint32_t slab_z0, uint32_t slab_z1,
+                         uint32_t devices, const uint64_t *row_histogram, uint32_t rows, uint32_t *out_bounds)
+{
+    if (devices == 0 || devices > kMaxSlabs || supersampling == 0) {
+        return;
+    }
+    static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "histogram element");
+    planJobSlabs(sample_resolution, supersampling, slab_z0, slab_z1, devices,
+                 reinterpret_cast<const unsigned long long *>(row_histogram), rows, out_bounds);
+}
+
 int o2v_b200_result_download(o2v_b200_engine *engine, void *host_dst, void *cuda_stream)
 {
     const int rc = engine->engine->download(host_dst, static_cast<cudaStream_t>(cuda_stream));

@@ -813,6 +813,15 @@ std::vector<int> defaultJobDevices()
     return devices;
 }
 
+void planJobSlabs(uint32_t sampleRes, uint32_t supersampling, uint32_t jobZ0, uint32_t jobZ1, uint32_t devices,
+                  const unsigned long long *histogram, uint32_t rows, uint32_t *bounds)
+{
+    planDeviceSlabs(sampleRes, supersampling, jobZ0, jobZ1, devices, bounds);
+    if (histogram != nullptr && rows != 0) {
+        balanceDeviceSlabs(std::vector<unsigned long long>(histogram, histogram + rows), 64u * supersampling, devices, bounds);
+    }
+}
+
 uint32_t planJobParts(uint32_t sampleRes, uint32_t slabZ0, uint32_t slabZ1, unsigned long long triangles, int requested,
                       uint32_t *bounds)
 {

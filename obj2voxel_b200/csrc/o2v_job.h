@@ -47,6 +47,10 @@ constexpr uint32_t kMaxJobParts = 128;
 uint32_t planJobParts(uint32_t sampleRes, uint32_t slabZ0, uint32_t slabZ1, unsigned long long triangles, int requested,
                       uint32_t *bounds);
 void accumulateStats(RunStats &total, const RunStats &part);
+/// The Z-slabs of a job over `devices` devices (see o2v_b200_plan_slabs): equal chunk rows, then — with a histogram of
+/// triangles per row of 64 * supersampling sample layers — cut so that every device gets about the same number.
+void planJobSlabs(uint32_t sampleRes, uint32_t supersampling, uint32_t jobZ0, uint32_t jobZ1, uint32_t devices,
+                  const unsigned long long *histogram, uint32_t rows, uint32_t *bounds);
 
 /// Runs the job.  mesh / textures: HOST pointers (o2v_b200_mesh layout).  Returns OBJ2VOXEL_ERR_OK,
 /// OBJ2VOXEL_ERR_DEVICE (message logged) or OBJ2VOXEL_ERR_IO_ERROR_DURING_VOXEL_WRITE.

@@ -198,6 +198,52 @@ def test_product_never_references_the_oracle():
                     "import oracle" not in text, os.path.join(dirpath, f)
 
 
+def plan_slabs(sample_res, supersampling, devices, histogram=None, z0=0, z1=0):
+    import ctypes as C
+
+    lib = o2v.load()
+    out = (C.c_uint32 * (devices + 1))()
+    if histogram is None:
+        lib.o2v_b200_plan_slabs(sample_res, supersampling, z0, z1, devices, None, 0, out)
+    else:
+        h = (C.c_uint64 * len(histogram))(*[int(x) for x in histogram])
+        lib.o2v_b200_plan_slabs(sample_res, supersampling, z0, z1, devices, h, len(histogram), out)
+    return list(out)
+
+
+def test_device_slabs_equal_rows_and_balanced_by_a_histogram():
+    """The job runner's Z-slabs (o2v_job.cpp: planDeviceSlabs, balanceDeviceSlabs) through their C-ABI window: equal chunk
+    rows without a histogram; with one, every device gets about the same number of triangles — the round-1 review's case,
+    cfg2's sphere on 4 slabs (few triangles near the poles, many at the equator rows... per unit of z the same: a sphere's
+    area per z is constant, so the lumps decide), and a mesh with nine tenths of its triangles at the bottom."""
+    from obj2voxel_b200 import meshes, slabs
+
+    assert plan_slabs(1024, 1, 4) == [0, 256, 512, 768, 1024]
+    assert plan_slabs(2048, 2, 4) == [0, 512, 1024, 1536, 2048]      # (sample resolution 2048 = 1024 x 2)
+    assert plan_slabs(320, 2, 4) == [0, 0, 128, 256, 320]            # rows of 128 samples: an output chunk row has one owner
+    assert plan_slabs(100, 1, 4) == [0, 0, 64, 64, 128]              # two rows: two devices sit the job out
+    assert plan_slabs(1024, 1, 4, histogram=[0] * 16) == [0, 256, 512, 768, 1024]  # nothing to go by
+
+    # cfg2's sphere at 1024: z extents of its triangles in voxel space (the oracle's transform: unit cube -> grid)
+    v = meshes.lumpy_sphere().reshape(-1, 3, 3)
+    lo, hi = v.reshape(-1, 3).min(axis=0), v.reshape(-1, 3).max(axis=0)
+    scale = 1024 / float((hi - lo).max())
+    z = (v[:, :, 2] - lo[2]) * scale
+    hist = slabs.z_row_histogram(z.min(axis=1), z.max(axis=1), (1.0, 0.0), 1024)
+    bounds = plan_slabs(1024, 1, 4, histogram=hist)
+    assert bounds[0] == 0 and bounds[-1] == 1024 and all(b % 64 == 0 for b in bounds) and bounds == sorted(bounds)
+    work = [hist[bounds[d] // 64:bounds[d + 1] // 64].sum() for d in range(4)]
+    assert max(work) <= 1.35 * (sum(work) / 4), (bounds, work)       # rows are the granularity: 16 rows for 4 devices
+    # the Python-side planner (slabs.balanced_slabs, what a torch.distributed job would use) cuts the same way within a row
+    other = slabs.balanced_slabs(hist, 1024, 4)
+    assert all(abs(a - b) <= 64 for a, b in zip(bounds, other)), (bounds, other)
+
+    skewed = [9000, 5000, 300, 200] + [100] * 12                     # nine tenths in the two bottom rows
+    assert plan_slabs(1024, 1, 2, histogram=skewed) == [0, 64, 1024]
+    # four devices: a row cannot be split, so one device sits out and the two heavy rows get a device each
+    assert plan_slabs(1024, 1, 4, histogram=skewed) == [0, 0, 64, 128, 1024]
+
+
 def plan_parts(sample_res, z0, z1, triangles, requested):
     lib = o2v.load()
     out = (C.c_uint32 * 130)()
